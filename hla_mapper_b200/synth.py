@@ -1,0 +1,397 @@
+"""Seeded synthetic inputs for the hla-mapper hot path.
+
+Two generators, both pure numpy so they run on the CPU box and on the GPU box:
+
+* :func:`make_db` writes an IPD-IMGT/HLA-shaped database in the *reference's on-disk layout*
+  (``db_{dna,rna}.info``, ``motif/<kind>/all/motif_all.txt``, ``motif/<kind>/loci/<g>.txt``,
+  ``mapper/<kind>/<g>/<g>.fas``, ``others/<kind>/hla_gen_others.fasta``; paths as read by
+  /root/reference/src/map_dna.cpp:299-365,572,735,824 and preselect.cpp:299-300).
+* :func:`make_reads` draws read pairs of the BASELINE.json config shapes from that database.
+  Pairs are generated in blocks of ``BLOCK`` with a counter-based Philox stream keyed by
+  (seed, block index), so any shard of a large run can be regenerated independently.
+
+Neither is part of the product path; they only make inputs.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+BLOCK = 65536
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+LOCUS_NAMES = [
+    "HLA-A", "HLA-B", "HLA-C", "HLA-E", "HLA-F", "HLA-G", "HLA-H", "HLA-DRA", "HLA-DRB1",
+    "HLA-DRB5", "HLA-DQA1", "HLA-DQB1", "HLA-DPA1", "HLA-DPB1", "HLA-DMA", "HLA-DMB",
+    "HLA-DOA", "HLA-DOB", "MICA", "MICB", "TAP1", "TAP2", "HLA-J", "HLA-L", "HLA-V",
+    "HLA-DQA2", "HLA-DQB2", "HLA-DPB2", "HLA-DRB3", "HLA-DRB4", "HLA-K",
+]
+# allele counts shaped like IPD-IMGT/HLA (A 8k, B 9k, C 8k, DRB1 4k, DQB1 2.5k, DPB1 2.5k, ...)
+_ALLELE_SHAPE = {
+    "HLA-A": 8000, "HLA-B": 9000, "HLA-C": 8000, "HLA-DRB1": 4000, "HLA-DQB1": 2500,
+    "HLA-DPB1": 2500,
+}
+
+
+@dataclass
+class SynthDB:
+    path: str
+    kind: str
+    loci: list
+    alleles: dict  # locus -> list of np.uint8 code arrays (0..3)
+    flanks: dict  # locus -> (left, right) code arrays: genomic context outside the alleles
+    others: list
+    v_size: int
+    seed: int
+    n_alleles: int = 0
+    n_bases: int = 0
+    meta: dict = field(default_factory=dict)
+
+
+def _mutate(rng, seq, rate):
+    """substitute `rate` of the sites with a different base"""
+    out = seq.copy()
+    n = len(seq)
+    k = rng.binomial(n, rate)
+    if k:
+        pos = rng.choice(n, size=k, replace=False)
+        out[pos] = (out[pos] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3
+    return out
+
+
+def _kmer_codes(seq, k=20):
+    """all k-mer codes (2 bit/base, first base most significant) of a code array"""
+    n = len(seq) - k + 1
+    if n <= 0:
+        return np.empty(0, dtype=np.uint64)
+    acc = np.zeros(n, dtype=np.uint64)
+    s = seq.astype(np.uint64)
+    for i in range(k):
+        acc = (acc << np.uint64(2)) | s[i:i + n]
+    return acc
+
+
+def _rc_codes(codes, k=20):
+    """reverse complement of packed k-mer codes"""
+    codes = np.asarray(codes, dtype=np.uint64)
+    out = np.zeros(len(codes), dtype=np.uint64)
+    c = codes.copy()
+    for _ in range(k):
+        out = (out << np.uint64(2)) | (np.uint64(3) - (c & np.uint64(3)))
+        c >>= np.uint64(2)
+    return out
+
+
+def _both_strands(codes, k=20):
+    return np.unique(np.concatenate([codes, _rc_codes(codes, k)]))
+
+
+def _codes_to_kmer_strings(codes, k=20):
+    codes = np.asarray(codes, dtype=np.uint64)
+    out = np.empty((len(codes), k + 1), dtype=np.uint8)
+    out[:, k] = 10
+    for i in range(k):
+        sh = np.uint64(2 * (k - 1 - i))
+        out[:, i] = _ACGT[((codes >> sh) & np.uint64(3)).astype(np.int64)]
+    return out.tobytes()
+
+
+def _write_fasta(path, names, seqs, width=60):
+    with open(path, "wb") as f:
+        for nm, s in zip(names, seqs):
+            f.write(b">" + nm.encode() + b"\n")
+            b = _ACGT[s].tobytes()
+            if width and len(b) > width:
+                f.write(b"\n".join(b[i:i + width] for i in range(0, len(b), width)))
+            else:
+                f.write(b)
+            f.write(b"\n")
+
+
+def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000), n_others=2000,
+            kind="dna", v_size=50, n_lineages=16, motif_stride=4, flank=300, write=True):
+    """Build (and write) a synthetic database.  `total_alleles` scales the IMGT-shaped counts."""
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0xDB]))
+    loci = LOCUS_NAMES[:n_loci]
+    shape = np.array([_ALLELE_SHAPE.get(g, 0) for g in loci], dtype=np.float64)
+    rest = shape == 0
+    shape[rest] = rng.integers(100, 1500, size=int(rest.sum()))
+    counts = np.maximum(2, np.round(shape * (total_alleles / shape.sum()))).astype(int)
+
+    alleles, flanks, ancestors = {}, {}, {}
+    motif_loci = {}
+    for gi, g in enumerate(loci):
+        L = int(rng.integers(len_range[0], len_range[1] + 1))
+        if gi % 3 == 0:
+            anc = rng.integers(0, 4, size=L, dtype=np.uint8)
+        else:  # paralog: 85-92 % identity to the head of the group, own length
+            head = ancestors[loci[gi - gi % 3]]
+            anc = _mutate(rng, np.resize(head, L), float(rng.uniform(0.08, 0.15)))
+        ancestors[g] = anc
+        flanks[g] = (rng.integers(0, 4, size=flank, dtype=np.uint8),
+                     rng.integers(0, 4, size=flank, dtype=np.uint8))
+        # polymorphic-site pool (10 % of sites); lineages carry alt alleles at ~15 % of them
+        pool = rng.choice(L, size=max(4, L // 10), replace=False)
+        nl = int(min(n_lineages, max(1, counts[gi] // 2)))
+        lineages = []
+        for _ in range(nl):
+            s = anc.copy()
+            pick = pool[rng.random(len(pool)) < 0.15]
+            s[pick] = (s[pick] + rng.integers(1, 4, size=len(pick), dtype=np.uint8)) & 3
+            lineages.append(s)
+        als = []
+        kset = [_kmer_codes(s)[::motif_stride] for s in lineages]
+        for a in range(int(counts[gi])):
+            base = lineages[a % nl]
+            if a < nl:
+                als.append(base)
+                continue
+            s = base.copy()
+            nsnp = int(rng.integers(1, 4))
+            pos = rng.integers(0, L, size=nsnp)
+            s[pos] = (s[pos] + rng.integers(1, 4, size=nsnp, dtype=np.uint8)) & 3
+            lo = [int(p) for p in pos]
+            if rng.random() < 0.05:  # occasional 1-3 bp indel
+                p = int(rng.integers(50, L - 50))
+                k = int(rng.integers(1, 4))
+                if rng.random() < 0.5:
+                    s = np.concatenate([s[:p], s[p + k:]])
+                else:
+                    s = np.concatenate([s[:p], rng.integers(0, 4, size=k, dtype=np.uint8), s[p:]])
+                lo.append(p)
+            als.append(s)
+            for p in lo:  # the motifs that see the private change
+                a0, a1 = max(0, p - 23), min(len(s), p + 23)
+                kset.append(_kmer_codes(s[a0:a1]))
+        alleles[g] = als
+        motif_loci[g] = _both_strands(np.concatenate(kset))
+
+    others = []
+    kset = []
+    for _ in range(n_others):
+        g = loci[int(rng.integers(0, len(loci)))]
+        s = _mutate(rng, ancestors[g], float(rng.uniform(0.10, 0.20)))
+        others.append(s)
+        kset.append(_kmer_codes(s)[::motif_stride])
+    motif_all = np.unique(np.concatenate([motif_loci[g] for g in loci] +
+                                         [_both_strands(np.concatenate(kset))]))
+
+    db = SynthDB(path=path, kind=kind, loci=loci, alleles=alleles, flanks=flanks, others=others,
+                 v_size=v_size, seed=seed)
+    db.n_alleles = int(sum(len(v) for v in alleles.values()))
+    db.n_bases = int(sum(len(s) for v in alleles.values() for s in v))
+    db.meta = {"motif_all": int(len(motif_all)), "n_others": len(others)}
+    if write:
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, f"db_{kind}.info"), "w") as f:
+            f.write("hla-mapper:4.3+\n")
+            for gi, g in enumerate(loci):
+                L = len(ancestors[g])
+                f.write(f"GENE:{g}:chr6:{29000000 + gi * 100000}:170805979:1:{L}:HLA\n")
+            f.write(f"SIZE:{v_size}\n")
+        os.makedirs(os.path.join(path, "motif", kind, "all"), exist_ok=True)
+        os.makedirs(os.path.join(path, "motif", kind, "loci"), exist_ok=True)
+        os.makedirs(os.path.join(path, "others", kind), exist_ok=True)
+        with open(os.path.join(path, "motif", kind, "all", "motif_all.txt"), "wb") as f:
+            f.write(_codes_to_kmer_strings(motif_all))
+        for g in loci:
+            with open(os.path.join(path, "motif", kind, "loci", g + ".txt"), "wb") as f:
+                f.write(_codes_to_kmer_strings(motif_loci[g]))
+            d = os.path.join(path, "mapper", kind, g)
+            os.makedirs(d, exist_ok=True)
+            names = [f"{g}*{i + 1:05d}" for i in range(len(alleles[g]))]
+            _write_fasta(os.path.join(d, g + ".fas"), names, alleles[g])
+        _write_fasta(os.path.join(path, "others", kind, "hla_gen_others.fasta"),
+                     [f"other_{i}" for i in range(len(others))], others)
+    return db
+
+
+@dataclass
+class ReadBatch:
+    n_pairs: int
+    bases1: np.ndarray
+    quals1: np.ndarray
+    offs1: np.ndarray
+    bases2: np.ndarray
+    quals2: np.ndarray
+    offs2: np.ndarray
+    truth_locus: np.ndarray  # index into db.loci, -1 = decoy
+    seed: int = 0
+    first_pair: int = 0
+
+    def ids(self, prefix="SYN"):
+        return [f"{prefix}:{self.first_pair + i}" for i in range(self.n_pairs)]
+
+    def slice(self, lo, hi):
+        o1, o2 = self.offs1, self.offs2
+        return ReadBatch(hi - lo, self.bases1[o1[lo]:o1[hi]], self.quals1[o1[lo]:o1[hi]],
+                         (o1[lo:hi + 1] - o1[lo]).astype(np.uint64),
+                         self.bases2[o2[lo]:o2[hi]], self.quals2[o2[lo]:o2[hi]],
+                         (o2[lo:hi + 1] - o2[lo]).astype(np.uint64), self.truth_locus[lo:hi],
+                         self.seed, self.first_pair + lo)
+
+
+_QBINS = np.frombuffer(b"?5+'", dtype=np.uint8)  # Q30 Q20 Q10 Q6, as in test_sequences
+_QPROB = np.array([0.955, 0.04, 0.004, 0.001])  # isolated low-quality calls are rare ...
+
+
+class _Source:
+    """flattened view of the diploid sample the reads are drawn from"""
+
+    def __init__(self, db: SynthDB, rng):
+        seqs, loc = [], []
+        for gi, g in enumerate(db.loci):
+            als = db.alleles[g]
+            for a in rng.integers(0, len(als), size=2):
+                l, r = db.flanks[g]
+                seqs.append(np.concatenate([l, als[int(a)], r]))
+                loc.append(gi)
+        self.lens = np.array([len(s) for s in seqs], dtype=np.int64)
+        self.starts = np.concatenate([[0], np.cumsum(self.lens)[:-1]]).astype(np.int64)
+        self.flat = np.concatenate(seqs).astype(np.uint8)
+        self.locus = np.array(loc, dtype=np.int32)
+
+
+def _block(db, src, rng, n, read_len, on_target, frag_mu, frag_sd, lowq_tail):
+    L = read_len
+    truth = np.full(n, -1, dtype=np.int32)
+    on = rng.random(n) < on_target
+    hap = rng.integers(0, len(src.lens), size=n)
+    frag = np.clip(np.round(rng.normal(frag_mu, frag_sd, size=n)).astype(np.int64), L, None)
+    frag = np.minimum(frag, src.lens[hap])
+    st = (rng.random(n) * (src.lens[hap] - frag + 1)).astype(np.int64)
+    ar = np.arange(L, dtype=np.int64)
+    i1 = (src.starts[hap] + st)[:, None] + ar[None, :]
+    i2 = (src.starts[hap] + st + frag - 1)[:, None] - ar[None, :]
+    r1 = src.flat[i1]
+    r2 = _COMP[src.flat[i2]]
+    flip = rng.random(n) < 0.5
+    r1f = np.where(flip[:, None], r2, r1)
+    r2f = np.where(flip[:, None], r1, r2)
+    truth[on] = src.locus[hap[on]]
+    # decoys: uniform random, 10 % low complexity
+    nd = int((~on).sum())
+    if nd:
+        d1 = rng.integers(0, 4, size=(nd, L), dtype=np.uint8)
+        d2 = rng.integers(0, 4, size=(nd, L), dtype=np.uint8)
+        lc = rng.random(nd) < 0.10
+        unit = rng.integers(0, 4, size=(nd, 3), dtype=np.uint8)
+        rep = unit[:, ar % 3]
+        d1[lc] = rep[lc]
+        r1f[~on] = d1
+        r2f[~on] = d2
+    # substitution errors ramping 0.2 % -> 1 % along the read
+    perr = np.linspace(0.002, 0.01, L)[None, :]
+    for r in (r1f, r2f):
+        e = rng.random((n, L)) < perr
+        r[e] = (r[e] + rng.integers(1, 4, size=int(e.sum()), dtype=np.uint8)) & 3
+    b1 = _ACGT[r1f]
+    b2 = _ACGT[r2f]
+    # a few N calls
+    for b in (b1, b2):
+        nn = rng.random((n, L)) < 0.0005
+        b[nn] = ord("N")
+    q1 = _QBINS[rng.choice(4, size=(n, L), p=_QPROB)]
+    q2 = _QBINS[rng.choice(4, size=(n, L), p=_QPROB)]
+    # ... low-quality calls cluster in tails / heads (this is what mtrim cuts)
+    for q in (q1, q2):
+        t = rng.random(n) < lowq_tail
+        tl = rng.integers(1, L // 2, size=n)
+        m = t[:, None] & (ar[None, :] >= (L - tl)[:, None])
+        q[m] = ord("'")
+        h = rng.random(n) < lowq_tail / 4
+        hl = rng.integers(1, L // 4, size=n)
+        m = h[:, None] & (ar[None, :] < hl[:, None])
+        q[m] = ord("+")
+    return b1, q1, b2, q2, truth
+
+
+def make_reads(db: SynthDB, n_pairs, read_len=150, seed=1001, on_target=1.0, frag_mu=400,
+               frag_sd=60, lowq_tail=0.10, indel_rate=1e-4, first_pair=0, ragged=False):
+    """Draw `n_pairs` pairs starting at global pair index `first_pair` (must be BLOCK-aligned
+    for shard reproducibility).  `ragged=True` additionally deletes/inserts bases so read
+    lengths vary (indel errors), which makes the batch ragged."""
+    assert first_pair % BLOCK == 0
+    src = _Source(db, np.random.Generator(np.random.Philox(key=[seed, 0x5A])))
+    B1, Q1, B2, Q2, TR = [], [], [], [], []
+    done = 0
+    blk = first_pair // BLOCK
+    while done < n_pairs:
+        rng = np.random.Generator(np.random.Philox(key=[seed, 1 + blk]))
+        b1, q1, b2, q2, tr = _block(db, src, rng, BLOCK, read_len, on_target, frag_mu, frag_sd,
+                                    lowq_tail)
+        take = min(BLOCK, n_pairs - done)
+        B1.append(b1[:take]); Q1.append(q1[:take]); B2.append(b2[:take]); Q2.append(q2[:take])
+        TR.append(tr[:take])
+        done += take
+        blk += 1
+    b1 = np.concatenate(B1); q1 = np.concatenate(Q1); b2 = np.concatenate(B2); q2 = np.concatenate(Q2)
+    truth = np.concatenate(TR)
+    L = read_len
+    if not ragged:
+        offs = (np.arange(n_pairs + 1, dtype=np.uint64) * np.uint64(L))
+        return ReadBatch(n_pairs, b1.reshape(-1), q1.reshape(-1), offs, b2.reshape(-1),
+                         q2.reshape(-1), offs.copy(), truth, seed, first_pair)
+    # ragged: per-read indel errors (rare) applied in a python loop over the affected reads
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0x1D, first_pair // BLOCK]))
+
+    def rag(b, q):
+        rows_b = [None] * n_pairs
+        rows_q = [None] * n_pairs
+        hit = rng.random(n_pairs) < min(1.0, indel_rate * L * 50)
+        for i in range(n_pairs):
+            if hit[i]:
+                p = int(rng.integers(1, L - 1))
+                if rng.random() < 0.5:
+                    rows_b[i] = np.delete(b[i], p); rows_q[i] = np.delete(q[i], p)
+                else:
+                    rows_b[i] = np.insert(b[i], p, _ACGT[rng.integers(0, 4)])
+                    rows_q[i] = np.insert(q[i], p, ord("?"))
+            else:
+                rows_b[i] = b[i]; rows_q[i] = q[i]
+        lens = np.array([len(r) for r in rows_b], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        return np.concatenate(rows_b), np.concatenate(rows_q), offs
+
+    fb1, fq1, o1 = rag(b1, q1)
+    fb2, fq2, o2 = rag(b2, q2)
+    return ReadBatch(n_pairs, fb1, fq1, o1, fb2, fq2, o2, truth, seed, first_pair)
+
+
+def write_fastq(batch: ReadBatch, path_r1, path_r2=None, prefix="SYN", suffix=True):
+    ids = batch.ids(prefix)
+    for path, b, q, o, tag in ((path_r1, batch.bases1, batch.quals1, batch.offs1, "/1"),
+                               (path_r2, batch.bases2, batch.quals2, batch.offs2, "/2")):
+        if path is None:
+            continue
+        with open(path, "wb") as f:
+            for i in range(batch.n_pairs):
+                a, e = int(o[i]), int(o[i + 1])
+                f.write(b"@" + ids[i].encode() + (tag.encode() if suffix else b"") + b"\n")
+                f.write(b[a:e].tobytes() + b"\n+\n" + q[a:e].tobytes() + b"\n")
+
+
+def read_fastq_pair(path_r1, path_r2=None):
+    """tiny FASTQ reader (4-line records) -> ReadBatch + id list"""
+    def rd(p):
+        ids, bs, qs = [], [], []
+        with open(p, "rb") as f:
+            while True:
+                h = f.readline()
+                if not h:
+                    break
+                s = f.readline().rstrip(b"\n"); f.readline(); q = f.readline().rstrip(b"\n")
+                ids.append(h.rstrip(b"\n").decode()); bs.append(s); qs.append(q)
+        lens = np.array([len(x) for x in bs], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        return ids, np.frombuffer(b"".join(bs), dtype=np.uint8), np.frombuffer(b"".join(qs), dtype=np.uint8), offs
+    i1, b1, q1, o1 = rd(path_r1)
+    if path_r2:
+        _, b2, q2, o2 = rd(path_r2)
+    else:
+        b2, q2, o2 = b1[:0], q1[:0], np.zeros(len(i1) + 1, dtype=np.uint64)
+    n = len(i1)
+    return ReadBatch(n, b1, q1, o1, b2, q2, o2, np.full(n, -1, np.int32)), i1

@@ -1,0 +1,202 @@
+/*
+ * hlamap.h — C-ABI of libhlamap, the B200-native hot path of hla-mapper.
+ *
+ * The reference (erickcastelli/hla-mapper v4.5.1) has no library / FFI surface:
+ * its hot path is a chain of file-coupled stages inside main_preselect() and
+ * main_dna_map() / main_rna_map().  Each entry point below replaces one of those
+ * stages and cites the reference lines it stands in for.  Everything is plain C:
+ * pointers + sizes, caller-owned buffers, int return codes (0 = ok, <0 = error,
+ * text via hlm_last_error()).  No exceptions, no global mutable state.
+ *
+ *   stage                      reference                                  entry point
+ *   -------------------------  -----------------------------------------  -------------------
+ *   DB layout reader           src/map_dna.cpp:299-365, map_rna.cpp:281-335,
+ *                              preselect.cpp:297-309, map_dna.cpp:565-581  hlm_db_open
+ *   global k-mer screen        src/preselect.cpp:707-731 (FASTQ),
+ *                              :484-506 (BAM-derived)                      hlm_screen_trim
+ *   quality trim (mtrim)       src/functions.cpp:89-145,
+ *                              src/preselect.cpp:1060-1149                 hlm_screen_trim
+ *   per-locus k-mer sort       src/map_dna.cpp:611-627, map_rna.cpp:544-560 hlm_screen_trim
+ *   aligner + SAM reducer      src/map_dna.cpp:749-776 (bwa aln/samse),
+ *                              :44-118 (read_sam_dna), map_rna.cpp:39-101  hlm_score
+ *   others back-fill, compare, src/map_dna.cpp:903-1029,
+ *   argmin, tie set            src/map_rna.cpp:925-1027                    hlm_assign
+ *   ThreadPool dispatch        src/ThreadPool.hpp:18-100                   hlm_run (stream pipeline)
+ */
+#ifndef HLAMAP_H
+#define HLAMAP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HLM_ABI_VERSION 1
+
+/* limits of this build */
+#define HLM_MAX_LOCI 31   /* loci + "others" must fit a uint32 mask            */
+#define HLM_MAX_READ 184  /* longest trimmed mate the 256-column tiles can hold */
+#define HLM_MOTIF 20      /* motif_size, src/main.cpp:73                        */
+#define HLM_SEED 12       /* aligner seed length (new)           */
+#define HLM_BAND 20       /* DP half band = v_mm_max, src/main.cpp:77           */
+
+/* error codes */
+#define HLM_OK 0
+#define HLM_E_ARG -1
+#define HLM_E_IO -2
+#define HLM_E_DB -3
+#define HLM_E_CUDA -4
+#define HLM_E_NOMEM -5
+#define HLM_E_TOOLONG -6
+#define HLM_E_NODEVICE -7
+
+/* screen variants: the reference has two differently-strided loops */
+#define HLM_SCREEN_FASTQ 0 /* preselect.cpp:707-731: stride 2, 3 after a hit   */
+#define HLM_SCREEN_BAM 1   /* preselect.cpp:484-506: stride 1, 2 after a hit   */
+
+/* how clipped bases enter the hla-mapper score (read_sam_dna) */
+#define HLM_CLIP_LEAD_ONLY 0 /* literal reference behaviour: the trailing token of
+                                splitcigar() is always "", so only the first CIGAR
+                                op is ever added (map_dna.cpp:60-78)            */
+#define HLM_CLIP_BOTH 1      /* what the code visibly intends: first + last op  */
+
+/* hlm_screen_out.flags bits */
+#define HLM_F_SCREENED 1 /* passed the >=minhit k-mer screen                   */
+#define HLM_F_KEPT 2     /* ... and both mates survived mtrim (pair is scored)  */
+
+typedef struct hlm_db hlm_db;
+typedef struct hlm_ctx hlm_ctx;
+typedef struct hlm_devbatch hlm_devbatch;
+
+typedef struct hlm_params {
+  int32_t struct_size;    /* sizeof(hlm_params), for forward compatibility      */
+  int32_t rna;            /* 0 = dna, 1 = rna (map_rna.cpp reducer + compare)    */
+  int32_t paired;         /* 1 = R1+R2, 0 = single-end (r0=)                     */
+  int32_t screen_variant; /* HLM_SCREEN_FASTQ | HLM_SCREEN_BAM                   */
+  int32_t v_size;         /* min read length; <=0: take SIZE: from db_*.info     */
+  int32_t minhit;         /* preselect.cpp:26 (3)                                */
+  int32_t mm_max;         /* bwa aln -n (20), main.cpp:77                        */
+  int32_t clip_mode;      /* HLM_CLIP_*                                          */
+  double tolerance;       /* main.cpp:80 (0.05); rna forces 0.08 map_rna.cpp:116 */
+  double mtrim_error;     /* main.cpp:81 ((double)0.08f)                         */
+  int32_t chunk_pairs;    /* pairs per pipeline chunk (0 = default)              */
+  int32_t skip_screen;    /* 1: treat every pair as screened (scoring-only runs) */
+  int64_t cand_capacity;  /* device candidate slots per chunk (0 = default)      */
+} hlm_params;
+
+/* SoA batch of read pairs.  bases/quals are the FASTQ lines as read (ASCII),
+ * concatenated; offs has n_pairs+1 entries.  For single-end leave mate 2 NULL.
+ * size_override1 (optional, single-end only) replaces len(trimmed R1) in the
+ * tolerance test, reproducing preselect.cpp:1199 (length of the header line). */
+typedef struct hlm_batch {
+  int64_t n_pairs;
+  const uint8_t* bases1;
+  const uint8_t* quals1;
+  const uint64_t* offs1;
+  const uint8_t* bases2;
+  const uint8_t* quals2;
+  const uint64_t* offs2;
+  const int32_t* size_override1;
+  /* RNA only, optional: split point inside the trimmed mate (0 = one block).  Stands in
+   * for the STAR splice pre-split of map_rna.cpp:648-801: a mate with a split is scored
+   * as two blocks that read_sam_rna sums (map_rna.cpp:39-101). */
+  const uint16_t* rna_split1;
+  const uint16_t* rna_split2;
+} hlm_batch;
+
+/* one entry per pair */
+typedef struct hlm_screen_out {
+  uint8_t* flags;       /* HLM_F_*                                              */
+  uint16_t* trim_lo1;   /* mtrim substring start / length per mate               */
+  uint16_t* trim_len1;
+  uint16_t* trim_lo2;
+  uint16_t* trim_len2;
+  uint32_t* locus_mask; /* bit g: pair is a candidate of DB locus g              */
+} hlm_screen_out;
+
+/* n_pairs x n_targets (n_targets = n_loci + 1, last column = "others"),
+ * row-major.  s = hla-mapper score (NM + clips + 1; 0 = no alignment);
+ * aln = affine alignment score of the reported alignment (1/-4/-6/-1/clip -5);
+ * nm / lead / trail = its edit count and clip lengths (reference orientation).
+ * RNA mode: s1 holds the per-(pair,target) sum of map_rna.cpp:39-101 and
+ * 0xFFFF marks "no record"; s2 is unused. */
+typedef struct hlm_score_out {
+  uint16_t* s1;
+  uint16_t* s2;
+  int16_t* aln1;
+  int16_t* aln2;
+  uint8_t* nm1;
+  uint8_t* nm2;
+  uint8_t* lead1;
+  uint8_t* lead2;
+  uint8_t* trail1;
+  uint8_t* trail2;
+} hlm_score_out;
+
+/* one entry per pair */
+typedef struct hlm_assign_out {
+  uint32_t* target_mask;  /* bit g = addressed to locus g, bit n_loci = others   */
+  uint32_t* visible_mask; /* targets whose score column is printed (not "-")     */
+  uint16_t* min_sum;      /* min_nm_sum (dna) / min_score (rna); 0 = none        */
+  uint16_t* others_s1;    /* "others" scores after the one-sided mate back-fill   */
+  uint16_t* others_s2;    /* (map_dna.cpp:903-915); dna paired only               */
+} hlm_assign_out;
+
+/* per-stage device time of the last hlm_run*, CUDA events on the library's own
+ * streams (ms), plus work counters used for GCUPS / roofline accounting */
+typedef struct hlm_profile {
+  double ms_h2d, ms_screen, ms_seed, ms_myers, ms_select, ms_dp, ms_assign, ms_d2h, ms_total;
+  int64_t n_pairs, n_kept, n_tasks, n_candidates, n_dp, n_dp_cells, n_myers_cols;
+  int64_t launches;
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t bases_bytes; /* bases+quals streamed by the screen kernel               */
+} hlm_profile;
+
+void hlm_params_default(hlm_params* p, int rna);
+int hlm_abi_version(void);
+
+/* DB: parses the reference on-disk layout (db_{dna,rna}.info, motif/.., mapper/.., others/..) */
+hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen);
+void hlm_db_close(hlm_db* db);
+int hlm_db_n_loci(const hlm_db* db);
+const char* hlm_db_locus_name(const hlm_db* db, int i); /* i == n_loci -> "others" */
+int hlm_db_size(const hlm_db* db);                      /* SIZE: line, or 50      */
+int64_t hlm_db_stat(const hlm_db* db, const char* key); /* "alleles","bases","tiles","kmers","seed_entries" */
+
+/* one context per GPU; not thread-safe; distinct contexts may run concurrently */
+hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* params, char* err,
+                        size_t errlen);
+void hlm_ctx_destroy(hlm_ctx* ctx);
+const char* hlm_last_error(const hlm_ctx* ctx);
+
+/* stage-wise entry points (host buffers in, host buffers out) */
+int hlm_screen_trim(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* out);
+int hlm_score(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, hlm_score_out* out);
+int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr,
+               const hlm_score_out* sc, hlm_assign_out* out);
+
+/* fused screen -> score -> assign over the context's pinned, double-buffered
+ * stream pipeline.  Any of scr / sc / asg may be NULL (result not copied back). */
+int hlm_run(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+            hlm_assign_out* asg);
+
+/* device-resident variant: upload once, run many times (kernel-only timing) */
+hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in);
+void hlm_batch_free(hlm_ctx* ctx, hlm_devbatch* b);
+int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b);
+int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out* sc,
+              hlm_assign_out* asg);
+
+int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out);
+
+/* INT32 micro-benchmark (IADD3 / IMAD / VIADDMNMX chains) used as the DP roofline
+ * denominator; returns giga warp-lane ops per second */
+int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,
+                   double* giga_viaddmnmx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLAMAP_H */

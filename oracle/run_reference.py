@@ -1,0 +1,118 @@
+"""Drive the UNMODIFIED reference binary (oracle/_ref/hla-mapper-ref, built by oracle/Makefile
+from /root/reference/src with a Boost header shim) through `hla-mapper dna|rna`, with
+`bwa` replaced by oracle/_ref/bwa (stand-in that calls the oracle aligner) and `samtools` by
+/bin/true.  Used to pin the oracle's screen / trim / locus sort / SAM reducer / compare
+restatements against the reference's own code, and to generate tests/golden/*.
+
+TEST INFRASTRUCTURE ONLY.  The reference reads its config from getpwuid()->pw_dir/.hla-mapper
+(/root/reference/src/main.cpp:266-267), so the harness writes that file and restores it.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import pwd
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BIN = os.path.join(HERE, "_ref", "hla-mapper-ref")
+BWA_BIN = os.path.join(HERE, "_ref", "bwa")
+
+
+def available():
+    return os.path.exists(REF_BIN) and os.path.exists(BWA_BIN)
+
+
+@contextlib.contextmanager
+def _config(db_path):
+    home = pwd.getpwuid(os.getuid()).pw_dir
+    cfg = os.path.join(home, ".hla-mapper")
+    bak = None
+    if os.path.exists(cfg):
+        bak = cfg + ".graft-bak"
+        shutil.move(cfg, bak)
+    with open(cfg, "w") as f:
+        f.write(f"db={db_path}\nsamtools=/bin/true\nbwa={BWA_BIN}\nwhatshap=DISABLED\n"
+                "freebayes=DISABLED\nblast=DISABLED\n")
+    try:
+        yield
+    finally:
+        os.remove(cfg)
+        if bak:
+            shutil.move(bak, cfg)
+
+
+def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, rna=False, threads=4,
+                  debug=True, exhaustive=False, extra=(), timeout=3600):
+    """returns the output directory (with trailing slash, as the reference stores it)"""
+    if os.path.exists(out_dir):
+        shutil.rmtree(out_dir)
+    cmd = [REF_BIN, "rna" if rna else "dna"]
+    if r0:
+        cmd.append(f"r0={r0}")
+    else:
+        cmd += [f"r1={r1}", f"r2={r2}"]
+    cmd += [f"sample={sample}", f"output={out_dir}", f"threads={threads}", "--skip-adjust",
+            "--quiet"]
+    if debug:
+        cmd.append("--debug")
+    cmd += list(extra)
+    env = dict(os.environ)
+    if exhaustive:
+        env["HLM_ORACLE_EXHAUSTIVE"] = "1"
+    with _config(db_path):
+        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env,
+                       timeout=timeout, cwd=os.path.dirname(out_dir.rstrip("/")) or ".")
+    return out_dir.rstrip("/") + "/"
+
+
+def parse_addressing_table(path):
+    """-> (target names, {read id: (score strings per target, Target string)})"""
+    rows = {}
+    with open(path) as f:
+        hdr = f.readline().rstrip("\n").split("\t")
+        names = hdr[1:-1]
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            rows[t[0]] = (t[1:-1], t[-1])
+    return names, rows
+
+
+def parse_fastq_ids(path, with_len=False):
+    out = {}
+    with open(path) as f:
+        while True:
+            h = f.readline()
+            if not h:
+                break
+            s = f.readline().rstrip("\n")
+            f.readline()
+            f.readline()
+            key = h.rstrip("\n").split(" ")[0][1:].replace("/1", "").replace("/2", "")
+            out[key] = s if not with_len else len(s)
+    return out
+
+
+def expected_table(buf, ids, loci, rna=False, paired=True):
+    """what the reference's addressing table must contain, from oracle/GPU output buffers.
+    loci = DB loci + ['others'].  Mirrors map_dna.cpp:932-1016 / map_rna.cpp:945-1013."""
+    rows = {}
+    T = len(loci)
+    for i, rid in enumerate(ids):
+        if not (buf.flags[i] & 2):
+            continue
+        cols = []
+        for g in range(T):
+            if not rna:
+                if (int(buf.visible_mask[i]) >> g) & 1:
+                    s1 = int(buf.others_s1[i]) if g == T - 1 else int(buf.s1[i, g])
+                    s2 = int(buf.others_s2[i]) if g == T - 1 else int(buf.s2[i, g])
+                    cols.append(f"{s1},{s2}" if paired else f"{s1}")
+                else:
+                    cols.append("-")
+            else:
+                cols.append(str(int(buf.s1[i, g])) if (int(buf.visible_mask[i]) >> g) & 1 else "-")
+        tg = [loci[g] for g in range(T) if (int(buf.target_mask[i]) >> g) & 1]
+        rows[rid] = (cols, ",".join(tg) if tg else "-")
+    return rows
