@@ -1,0 +1,206 @@
+"""Python binding of libhlamap's C-ABI (include/hlamap.h) via ctypes.
+
+This is the host-side mirror of the reference's stage boundaries for the hot path
+(`main_preselect` screen+trim -> per-locus sort -> scoring -> compare/assign); every call goes
+through the exported C symbols, i.e. exactly what a C/C++ caller would bind.  There is NO CPU
+fallback: if the CUDA library or a GPU is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import Buffers, HlmAssignOut, HlmBatch, HlmParams, HlmProfile, HlmScoreOut, HlmScreenOut
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhlamap.so")
+
+# every symbol include/hlamap.h declares
+SYMBOLS = [
+    "hlm_params_default", "hlm_abi_version", "hlm_db_open", "hlm_db_close", "hlm_db_n_loci",
+    "hlm_db_locus_name", "hlm_db_size", "hlm_db_stat", "hlm_ctx_create", "hlm_ctx_destroy",
+    "hlm_last_error", "hlm_screen_trim", "hlm_score", "hlm_assign", "hlm_run", "hlm_batch_upload",
+    "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
+]
+
+_lib = None
+
+
+class HlmError(RuntimeError):
+    pass
+
+
+def lib():
+    """load libhlamap.so (in-tree); raises if it has not been built"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HlmError(f"{LIB_PATH} is missing: run `python -m hla_mapper_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.hlm_params_default.argtypes = [C.POINTER(HlmParams), C.c_int]
+    L.hlm_db_open.restype = C.c_void_p
+    L.hlm_db_open.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.hlm_db_close.argtypes = [C.c_void_p]
+    L.hlm_db_n_loci.argtypes = [C.c_void_p]
+    L.hlm_db_locus_name.restype = C.c_char_p
+    L.hlm_db_locus_name.argtypes = [C.c_void_p, C.c_int]
+    L.hlm_db_size.argtypes = [C.c_void_p]
+    L.hlm_db_stat.restype = C.c_int64
+    L.hlm_db_stat.argtypes = [C.c_void_p, C.c_char_p]
+    L.hlm_ctx_create.restype = C.c_void_p
+    L.hlm_ctx_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(HlmParams), C.c_char_p, C.c_size_t]
+    L.hlm_ctx_destroy.argtypes = [C.c_void_p]
+    L.hlm_last_error.restype = C.c_char_p
+    L.hlm_last_error.argtypes = [C.c_void_p]
+    L.hlm_screen_trim.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut)]
+    L.hlm_score.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
+                            C.POINTER(HlmScoreOut)]
+    L.hlm_assign.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
+                             C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
+    L.hlm_run.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
+                          C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
+    L.hlm_batch_upload.restype = C.c_void_p
+    L.hlm_batch_upload.argtypes = [C.c_void_p, C.POINTER(HlmBatch)]
+    L.hlm_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.hlm_run_device.argtypes = [C.c_void_p, C.c_void_p]
+    L.hlm_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(HlmScreenOut), C.POINTER(HlmScoreOut),
+                            C.POINTER(HlmAssignOut)]
+    L.hlm_get_profile.argtypes = [C.c_void_p, C.POINTER(HlmProfile)]
+    L.hlm_int32_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
+    _lib = L
+    return L
+
+
+class Database:
+    """hlm_db: the reference's on-disk database (db_*.info, motif/, mapper/, others/)"""
+
+    def __init__(self, path, rna=0):
+        err = C.create_string_buffer(512)
+        self.h = lib().hlm_db_open(str(path).encode(), int(rna), err, 512)
+        if not self.h:
+            raise HlmError(err.value.decode())
+        self.rna = int(rna)
+        self.n_loci = lib().hlm_db_n_loci(self.h)
+        self.loci = [lib().hlm_db_locus_name(self.h, i).decode() for i in range(self.n_loci + 1)]
+        self.v_size = lib().hlm_db_size(self.h)
+
+    def stat(self, key):
+        return int(lib().hlm_db_stat(self.h, key.encode()))
+
+    def close(self):
+        if self.h:
+            lib().hlm_db_close(self.h)
+            self.h = None
+
+
+class Mapper:
+    """hlm_ctx: one context per GPU"""
+
+    def __init__(self, db: Database, device=0, params: HlmParams | None = None, **kw):
+        self.db = db
+        self.params = params or _abi.default_params(db.rna, **kw)
+        err = C.create_string_buffer(512)
+        self.h = lib().hlm_ctx_create(db.h, int(device), C.byref(self.params), err, 512)
+        if not self.h:
+            raise HlmError(err.value.decode())
+        self.T = db.n_loci + 1
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HlmError(f"libhlamap rc={rc}: {lib().hlm_last_error(self.h).decode()}")
+
+    def _batch(self, rb, **kw):
+        return _abi.make_batch(rb, paired=bool(self.params.paired), **kw)
+
+    def run(self, rb, buffers=None, **kw):
+        b = self._batch(rb, **kw)
+        buf = buffers or Buffers(rb.n_pairs, self.T)
+        self._check(lib().hlm_run(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc),
+                                  C.byref(buf.asg)))
+        return buf
+
+    def screen_trim(self, rb, buffers=None, **kw):
+        b = self._batch(rb, **kw)
+        buf = buffers or Buffers(rb.n_pairs, self.T)
+        self._check(lib().hlm_screen_trim(self.h, C.byref(b), C.byref(buf.scr)))
+        return buf
+
+    def score(self, rb, buf, **kw):
+        b = self._batch(rb, **kw)
+        self._check(lib().hlm_score(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc)))
+        return buf
+
+    def assign(self, rb, buf, **kw):
+        b = self._batch(rb, **kw)
+        self._check(lib().hlm_assign(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc),
+                                     C.byref(buf.asg)))
+        return buf
+
+    # device-resident path (kernel-only timing)
+    def upload(self, rb, **kw):
+        b = self._batch(rb, **kw)
+        h = lib().hlm_batch_upload(self.h, C.byref(b))
+        if not h:
+            raise HlmError("hlm_batch_upload failed: " + lib().hlm_last_error(self.h).decode())
+        return h
+
+    def run_device(self, dev_batch):
+        self._check(lib().hlm_run_device(self.h, dev_batch))
+
+    def fetch(self, dev_batch, n_pairs, buffers=None):
+        buf = buffers or Buffers(n_pairs, self.T)
+        self._check(lib().hlm_fetch(self.h, dev_batch, C.byref(buf.scr), C.byref(buf.sc),
+                                    C.byref(buf.asg)))
+        return buf
+
+    def free(self, dev_batch):
+        lib().hlm_batch_free(self.h, dev_batch)
+
+    def profile(self):
+        p = HlmProfile()
+        lib().hlm_get_profile(self.h, C.byref(p))
+        return {k: getattr(p, k) for k, _ in HlmProfile._fields_}
+
+    def close(self):
+        if self.h:
+            lib().hlm_ctx_destroy(self.h)
+            self.h = None
+
+
+def int32_peak(device=0):
+    """measured giga lane-ops/s of IADD3, IMAD, mixed and VIADDMNMX chains"""
+    v = [C.c_double(0) for _ in range(4)]
+    rc = lib().hlm_int32_peak(int(device), *[C.byref(x) for x in v])
+    if rc != 0:
+        raise HlmError(f"hlm_int32_peak rc={rc}")
+    return dict(zip(("iadd3", "imad", "mix", "viaddmnmx"), (x.value for x in v)))
+
+
+def addressing_table(buf, ids, loci, rna=False, paired=True):
+    """rows of <sample>_addressing_table.txt (map_dna.cpp:1036-1051 / map_rna.cpp:1028-1046)
+    from result buffers: {read id: ([score column strings], Target string)}"""
+    rows = {}
+    T = len(loci)
+    for i, rid in enumerate(ids):
+        if not (buf.flags[i] & _abi.HLM_F_KEPT):
+            continue
+        cols = []
+        vm = int(buf.visible_mask[i])
+        for g in range(T):
+            if not (vm >> g) & 1:
+                cols.append("-")
+            elif rna:
+                cols.append(str(int(buf.s1[i, g])))
+            else:
+                s1 = int(buf.others_s1[i]) if g == T - 1 else int(buf.s1[i, g])
+                s2 = int(buf.others_s2[i]) if g == T - 1 else int(buf.s2[i, g])
+                cols.append(f"{s1},{s2}" if paired else f"{s1}")
+        tm = int(buf.target_mask[i])
+        tg = [loci[g] for g in range(T) if (tm >> g) & 1]
+        rows[rid] = (cols, ",".join(tg) if tg else "-")
+    return rows

@@ -1,0 +1,870 @@
+// hlm_api.cu — the C-ABI of libhlamap and the host runtime behind it.
+//
+// Replaces the reference's per-read ThreadPool dispatch (src/ThreadPool.hpp:18-100, one
+// packaged_task + two global-mutex acquisitions per read, preselect.cpp:696-745) with a
+// chunked, double-buffered CUDA-stream pipeline: two slots, each with its own stream, pinned
+// staging buffers and device work buffers; while slot A's kernels run, slot B's inputs are
+// staged and copied, and A's results drain back.  No host<->device synchronisation happens
+// inside a chunk; all kernel grids are persistent (multiples of the SM count) and read their
+// work counts from device memory.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hlm_db.h"
+#include "hlm_kernels.cuh"
+
+#define HLM_STAGE_SCREEN 1
+#define HLM_STAGE_SCORE 2
+#define HLM_STAGE_ASSIGN 4
+
+namespace {
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+enum { EV_START, EV_H2D, EV_SCREEN, EV_SEED, EV_MYERS, EV_SEL0, EV_DP0, EV_SEL1, EV_DP1, EV_ASSIGN,
+       EV_D2H, EV_COUNT };
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[EV_COUNT];
+  Buf h_in, h_out, d_in, d_out, d_units, d_unit_meta, d_cand, d_dp, d_tasks, d_counters;
+  HlmChunk ck;
+  bool busy = false;
+  int64_t first = 0, n = 0;
+  size_t out_off[32];
+  size_t out_bytes = 0;
+};
+
+}  // namespace
+
+struct hlm_devbatch {
+  int64_t n_pairs = 0;
+  Buf in, out;
+  size_t in_off[16];
+  size_t out_off[32];
+  int64_t max_len = 0;
+  bool paired = true;
+  bool has_override = false, has_split1 = false, has_split2 = false;
+  int64_t read_bytes = 0;
+};
+
+struct hlm_ctx {
+  const hlm_db* db = nullptr;
+  hlm_params p;
+  HlmKParams kp;
+  HlmDevDB ddb;
+  int device = 0, sms = 148;
+  int n_targets = 0, units_per_pair = 2;
+  int64_t chunk_pairs = 0, cand_cap = 0;
+  Slot slot[2];
+  std::string err;
+  hlm_profile prof;
+  cudaEvent_t run_start = nullptr;
+};
+
+namespace {
+
+bool cuda_ok(hlm_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  c->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CU(call)                                   \
+  do {                                             \
+    if (!cuda_ok(ctx, (call), #call)) return HLM_E_CUDA; \
+  } while (0)
+
+size_t align16(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int ensure_dev(hlm_ctx* ctx, Buf& b, size_t need) {
+  if (need <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = need + need / 8 + 4096;
+  if (!cuda_ok(ctx, cudaMalloc(&b.p, cap), "cudaMalloc")) return HLM_E_NOMEM;
+  b.cap = cap;
+  return 0;
+}
+int ensure_pinned(hlm_ctx* ctx, Buf& b, size_t need) {
+  if (need <= b.cap) return 0;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = need + need / 8 + 4096;
+  if (!cuda_ok(ctx, cudaMallocHost(&b.p, cap), "cudaMallocHost")) return HLM_E_NOMEM;
+  b.cap = cap;
+  return 0;
+}
+
+// output block layout for n pairs and T targets; returns total bytes
+enum { O_FLAGS, O_LO1, O_LEN1, O_LO2, O_LEN2, O_MASK, O_S1, O_S2, O_ALN1, O_ALN2, O_NM1, O_NM2,
+       O_LEAD1, O_LEAD2, O_TRAIL1, O_TRAIL2, O_TARGET, O_VISIBLE, O_MINSUM, O_OS1, O_OS2, O_COUNTERS,
+       O_COUNT };
+size_t out_layout(int64_t n, int T, size_t* off) {
+  size_t sz[O_COUNT] = {(size_t)n, 2u * n, 2u * n, 2u * n, 2u * n, 4u * n,
+                        2u * n * T, 2u * n * T, 2u * n * T, 2u * n * T,
+                        (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T,
+                        (size_t)n * T, 4u * n, 4u * n, 2u * n, 2u * n, 2u * n, 64};
+  size_t o = 0;
+  for (int i = 0; i < O_COUNT; i++) {
+    off[i] = o;
+    o += align16(sz[i]);
+  }
+  return o;
+}
+
+void bind_outputs(HlmChunk& ck, uint8_t* base, const size_t* off, int64_t first, int T) {
+  ck.flags = base + off[O_FLAGS] + first;
+  ck.trim_lo1 = (uint16_t*)(base + off[O_LO1]) + first;
+  ck.trim_len1 = (uint16_t*)(base + off[O_LEN1]) + first;
+  ck.trim_lo2 = (uint16_t*)(base + off[O_LO2]) + first;
+  ck.trim_len2 = (uint16_t*)(base + off[O_LEN2]) + first;
+  ck.locus_mask = (uint32_t*)(base + off[O_MASK]) + first;
+  ck.s1 = (uint16_t*)(base + off[O_S1]) + first * T;
+  ck.s2 = (uint16_t*)(base + off[O_S2]) + first * T;
+  ck.aln1 = (int16_t*)(base + off[O_ALN1]) + first * T;
+  ck.aln2 = (int16_t*)(base + off[O_ALN2]) + first * T;
+  ck.nm1 = base + off[O_NM1] + first * T;
+  ck.nm2 = base + off[O_NM2] + first * T;
+  ck.lead1 = base + off[O_LEAD1] + first * T;
+  ck.lead2 = base + off[O_LEAD2] + first * T;
+  ck.trail1 = base + off[O_TRAIL1] + first * T;
+  ck.trail2 = base + off[O_TRAIL2] + first * T;
+  ck.target_mask = (uint32_t*)(base + off[O_TARGET]) + first;
+  ck.visible_mask = (uint32_t*)(base + off[O_VISIBLE]) + first;
+  ck.min_sum = (uint16_t*)(base + off[O_MINSUM]) + first;
+  ck.others_s1 = (uint16_t*)(base + off[O_OS1]) + first;
+  ck.others_s2 = (uint16_t*)(base + off[O_OS2]) + first;
+}
+
+int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
+  int U = ctx->units_per_pair, T = ctx->n_targets;
+  int rc;
+  if ((rc = ensure_dev(ctx, s.d_units, (size_t)n * U * 36 * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_unit_meta, align16((size_t)n * U * 2) + (size_t)n * U * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_dp, (size_t)ctx->cand_cap * 4))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_tasks, align16((size_t)n * U * T * 4) + (size_t)n * U * T * 8 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
+  HlmChunk& ck = s.ck;
+  ck.units_per_pair = U;
+  ck.unit_planes = (uint32_t*)s.d_units.p;
+  ck.unit_len = (uint16_t*)s.d_unit_meta.p;
+  ck.unit_mask = (uint32_t*)((uint8_t*)s.d_unit_meta.p + align16((size_t)n * U * 2));
+  ck.cand = (uint64_t*)s.d_cand.p;
+  ck.cand_cap = ctx->cand_cap;
+  ck.dp_list = (uint32_t*)s.d_dp.p;
+  ck.dp_cap = ctx->cand_cap;
+  ck.counters = (unsigned long long*)s.d_counters.p;
+  ck.task_emin = (uint32_t*)s.d_tasks.p;
+  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + align16((size_t)n * U * T * 4));
+  return 0;
+}
+
+void launch_stages(hlm_ctx* ctx, Slot& s, int stages) {
+  const HlmChunk& ck = s.ck;
+  int T = ctx->n_targets, sms = ctx->sms;
+  cudaStream_t st = s.st;
+  hlm_launch_clear_tasks(ck, T, sms, st);
+  if (stages & HLM_STAGE_SCREEN) hlm_launch_screen(ctx->ddb, ctx->kp, ck, sms, st);
+  cudaEventRecord(s.ev[EV_SCREEN], st);
+  if (stages & HLM_STAGE_SCORE) {
+    hlm_launch_pack(ctx->kp, ck, sms, st);
+    hlm_launch_seed(ctx->ddb, ctx->kp, ck, sms, st);
+    cudaEventRecord(s.ev[EV_SEED], st);
+    hlm_launch_myers(ctx->ddb, ctx->kp, ck, T, sms, st);
+    cudaEventRecord(s.ev[EV_MYERS], st);
+    hlm_launch_select(ctx->ddb, ctx->kp, ck, T, 0, sms, st);
+    cudaEventRecord(s.ev[EV_SEL0], st);
+    hlm_launch_dp(ctx->ddb, ctx->kp, ck, T, sms, st);
+    cudaEventRecord(s.ev[EV_DP0], st);
+    hlm_launch_select(ctx->ddb, ctx->kp, ck, T, 1, sms, st);
+    cudaEventRecord(s.ev[EV_SEL1], st);
+    hlm_launch_dp(ctx->ddb, ctx->kp, ck, T, sms, st);
+    cudaEventRecord(s.ev[EV_DP1], st);
+    hlm_launch_scores(ctx->kp, ck, T, sms, st);
+    ctx->prof.launches += 11;
+  } else {
+    for (int e = EV_SEED; e <= EV_DP1; e++) cudaEventRecord(s.ev[e], st);
+  }
+  if (stages & HLM_STAGE_ASSIGN) {
+    hlm_launch_assign(ctx->kp, ck, T, sms, st);
+    ctx->prof.launches += 1;
+  }
+  cudaEventRecord(s.ev[EV_ASSIGN], st);
+  ctx->prof.launches += 1 + ((stages & HLM_STAGE_SCREEN) ? 1 : 0);
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// wait for a slot's chunk, fold its timings / counters into the profile
+int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
+  if (!s.busy) return 0;
+  CU(cudaEventSynchronize(s.ev[EV_D2H]));
+  s.busy = false;
+  hlm_profile& pr = ctx->prof;
+  pr.ms_h2d += ev_ms(s.ev[EV_START], s.ev[EV_H2D]);
+  pr.ms_screen += ev_ms(s.ev[EV_H2D], s.ev[EV_SCREEN]);
+  pr.ms_seed += ev_ms(s.ev[EV_SCREEN], s.ev[EV_SEED]);
+  pr.ms_myers += ev_ms(s.ev[EV_SEED], s.ev[EV_MYERS]);
+  pr.ms_select += ev_ms(s.ev[EV_MYERS], s.ev[EV_SEL0]) + ev_ms(s.ev[EV_DP0], s.ev[EV_SEL1]);
+  pr.ms_dp += ev_ms(s.ev[EV_SEL0], s.ev[EV_DP0]) + ev_ms(s.ev[EV_SEL1], s.ev[EV_DP1]);
+  pr.ms_assign += ev_ms(s.ev[EV_DP1], s.ev[EV_ASSIGN]);
+  pr.ms_d2h += ev_ms(s.ev[EV_ASSIGN], s.ev[EV_D2H]);
+  float t = ev_ms(ctx->run_start, s.ev[EV_D2H]);
+  if (t > pr.ms_total) pr.ms_total = t;
+  if (counters_host) {
+    pr.n_candidates += (int64_t)counters_host[0];
+    pr.n_kept += (int64_t)counters_host[3];
+    pr.n_dp_cells += (int64_t)counters_host[4];
+    pr.n_myers_cols += (int64_t)counters_host[5];
+    pr.n_dp += (int64_t)counters_host[6];
+    if (counters_host[2]) {
+      ctx->err = "candidate capacity exceeded in a chunk: raise hlm_params.cand_capacity or lower chunk_pairs";
+      return HLM_E_NOMEM;
+    }
+    if (counters_host[7]) {
+      ctx->err = "a trimmed read is longer than HLM_MAX_READ (184)";
+      return HLM_E_TOOLONG;
+    }
+  }
+  return 0;
+}
+
+struct HostIO {
+  const hlm_batch* in = nullptr;
+  const hlm_screen_out* scr_in = nullptr;  // provided screen results (score / assign stages)
+  const hlm_score_out* sc_in = nullptr;    // provided scores (assign stage)
+  hlm_screen_out* scr = nullptr;
+  hlm_score_out* sc = nullptr;
+  hlm_assign_out* asg = nullptr;
+};
+
+template <class Tp>
+void copy_out(Tp* dst, const uint8_t* base, size_t off, int64_t first, int64_t n, int per) {
+  if (dst) memcpy(dst + first * per, base + off, sizeof(Tp) * (size_t)n * per);
+}
+
+void scatter_results(hlm_ctx* ctx, Slot& s, const HostIO& io) {
+  const uint8_t* b = (const uint8_t*)s.h_out.p;
+  const size_t* o = s.out_off;
+  int T = ctx->n_targets;
+  int64_t f = s.first, n = s.n;
+  if (io.scr) {
+    copy_out(io.scr->flags, b, o[O_FLAGS], f, n, 1);
+    copy_out(io.scr->trim_lo1, b, o[O_LO1], f, n, 1);
+    copy_out(io.scr->trim_len1, b, o[O_LEN1], f, n, 1);
+    copy_out(io.scr->trim_lo2, b, o[O_LO2], f, n, 1);
+    copy_out(io.scr->trim_len2, b, o[O_LEN2], f, n, 1);
+    copy_out(io.scr->locus_mask, b, o[O_MASK], f, n, 1);
+  }
+  if (io.sc) {
+    copy_out(io.sc->s1, b, o[O_S1], f, n, T);
+    copy_out(io.sc->s2, b, o[O_S2], f, n, T);
+    copy_out(io.sc->aln1, b, o[O_ALN1], f, n, T);
+    copy_out(io.sc->aln2, b, o[O_ALN2], f, n, T);
+    copy_out(io.sc->nm1, b, o[O_NM1], f, n, T);
+    copy_out(io.sc->nm2, b, o[O_NM2], f, n, T);
+    copy_out(io.sc->lead1, b, o[O_LEAD1], f, n, T);
+    copy_out(io.sc->lead2, b, o[O_LEAD2], f, n, T);
+    copy_out(io.sc->trail1, b, o[O_TRAIL1], f, n, T);
+    copy_out(io.sc->trail2, b, o[O_TRAIL2], f, n, T);
+  }
+  if (io.asg) {
+    copy_out(io.asg->target_mask, b, o[O_TARGET], f, n, 1);
+    copy_out(io.asg->visible_mask, b, o[O_VISIBLE], f, n, 1);
+    copy_out(io.asg->min_sum, b, o[O_MINSUM], f, n, 1);
+    copy_out(io.asg->others_s1, b, o[O_OS1], f, n, 1);
+    copy_out(io.asg->others_s2, b, o[O_OS2], f, n, 1);
+  }
+}
+
+int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
+  for (int64_t i = 0; i < in->n_pairs; i++) {
+    if (in->offs1[i + 1] < in->offs1[i] || in->offs1[i + 1] - in->offs1[i] > HLM_RAW_MAX) {
+      ctx->err = "read 1 longer than 256 bases (or offsets not ascending)";
+      return HLM_E_TOOLONG;
+    }
+    if (ctx->p.paired && (in->offs2[i + 1] < in->offs2[i] || in->offs2[i + 1] - in->offs2[i] > HLM_RAW_MAX)) {
+      ctx->err = "read 2 longer than 256 bases (or offsets not ascending)";
+      return HLM_E_TOOLONG;
+    }
+  }
+  return 0;
+}
+
+// host-buffer pipeline over chunks
+int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
+  const hlm_batch* in = io.in;
+  if (!in || in->n_pairs < 0) {
+    ctx->err = "bad batch";
+    return HLM_E_ARG;
+  }
+  bool need_reads = stages & (HLM_STAGE_SCREEN | HLM_STAGE_SCORE);
+  if (need_reads) {
+    if (!in->bases1 || !in->offs1 || ((stages & HLM_STAGE_SCREEN) && !in->quals1) ||
+        (ctx->p.paired && (!in->bases2 || !in->offs2 || ((stages & HLM_STAGE_SCREEN) && !in->quals2)))) {
+      ctx->err = "batch is missing read arrays";
+      return HLM_E_ARG;
+    }
+    int rc = check_lengths(ctx, in);
+    if (rc) return rc;
+  }
+  CU(cudaSetDevice(ctx->device));
+  memset(&ctx->prof, 0, sizeof ctx->prof);
+  int T = ctx->n_targets;
+  bool paired = ctx->p.paired;
+  int64_t N = in->n_pairs, C = ctx->chunk_pairs;
+  auto t0 = std::chrono::steady_clock::now();
+  CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
+  CU(cudaStreamWaitEvent(ctx->slot[1].st, ctx->run_start, 0));
+  int rc = 0;
+  int64_t k = 0;
+  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
+    Slot& s = ctx->slot[k & 1];
+    int64_t n = std::min(C, N - first);
+    // drain the slot's previous chunk
+    if (s.busy) {
+      rc = finish_slot(ctx, s, (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]));
+      scatter_results(ctx, s, io);
+      if (rc) break;
+    }
+    // ---- stage inputs into pinned memory
+    size_t b1 = 0, b2 = 0;
+    uint64_t f1 = 0, f2 = 0;
+    if (need_reads) {
+      f1 = in->offs1[first];
+      b1 = (size_t)(in->offs1[first + n] - f1);
+      if (paired) {
+        f2 = in->offs2[first];
+        b2 = (size_t)(in->offs2[first + n] - f2);
+      }
+    }
+    bool q = stages & HLM_STAGE_SCREEN;
+    size_t io_off[16], o = 0;
+    auto sec = [&](int i, size_t bytes) { io_off[i] = o; o += align16(bytes + 32); };
+    sec(0, b1);                       // bases1 (16 bytes of lead padding inside)
+    sec(1, q ? b1 : 0);               // quals1
+    sec(2, b2);                       // bases2
+    sec(3, q ? b2 : 0);               // quals2
+    sec(4, (n + 1) * 8);              // offs1
+    sec(5, paired ? (n + 1) * 8 : 0); // offs2
+    sec(6, in->size_override1 ? n * 4 : 0);
+    sec(7, in->rna_split1 ? n * 2 : 0);
+    sec(8, in->rna_split2 ? n * 2 : 0);
+    size_t in_bytes = o;
+    if ((rc = ensure_pinned(ctx, s.h_in, in_bytes))) break;
+    if ((rc = ensure_dev(ctx, s.d_in, in_bytes))) break;
+    size_t out_bytes = out_layout(n, T, s.out_off);
+    s.out_bytes = out_bytes;
+    if ((rc = ensure_pinned(ctx, s.h_out, out_bytes))) break;
+    if ((rc = ensure_dev(ctx, s.d_out, out_bytes))) break;
+    if ((rc = ensure_work(ctx, s, n))) break;
+    uint8_t* h = (uint8_t*)s.h_in.p;
+    uint8_t* d = (uint8_t*)s.d_in.p;
+    if (need_reads) {
+      memcpy(h + io_off[0] + 16, in->bases1 + f1, b1);
+      if (q) memcpy(h + io_off[1] + 16, in->quals1 + f1, b1);
+      memcpy(h + io_off[4], in->offs1 + first, (n + 1) * 8);
+      if (paired) {
+        memcpy(h + io_off[2] + 16, in->bases2 + f2, b2);
+        if (q) memcpy(h + io_off[3] + 16, in->quals2 + f2, b2);
+        memcpy(h + io_off[5], in->offs2 + first, (n + 1) * 8);
+      }
+    }
+    if (in->size_override1) memcpy(h + io_off[6], in->size_override1 + first, n * 4);
+    if (in->rna_split1) memcpy(h + io_off[7], in->rna_split1 + first, n * 2);
+    if (in->rna_split2) memcpy(h + io_off[8], in->rna_split2 + first, n * 2);
+    HlmChunk& ck = s.ck;
+    ck.n_pairs = n;
+    // offsets stay absolute: bias the base pointers instead
+    ck.bases1 = d + io_off[0] + 16 - f1;
+    ck.quals1 = d + io_off[1] + 16 - f1;
+    ck.bases2 = d + io_off[2] + 16 - f2;
+    ck.quals2 = d + io_off[3] + 16 - f2;
+    ck.offs1 = (const uint64_t*)(d + io_off[4]);
+    ck.offs2 = (const uint64_t*)(d + io_off[5]);
+    ck.size_override1 = in->size_override1 ? (const int32_t*)(d + io_off[6]) : nullptr;
+    ck.rna_split1 = in->rna_split1 ? (const uint16_t*)(d + io_off[7]) : nullptr;
+    ck.rna_split2 = in->rna_split2 ? (const uint16_t*)(d + io_off[8]) : nullptr;
+    bind_outputs(ck, (uint8_t*)s.d_out.p, s.out_off, 0, T);
+    s.first = first;
+    s.n = n;
+    cudaStream_t st = s.st;
+    CU(cudaEventRecord(s.ev[EV_START], st));
+    CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+    ctx->prof.h2d_bytes += (int64_t)in_bytes;
+    // provided stage results (stage-wise entry points)
+    uint8_t* ho = (uint8_t*)s.h_out.p;
+    uint8_t* dout = (uint8_t*)s.d_out.p;
+    if (!(stages & HLM_STAGE_SCREEN) && io.scr_in) {
+      const hlm_screen_out* si = io.scr_in;
+      memcpy(ho + s.out_off[O_FLAGS], si->flags + first, n);
+      memcpy(ho + s.out_off[O_LO1], si->trim_lo1 + first, 2 * n);
+      memcpy(ho + s.out_off[O_LEN1], si->trim_len1 + first, 2 * n);
+      if (si->trim_lo2) memcpy(ho + s.out_off[O_LO2], si->trim_lo2 + first, 2 * n);
+      else memset(ho + s.out_off[O_LO2], 0, 2 * n);
+      if (si->trim_len2) memcpy(ho + s.out_off[O_LEN2], si->trim_len2 + first, 2 * n);
+      else memset(ho + s.out_off[O_LEN2], 0, 2 * n);
+      memcpy(ho + s.out_off[O_MASK], si->locus_mask + first, 4 * n);
+      size_t bytes = s.out_off[O_MASK] + 4 * n;
+      CU(cudaMemcpyAsync(dout, ho, bytes, cudaMemcpyHostToDevice, st));
+      ctx->prof.h2d_bytes += (int64_t)bytes;
+    }
+    if (!(stages & HLM_STAGE_SCORE) && (stages & HLM_STAGE_ASSIGN) && io.sc_in) {
+      memcpy(ho + s.out_off[O_S1], io.sc_in->s1 + first * T, 2 * n * T);
+      if (io.sc_in->s2) memcpy(ho + s.out_off[O_S2], io.sc_in->s2 + first * T, 2 * n * T);
+      else memset(ho + s.out_off[O_S2], 0, 2 * n * T);
+      size_t a = s.out_off[O_S1], e = s.out_off[O_S2] + 2 * n * T;
+      CU(cudaMemcpyAsync(dout + a, ho + a, e - a, cudaMemcpyHostToDevice, st));
+      ctx->prof.h2d_bytes += (int64_t)(e - a);
+    }
+    CU(cudaEventRecord(s.ev[EV_H2D], st));
+    launch_stages(ctx, s, stages);
+    CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 64,
+                       cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    ctx->prof.d2h_bytes += (int64_t)out_bytes;
+    CU(cudaEventRecord(s.ev[EV_D2H], st));
+    s.busy = true;
+    ctx->prof.bases_bytes += (int64_t)(q ? 2 : 1) * (int64_t)(b1 + b2);
+  }
+  for (int i = 0; i < 2; i++) {
+    Slot& s = ctx->slot[(k + i) & 1];
+    if (s.busy) {
+      int r2 = finish_slot(ctx, s, (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]));
+      if (r2 == 0) scatter_results(ctx, s, io);
+      if (rc == 0) rc = r2;
+    }
+  }
+  ctx->prof.n_pairs = N;
+  (void)t0;
+  cudaError_t e = cudaGetLastError();
+  if (rc == 0 && e != cudaSuccess) {
+    ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+    rc = HLM_E_CUDA;
+  }
+  return rc;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int hlm_abi_version(void) { return HLM_ABI_VERSION; }
+
+void hlm_params_default(hlm_params* p, int rna) {
+  memset(p, 0, sizeof *p);
+  p->struct_size = (int32_t)sizeof *p;
+  p->rna = rna ? 1 : 0;
+  p->paired = 1;
+  p->screen_variant = HLM_SCREEN_FASTQ;
+  p->v_size = 0;
+  p->minhit = 3;                        // preselect.cpp:26
+  p->mm_max = 20;                       // main.cpp:77
+  p->clip_mode = HLM_CLIP_LEAD_ONLY;
+  p->tolerance = rna ? 0.08 : 0.05;     // main.cpp:80, map_rna.cpp:116
+  p->mtrim_error = (double)0.08f;       // main.cpp:81: `double v_mtrim_error = 0.08f;`
+  p->chunk_pairs = 0;
+  p->skip_screen = 0;
+  p->cand_capacity = 0;
+}
+
+hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen) {
+  std::string e;
+  hlm_db* db = db_dir ? hlm_db_build(db_dir, rna, e) : nullptr;
+  if (!db && err && errlen) snprintf(err, errlen, "%s", e.empty() ? "bad db_dir" : e.c_str());
+  return db;
+}
+
+void hlm_db_close(hlm_db* db) {
+  if (!db) return;
+  for (auto& d : db->devs) {
+    cudaSetDevice(d.device);
+    for (void* p : d.ptrs)
+      if (p) cudaFree(p);
+  }
+  delete db;
+}
+int hlm_db_n_loci(const hlm_db* db) { return db ? db->n_loci : 0; }
+const char* hlm_db_locus_name(const hlm_db* db, int i) {
+  return (db && i >= 0 && i <= db->n_loci) ? db->names[i].c_str() : nullptr;
+}
+int hlm_db_size(const hlm_db* db) { return db ? db->v_size : 0; }
+int64_t hlm_db_stat(const hlm_db* db, const char* key) {
+  if (!db || !key) return -1;
+  std::string k(key);
+  if (k == "alleles") return db->n_alleles;
+  if (k == "bases") return db->n_bases;
+  if (k == "tiles") return (int64_t)(db->tiles.size() / HLM_TILE_WORDS);
+  if (k == "tiles_raw") return db->n_tiles_raw;
+  if (k == "kmers") return db->n_kmers;
+  if (k == "kmers_skipped") return db->n_kmers_skipped;
+  if (k == "kt_slots") return (int64_t)db->kt.size();
+  if (k == "seed_entries") return (int64_t)db->seed_ent.size();
+  return -1;
+}
+
+static int upload_db(hlm_ctx* ctx, hlm_db* db) {
+  for (auto& d : db->devs)
+    if (d.device == ctx->device) {
+      ctx->ddb = d.view;
+      d.refs++;
+      return 0;
+    }
+  hlm_db::Dev dv;
+  dv.device = ctx->device;
+  dv.refs = 1;
+  for (auto& p : dv.ptrs) p = nullptr;
+  auto up = [&](int slot, const void* src, size_t bytes, const void** out) -> int {
+    void* p = nullptr;
+    if (!cuda_ok(ctx, cudaMalloc(&p, bytes + 256), "cudaMalloc(db)")) return HLM_E_NOMEM;
+    if (!cuda_ok(ctx, cudaMemset(p, 0, bytes + 256), "cudaMemset(db)")) return HLM_E_CUDA;
+    if (bytes && !cuda_ok(ctx, cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(db)"))
+      return HLM_E_CUDA;
+    dv.ptrs[slot] = p;
+    *out = p;
+    return 0;
+  };
+  HlmDevDB v;
+  memset(&v, 0, sizeof v);
+  int rc;
+  if ((rc = up(0, db->kt.data(), db->kt.size() * 8, (const void**)&v.kt))) return rc;
+  if ((rc = up(1, db->mask_tab.data(), db->mask_tab.size() * 4, (const void**)&v.mask_tab))) return rc;
+  if ((rc = up(2, db->tiles.data(), db->tiles.size() * 4, (const void**)&v.tiles))) return rc;
+  if ((rc = up(3, db->seed_off.data(), db->seed_off.size() * 4, (const void**)&v.seed_off))) return rc;
+  if ((rc = up(4, db->seed_ent.data(), db->seed_ent.size() * 4, (const void**)&v.seed_ent))) return rc;
+  v.kt_bits = db->kt_bits;
+  v.n_loci = db->n_loci;
+  for (int g = 0; g < db->n_loci + 2; g++) v.tile_start[g] = db->tile_start[g];
+  for (int g = db->n_loci + 2; g < HLM_MAX_LOCI + 3; g++) v.tile_start[g] = 0xFFFFFFFFu;
+  dv.view = v;
+  db->devs.push_back(dv);
+  ctx->ddb = v;
+  return 0;
+}
+
+hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* params, char* err,
+                        size_t errlen) {
+  auto fail = [&](const std::string& m) -> hlm_ctx* {
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+    return nullptr;
+  };
+  if (!db) return fail("null db");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("libhlamap needs a CUDA device: there is no CPU path (no device found)");
+  if (cuda_device < 0 || cuda_device >= ndev) return fail("cuda_device out of range");
+  hlm_ctx* ctx = new hlm_ctx();
+  ctx->db = db;
+  ctx->device = cuda_device;
+  if (params) {
+    memcpy(&ctx->p, params, std::min((size_t)params->struct_size, sizeof(hlm_params)));
+    if ((size_t)params->struct_size < sizeof(hlm_params)) {
+      hlm_params d;
+      hlm_params_default(&d, params->rna);
+      memcpy((char*)&ctx->p + params->struct_size, (char*)&d + params->struct_size,
+             sizeof(hlm_params) - params->struct_size);
+    }
+  } else {
+    hlm_params_default(&ctx->p, db->rna);
+  }
+  hlm_params& p = ctx->p;
+  if (p.rna != db->rna) {
+    delete ctx;
+    return fail("params.rna does not match the database kind");
+  }
+  if (cudaSetDevice(cuda_device) != cudaSuccess) {
+    delete ctx;
+    return fail("cudaSetDevice failed");
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  ctx->sms = prop.multiProcessorCount;
+  ctx->n_targets = db->n_loci + 1;
+  ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
+  ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 32768;
+  ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 4096;
+  if (ctx->cand_cap >= (1ll << 32)) ctx->cand_cap = (1ll << 32) - 1;
+  if (ctx->chunk_pairs * ctx->units_per_pair >= (1ll << 26)) {
+    delete ctx;
+    return fail("chunk_pairs too large for the 26-bit unit id");
+  }
+  HlmKParams& kp = ctx->kp;
+  memset(&kp, 0, sizeof kp);
+  kp.rna = p.rna;
+  kp.paired = p.paired;
+  kp.screen_variant = p.screen_variant;
+  kp.v_size = p.v_size > 0 ? p.v_size : db->v_size;
+  kp.minhit = p.minhit;
+  kp.mm_max = p.mm_max;
+  kp.clip_mode = p.clip_mode;
+  kp.skip_screen = p.skip_screen;
+  kp.tolerance = p.tolerance;
+  kp.n_loci = db->n_loci;
+  // mtrim's test, evaluated once per quality byte with the reference's own expression
+  // (functions.cpp:99-103): P = pow(10, phred / -10) <= v_mtrim_error, phred = char - 33
+  for (int c = 0; c < 256; c++) {
+    double chr_phred = (double)((int)(signed char)c - 33);
+    double P = pow((double)10, (chr_phred / (double)(-10)));
+    if (P <= p.mtrim_error) kp.good_q[c >> 5] |= 1u << (c & 31);
+  }
+  if (upload_db(ctx, const_cast<hlm_db*>(db)) != 0) {
+    std::string m = ctx->err;
+    delete ctx;
+    return fail(m);
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaStreamCreateWithFlags(&ctx->slot[i].st, cudaStreamNonBlocking);
+    for (int e = 0; e < EV_COUNT; e++) cudaEventCreate(&ctx->slot[i].ev[e]);
+    memset(&ctx->slot[i].ck, 0, sizeof(HlmChunk));
+  }
+  cudaEventCreate(&ctx->run_start);
+  memset(&ctx->prof, 0, sizeof ctx->prof);
+  return ctx;
+}
+
+void hlm_ctx_destroy(hlm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; i++) {
+    Slot& s = ctx->slot[i];
+    for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters})
+      if (b->p) cudaFree(b->p);
+    for (Buf* b : {&s.h_in, &s.h_out})
+      if (b->p) cudaFreeHost(b->p);
+    for (int e = 0; e < EV_COUNT; e++) cudaEventDestroy(s.ev[e]);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  cudaEventDestroy(ctx->run_start);
+  hlm_db* db = const_cast<hlm_db*>(ctx->db);
+  for (auto& d : db->devs)
+    if (d.device == ctx->device) d.refs--;
+  delete ctx;
+}
+
+const char* hlm_last_error(const hlm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int hlm_screen_trim(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* out) {
+  if (!ctx || !in || !out) return HLM_E_ARG;
+  HostIO io;
+  io.in = in;
+  io.scr = out;
+  return run_host(ctx, io, HLM_STAGE_SCREEN);
+}
+
+int hlm_score(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, hlm_score_out* out) {
+  if (!ctx || !in || !scr || !out) return HLM_E_ARG;
+  HostIO io;
+  io.in = in;
+  io.scr_in = scr;
+  io.sc = out;
+  return run_host(ctx, io, HLM_STAGE_SCORE);
+}
+
+int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, const hlm_score_out* sc,
+               hlm_assign_out* out) {
+  if (!ctx || !in || !scr || !sc || !out) return HLM_E_ARG;
+  HostIO io;
+  io.in = in;
+  io.scr_in = scr;
+  io.sc_in = sc;
+  io.asg = out;
+  return run_host(ctx, io, HLM_STAGE_ASSIGN);
+}
+
+int hlm_run(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+            hlm_assign_out* asg) {
+  if (!ctx || !in) return HLM_E_ARG;
+  HostIO io;
+  io.in = in;
+  io.scr = scr;
+  io.sc = sc;
+  io.asg = asg;
+  return run_host(ctx, io, HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ASSIGN);
+}
+
+// ---------------------------------------------------------------- device-resident batches
+hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in) {
+  if (!ctx || !in) return nullptr;
+  if (check_lengths(ctx, in)) return nullptr;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  hlm_devbatch* b = new hlm_devbatch();
+  int64_t n = in->n_pairs;
+  bool paired = ctx->p.paired;
+  b->n_pairs = n;
+  b->paired = paired;
+  size_t b1 = (size_t)in->offs1[n], b2 = paired ? (size_t)in->offs2[n] : 0;
+  size_t o = 0;
+  auto sec = [&](int i, size_t bytes) { b->in_off[i] = o; o += align16(bytes + 32); };
+  sec(0, b1); sec(1, b1); sec(2, b2); sec(3, b2);
+  sec(4, (n + 1) * 8); sec(5, paired ? (n + 1) * 8 : 0);
+  sec(6, in->size_override1 ? n * 4 : 0);
+  sec(7, in->rna_split1 ? n * 2 : 0);
+  sec(8, in->rna_split2 ? n * 2 : 0);
+  if (ensure_dev(ctx, b->in, o)) { delete b; return nullptr; }
+  uint8_t* d = (uint8_t*)b->in.p;
+  auto cp = [&](int i, const void* src, size_t bytes, size_t lead) {
+    if (src && bytes) cudaMemcpy(d + b->in_off[i] + lead, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cp(0, in->bases1, b1, 16); cp(1, in->quals1, b1, 16);
+  cp(2, in->bases2, b2, 16); cp(3, in->quals2, b2, 16);
+  cp(4, in->offs1, (n + 1) * 8, 0);
+  if (paired) cp(5, in->offs2, (n + 1) * 8, 0);
+  cp(6, in->size_override1, n * 4, 0);
+  cp(7, in->rna_split1, n * 2, 0);
+  cp(8, in->rna_split2, n * 2, 0);
+  b->read_bytes = 2 * (int64_t)(b1 + b2);
+  b->has_override = in->size_override1 != nullptr;
+  b->has_split1 = in->rna_split1 != nullptr;
+  b->has_split2 = in->rna_split2 != nullptr;
+  size_t ob = out_layout(n, ctx->n_targets, b->out_off);
+  if (ensure_dev(ctx, b->out, ob)) { cudaFree(b->in.p); delete b; return nullptr; }
+  if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "upload failed"; }
+  return b;
+}
+
+void hlm_batch_free(hlm_ctx* ctx, hlm_devbatch* b) {
+  if (!b) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (b->in.p) cudaFree(b->in.p);
+  if (b->out.p) cudaFree(b->out.p);
+  delete b;
+}
+
+int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
+  if (!ctx || !b) return HLM_E_ARG;
+  CU(cudaSetDevice(ctx->device));
+  memset(&ctx->prof, 0, sizeof ctx->prof);
+  int T = ctx->n_targets;
+  int64_t N = b->n_pairs, C = ctx->chunk_pairs;
+  uint8_t* d = (uint8_t*)b->in.p;
+  CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
+  CU(cudaStreamWaitEvent(ctx->slot[1].st, ctx->run_start, 0));
+  int rc = 0;
+  int64_t k = 0;
+  unsigned long long cnt[8];
+  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
+    Slot& s = ctx->slot[k & 1];
+    int64_t n = std::min(C, N - first);
+    if (s.busy) {
+      if ((rc = ensure_pinned(ctx, s.h_out, 4096))) break;
+      rc = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
+      if (rc) break;
+    }
+    if ((rc = ensure_pinned(ctx, s.h_out, 4096))) break;
+    if ((rc = ensure_work(ctx, s, n))) break;
+    HlmChunk& ck = s.ck;
+    ck.n_pairs = n;
+    ck.bases1 = d + b->in_off[0] + 16;
+    ck.quals1 = d + b->in_off[1] + 16;
+    ck.bases2 = d + b->in_off[2] + 16;
+    ck.quals2 = d + b->in_off[3] + 16;
+    ck.offs1 = (const uint64_t*)(d + b->in_off[4]) + first;
+    ck.offs2 = (const uint64_t*)(d + b->in_off[5]) + first;
+    ck.size_override1 = b->has_override ? (const int32_t*)(d + b->in_off[6]) + first : nullptr;
+    ck.rna_split1 = b->has_split1 ? (const uint16_t*)(d + b->in_off[7]) + first : nullptr;
+    ck.rna_split2 = b->has_split2 ? (const uint16_t*)(d + b->in_off[8]) + first : nullptr;
+    bind_outputs(ck, (uint8_t*)b->out.p, b->out_off, first, T);
+    s.first = first;
+    s.n = n;
+    cudaStream_t st = s.st;
+    CU(cudaEventRecord(s.ev[EV_START], st));
+    CU(cudaEventRecord(s.ev[EV_H2D], st));
+    launch_stages(ctx, s, HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ASSIGN);
+    CU(cudaMemcpyAsync(s.h_out.p, ck.counters, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(s.ev[EV_D2H], st));
+    s.busy = true;
+    uint64_t nb = 0;
+    (void)nb;
+  }
+  (void)cnt;
+  for (int i = 0; i < 2; i++) {
+    Slot& s = ctx->slot[(k + i) & 1];
+    if (s.busy) {
+      int r2 = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
+      if (rc == 0) rc = r2;
+    }
+  }
+  ctx->prof.n_pairs = N;
+  ctx->prof.bases_bytes = b->read_bytes;
+  cudaError_t e = cudaGetLastError();
+  if (rc == 0 && e != cudaSuccess) {
+    ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+    rc = HLM_E_CUDA;
+  }
+  return rc;
+}
+
+int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out* sc,
+              hlm_assign_out* asg) {
+  if (!ctx || !b) return HLM_E_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int T = ctx->n_targets;
+  int64_t n = b->n_pairs;
+  const uint8_t* d = (const uint8_t*)b->out.p;
+  const size_t* o = b->out_off;
+  auto get = [&](void* dst, int sec, size_t bytes) -> int {
+    if (!dst) return 0;
+    return cudaMemcpy(dst, d + o[sec], bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : HLM_E_CUDA;
+  };
+  int rc = 0;
+  if (scr) {
+    rc |= get(scr->flags, O_FLAGS, n); rc |= get(scr->trim_lo1, O_LO1, 2 * n);
+    rc |= get(scr->trim_len1, O_LEN1, 2 * n); rc |= get(scr->trim_lo2, O_LO2, 2 * n);
+    rc |= get(scr->trim_len2, O_LEN2, 2 * n); rc |= get(scr->locus_mask, O_MASK, 4 * n);
+  }
+  if (sc) {
+    rc |= get(sc->s1, O_S1, 2 * n * T); rc |= get(sc->s2, O_S2, 2 * n * T);
+    rc |= get(sc->aln1, O_ALN1, 2 * n * T); rc |= get(sc->aln2, O_ALN2, 2 * n * T);
+    rc |= get(sc->nm1, O_NM1, n * T); rc |= get(sc->nm2, O_NM2, n * T);
+    rc |= get(sc->lead1, O_LEAD1, n * T); rc |= get(sc->lead2, O_LEAD2, n * T);
+    rc |= get(sc->trail1, O_TRAIL1, n * T); rc |= get(sc->trail2, O_TRAIL2, n * T);
+  }
+  if (asg) {
+    rc |= get(asg->target_mask, O_TARGET, 4 * n); rc |= get(asg->visible_mask, O_VISIBLE, 4 * n);
+    rc |= get(asg->min_sum, O_MINSUM, 2 * n); rc |= get(asg->others_s1, O_OS1, 2 * n);
+    rc |= get(asg->others_s2, O_OS2, 2 * n);
+  }
+  if (rc) ctx->err = "cudaMemcpy (fetch) failed";
+  return rc ? HLM_E_CUDA : 0;
+}
+
+int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out) {
+  if (!ctx || !out) return HLM_E_ARG;
+  *out = ctx->prof;
+  return 0;
+}
+
+int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,
+                   double* giga_viaddmnmx) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cuda_device < 0 || cuda_device >= ndev)
+    return HLM_E_NODEVICE;
+  cudaSetDevice(cuda_device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  int sms = prop.multiProcessorCount;
+  double* outs[4] = {giga_iadd, giga_imad, giga_mix, giga_viaddmnmx};
+  for (int w = 0; w < 4; w++)
+    if (outs[w]) *outs[w] = hlm_int_peak_run(w, sms, 0);
+  return 0;
+}
+
+}  // extern "C"

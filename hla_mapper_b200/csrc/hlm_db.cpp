@@ -1,0 +1,293 @@
+// hlm_db.cpp — parses the hla-mapper database layout and builds the packed GPU indexes.
+//
+// Reads exactly the files the reference reads for the hot path:
+//   db_{dna,rna}.info                        src/map_dna.cpp:299-365, src/map_rna.cpp:281-335
+//   motif/<kind>/all/motif_all.txt           src/preselect.cpp:297-309
+//   motif/<kind>/loci/<g>.txt                src/map_dna.cpp:565-581, src/map_rna.cpp:498-514
+//   mapper/<kind>/<g>/<g>.fas                src/map_dna.cpp:735,  src/map_rna.cpp:833
+//   others/<kind>/hla_gen_others.fasta       src/map_dna.cpp:824,  src/map_rna.cpp:858
+#include "hlm_db.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <thread>
+
+namespace {
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  out.resize(got);
+  return true;
+}
+
+inline int base_code(unsigned char c) {
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+  }
+}
+
+// motif lines -> (key, mask bit).  A line can only ever equal seq.substr(c,20) when it is
+// exactly 20 bytes; a 20-byte line holding a non-ACGT byte is not representable in 2 bits and
+// is counted in n_kmers_skipped (it could only match a read with the same byte in place).
+void load_motifs(const std::string& path, uint32_t bit,
+                 std::vector<std::pair<uint64_t, uint32_t>>& out, int64_t& skipped) {
+  std::vector<char> buf;
+  if (!read_file(path, buf)) return;
+  size_t i = 0, n = buf.size();
+  while (i < n) {
+    size_t e = i;
+    while (e < n && buf[e] != '\n') e++;
+    if (e - i == HLM_MOTIF) {
+      uint64_t key = 0;
+      bool ok = true;
+      for (int x = 0; x < HLM_MOTIF; x++) {
+        unsigned char c = (unsigned char)buf[i + x];
+        int code = (c == 'A') ? 0 : (c == 'C') ? 1 : (c == 'G') ? 2 : (c == 'T') ? 3 : 4;
+        if (code > 3) {
+          ok = false;
+          break;
+        }
+        key |= (uint64_t)code << (2 * x);
+      }
+      if (ok) out.emplace_back(key, bit);
+      else skipped++;
+    }
+    i = e + 1;
+  }
+}
+
+struct Planes {
+  std::vector<uint32_t> p0, p1, nm;
+  int len = 0;
+};
+
+// FASTA -> bit planes of each N-padded allele
+void load_fasta(const std::string& path, std::vector<Planes>& out, int64_t& n_bases) {
+  std::vector<char> buf;
+  if (!read_file(path, buf)) return;
+  std::vector<uint8_t> codes;
+  auto flush = [&](bool have) {
+    if (!have) return;
+    Planes P;
+    P.len = (int)codes.size();
+    size_t nw = (size_t)(HLM_PAD + P.len + HLM_PAD + 31) / 32 + 8;
+    P.p0.assign(nw, 0);
+    P.p1.assign(nw, 0);
+    P.nm.assign(nw, 0xFFFFFFFFu);
+    for (int x = 0; x < P.len; x++) {
+      int c = codes[x];
+      if (c > 3) continue;
+      size_t col = (size_t)HLM_PAD + x;
+      uint32_t b = 1u << (col & 31);
+      P.nm[col >> 5] &= ~b;
+      if (c & 1) P.p0[col >> 5] |= b;
+      if (c & 2) P.p1[col >> 5] |= b;
+    }
+    n_bases += P.len;
+    out.push_back(std::move(P));
+    codes.clear();
+  };
+  size_t i = 0, n = buf.size();
+  bool have = false;
+  while (i < n) {
+    size_t e = i;
+    while (e < n && buf[e] != '\n') e++;
+    size_t le = e;
+    while (le > i && (buf[le - 1] == '\r')) le--;
+    if (le > i) {
+      if (buf[i] == '>') {
+        flush(have);
+        have = true;
+      } else if (have) {
+        for (size_t x = i; x < le; x++) codes.push_back((uint8_t)base_code((unsigned char)buf[x]));
+      }
+    }
+    i = e + 1;
+  }
+  flush(have);
+}
+
+inline uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  h *= 0xff51afd7ed558ccdull;
+  return h ^ (h >> 32);
+}
+
+}  // namespace
+
+hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
+  std::string base(dir);
+  const char* kind = rna ? "rna" : "dna";
+  std::vector<char> info;
+  std::string info_path = base + "/db_" + kind + ".info";
+  if (!read_file(info_path, info)) {
+    err = "Error accessing database " + info_path;
+    return nullptr;
+  }
+  hlm_db* db = new hlm_db();
+  db->rna = rna;
+  bool version_ok = false;
+  {
+    size_t i = 0, n = info.size();
+    while (i < n) {
+      size_t e = i;
+      while (e < n && info[e] != '\n') e++;
+      std::string line(info.data() + i, e - i);
+      if (line == "hla-mapper:4.3+") version_ok = true;
+      else if (line.compare(0, 5, "GENE:") == 0) {
+        size_t q = line.find(':', 5);
+        std::string g = line.substr(5, q == std::string::npos ? std::string::npos : q - 5);
+        g.erase(std::remove(g.begin(), g.end(), ' '), g.end());
+        if (!g.empty() && db->n_loci < HLM_MAX_LOCI) {
+          db->names.push_back(g);
+          db->n_loci++;
+        }
+      } else if (line.compare(0, 5, "SIZE:") == 0) {
+        db->v_size = atoi(line.c_str() + 5);
+      }
+      i = e + 1;
+    }
+  }
+  if (!version_ok) {
+    err = "The database is not compatible with this version of hla-mapper.";
+    delete db;
+    return nullptr;
+  }
+  db->names.push_back("others");
+
+  // ---- k-mer screen index
+  {
+    std::vector<std::pair<uint64_t, uint32_t>> kv;
+    load_motifs(base + "/motif/" + kind + "/all/motif_all.txt", 1u << 31, kv, db->n_kmers_skipped);
+    for (int g = 0; g < db->n_loci; g++)
+      load_motifs(base + "/motif/" + kind + "/loci/" + db->names[g] + ".txt", 1u << g, kv,
+                  db->n_kmers_skipped);
+    std::sort(kv.begin(), kv.end());
+    std::vector<std::pair<uint64_t, uint32_t>> uniq;
+    for (size_t i = 0; i < kv.size();) {
+      uint64_t k = kv[i].first;
+      uint32_t m = 0;
+      while (i < kv.size() && kv[i].first == k) m |= kv[i++].second;
+      uniq.emplace_back(k, m);
+    }
+    db->n_kmers = (int64_t)uniq.size();
+    int bits = 10;
+    while ((1ull << bits) < 2 * uniq.size() + 2) bits++;
+    db->kt_bits = bits;
+    db->kt.assign(1ull << bits, 0);
+    std::map<uint32_t, uint32_t> mask_id;
+    uint64_t cap_mask = (1ull << bits) - 1;
+    for (auto& e : uniq) {
+      auto it = mask_id.find(e.second);
+      if (it == mask_id.end()) {
+        it = mask_id.emplace(e.second, (uint32_t)db->mask_tab.size()).first;
+        db->mask_tab.push_back(e.second);
+      }
+      uint64_t h = hlm_kt_hash(e.first, bits);
+      while (db->kt[h] & HLM_KT_OCC) h = (h + 1) & cap_mask;
+      db->kt[h] = HLM_KT_OCC | ((uint64_t)it->second << 40) | e.first;
+    }
+    if (db->mask_tab.size() > 65535) {
+      err = "too many distinct motif membership masks";
+      delete db;
+      return nullptr;
+    }
+    if (db->mask_tab.empty()) db->mask_tab.push_back(0);
+  }
+
+  // ---- tiles: per locus, distinct 256-column windows at stride 32 of the padded alleles
+  db->tile_start.assign(db->n_loci + 2, 0);
+  for (int g = 0; g <= db->n_loci; g++) {
+    db->tile_start[g] = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+    std::vector<Planes> al;
+    std::string path = g < db->n_loci
+                           ? base + "/mapper/" + kind + "/" + db->names[g] + "/" + db->names[g] + ".fas"
+                           : base + "/others/" + kind + "/hla_gen_others.fasta";
+    load_fasta(path, al, db->n_bases);
+    db->n_alleles += (int64_t)al.size();
+    size_t raw = 0;
+    for (auto& P : al) raw += (size_t)(HLM_PAD + P.len) / 32 + 1;
+    db->n_tiles_raw += (int64_t)raw;
+    size_t cap = 1024;
+    while (cap < raw * 2) cap <<= 1;
+    std::vector<uint32_t> slot(cap, 0xFFFFFFFFu);  // tile id per hash slot
+    uint32_t w[HLM_TILE_WORDS];
+    for (auto& P : al) {
+      int jmax = (HLM_PAD + P.len) / 32;
+      for (int j = 0; j <= jmax; j++) {
+        uint64_t h = 0x1234567ull;
+        for (int x = 0; x < 8; x++) {
+          w[x] = P.p0[j + x];
+          w[8 + x] = P.p1[j + x];
+          w[16 + x] = P.nm[j + x];
+        }
+        for (int x = 0; x < HLM_TILE_WORDS; x += 2) h = mix64(h, (uint64_t)w[x] | ((uint64_t)w[x + 1] << 32));
+        size_t s = h & (cap - 1);
+        bool found = false;
+        while (slot[s] != 0xFFFFFFFFu) {
+          if (memcmp(&db->tiles[(size_t)slot[s] * HLM_TILE_WORDS], w, sizeof w) == 0) {
+            found = true;
+            break;
+          }
+          s = (s + 1) & (cap - 1);
+        }
+        if (!found) {
+          slot[s] = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+          db->tiles.insert(db->tiles.end(), w, w + HLM_TILE_WORDS);
+        }
+      }
+    }
+  }
+  size_t n_tiles = db->tiles.size() / HLM_TILE_WORDS;
+  db->tile_start[db->n_loci + 1] = (uint32_t)n_tiles;
+  if (n_tiles >= (1u << 24)) {
+    err = "too many distinct tiles for the 24-bit tile id";
+    delete db;
+    return nullptr;
+  }
+
+  // ---- seed index: CSR over 12-mers of every tile column in [OFF_MIN, 256-12]
+  db->seed_off.assign((size_t)HLM_SEED_CODES + 1, 0);
+  auto scan = [&](bool fill, std::vector<uint32_t>& cursor) {
+    for (size_t t = 0; t < n_tiles; t++) {
+      const uint32_t* T = &db->tiles[t * HLM_TILE_WORDS];
+      uint32_t code = 0;
+      int run = 0;
+      for (int c = HLM_OFF_MIN; c < HLM_TILE_COLS; c++) {
+        int isn = (T[16 + (c >> 5)] >> (c & 31)) & 1;
+        if (isn) {
+          run = 0;
+          code = 0;
+          continue;
+        }
+        uint32_t b = ((T[c >> 5] >> (c & 31)) & 1) | (((T[8 + (c >> 5)] >> (c & 31)) & 1) << 1);
+        code = (code >> 2) | (b << (2 * (HLM_SEED - 1)));
+        if (++run >= HLM_SEED) {
+          int o = c - HLM_SEED + 1;
+          if (!fill) db->seed_off[code + 1]++;
+          else db->seed_ent[cursor[code]++] = ((uint32_t)t << 8) | (uint32_t)o;
+        }
+      }
+    }
+  };
+  std::vector<uint32_t> cursor;
+  scan(false, cursor);
+  for (size_t c = 0; c < HLM_SEED_CODES; c++) db->seed_off[c + 1] += db->seed_off[c];
+  db->seed_ent.resize(db->seed_off[HLM_SEED_CODES]);
+  cursor.assign(db->seed_off.begin(), db->seed_off.end() - 1);
+  scan(true, cursor);
+  return db;
+}

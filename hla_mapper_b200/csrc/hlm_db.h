@@ -1,0 +1,42 @@
+// hlm_db.h — host-side database: reference layout parser + packed index builder.
+#ifndef HLM_DB_H
+#define HLM_DB_H
+
+#include <string>
+#include <vector>
+
+#include "hlm_common.h"
+
+struct hlm_db {
+  int rna = 0;
+  int n_loci = 0;
+  int v_size = 50;  // src/main.cpp:79; overridden by SIZE: (map_dna.cpp:351-354)
+  std::vector<std::string> names;  // n_loci + "others"
+
+  // k-mer screen index
+  std::vector<uint64_t> kt;
+  std::vector<uint32_t> mask_tab;
+  int kt_bits = 0;
+  int64_t n_kmers = 0;
+  int64_t n_kmers_skipped = 0;  // 20-char motif lines holding a non-ACGT byte
+
+  // tiles + seed index
+  std::vector<uint32_t> tiles;
+  std::vector<uint32_t> tile_start;  // n_loci + 2
+  std::vector<uint32_t> seed_off;
+  std::vector<uint32_t> seed_ent;
+  int64_t n_alleles = 0, n_bases = 0, n_tiles_raw = 0;
+
+  // device copies, one per CUDA device that has a context on this DB
+  struct Dev {
+    int device;
+    HlmDevDB view;
+    void* ptrs[5];
+    int refs;
+  };
+  std::vector<Dev> devs;
+};
+
+hlm_db* hlm_db_build(const char* dir, int rna, std::string& err);
+
+#endif

@@ -1,0 +1,842 @@
+// hlm_kernels.cu — hand-written sm_100a kernels of the hla-mapper hot path.
+//
+//   k_screen       warp per pair: 20-mer screen (preselect.cpp:707-731 / :484-506), mtrim
+//                  (functions.cpp:89-145), pair filter (preselect.cpp:1132) and per-locus
+//                  candidate mask (map_dna.cpp:611-627) in one streaming pass over the reads.
+//   k_pack_units   warp per pair: 2-bit/bit-plane packing of the trimmed mates (both strands).
+//   k_seed         warp per unit: 12-mer seed lookups in the tile index -> candidate list.
+//   k_myers        thread per candidate: bit-parallel banded edit distance (lower bound).
+//   k_select       thread per candidate: which candidates still need the affine DP.
+//   k_dp           thread per candidate: banded affine-gap DP in registers (DPX min/max).
+//   k_scores       warp per pair, lane per target: SAM-reducer semantics (map_dna.cpp:44-118,
+//                  map_rna.cpp:39-101) on the per-task best alignment.
+//   k_assign       warp per pair, lane per target: others back-fill, tolerance filter, argmin,
+//                  tie set (map_dna.cpp:903-1029, map_rna.cpp:925-1027).
+//
+// All of it is integer / byte work: HBM-, L2- or INT32-bound, no tensor-core shape anywhere.
+#include "hlm_kernels.cuh"
+
+#include "hlm_core.cuh"
+
+#define FULL 0xFFFFFFFFu
+#define WARPS_PER_BLOCK 8
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+  // streaming read: read bases / qualities are touched once
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// bytes [8*lane, 8*lane+8) of the byte string p[0..len); zero beyond len.  len <= 256.
+__device__ __forceinline__ uint64_t warp_load8(const uint8_t* p, int len, int lane) {
+  uintptr_t a = (uintptr_t)p;
+  int shift = (int)(a & 7);
+  const uint64_t* q = (const uint64_t*)(a - shift);
+  int nwords = (shift + len + 7) >> 3;
+  uint64_t w = (lane < nwords) ? ld_stream_u64(q + lane) : 0ull;
+  uint64_t wn = __shfl_down_sync(FULL, w, 1);
+  uint64_t w32 = (nwords > 32 && lane == 0) ? ld_stream_u64(q + 32) : 0ull;
+  w32 = __shfl_sync(FULL, w32, 0);
+  if (lane == 31) wn = w32;
+  uint64_t v = shift ? (w >> (8 * shift)) | (wn << (64 - 8 * shift)) : w;
+  int rem = len - 8 * lane;
+  if (rem <= 0) v = 0;
+  else if (rem < 8) v &= (1ull << (8 * rem)) - 1;
+  return v;
+}
+
+// 8 ASCII bases -> 2-bit stream (16 bits), plane bits (8 each).  Only upper-case ACGT are
+// bases (the reference compares raw strings); everything else, and padding, is N.
+__device__ __forceinline__ void encode8(uint64_t v, uint32_t& pk, uint32_t& b0, uint32_t& b1,
+                                        uint32_t& bn) {
+  pk = 0; b0 = 0; b1 = 0; bn = 0;
+#pragma unroll
+  for (int x = 0; x < 8; x++) {
+    uint32_t c = (uint32_t)(v >> (8 * x)) & 0xFFu;
+    bool isb = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+    uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+    code = isb ? code : 0u;
+    pk |= code << (2 * x);
+    b0 |= (code & 1u) << x;
+    b1 |= (code >> 1) << x;
+    bn |= (isb ? 0u : 1u) << x;
+  }
+}
+
+struct WarpScratch {
+  uint32_t sq[18];    // 2-bit stream of R1 (16 bases / word) + zero padding
+  uint32_t p0[9];     // planes of the mate being processed (+1 pad word)
+  uint32_t p1[9];
+  uint32_t pn[9];
+  uint32_t good[9];   // mtrim "good quality" bits
+  uint32_t hits[8];   // global-screen hit bits per R1 position
+  uint32_t rev[3][8]; // scratch for reverse complement
+};
+
+__device__ __forceinline__ uint32_t probe_kmer(const HlmDevDB& db, uint64_t key) {
+  uint64_t mask = (1ull << db.kt_bits) - 1;
+  uint64_t h = hlm_kt_hash(key, db.kt_bits);
+  for (;;) {
+    uint64_t s = __ldg(db.kt + h);
+    if (!(s & HLM_KT_OCC)) return 0u;
+    if ((s & HLM_KT_KEYMASK) == key) return __ldg(db.mask_tab + ((s >> 40) & 0xFFFFu));
+    h = (h + 1) & mask;
+  }
+}
+
+// first set bit at or after pos (< limit), or -1
+__device__ __forceinline__ int next_one(const uint32_t* m, int pos, int limit) {
+  while (pos < limit) {
+    uint32_t w = m[pos >> 5] >> (pos & 31);
+    if (w) {
+      int p = pos + __ffs(w) - 1;
+      return p < limit ? p : -1;
+    }
+    pos = (pos | 31) + 1;
+  }
+  return -1;
+}
+// first clear bit at or after pos, or limit
+__device__ __forceinline__ int next_zero(const uint32_t* m, int pos, int limit) {
+  while (pos < limit) {
+    uint32_t w = (~m[pos >> 5]) >> (pos & 31);
+    if (w) {
+      int p = pos + __ffs(w) - 1;
+      return p < limit ? p : limit;
+    }
+    pos = (pos | 31) + 1;
+  }
+  return limit;
+}
+
+// mtrim (functions.cpp:89-145) on the good-quality bit string.  Interior runs score
+// end-start = length-1, the run touching the end scores length (end = qual.length()); the
+// first strictly larger score wins, starting from 0.
+__device__ __forceinline__ bool mtrim_bits(const uint32_t* good, int qlen, int slen, int v_size,
+                                           int& lo, int& len) {
+  int low = 0, high = 0, pos = 0;
+  while (pos < qlen) {
+    int s = next_one(good, pos, qlen);
+    if (s < 0) break;
+    int e = next_zero(good, s, qlen);
+    if (e < qlen) {
+      if ((e - 1 - s) > (high - low)) { low = s; high = e - 1; }
+    } else {
+      if ((qlen - s) > (high - low)) { low = s; high = qlen; }
+    }
+    pos = e;
+  }
+  len = 0;
+  if (low < high) {
+    len = high - low + 1;
+    if (low > slen) len = 0;
+    else if (low + len > slen) len = slen - low;
+  }
+  lo = low;
+  return len >= v_size && len > 0;
+}
+
+// load one mate's bases into the warp scratch planes (and the 2-bit stream when sq != null)
+__device__ __forceinline__ void stage_bases(const uint8_t* p, int len, int lane, WarpScratch& ws,
+                                            bool want_stream) {
+  uint64_t v = warp_load8(p, len, lane);
+  uint32_t pk, b0, b1, bn;
+  encode8(v, pk, b0, b1, bn);
+  // assemble words with shuffles: word w of a plane = bytes of lanes 4w..4w+3
+  uint32_t x0 = b0 << (8 * (lane & 3)), x1 = b1 << (8 * (lane & 3)), xn = bn << (8 * (lane & 3));
+  x0 |= __shfl_xor_sync(FULL, x0, 1); x0 |= __shfl_xor_sync(FULL, x0, 2);
+  x1 |= __shfl_xor_sync(FULL, x1, 1); x1 |= __shfl_xor_sync(FULL, x1, 2);
+  xn |= __shfl_xor_sync(FULL, xn, 1); xn |= __shfl_xor_sync(FULL, xn, 2);
+  uint32_t s2 = pk << (16 * (lane & 1));
+  s2 |= __shfl_xor_sync(FULL, s2, 1);
+  if ((lane & 3) == 0) {
+    ws.p0[lane >> 2] = x0;
+    ws.p1[lane >> 2] = x1;
+    ws.pn[lane >> 2] = xn;
+  }
+  if (want_stream && (lane & 1) == 0) ws.sq[lane >> 1] = s2;
+  if (lane == 0) {
+    ws.p0[8] = 0; ws.p1[8] = 0; ws.pn[8] = 0xFFFFFFFFu;
+    if (want_stream) { ws.sq[16] = 0; ws.sq[17] = 0; }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void stage_quals(const uint8_t* p, int len, int lane, WarpScratch& ws,
+                                            const HlmKParams& kp) {
+  uint64_t v = warp_load8(p, len, lane);
+  uint32_t g = 0;
+#pragma unroll
+  for (int x = 0; x < 8; x++) {
+    uint32_t c = (uint32_t)(v >> (8 * x)) & 0xFFu;
+    uint32_t ok = (kp.good_q[c >> 5] >> (c & 31)) & 1u;
+    if (8 * lane + x >= len) ok = 0;
+    g |= ok << x;
+  }
+  uint32_t x0 = g << (8 * (lane & 3));
+  x0 |= __shfl_xor_sync(FULL, x0, 1); x0 |= __shfl_xor_sync(FULL, x0, 2);
+  if ((lane & 3) == 0) ws.good[lane >> 2] = x0;
+  if (lane == 0) ws.good[8] = 0;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ k_screen
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
+  __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpScratch& ws = scratch[wib];
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  unsigned long long kept_local = 0;
+  for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
+    uint64_t o1 = ck.offs1[pair];
+    int l1 = (int)(ck.offs1[pair + 1] - o1);
+    uint64_t o2 = 0;
+    int l2 = 0;
+    if (kp.paired) {
+      o2 = ck.offs2[pair];
+      l2 = (int)(ck.offs2[pair + 1] - o2);
+    }
+    // length pre-checks: preselect.cpp:707-710 (paired FASTQ), :484-485 (BAM, R1 only), :918-919
+    bool ok = !(l1 < HLM_MOTIF || l1 < kp.v_size);
+    if (kp.paired && kp.screen_variant == HLM_SCREEN_FASTQ && (l2 < HLM_MOTIF || l2 < kp.v_size))
+      ok = false;
+    uint32_t myval[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) myval[r] = 0;
+    bool screened = false;
+    if (ok) {
+      stage_bases(ck.bases1 + o1, l1, lane, ws, true);
+      int npos = l1 - HLM_MOTIF;  // positions c < npos are probed (the last window never is)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        int c = r * 32 + lane;
+        uint32_t val = 0;
+        if (c < npos) {
+          int w = c >> 4, s = 2 * (c & 15);
+          uint64_t lo = (uint64_t)ws.sq[w] | ((uint64_t)ws.sq[w + 1] << 32);
+          uint64_t key = lo >> s;
+          if (s) key |= (uint64_t)ws.sq[w + 2] << (64 - s);
+          key &= HLM_KT_KEYMASK;
+          uint32_t nn = hlm_funnel(ws.pn[c >> 5], ws.pn[(c >> 5) + 1], c & 31) & 0xFFFFFu;
+          if (nn == 0) val = probe_kmer(db, key);
+        }
+        myval[r] = val;
+        uint32_t hb = __ballot_sync(FULL, val >> 31);
+        if (lane == 0) ws.hits[r] = hb;
+      }
+      __syncwarp();
+      if (kp.skip_screen) {
+        screened = true;
+      } else {
+        // the reference's strided scan: FASTQ loop `if hit {hit++;c++}; ...; c++` inside
+        // for(;;c++); BAM loop without the trailing c++.  Uniform across the warp.
+        int hitcount = 0;
+        int step = kp.screen_variant == HLM_SCREEN_FASTQ ? 2 : 1;
+        for (int c = 0; c < npos; c += step) {
+          if ((ws.hits[c >> 5] >> (c & 31)) & 1u) {
+            hitcount++;
+            c++;
+          }
+          if (hitcount == kp.minhit) {
+            screened = true;
+            break;
+          }
+        }
+      }
+    }
+    int lo1 = 0, n1 = 0, lo2 = 0, n2 = 0;
+    uint32_t fl = 0, lmask = 0;
+    if (screened) {
+      fl |= HLM_F_SCREENED;
+      stage_quals(ck.quals1 + o1, l1, lane, ws, kp);
+      bool k1 = mtrim_bits(ws.good, l1, l1, kp.v_size, lo1, n1);
+      bool k2 = true;
+      __syncwarp();
+      if (kp.paired) {
+        stage_quals(ck.quals2 + o2, l2, lane, ws, kp);
+        k2 = mtrim_bits(ws.good, l2, l2, kp.v_size, lo2, n2);
+        __syncwarp();
+      }
+      if (!k1) n1 = 0;
+      if (!k2) n2 = 0;
+      if (k1 && k2) {
+        fl |= HLM_F_KEPT;
+        // map_dna.cpp:611-627: any 20-mer of the trimmed R1 at c < len-20, both mates >= 20
+        if (n1 >= HLM_MOTIF && (!kp.paired || n2 >= HLM_MOTIF)) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            int c = r * 32 + lane;
+            if (c >= lo1 && c < lo1 + n1 - HLM_MOTIF) m |= myval[r];
+          }
+          m = __reduce_or_sync(FULL, m);
+          lmask = m & 0x7FFFFFFFu;
+        }
+      }
+    }
+    if (lane == 0) {
+      ck.flags[pair] = (uint8_t)fl;
+      ck.trim_lo1[pair] = (uint16_t)lo1;
+      ck.trim_len1[pair] = (uint16_t)n1;
+      ck.trim_lo2[pair] = (uint16_t)lo2;
+      ck.trim_len2[pair] = (uint16_t)n2;
+      ck.locus_mask[pair] = lmask;
+      if (fl & HLM_F_KEPT) kept_local++;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && kept_local) atomicAdd(&ck.counters[3], kept_local);
+}
+
+// ------------------------------------------------------------------ k_pack_units
+// unit layout per pair: dna: [mate]; rna: [mate*3 + {whole, block A, block B}]
+__device__ __forceinline__ void write_unit(const HlmChunk& ck, int64_t unit, WarpScratch& ws, int lo,
+                                           int n, uint32_t tmask, int lane) {
+  uint32_t* out = ck.unit_planes + unit * 36;
+  // forward planes: bits [lo, lo+n) of the staged planes
+  uint32_t f0 = 0, f1 = 0, fn = 0xFFFFFFFFu;
+  if (lane < 6) {
+    int b = lo + 32 * lane;
+    int w = b >> 5, s = b & 31;
+    uint32_t a0 = w < 8 ? ws.p0[w] : 0u, a1 = w + 1 < 8 ? ws.p0[w + 1] : 0u;
+    uint32_t c0 = w < 8 ? ws.p1[w] : 0u, c1 = w + 1 < 8 ? ws.p1[w + 1] : 0u;
+    uint32_t e0 = w < 8 ? ws.pn[w] : 0xFFFFFFFFu, e1 = w + 1 < 8 ? ws.pn[w + 1] : 0xFFFFFFFFu;
+    f0 = hlm_funnel(a0, a1, s);
+    f1 = hlm_funnel(c0, c1, s);
+    fn = hlm_funnel(e0, e1, s);
+    int rem = n - 32 * lane;
+    uint32_t valid = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    fn |= ~valid;
+    f0 &= ~fn;
+    f1 &= ~fn;
+    out[lane] = f0;
+    out[6 + lane] = f1;
+    out[12 + lane] = fn;
+    // bit-reversed words for the reverse complement (word 5-lane of the 192-bit reversal)
+    ws.rev[0][5 - lane] = __brev(f0);
+    ws.rev[1][5 - lane] = __brev(f1);
+    ws.rev[2][5 - lane] = __brev(fn);
+  }
+  if (lane >= 6 && lane < 8) {
+    ws.rev[0][lane] = 0;
+    ws.rev[1][lane] = 0;
+    ws.rev[2][lane] = 0xFFFFFFFFu;
+  }
+  __syncwarp();
+  if (lane < 6) {
+    int sh = 192 - n;  // rc bit i = reversed bit i + sh
+    int w = lane + (sh >> 5), s = sh & 31;
+    uint32_t a0 = w < 6 ? ws.rev[0][w] : 0u, a1 = w + 1 < 6 ? ws.rev[0][w + 1] : 0u;
+    uint32_t c0 = w < 6 ? ws.rev[1][w] : 0u, c1 = w + 1 < 6 ? ws.rev[1][w + 1] : 0u;
+    uint32_t e0 = w < 6 ? ws.rev[2][w] : 0xFFFFFFFFu, e1 = w + 1 < 6 ? ws.rev[2][w + 1] : 0xFFFFFFFFu;
+    uint32_t rn = hlm_funnel(e0, e1, s);
+    int rem = n - 32 * lane;
+    uint32_t valid = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    rn |= ~valid;
+    uint32_t r0 = ~hlm_funnel(a0, a1, s) & ~rn;  // complement = 3 - code
+    uint32_t r1 = ~hlm_funnel(c0, c1, s) & ~rn;
+    out[18 + lane] = r0;
+    out[24 + lane] = r1;
+    out[30 + lane] = rn;
+  }
+  if (lane == 0) {
+    ck.unit_len[unit] = (uint16_t)n;
+    ck.unit_mask[unit] = tmask;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_pack_units(HlmKParams kp, HlmChunk ck) {
+  __shared__ WarpScratch scratch[WARPS_PER_BLOCK];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpScratch& ws = scratch[wib];
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  int U = ck.units_per_pair;
+  int nm = kp.paired ? 2 : 1;
+  for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
+    if (lane < U) ck.unit_len[pair * U + lane] = 0;
+    __syncwarp();
+    if (!(ck.flags[pair] & HLM_F_KEPT)) continue;
+    uint32_t lmask = ck.locus_mask[pair];
+    uint32_t others = 1u << kp.n_loci;
+    for (int m = 0; m < nm; m++) {
+      const uint8_t* p = m == 0 ? ck.bases1 + ck.offs1[pair] : ck.bases2 + ck.offs2[pair];
+      int l = m == 0 ? (int)(ck.offs1[pair + 1] - ck.offs1[pair]) : (int)(ck.offs2[pair + 1] - ck.offs2[pair]);
+      int lo = m == 0 ? ck.trim_lo1[pair] : ck.trim_lo2[pair];
+      int n = m == 0 ? ck.trim_len1[pair] : ck.trim_len2[pair];
+      if (n > HLM_MAX_READ) {  // does not fit the 256-column tiles: reported by the host
+        if (lane == 0) ck.counters[7] = 1;
+        continue;
+      }
+      stage_bases(p, l, lane, ws, false);
+      if (!kp.rna) {
+        write_unit(ck, pair * U + m, ws, lo, n, lmask | others, lane);
+      } else {
+        const uint16_t* sp = m == 0 ? ck.rna_split1 : ck.rna_split2;
+        int split = sp ? sp[pair] : 0;
+        if (!(split > 0 && split < n)) split = 0;
+        // whole mate: always vs others (map_rna.cpp:858-892); vs loci only when unsplit
+        write_unit(ck, pair * U + m * 3, ws, lo, n, split ? others : (lmask | others), lane);
+        if (split) {
+          write_unit(ck, pair * U + m * 3 + 1, ws, lo, split, lmask, lane);
+          write_unit(ck, pair * U + m * 3 + 2, ws, lo + split, n - split, lmask, lane);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_clear_tasks
+__global__ void k_clear_tasks(HlmChunk ck, int64_t n_tasks) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (i == 0) {
+    ck.counters[0] = 0; ck.counters[1] = 0; ck.counters[2] = 0; ck.counters[3] = 0;
+    ck.counters[4] = 0; ck.counters[5] = 0; ck.counters[6] = 0; ck.counters[7] = 0;
+  }
+  for (; i < n_tasks; i += stride) {
+    ck.task_emin[i] = 0xFFFFFFFFu;
+    ck.task_best[i] = HLM_BEST_NONE;
+  }
+}
+
+// ------------------------------------------------------------------ k_seed
+__device__ __forceinline__ int tile_locus(const HlmDevDB& db, uint32_t tile) {
+  int g = 0;
+  // tile_start is ascending; n_loci + 1 target sets
+  int lo = 0, hi = db.n_loci + 1;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (tile >= db.tile_start[mid]) lo = mid; else hi = mid;
+  }
+  g = lo;
+  return g;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
+  __shared__ uint32_t s_rd[WARPS_PER_BLOCK][36];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t* rd = s_rd[wib];
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  int64_t n_units = ck.n_pairs * ck.units_per_pair;
+  for (int64_t unit = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; unit < n_units; unit += nwarps) {
+    int n = ck.unit_len[unit];
+    if (n == 0) continue;
+    uint32_t umask = ck.unit_mask[unit];
+    __syncwarp();
+    rd[lane] = ck.unit_planes[unit * 36 + lane];
+    if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * 36 + 32 + lane];
+    __syncwarp();
+    int Q = n / HLM_SEED;
+    // lane (strand*16 + q) owns seed q of that strand
+    int my_q = lane & 15, my_strand = lane >> 4;
+    uint32_t my_a = 0, my_b = 0;
+    if (my_q < Q) {
+      uint32_t code;
+      if (hlm_seed_code(rd + 18 * my_strand, my_q, &code)) {
+        my_a = __ldg(db.seed_off + code);
+        my_b = __ldg(db.seed_off + code + 1);
+      }
+    }
+    for (int strand = 0; strand < 2; strand++) {
+      const uint32_t* R = rd + 18 * strand;
+      for (int q = 0; q < Q; q++) {
+        uint32_t a = __shfl_sync(FULL, my_a, strand * 16 + q);
+        uint32_t b = __shfl_sync(FULL, my_b, strand * 16 + q);
+        for (uint32_t base = a; base < b; base += 32) {
+          uint32_t idx = base + lane;
+          bool own = false;
+          uint32_t tile = 0;
+          int off = 0;
+          if (idx < b) {
+            uint32_t e = __ldg(db.seed_ent + idx);
+            tile = e >> 8;
+            off = (int)(e & 0xFFu) - q * HLM_SEED;
+            if (off >= HLM_OFF_MIN && off < HLM_OFF_MIN + HLM_TILE_STRIDE) {
+              int g = tile_locus(db, tile);
+              if ((umask >> g) & 1u) {
+                // candidate (tile, off) belongs to the FIRST read seed that matches it
+                const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+                own = true;
+                for (int qq = 0; qq < q; qq++) {
+                  if (hlm_seed_match(R, T, off, qq)) {
+                    own = false;
+                    break;
+                  }
+                }
+              }
+            }
+          }
+          uint32_t bal = __ballot_sync(FULL, own);
+          if (bal) {
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(&ck.counters[0], (unsigned long long)__popc(bal));
+            pos = __shfl_sync(FULL, pos, 0);
+            if (own) {
+              unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
+              if ((int64_t)at < ck.cand_cap)
+                ck.cand[at] = HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF);
+              else
+                ck.counters[2] = 1;  // overflow: the host re-runs the chunk in two halves
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_myers
+__global__ void __launch_bounds__(256)
+k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
+  int64_t ncand = (int64_t)ck.counters[0];
+  if (ncand > ck.cand_cap) ncand = ck.cand_cap;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long rows = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
+    uint64_t c = ck.cand[i];
+    uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
+    int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
+    int n = ck.unit_len[unit];
+    const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
+    const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+    int lb = hlm_myers_lb(rd, n, T, off);
+    if (lb > 254) lb = 254;
+    ck.cand[i] = (c & ~0xFFull) | (uint64_t)lb;
+    if (lb <= kp.mm_max) {
+      int g = tile_locus(db, tile);
+      atomicMin(&ck.task_emin[(int64_t)unit * n_targets + g], (uint32_t)lb);
+    }
+    rows += n;
+  }
+  // one atomic per warp
+  for (int o = 16; o; o >>= 1) rows += __shfl_xor_sync(FULL, rows, o);
+  if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&ck.counters[5], rows);
+}
+
+// ------------------------------------------------------------------ k_select
+// round 0: candidates whose lower bound equals the task minimum.
+// round 1: candidates with emin < lb <= cost of the best alignment found in round 0.
+// After round 1 no unevaluated candidate can tie or beat the best (cost >= lb).
+__global__ void __launch_bounds__(256)
+k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
+  int64_t ncand = (int64_t)ck.counters[0];
+  if (ncand > ck.cand_cap) ncand = ck.cand_cap;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int lane = threadIdx.x & 31;
+  int64_t nloop = (ncand + stride - 1) / stride;
+  for (int64_t it = 0; it < nloop; it++) {
+    int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    if (i < ncand) {
+      uint64_t c = ck.cand[i];
+      int lb = (int)HLM_CAND_LB(c);
+      if (lb <= kp.mm_max) {
+        int g = tile_locus(db, HLM_CAND_TILE(c));
+        int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
+        int emin = (int)ck.task_emin[task];
+        if (round == 0) take = (lb == emin);
+        else {
+          unsigned long long b = ck.task_best[task];
+          take = (lb > emin) && b != HLM_BEST_NONE && lb <= HLM_BEST_COST(b);
+        }
+      }
+    }
+    uint32_t bal = __ballot_sync(FULL, take);
+    if (bal) {
+      unsigned long long pos = 0;
+      if (lane == 0) pos = atomicAdd(&ck.counters[1], (unsigned long long)__popc(bal));
+      pos = __shfl_sync(FULL, pos, 0);
+      if (take) {
+        unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
+        if ((int64_t)at < ck.dp_cap) ck.dp_list[at] = (uint32_t)i;
+        else ck.counters[2] = 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_dp
+__global__ void __launch_bounds__(128)
+k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
+  int64_t nd = (int64_t)ck.counters[1];
+  if (nd > ck.dp_cap) nd = ck.dp_cap;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long cells = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) {
+    uint64_t c = ck.cand[ck.dp_list[i]];
+    uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
+    int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
+    int n = ck.unit_len[unit];
+    const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
+    const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+    HlmAln a = hlm_dp_align(rd, n, T, off);
+    int g = tile_locus(db, tile);
+    atomicMin(&ck.task_best[(int64_t)unit * n_targets + g],
+              (unsigned long long)HLM_BEST_PACK(a.cost, a.S, a.lead, a.trail));
+    cells += (unsigned long long)n * HLM_NB;
+  }
+  for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
+  if ((threadIdx.x & 31) == 0 && cells) {
+    atomicAdd(&ck.counters[4], cells);
+  }
+}
+
+__global__ void k_dp_round_end(HlmChunk ck) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ck.counters[6] += ck.counters[1];
+    ck.counters[1] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ k_scores
+// lane g of the warp handles target g of one pair.  dna: read_sam_dna (map_dna.cpp:44-118):
+// score = NM + leading clip (+ trailing clip in CLIP_BOTH) + 1, 0 when nothing mapped.
+// rna: read_sam_rna (map_rna.cpp:39-101): sum over blocks and mates of NM + clips for mapped
+// records (clips only while mm != len(SEQ)) and len(SEQ) for unmapped ones.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_scores(HlmKParams kp, HlmChunk ck, int n_targets) {
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  int U = ck.units_per_pair;
+  for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
+    if (lane >= n_targets) continue;
+    int g = lane;
+    int64_t o = pair * n_targets + g;
+    bool kept = ck.flags[pair] & HLM_F_KEPT;
+    if (!kp.rna) {
+      for (int m = 0; m < 2; m++) {
+        uint16_t s = 0;
+        int16_t aln = 0;
+        uint8_t nm = 0, lead = 0, trail = 0;
+        if (kept && (m == 0 || kp.paired)) {
+          int64_t unit = pair * U + m;
+          if (ck.unit_len[unit] && ((ck.unit_mask[unit] >> g) & 1u)) {
+            unsigned long long b = ck.task_best[unit * n_targets + g];
+            if (b != HLM_BEST_NONE && HLM_BEST_COST(b) <= kp.mm_max) {
+              int cost = HLM_BEST_COST(b), ld = HLM_BEST_LEAD(b), tr = HLM_BEST_TRAIL(b);
+              int nmv = cost - ld - tr;
+              s = (uint16_t)(nmv + ld + (kp.clip_mode == HLM_CLIP_BOTH ? tr : 0) + 1);
+              aln = (int16_t)HLM_BEST_S(b);
+              nm = (uint8_t)nmv;
+              lead = (uint8_t)ld;
+              trail = (uint8_t)tr;
+            }
+          }
+        }
+        if (m == 0) {
+          ck.s1[o] = s; ck.aln1[o] = aln; ck.nm1[o] = nm; ck.lead1[o] = lead; ck.trail1[o] = trail;
+        } else {
+          ck.s2[o] = s; ck.aln2[o] = aln; ck.nm2[o] = nm; ck.lead2[o] = lead; ck.trail2[o] = trail;
+        }
+      }
+    } else {
+      int sum = 0;
+      bool any = false;
+      if (kept) {
+        for (int u = 0; u < U; u++) {
+          int64_t unit = pair * U + u;
+          int len = ck.unit_len[unit];
+          if (!len || !((ck.unit_mask[unit] >> g) & 1u)) continue;
+          any = true;
+          unsigned long long b = ck.task_best[unit * n_targets + g];
+          if (b != HLM_BEST_NONE && HLM_BEST_COST(b) <= kp.mm_max) {
+            int ld = HLM_BEST_LEAD(b), tr = HLM_BEST_TRAIL(b);
+            int mm = HLM_BEST_COST(b) - ld - tr;
+            if (ld > 0 && mm != len) mm += ld;
+            if (kp.clip_mode == HLM_CLIP_BOTH && tr > 0 && mm != len) mm += tr;
+            sum += mm;
+          } else {
+            sum += len;
+          }
+        }
+      }
+      ck.s1[o] = any ? (uint16_t)sum : (uint16_t)0xFFFF;
+      ck.s2[o] = 0; ck.aln1[o] = 0; ck.aln2[o] = 0; ck.nm1[o] = 0; ck.nm2[o] = 0;
+      ck.lead1[o] = 0; ck.lead2[o] = 0; ck.trail1[o] = 0; ck.trail2[o] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_assign
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_assign(HlmKParams kp, HlmChunk ck, int n_targets) {
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  int G = n_targets - 1;
+  for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
+    bool kept = ck.flags[pair] & HLM_F_KEPT;
+    int g = lane;
+    bool act = g < n_targets;
+    int64_t o = pair * n_targets + (act ? g : 0);
+    uint32_t tmask = 0, vmask = 0;
+    int minsum = 0, o1 = 0, o2 = 0;
+    if (kept) {
+      int len1 = ck.trim_len1[pair];
+      int len2 = kp.paired ? ck.trim_len2[pair] : 0;
+      if (!kp.paired && ck.size_override1) len1 = ck.size_override1[pair];  // preselect.cpp:1199
+      if (!kp.rna) {
+        int s1 = act ? ck.s1[o] : 0, s2 = (act && kp.paired) ? ck.s2[o] : 0;
+        // others back-fill (map_dna.cpp:903-915)
+        o1 = __shfl_sync(FULL, s1, G);
+        o2 = __shfl_sync(FULL, s2, G);
+        if (kp.paired) {
+          if (o1 != 0 && o2 == 0) o2 = o1;
+          else if (o2 != 0 && o1 == 0) o1 = o2;
+          if (g == G) { s1 = o1; s2 = o2; }
+        }
+        int nm_sum = 10000;
+        bool valid = false;
+        if (act) {
+          if (kp.paired) {
+            if (s1 != 0 && s2 != 0 && s1 != 10000 && s2 != 10000) {
+              int v1 = (int)(len1 * kp.tolerance), v2 = (int)(len2 * kp.tolerance);
+              if ((s1 - 1) <= v1 && (s2 - 1) <= v2) { valid = true; nm_sum = s1 + s2; }
+            }
+          } else if (s1 != 0 && s1 != 10000) {
+            int v1 = (int)(len1 * kp.tolerance);
+            if ((s1 - 1) <= v1) { valid = true; nm_sum = s1; }
+          }
+        }
+        vmask = __ballot_sync(FULL, valid);
+        int mn = __reduce_min_sync(FULL, valid ? nm_sum : 100000);
+        if (vmask) {
+          // Target = every g whose nm_sum equals the minimum (invalid ones hold 10000)
+          tmask = __ballot_sync(FULL, act && nm_sum == mn);
+          minsum = mn;
+        }
+      } else {
+        int v = act ? ck.s1[o] : 0xFFFF;
+        int nm_sum = (v == 0xFFFF) ? 1000 : v;
+        bool vis = act && nm_sum != 1000;
+        vmask = __ballot_sync(FULL, vis);
+        int mn = __reduce_min_sync(FULL, act ? nm_sum : 1000);
+        if (mn > 1000) mn = 1000;
+        if (vmask) {
+          bool t = false;
+          if (act && nm_sum == mn) {
+            if (g != G) {
+              float mx = (float)((len1 * 2) * kp.tolerance);  // map_rna.cpp:975
+              t = ((float)mn <= mx);
+            } else {
+              t = mn < 30;  // min_score_others, map_rna.cpp:939
+            }
+          }
+          tmask = __ballot_sync(FULL, t);
+          minsum = mn;
+        }
+      }
+    }
+    if (lane == 0) {
+      ck.target_mask[pair] = tmask;
+      ck.visible_mask[pair] = vmask;
+      ck.min_sum[pair] = (uint16_t)minsum;
+      ck.others_s1[pair] = (uint16_t)o1;
+      ck.others_s2[pair] = (uint16_t)o2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ INT32 peak micro-kernels
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_int_peak(int* out, int iters, int seed) {
+  int a = threadIdx.x + seed, b = blockIdx.x ^ seed, c = a * 3 + 1, d = b * 5 + 2;
+  int e = a + 7, f = b + 11, g = c + 13, h = d + 17;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      if (WHICH == 0) {  // IADD3 chains (alu pipe)
+        a = a + b + seed; c = c + d + seed; e = e + f + seed; g = g + h + seed;
+        b = b + a + seed; d = d + c + seed; f = f + e + seed; h = h + g + seed;
+      } else if (WHICH == 1) {  // IMAD chains (fma pipe)
+        a = a * seed + b; c = c * seed + d; e = e * seed + f; g = g * seed + h;
+        b = b * seed + a; d = d * seed + c; f = f * seed + e; h = h * seed + g;
+      } else if (WHICH == 2) {  // mixed add + mad
+        a = a + b + seed; c = c * seed + d; e = e + f + seed; g = g * seed + h;
+        b = b + a + seed; d = d * seed + c; f = f + e + seed; h = h * seed + g;
+      } else {  // VIADDMNMX chains (what the DP issues)
+        a = __viaddmax_s32(a, seed, b); c = __viaddmax_s32(c, seed, d);
+        e = __viaddmax_s32(e, seed, f); g = __viaddmax_s32(g, seed, h);
+        b = __viaddmax_s32(b, seed, a); d = __viaddmax_s32(d, seed, c);
+        f = __viaddmax_s32(f, seed, e); h = __viaddmax_s32(h, seed, g);
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+}
+
+double hlm_int_peak_run(int which, int sms, cudaStream_t st) {
+  int blocks = sms * 8, threads = 256, iters = 4096;
+  int* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(int)) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, st);
+    switch (which) {
+      case 0: k_int_peak<0><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      case 1: k_int_peak<1><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      case 2: k_int_peak<2><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      default: k_int_peak<3><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+    }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+    double g = ops / (ms * 1e-3) / 1e9;
+    if (rep > 0 && g > best) best = g;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+// ------------------------------------------------------------------ launchers
+static inline int grid_for(int sms, int per_sm) { return sms * per_sm; }
+
+void hlm_launch_screen(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
+                       cudaStream_t st) {
+  k_screen<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(db, kp, ck);
+}
+void hlm_launch_pack(const HlmKParams& kp, const HlmChunk& ck, int sms, cudaStream_t st) {
+  k_pack_units<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(kp, ck);
+}
+void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStream_t st) {
+  int64_t n_tasks = ck.n_pairs * ck.units_per_pair * n_targets;
+  k_clear_tasks<<<grid_for(sms, 8), 256, 0, st>>>(ck, n_tasks);
+}
+void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
+                     cudaStream_t st) {
+  k_seed<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(db, kp, ck);
+}
+void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                      int sms, cudaStream_t st) {
+  k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets);
+}
+void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                       int round, int sms, cudaStream_t st) {
+  k_select<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, round);
+}
+void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                   int sms, cudaStream_t st) {
+  k_dp<<<grid_for(sms, 4), 128, 0, st>>>(db, kp, ck, n_targets);
+  k_dp_round_end<<<1, 32, 0, st>>>(ck);
+}
+void hlm_launch_scores(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
+                       cudaStream_t st) {
+  k_scores<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(kp, ck, n_targets);
+}
+void hlm_launch_assign(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
+                       cudaStream_t st) {
+  k_assign<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(kp, ck, n_targets);
+}

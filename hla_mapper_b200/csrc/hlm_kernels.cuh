@@ -1,0 +1,68 @@
+// hlm_kernels.cuh — launch interface of the sm_100a kernels (hlm_kernels.cu).
+#ifndef HLM_KERNELS_CUH
+#define HLM_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "hlm_common.h"
+
+// per-chunk device state
+struct HlmChunk {
+  // inputs (device)
+  int64_t n_pairs;
+  const uint8_t *bases1, *quals1, *bases2, *quals2;
+  const uint64_t *offs1, *offs2;
+  const int32_t* size_override1;
+  const uint16_t *rna_split1, *rna_split2;
+  // screen outputs
+  uint8_t* flags;
+  uint16_t *trim_lo1, *trim_len1, *trim_lo2, *trim_len2;
+  uint32_t* locus_mask;
+  // units: units_per_pair * n_pairs; 36 words each (fwd planes, rc planes)
+  int units_per_pair;
+  uint32_t* unit_planes;
+  uint16_t* unit_len;    // 0 = inactive
+  uint32_t* unit_mask;   // targets this unit is scored against
+  // scoring work
+  uint64_t* cand;        // candidate records
+  int64_t cand_cap;
+  uint32_t* dp_list;     // indices into cand
+  int64_t dp_cap;
+  unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
+                                 // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total, [7] spare
+  uint32_t* task_emin;   // units * n_targets
+  unsigned long long* task_best;
+  // outputs
+  uint16_t *s1, *s2;
+  int16_t *aln1, *aln2;
+  uint8_t *nm1, *nm2, *lead1, *lead2, *trail1, *trail2;
+  uint32_t *target_mask, *visible_mask;
+  uint16_t *min_sum, *others_s1, *others_s2;
+};
+
+struct HlmKParams {
+  int rna, paired, screen_variant, v_size, minhit, mm_max, clip_mode, skip_screen;
+  double tolerance;
+  uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
+  int n_loci;
+};
+
+void hlm_launch_screen(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
+                       cudaStream_t st);
+void hlm_launch_pack(const HlmKParams& kp, const HlmChunk& ck, int sms, cudaStream_t st);
+void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStream_t st);
+void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
+                     cudaStream_t st);
+void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                      int sms, cudaStream_t st);
+void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                       int round, int sms, cudaStream_t st);
+void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                   int sms, cudaStream_t st);
+void hlm_launch_scores(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
+                       cudaStream_t st);
+void hlm_launch_assign(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
+                       cudaStream_t st);
+double hlm_int_peak_run(int which, int sms, cudaStream_t st);
+
+#endif

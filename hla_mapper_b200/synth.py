@@ -336,7 +336,7 @@ def make_reads(db: SynthDB, n_pairs, read_len=150, seed=1001, on_target=1.0, fra
         return ReadBatch(n_pairs, b1.reshape(-1), q1.reshape(-1), offs, b2.reshape(-1),
                          q2.reshape(-1), offs.copy(), truth, seed, first_pair)
     # ragged: per-read indel errors (rare) applied in a python loop over the affected reads
-    rng = np.random.Generator(np.random.Philox(key=[seed, 0x1D, first_pair // BLOCK]))
+    rng = np.random.Generator(np.random.Philox(key=[seed, (1 << 40) + first_pair // BLOCK]))
 
     def rag(b, q):
         rows_b = [None] * n_pairs

@@ -1,0 +1,128 @@
+// hostsim.cpp — compiles the product's scoring arithmetic (hla_mapper_b200/csrc/hlm_core.cuh)
+// and its host-side index builder (hlm_db.cpp) as plain C++ so the CPU test-suite can check
+// them against the oracle without a GPU.  TEST-ONLY: never part of the product path.
+#include <cstring>
+#include <string>
+
+#include "../../hla_mapper_b200/csrc/hlm_core.cuh"
+#include "../../hla_mapper_b200/csrc/hlm_db.h"
+
+static void pack_read(const uint8_t* codes, int n, uint32_t* rd) {
+  memset(rd, 0, 18 * 4);
+  for (int w = 0; w < 6; w++) rd[12 + w] = 0xFFFFFFFFu;
+  for (int i = 0; i < n; i++) {
+    int c = codes[i];
+    if (c > 3) continue;
+    rd[12 + (i >> 5)] &= ~(1u << (i & 31));
+    if (c & 1) rd[i >> 5] |= 1u << (i & 31);
+    if (c & 2) rd[6 + (i >> 5)] |= 1u << (i & 31);
+  }
+}
+static void pack_tile(const uint8_t* cols, uint32_t* t) {
+  memset(t, 0, 24 * 4);
+  for (int c = 0; c < 256; c++) {
+    int v = cols[c];
+    if (v > 3) {
+      t[16 + (c >> 5)] |= 1u << (c & 31);
+      continue;
+    }
+    if (v & 1) t[c >> 5] |= 1u << (c & 31);
+    if (v & 2) t[8 + (c >> 5)] |= 1u << (c & 31);
+  }
+}
+
+extern "C" {
+int hs_myers(const uint8_t* read, int n, const uint8_t* tile_cols, int off) {
+  uint32_t rd[18], t[24];
+  pack_read(read, n, rd);
+  pack_tile(tile_cols, t);
+  return hlm_myers_lb(rd, n, t, off);
+}
+void hs_dp(const uint8_t* read, int n, const uint8_t* tile_cols, int off, int* out4) {
+  uint32_t rd[18], t[24];
+  pack_read(read, n, rd);
+  pack_tile(tile_cols, t);
+  HlmAln a = hlm_dp_align(rd, n, t, off);
+  out4[0] = a.S; out4[1] = a.cost; out4[2] = a.lead; out4[3] = a.trail;
+}
+int hs_seed(const uint8_t* read, int n, const uint8_t* tile_cols, int off, int q, uint32_t* code) {
+  uint32_t rd[18], t[24];
+  pack_read(read, n, rd);
+  pack_tile(tile_cols, t);
+  int ok = hlm_seed_code(rd, q, code) ? 1 : 0;
+  return ok | (hlm_seed_match(rd, t, off, q) ? 2 : 0);
+}
+// index builder
+void* hs_db_open(const char* dir, int rna, char* err, size_t errlen) {
+  std::string e;
+  hlm_db* db = hlm_db_build(dir, rna, e);
+  if (!db && err) snprintf(err, errlen, "%s", e.c_str());
+  return db;
+}
+void hs_db_close(void* p) { delete (hlm_db*)p; }
+int64_t hs_db_stat(void* p, int what) {
+  hlm_db* db = (hlm_db*)p;
+  switch (what) {
+    case 0: return db->n_loci;
+    case 1: return db->n_kmers;
+    case 2: return (int64_t)(db->tiles.size() / HLM_TILE_WORDS);
+    case 3: return db->n_tiles_raw;
+    case 4: return (int64_t)db->seed_ent.size();
+    case 5: return db->n_alleles;
+    case 6: return db->v_size;
+    case 7: return db->n_kmers_skipped;
+    default: return -1;
+  }
+}
+uint32_t hs_db_kmer(void* p, const char* kmer20) {
+  hlm_db* db = (hlm_db*)p;
+  uint64_t key = 0;
+  for (int x = 0; x < 20; x++) {
+    int c = kmer20[x] == 'A' ? 0 : kmer20[x] == 'C' ? 1 : kmer20[x] == 'G' ? 2 : kmer20[x] == 'T' ? 3 : 4;
+    if (c > 3) return 0;
+    key |= (uint64_t)c << (2 * x);
+  }
+  uint64_t mask = (1ull << db->kt_bits) - 1, h = hlm_kt_hash(key, db->kt_bits);
+  for (;;) {
+    uint64_t s = db->kt[h];
+    if (!(s & HLM_KT_OCC)) return 0;
+    if ((s & HLM_KT_KEYMASK) == key) return db->mask_tab[(s >> 40) & 0xFFFF];
+    h = (h + 1) & mask;
+  }
+}
+// all (tile, off) candidates of one locus for a read strand, straight from the seed index
+int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* out, int cap) {
+  hlm_db* db = (hlm_db*)p;
+  uint32_t rd[18];
+  pack_read(read, n, rd);
+  int cnt = 0;
+  for (int q = 0; q < n / HLM_SEED; q++) {
+    uint32_t code;
+    if (!hlm_seed_code(rd, q, &code)) continue;
+    for (uint32_t i = db->seed_off[code]; i < db->seed_off[code + 1]; i++) {
+      uint32_t e = db->seed_ent[i], tile = e >> 8;
+      int off = (int)(e & 0xFF) - q * HLM_SEED;
+      if (off < HLM_OFF_MIN || off >= HLM_OFF_MIN + HLM_TILE_STRIDE) continue;
+      if (tile < db->tile_start[locus] || tile >= db->tile_start[locus + 1]) continue;
+      bool first = true;
+      for (int qq = 0; qq < q && first; qq++)
+        if (hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, qq)) first = false;
+      if (!first) continue;
+      if (cnt < cap) out[cnt] = (tile << 8) | (uint32_t)off;
+      cnt++;
+    }
+  }
+  return cnt;
+}
+int hs_db_eval(void* p, const uint8_t* read, int n, uint32_t cand, int* out5) {
+  hlm_db* db = (hlm_db*)p;
+  uint32_t rd[18];
+  pack_read(read, n, rd);
+  const uint32_t* T = &db->tiles[(size_t)(cand >> 8) * HLM_TILE_WORDS];
+  int off = cand & 0xFF;
+  out5[0] = hlm_myers_lb(rd, n, T, off);
+  HlmAln a = hlm_dp_align(rd, n, T, off);
+  out5[1] = a.S; out5[2] = a.cost; out5[3] = a.lead; out5[4] = a.trail;
+  return 0;
+}
+}
