@@ -112,8 +112,8 @@ HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* 
 
 // ------------------------------------------------------------------ banded affine-gap DP
 // One candidate per thread; the 41 H and 41 E band cells live in registers (diagonal-indexed,
-// so no shifting between rows).  Same recurrence, constants and tie rules as oracle/hlm_oracle.c
-// orc_align(); results are bit-identical.
+// so no shifting between rows).  Same recurrence, constants and tie rules as the aligner
+// definition of DESIGN.md §3 (the test-suite checks bit-identity against the CPU oracle).
 struct HlmAln {
   int S, cost, lead, trail;
 };

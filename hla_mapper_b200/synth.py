@@ -112,7 +112,8 @@ def _write_fasta(path, names, seqs, width=60):
 
 
 def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000), n_others=2000,
-            kind="dna", v_size=50, n_lineages=16, motif_stride=4, flank=300, write=True):
+            kind="dna", v_size=50, n_lineages=16, motif_stride=4, flank=300, write=True,
+            paralog_div=(0.08, 0.15), others_div=(0.10, 0.20)):
     """Build (and write) a synthetic database.  `total_alleles` scales the IMGT-shaped counts."""
     rng = np.random.Generator(np.random.Philox(key=[seed, 0xDB]))
     loci = LOCUS_NAMES[:n_loci]
@@ -129,7 +130,7 @@ def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000
             anc = rng.integers(0, 4, size=L, dtype=np.uint8)
         else:  # paralog: 85-92 % identity to the head of the group, own length
             head = ancestors[loci[gi - gi % 3]]
-            anc = _mutate(rng, np.resize(head, L), float(rng.uniform(0.08, 0.15)))
+            anc = _mutate(rng, np.resize(head, L), float(rng.uniform(*paralog_div)))
         ancestors[g] = anc
         flanks[g] = (rng.integers(0, 4, size=flank, dtype=np.uint8),
                      rng.integers(0, 4, size=flank, dtype=np.uint8))
@@ -173,7 +174,7 @@ def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000
     kset = []
     for _ in range(n_others):
         g = loci[int(rng.integers(0, len(loci)))]
-        s = _mutate(rng, ancestors[g], float(rng.uniform(0.10, 0.20)))
+        s = _mutate(rng, ancestors[g], float(rng.uniform(*others_div)))
         others.append(s)
         kset.append(_kmer_codes(s)[::motif_stride])
     motif_all = np.unique(np.concatenate([motif_loci[g] for g in loci] +

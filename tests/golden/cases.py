@@ -1,0 +1,50 @@
+"""Seeded golden cases shared by make_golden.py (which runs the UNMODIFIED reference on them,
+in the build container) and the tests (which regenerate the same inputs from the seeds)."""
+import numpy as np
+
+from hla_mapper_b200 import _abi, synth
+
+DB_SMALL = dict(seed=7, n_loci=6, total_alleles=120, len_range=(600, 800), n_others=20)
+DB_PARALOG = dict(seed=20240813, n_loci=9, total_alleles=300, len_range=(700, 900), n_others=40)
+
+DB_TIES = dict(seed=99, n_loci=6, total_alleles=90, len_range=(600, 800), n_others=12,
+               paralog_div=(0.002, 0.01), others_div=(0.002, 0.02))
+
+CASES = {
+    # name: (db kwargs, reads kwargs, mode)
+    "dna_paired": (DB_SMALL, dict(n_pairs=1500, read_len=150, seed=11, on_target=0.7, frag_mu=300,
+                                  frag_sd=40), "paired"),
+    "dna_paired_100": (DB_PARALOG, dict(n_pairs=1500, read_len=100, seed=1002, on_target=0.5,
+                                        frag_mu=250, frag_sd=30, lowq_tail=0.3), "paired"),
+    "dna_ties": (DB_TIES, dict(n_pairs=1200, read_len=150, seed=77, on_target=0.9, frag_mu=300,
+                               frag_sd=40, lowq_tail=0.2), "paired"),
+    "dna_ragged": (DB_SMALL, dict(n_pairs=800, read_len=120, seed=12, on_target=0.8, frag_mu=260,
+                                  frag_sd=30, ragged=True), "paired"),
+    "dna_single": (DB_SMALL, dict(n_pairs=800, read_len=120, seed=13, on_target=0.8, frag_mu=260,
+                                  frag_sd=30, ragged=True), "single"),
+}
+
+
+def inputs(name, root):
+    """(SynthDB written under root, ReadBatch, params, header lines R1)"""
+    import os
+
+    dbk, rk, mode = CASES[name]
+    db = synth.make_db(os.path.join(root, f"db_{dbk['seed']}"), **dbk)
+    rk = dict(rk)
+    n = rk.pop("n_pairs")
+    rb = synth.make_reads(db, n, **rk)
+    p = _abi.default_params(paired=1 if mode == "paired" else 0)
+    return db, rb, p, mode
+
+
+def header_lines(rb, mode):
+    """the FASTQ header line of R1/R0 as synth.write_fastq writes it"""
+    return ["@" + i + ("/1" if mode == "paired" else "") for i in rb.ids()]
+
+
+def size_override(rb, mode):
+    """single-end: sequence_size_r1 = length of the id line (preselect.cpp:1199)"""
+    if mode == "paired":
+        return None
+    return np.array([len(h) for h in header_lines(rb, mode)], dtype=np.int32)

@@ -1,0 +1,83 @@
+"""Generates tests/golden/*.json.gz by running the UNMODIFIED reference binary
+(oracle/_ref/hla-mapper-ref, built from /root/reference/src by oracle/Makefile) on seeded
+synthetic inputs.  Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+What is recorded per case is what the reference itself wrote: the ids in selected.R*.fastq, the
+trimmed sequences of selected.trim.R*.fastq, the sorted_<gene> candidate lists, every row of
+<sample>_addressing_table.txt and the per-gene <sample>_<gene>_R1.fastq membership.  The
+aligner inside the stand-in `bwa` is the oracle's (the real bwa is not available: the scores
+themselves are therefore "parity unpinned", everything around them is the reference's code)."""
+import gzip
+import json
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, HERE)
+
+import cases  # noqa: E402
+import run_reference as rr  # noqa: E402
+from hla_mapper_b200 import synth  # noqa: E402
+
+
+def fastq_records(path):
+    out = {}
+    if not os.path.exists(path):
+        return out
+    with open(path) as f:
+        while True:
+            h = f.readline()
+            if not h:
+                break
+            s = f.readline().rstrip("\n")
+            f.readline()
+            f.readline()
+            key = h.rstrip("\n").split(" ")[0][1:].replace("/1", "").replace("/2", "")
+            out[key] = s
+    return out
+
+
+def main():
+    assert rr.available(), "build oracle/_ref first: make -C oracle ref"
+    for name in cases.CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            db, rb, p, mode = cases.inputs(name, tmp)
+            if mode == "paired":
+                r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
+                synth.write_fastq(rb, r1, r2)
+                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2)
+                tag = "R1"
+            else:
+                r0 = os.path.join(tmp, "r0.fq")
+                synth.write_fastq(rb, r0, None, suffix=False)
+                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r0=r0)
+                tag = "R0"
+            names, rows = rr.parse_addressing_table(out + "G_addressing_table.txt")
+            sel = fastq_records(out + f"G_selected.{tag}.fastq")
+            trim1 = fastq_records(out + f"G_selected.trim.{tag}.fastq")
+            trim2 = fastq_records(out + "G_selected.trim.R2.fastq") if mode == "paired" else {}
+            sorted_ = {g: sorted(fastq_records(out + f"G_sorted_{g}_{tag}.fastq")) for g in names[:-1]}
+            emitted = {g: sorted(fastq_records(out + f"G_{g}_{tag}.fastq")) for g in names[:-1]}
+            gold = {
+                "case": name, "mode": mode, "targets": names,
+                "selected": sorted(sel),
+                "trim1": trim1, "trim2": trim2,
+                "sorted": sorted_, "emitted": emitted,
+                "table": {k: [v[0], v[1]] for k, v in rows.items()},
+            }
+            path = os.path.join(HERE, name + ".json.gz")
+            with gzip.GzipFile(path, "wb", mtime=0) as f:
+                f.write(json.dumps(gold, sort_keys=True).encode())
+            multi = sum(1 for v in rows.values() if "," in v[1])
+            print(f"{name}: {len(sel)} selected, {len(trim1)} kept, {len(rows)} rows "
+                  f"({multi} multi-target) -> {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    main()

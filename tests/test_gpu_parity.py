@@ -1,0 +1,210 @@
+"""Parity tests proper: libhlamap (CUDA, through the C-ABI) vs the CPU oracle on the same seeded
+inputs - every output field bit-exact - plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+
+from hla_mapper_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b, fields=None):
+    for k in fields or a.FIELDS:
+        x, y = getattr(a, k), getattr(b, k)
+        if not np.array_equal(x, y):
+            idx = np.argwhere(x != y)
+            raise AssertionError(f"{k}: {len(idx)} mismatches, first at {idx[0].tolist()}: "
+                                 f"oracle={x[tuple(idx[0])]} gpu={y[tuple(idx[0])]}")
+
+
+@pytest.fixture(scope="module")
+def gdb(small_db):
+    from hla_mapper_b200 import api
+
+    db = api.Database(small_db.path)
+    yield db
+    db.close()
+
+
+@pytest.fixture(scope="module")
+def odb(orc, small_db):
+    return orc.OracleDB(small_db.path)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("clip", [0, 1])
+def test_fused_run_matches_exhaustive_oracle(orc, odb, gdb, small_reads, variant, clip):
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params(screen_variant=variant, clip_mode=clip)
+    want, _ = orc.run(odb, p, small_reads, mode=0)
+    m = api.Mapper(gdb, 0, p)
+    got = m.run(small_reads)
+    m.close()
+    _same(want, got)
+    assert ((got.flags & 2) != 0).sum() > 300
+
+
+def test_stagewise_and_device_resident_entry_points(orc, odb, gdb, small_reads):
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params()
+    want, _ = orc.run(odb, p, small_reads, mode=1)
+    m = api.Mapper(gdb, 0, p)
+    b = m.screen_trim(small_reads)
+    m.score(small_reads, b)
+    m.assign(small_reads, b)
+    _same(want, b)
+    h = m.upload(small_reads)
+    m.run_device(h)
+    _same(want, m.fetch(h, small_reads.n_pairs))
+    m.run_device(h)  # idempotent
+    _same(want, m.fetch(h, small_reads.n_pairs))
+    m.free(h)
+    assert m.profile()["launches"] > 0
+    m.close()
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 512, 100000])
+def test_chunking_does_not_change_results(orc, odb, gdb, small_db, chunk):
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 700, read_len=120, seed=12, on_target=0.8, frag_mu=260,
+                          frag_sd=30, ragged=True)
+    p = _abi.default_params()
+    want, _ = orc.run(odb, p, rb, mode=1)
+    m = api.Mapper(gdb, 0, p, chunk_pairs=chunk)
+    _same(want, m.run(rb))
+    m.close()
+
+
+def test_single_end_with_header_length_quirk(orc, odb, gdb, small_db):
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 900, read_len=150, seed=21, on_target=0.8, frag_mu=300, frag_sd=30)
+    so = np.random.default_rng(4).integers(8, 60, size=rb.n_pairs).astype(np.int32)  # preselect.cpp:1199
+    p = _abi.default_params(paired=0)
+    want, _ = orc.run(odb, p, rb, mode=1, size_override1=so)
+    m = api.Mapper(gdb, 0, p)
+    _same(want, m.run(rb, size_override1=so))
+    m.close()
+    assert len(set(want.target_mask.tolist())) > 2
+
+
+def test_edge_cases_empty_short_long_and_n(orc, odb, gdb, small_db):
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params()
+    m = api.Mapper(gdb, 0, p)
+    # empty batch
+    z8, z64 = np.zeros(0, np.uint8), np.zeros(1, np.uint64)
+    e = synth.ReadBatch(0, z8, z8, z64, z8, z8, z64, np.zeros(0, np.int32))
+    assert m.run(e).flags.shape == (0,)
+    # hand-made ragged batch: empty reads, < 20, < v_size, all-N, low quality, 256-base reads
+    src = synth.make_reads(small_db, 64, read_len=150, seed=5, on_target=1.0, frag_mu=300, frag_sd=20)
+    rows1, rows2, q1, q2 = [], [], [], []
+    rng = np.random.default_rng(8)
+    for i in range(64):
+        b1 = src.bases1[150 * i:150 * i + 150].copy(); b2 = src.bases2[150 * i:150 * i + 150].copy()
+        a1 = src.quals1[150 * i:150 * i + 150].copy(); a2 = src.quals2[150 * i:150 * i + 150].copy()
+        kind = i % 8
+        if kind == 0: b1, a1 = b1[:0], a1[:0]
+        elif kind == 1: b1, a1 = b1[:19], a1[:19]
+        elif kind == 2: b2, a2 = b2[:49], a2[:49]
+        elif kind == 3: b1[:] = ord("N")
+        elif kind == 4: a1[:] = ord("'")
+        elif kind == 5:
+            b1 = np.concatenate([b1, b1[:106]]); a1 = np.concatenate([a1, a1[:106]])  # 256 bases
+        elif kind == 6: b1[rng.integers(0, 150, size=6)] = ord("n")  # lower case is not a base
+        rows1.append(b1); rows2.append(b2); q1.append(a1); q2.append(a2)
+    o1 = np.concatenate([[0], np.cumsum([len(x) for x in rows1])]).astype(np.uint64)
+    o2 = np.concatenate([[0], np.cumsum([len(x) for x in rows2])]).astype(np.uint64)
+    rb = synth.ReadBatch(64, np.concatenate(rows1), np.concatenate(q1), o1, np.concatenate(rows2),
+                         np.concatenate(q2), o2, np.full(64, -1, np.int32))
+    # the 256-base reads trim to > HLM_MAX_READ: both sides must refuse them the same way
+    from hla_mapper_b200 import api as _api
+    with pytest.raises(_api.HlmError, match="longer than HLM_MAX_READ"):
+        m.run(rb)
+    keep = [i for i in range(64) if i % 8 != 5]
+    rows = lambda R: [R[i] for i in keep]
+    o1 = np.concatenate([[0], np.cumsum([len(x) for x in rows(rows1)])]).astype(np.uint64)
+    o2 = np.concatenate([[0], np.cumsum([len(x) for x in rows(rows2)])]).astype(np.uint64)
+    rb = synth.ReadBatch(len(keep), np.concatenate(rows(rows1)), np.concatenate(rows(q1)), o1,
+                         np.concatenate(rows(rows2)), np.concatenate(rows(q2)), o2,
+                         np.full(len(keep), -1, np.int32))
+    want, _ = orc.run(odb, p, rb, mode=0)
+    _same(want, m.run(rb))
+    m.close()
+
+
+def test_rna_mode_with_split_blocks(orc, tmp_path_factory):
+    from hla_mapper_b200 import api
+
+    d = tmp_path_factory.mktemp("db_rna")
+    db = synth.make_db(str(d / "db"), seed=17, n_loci=5, total_alleles=80, len_range=(500, 700),
+                       n_others=10, kind="rna")
+    rb = synth.make_reads(db, 800, read_len=100, seed=1004, on_target=0.8, frag_mu=220, frag_sd=25)
+    rng = np.random.default_rng(2)
+    sp1 = np.where(rng.random(800) < 0.3, rng.integers(20, 80, size=800), 0).astype(np.uint16)
+    sp2 = np.where(rng.random(800) < 0.3, rng.integers(20, 80, size=800), 0).astype(np.uint16)
+    p = _abi.default_params(rna=1)
+    od = orc.OracleDB(db.path, rna=1)
+    want, _ = orc.run(od, p, rb, mode=0, rna_split1=sp1, rna_split2=sp2)
+    gd = api.Database(db.path, rna=1)
+    m = api.Mapper(gd, 0, p)
+    got = m.run(rb, rna_split1=sp1, rna_split2=sp2)
+    m.close(); gd.close()
+    _same(want, got)
+    assert (got.target_mask != 0).sum() > 100
+
+
+def test_medium_db_fast_oracle_prefix_and_properties(orc, tmp_path_factory):
+    """4 000-allele database: fast oracle on a prefix; at full size the size-independent
+    properties: chunk invariance, idempotence, pair-order invariance, assignment consistency"""
+    from hla_mapper_b200 import api
+
+    d = tmp_path_factory.mktemp("db_med")
+    db = synth.make_db(str(d / "db"), seed=42, n_loci=24, total_alleles=4000, n_others=200)
+    rb = synth.make_reads(db, 60000, read_len=150, seed=1001, on_target=0.9)
+    p = _abi.default_params()
+    gd = api.Database(db.path)
+    m = api.Mapper(gd, 0, p)
+    got = m.run(rb)
+    od = orc.OracleDB(db.path)
+    sub = rb.slice(0, 400)
+    want, _ = orc.run(od, p, sub, mode=1)
+    pre = _abi.Buffers(400, gd.n_loci + 1)
+    for k in pre.FIELDS:
+        getattr(pre, k)[...] = getattr(got, k)[:400]
+    _same(want, pre)
+    # chunk invariance + idempotence
+    m2 = api.Mapper(gd, 0, p, chunk_pairs=4099)
+    _same(got, m2.run(rb))
+    _same(got, m2.run(rb))
+    m2.close()
+    # pair-order invariance: a permuted batch gives permuted results
+    perm = np.random.default_rng(0).permutation(rb.n_pairs)
+    L = 150
+    b1 = rb.bases1.reshape(-1, L)[perm].reshape(-1); q1 = rb.quals1.reshape(-1, L)[perm].reshape(-1)
+    b2 = rb.bases2.reshape(-1, L)[perm].reshape(-1); q2 = rb.quals2.reshape(-1, L)[perm].reshape(-1)
+    rp = synth.ReadBatch(rb.n_pairs, b1, q1, rb.offs1, b2, q2, rb.offs2, rb.truth_locus[perm])
+    gp = m.run(rp)
+    for k in got.FIELDS:
+        assert np.array_equal(getattr(got, k)[perm], getattr(gp, k)), k
+    # assignment consistency (map_dna.cpp:932-1001): every target holds the minimum pair sum
+    T = gd.n_loci + 1
+    s1 = got.s1.astype(np.int64).copy(); s2 = got.s2.astype(np.int64).copy()
+    s1[:, T - 1] = got.others_s1; s2[:, T - 1] = got.others_s2
+    vis = ((got.visible_mask[:, None] >> np.arange(T)[None, :]) & 1).astype(bool)
+    tgt = ((got.target_mask[:, None] >> np.arange(T)[None, :]) & 1).astype(bool)
+    sums = np.where(vis, s1 + s2, 10 ** 6)
+    mn = sums.min(axis=1)
+    has = vis.any(axis=1)
+    assert np.array_equal(tgt, (sums == mn[:, None]) & has[:, None])
+    assert np.array_equal(got.min_sum[has], mn[has].astype(np.uint16))
+    # sanity: reads go home
+    tl = rb.truth_locus
+    kept = (got.flags & 2) != 0
+    home = ((got.target_mask >> np.maximum(tl, 0).astype(np.uint32)) & 1).astype(bool) & (tl >= 0)
+    assert home.sum() > 0.8 * (kept & (tl >= 0)).sum()
+    m.close(); gd.close()
