@@ -255,6 +255,8 @@ def run_b200(args):
                      "peak_source": hbm_src},
         "k_seed": {"ms_per_step": round(per("ms_seed"), 3),
                    "candidates_per_step": int(stage["n_candidates"] / K)},
+        "k_expand": {"ms_per_step": round(per("ms_expand"), 3),
+                     "seed_candidates_per_step": int(stage["n_seed_candidates"] / K)},
         "k_select": {"ms_per_step": round(per("ms_select"), 3)},
         "k_scores+k_assign": {"ms_per_step": round(per("ms_assign"), 3)},
     }

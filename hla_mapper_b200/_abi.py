@@ -57,9 +57,9 @@ class HlmAssignOut(C.Structure):
 
 class HlmProfile(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_h2d", "ms_screen", "ms_seed", "ms_myers",
-                                          "ms_select", "ms_dp", "ms_assign", "ms_d2h",
-                                          "ms_total")] + \
-               [(k, C.c_int64) for k in ("n_pairs", "n_kept", "n_tasks", "n_candidates", "n_dp",
+                                          "ms_expand", "ms_select", "ms_dp", "ms_assign",
+                                          "ms_d2h", "ms_total")] + \
+               [(k, C.c_int64) for k in ("n_pairs", "n_kept", "n_seed_candidates", "n_candidates", "n_dp",
                                          "n_dp_cells", "n_myers_cols", "launches", "h2d_bytes",
                                          "d2h_bytes", "bases_bytes")]
 

@@ -30,8 +30,8 @@ struct Buf {
   size_t cap = 0;
 };
 
-enum { EV_START, EV_H2D, EV_SCREEN, EV_SEED, EV_MYERS, EV_SEL0, EV_DP0, EV_SEL1, EV_DP1, EV_ASSIGN,
-       EV_D2H, EV_COUNT };
+enum { EV_START, EV_H2D, EV_SCREEN, EV_SEED, EV_MYA, EV_EX0, EV_MYB0, EV_SEL0, EV_DP0, EV_EX1,
+       EV_MYB1, EV_SEL1, EV_DP1, EV_ASSIGN, EV_D2H, EV_COUNT };
 
 struct Slot {
   cudaStream_t st = nullptr;
@@ -114,7 +114,7 @@ size_t out_layout(int64_t n, int T, size_t* off) {
   size_t sz[O_COUNT] = {(size_t)n, 2u * n, 2u * n, 2u * n, 2u * n, 4u * n,
                         2u * n * T, 2u * n * T, 2u * n * T, 2u * n * T,
                         (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T,
-                        (size_t)n * T, 4u * n, 4u * n, 2u * n, 2u * n, 2u * n, 64};
+                        (size_t)n * T, 4u * n, 4u * n, 2u * n, 2u * n, 2u * n, 8 * HLM_N_COUNTERS};
   size_t o = 0;
   for (int i = 0; i < O_COUNT; i++) {
     off[i] = o;
@@ -154,7 +154,7 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   if ((rc = ensure_dev(ctx, s.d_unit_meta, align16((size_t)n * U * 2) + (size_t)n * U * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
   if ((rc = ensure_dev(ctx, s.d_dp, (size_t)ctx->cand_cap * 4))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_tasks, align16((size_t)n * U * T * 4) + (size_t)n * U * T * 8 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_tasks, 2 * align16((size_t)n * U * T * 4) + (size_t)n * U * T * 8 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
   HlmChunk& ck = s.ck;
   ck.units_per_pair = U;
@@ -167,7 +167,8 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   ck.dp_cap = ctx->cand_cap;
   ck.counters = (unsigned long long*)s.d_counters.p;
   ck.task_emin = (uint32_t*)s.d_tasks.p;
-  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + align16((size_t)n * U * T * 4));
+  ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16((size_t)n * U * T * 4));
+  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 2 * align16((size_t)n * U * T * 4));
   return 0;
 }
 
@@ -179,21 +180,32 @@ void launch_stages(hlm_ctx* ctx, Slot& s, int stages) {
   if (stages & HLM_STAGE_SCREEN) hlm_launch_screen(ctx->ddb, ctx->kp, ck, sms, st);
   cudaEventRecord(s.ev[EV_SCREEN], st);
   if (stages & HLM_STAGE_SCORE) {
+    size_t n_tasks = (size_t)ck.n_pairs * ck.units_per_pair * T;
     hlm_launch_pack(ctx->kp, ck, sms, st);
     hlm_launch_seed(ctx->ddb, ctx->kp, ck, sms, st);
+    hlm_launch_snapshot(ck, 0, st);
     cudaEventRecord(s.ev[EV_SEED], st);
-    hlm_launch_myers(ctx->ddb, ctx->kp, ck, T, sms, st);
-    cudaEventRecord(s.ev[EV_MYERS], st);
+    hlm_launch_myers(ctx->ddb, ctx->kp, ck, T, 0, sms, st);
+    cudaMemcpyAsync(ck.task_emin0, ck.task_emin, n_tasks * 4, cudaMemcpyDeviceToDevice, st);
+    cudaEventRecord(s.ev[EV_MYA], st);
+    hlm_launch_expand(ctx->ddb, ctx->kp, ck, T, 0, sms, st);
+    cudaEventRecord(s.ev[EV_EX0], st);
+    hlm_launch_myers(ctx->ddb, ctx->kp, ck, T, 1, sms, st);
+    cudaEventRecord(s.ev[EV_MYB0], st);
     hlm_launch_select(ctx->ddb, ctx->kp, ck, T, 0, sms, st);
     cudaEventRecord(s.ev[EV_SEL0], st);
     hlm_launch_dp(ctx->ddb, ctx->kp, ck, T, sms, st);
     cudaEventRecord(s.ev[EV_DP0], st);
+    hlm_launch_expand(ctx->ddb, ctx->kp, ck, T, 1, sms, st);
+    cudaEventRecord(s.ev[EV_EX1], st);
+    hlm_launch_myers(ctx->ddb, ctx->kp, ck, T, 2, sms, st);
+    cudaEventRecord(s.ev[EV_MYB1], st);
     hlm_launch_select(ctx->ddb, ctx->kp, ck, T, 1, sms, st);
     cudaEventRecord(s.ev[EV_SEL1], st);
     hlm_launch_dp(ctx->ddb, ctx->kp, ck, T, sms, st);
     cudaEventRecord(s.ev[EV_DP1], st);
     hlm_launch_scores(ctx->kp, ck, T, sms, st);
-    ctx->prof.launches += 11;
+    ctx->prof.launches += 19;
   } else {
     for (int e = EV_SEED; e <= EV_DP1; e++) cudaEventRecord(s.ev[e], st);
   }
@@ -220,8 +232,10 @@ int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
   pr.ms_h2d += ev_ms(s.ev[EV_START], s.ev[EV_H2D]);
   pr.ms_screen += ev_ms(s.ev[EV_H2D], s.ev[EV_SCREEN]);
   pr.ms_seed += ev_ms(s.ev[EV_SCREEN], s.ev[EV_SEED]);
-  pr.ms_myers += ev_ms(s.ev[EV_SEED], s.ev[EV_MYERS]);
-  pr.ms_select += ev_ms(s.ev[EV_MYERS], s.ev[EV_SEL0]) + ev_ms(s.ev[EV_DP0], s.ev[EV_SEL1]);
+  pr.ms_myers += ev_ms(s.ev[EV_SEED], s.ev[EV_MYA]) + ev_ms(s.ev[EV_EX0], s.ev[EV_MYB0]) +
+                 ev_ms(s.ev[EV_EX1], s.ev[EV_MYB1]);
+  pr.ms_expand += ev_ms(s.ev[EV_MYA], s.ev[EV_EX0]) + ev_ms(s.ev[EV_DP0], s.ev[EV_EX1]);
+  pr.ms_select += ev_ms(s.ev[EV_MYB0], s.ev[EV_SEL0]) + ev_ms(s.ev[EV_MYB1], s.ev[EV_SEL1]);
   pr.ms_dp += ev_ms(s.ev[EV_SEL0], s.ev[EV_DP0]) + ev_ms(s.ev[EV_SEL1], s.ev[EV_DP1]);
   pr.ms_assign += ev_ms(s.ev[EV_DP1], s.ev[EV_ASSIGN]);
   pr.ms_d2h += ev_ms(s.ev[EV_ASSIGN], s.ev[EV_D2H]);
@@ -229,6 +243,7 @@ int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
   if (t > pr.ms_total) pr.ms_total = t;
   if (counters_host) {
     pr.n_candidates += (int64_t)counters_host[0];
+    pr.n_seed_candidates += (int64_t)counters_host[8];
     pr.n_kept += (int64_t)counters_host[3];
     pr.n_dp_cells += (int64_t)counters_host[4];
     pr.n_myers_cols += (int64_t)counters_host[5];
@@ -435,7 +450,7 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     }
     CU(cudaEventRecord(s.ev[EV_H2D], st));
     launch_stages(ctx, s, stages);
-    CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 64,
+    CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 8 * HLM_N_COUNTERS,
                        cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
     ctx->prof.d2h_bytes += (int64_t)out_bytes;
@@ -517,6 +532,8 @@ int64_t hlm_db_stat(const hlm_db* db, const char* key) {
   if (k == "kmers_skipped") return db->n_kmers_skipped;
   if (k == "kt_slots") return (int64_t)db->kt.size();
   if (k == "seed_entries") return (int64_t)db->seed_ent.size();
+  if (k == "reps") return db->n_reps;
+  if (k == "children") return (int64_t)db->child_ent.size();
   return -1;
 }
 
@@ -549,6 +566,10 @@ static int upload_db(hlm_ctx* ctx, hlm_db* db) {
   if ((rc = up(2, db->tiles.data(), db->tiles.size() * 4, (const void**)&v.tiles))) return rc;
   if ((rc = up(3, db->seed_off.data(), db->seed_off.size() * 4, (const void**)&v.seed_off))) return rc;
   if ((rc = up(4, db->seed_ent.data(), db->seed_ent.size() * 4, (const void**)&v.seed_ent))) return rc;
+  if ((rc = up(5, db->tile_diff.data(), db->tile_diff.size() * 4, (const void**)&v.tile_diff))) return rc;
+  if ((rc = up(6, db->child_off.data(), db->child_off.size() * 4, (const void**)&v.child_off))) return rc;
+  if ((rc = up(7, db->child_ent.data(), db->child_ent.size() * 4, (const void**)&v.child_ent))) return rc;
+  if ((rc = up(8, db->child_diff.data(), db->child_diff.size() * 4, (const void**)&v.child_diff))) return rc;
   v.kt_bits = db->kt_bits;
   v.n_loci = db->n_loci;
   for (int g = 0; g < db->n_loci + 2; g++) v.tile_start[g] = db->tile_start[g];
@@ -599,7 +620,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
   ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 32768;
-  ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 4096;
+  ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 2048;
   if (ctx->cand_cap >= (1ll << 32)) ctx->cand_cap = (1ll << 32) - 1;
   if (ctx->chunk_pairs * ctx->units_per_pair >= (1ll << 26)) {
     delete ctx;
@@ -788,7 +809,7 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
     CU(cudaEventRecord(s.ev[EV_START], st));
     CU(cudaEventRecord(s.ev[EV_H2D], st));
     launch_stages(ctx, s, HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ASSIGN);
-    CU(cudaMemcpyAsync(s.h_out.p, ck.counters, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.h_out.p, ck.counters, 8 * HLM_N_COUNTERS, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev[EV_D2H], st));
     s.busy = true;
     uint64_t nb = 0;

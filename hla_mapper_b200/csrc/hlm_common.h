@@ -11,8 +11,14 @@
 //                        identical content are stored once per locus.  A tile is 24 words:
 //                        p0[8] (low code bit), p1[8] (high code bit), nm[8] (1 = N), column c at
 //                        bit (c & 31) of word (c >> 5).
+// tile hierarchy       a tile that differs from an earlier tile of the same locus and window
+//                        index in <= HLM_KMAX columns is a "child" of that "rep": tile_diff =
+//                        ndiff << 24 | differing columns; children of rep t are
+//                        child_ent[child_off[t] .. child_off[t+1]).
 // seed index           CSR over all 4^12 12-mers: seed_off[code] .. seed_off[code+1] index
-//                        seed_ent[], entries (tile_id << 8 | column) sorted by (tile, column).
+//                        seed_ent[], entries (column << 24 | tile_id) sorted by (column, tile).
+//                        Reps list every seed; children only the seeds covering a differing
+//                        column (their other candidates come from expanding the rep).
 // packed reads         a "unit" (trimmed mate, or an RNA block of it) is 18 words: r0[6], r1[6],
 //                        rn[6], base i at bit (i & 31) of word (i >> 5); bits >= len are 0 in
 //                        r0/r1 and 1 in rn.
@@ -33,6 +39,9 @@
 #define HLM_READ_WORDS 6
 #define HLM_RAW_MAX 256             /* longest raw read line the screen kernel accepts     */
 #define HLM_SEED_CODES (1u << (2 * HLM_SEED))
+#define HLM_KMAX 3                  /* a child tile differs from its rep in <= KMAX columns  */
+#define HLM_DIFF_N(d) ((int)((d) >> 24))
+#define HLM_DIFF_COL(d, i) ((int)(((d) >> (8 * (i))) & 0xFFu))
 
 #define HLM_KT_OCC (1ull << 63)
 #define HLM_KT_KEYMASK ((1ull << 40) - 1)
@@ -64,6 +73,10 @@ struct HlmDevDB {
   const uint32_t* tiles;     /* n_tiles * 24 words                           */
   const uint32_t* seed_off;  /* 4^12 + 1                                     */
   const uint32_t* seed_ent;
+  const uint32_t* tile_diff; /* per tile: ndiff << 24 | diff columns (0 = rep)        */
+  const uint32_t* child_off; /* n_tiles + 1                                           */
+  const uint32_t* child_ent; /* child tile ids                                        */
+  const uint32_t* child_diff;
   uint32_t tile_start[HLM_MAX_LOCI + 3]; /* first tile id of locus g; [n_loci+1] = n_tiles */
   int n_loci;
 };

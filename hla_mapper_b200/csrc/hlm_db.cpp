@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <thread>
 
 namespace {
@@ -208,7 +209,9 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     if (db->mask_tab.empty()) db->mask_tab.push_back(0);
   }
 
-  // ---- tiles: per locus, distinct 256-column windows at stride 32 of the padded alleles
+  // ---- tiles: per locus, distinct 256-column windows at stride 32 of the padded alleles.
+  // A new window that differs from an earlier window of the same locus and window index in
+  // <= HLM_KMAX columns becomes a "child" of that representative; everything else is a "rep".
   db->tile_start.assign(db->n_loci + 2, 0);
   for (int g = 0; g <= db->n_loci; g++) {
     db->tile_start[g] = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
@@ -224,6 +227,10 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     size_t cap = 1024;
     while (cap < raw * 2) cap <<= 1;
     std::vector<uint32_t> slot(cap, 0xFFFFFFFFu);  // tile id per hash slot
+    // reps indexed by (window index, word-column x, content of that word-column): two windows
+    // within KMAX differing columns share >= 8 - KMAX of their 8 word-columns
+    std::unordered_map<uint64_t, std::vector<uint32_t>> rep_lsh;
+    std::vector<uint32_t> seen;
     uint32_t w[HLM_TILE_WORDS];
     for (auto& P : al) {
       int jmax = (HLM_PAD + P.len) / 32;
@@ -244,10 +251,48 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
           }
           s = (s + 1) & (cap - 1);
         }
-        if (!found) {
-          slot[s] = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
-          db->tiles.insert(db->tiles.end(), w, w + HLM_TILE_WORDS);
+        if (found) continue;
+        uint32_t id = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+        slot[s] = id;
+        db->tiles.insert(db->tiles.end(), w, w + HLM_TILE_WORDS);
+        // nearest representative at this window index
+        uint32_t best_rep = id, best_diff = 0;
+        int best_n = HLM_KMAX + 1;
+        uint64_t keys[8];
+        seen.clear();
+        for (int x = 0; x < 8; x++) {
+          uint64_t kx = mix64(mix64((uint64_t)j * 8 + x, (uint64_t)w[x] | ((uint64_t)w[8 + x] << 32)), w[16 + x]);
+          keys[x] = kx;
+          auto it = rep_lsh.find(kx);
+          if (it != rep_lsh.end())
+            for (uint32_t r : it->second) seen.push_back(r);
         }
+        std::sort(seen.begin(), seen.end());
+        seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
+        for (uint32_t r : seen) {
+          const uint32_t* R = &db->tiles[(size_t)r * HLM_TILE_WORDS];
+          int n = 0;
+          uint32_t dmask[8];
+          for (int x = 0; x < 8 && n < best_n; x++) {
+            dmask[x] = (w[x] ^ R[x]) | (w[8 + x] ^ R[8 + x]) | (w[16 + x] ^ R[16 + x]);
+            n += __builtin_popcount(dmask[x]);
+          }
+          if (n >= best_n) continue;
+          uint32_t d = (uint32_t)n << 24;
+          int k = 0;
+          for (int x = 0; x < 8; x++)
+            for (uint32_t m = dmask[x]; m; m &= m - 1) d |= (uint32_t)(32 * x + __builtin_ctz(m)) << (8 * k++);
+          best_n = n;
+          best_rep = r;
+          best_diff = d;
+          if (n == 1) break;
+        }
+        if (best_rep == id) {
+          for (int x = 0; x < 8; x++) rep_lsh[keys[x]].push_back(id);
+          db->n_reps++;
+        }
+        db->tile_parent.push_back(best_rep);
+        db->tile_diff.push_back(best_diff);
       }
     }
   }
@@ -258,12 +303,32 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     delete db;
     return nullptr;
   }
+  // children CSR
+  db->child_off.assign(n_tiles + 1, 0);
+  for (size_t t = 0; t < n_tiles; t++)
+    if (db->tile_parent[t] != t) db->child_off[db->tile_parent[t] + 1]++;
+  for (size_t t = 0; t < n_tiles; t++) db->child_off[t + 1] += db->child_off[t];
+  db->child_ent.resize(db->child_off[n_tiles]);
+  db->child_diff.resize(db->child_off[n_tiles]);
+  {
+    std::vector<uint32_t> cur(db->child_off.begin(), db->child_off.end() - 1);
+    for (size_t t = 0; t < n_tiles; t++)
+      if (db->tile_parent[t] != t) {
+        uint32_t at = cur[db->tile_parent[t]]++;
+        db->child_ent[at] = (uint32_t)t;
+        db->child_diff[at] = db->tile_diff[t];
+      }
+  }
 
-  // ---- seed index: CSR over 12-mers of every tile column in [OFF_MIN, 256-12]
+  // ---- seed index: CSR over 12-mers.  Reps: every seed start column in [OFF_MIN, 256-12];
+  // children: only the seeds that cover one of their differing columns (every other seed of a
+  // child is also a seed of its rep; such candidates are produced by expanding the rep).
   db->seed_off.assign((size_t)HLM_SEED_CODES + 1, 0);
   auto scan = [&](bool fill, std::vector<uint32_t>& cursor) {
     for (size_t t = 0; t < n_tiles; t++) {
       const uint32_t* T = &db->tiles[t * HLM_TILE_WORDS];
+      uint32_t dd = db->tile_diff[t];
+      int nd = HLM_DIFF_N(dd);
       uint32_t code = 0;
       int run = 0;
       for (int c = HLM_OFF_MIN; c < HLM_TILE_COLS; c++) {
@@ -277,8 +342,16 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         code = (code >> 2) | (b << (2 * (HLM_SEED - 1)));
         if (++run >= HLM_SEED) {
           int o = c - HLM_SEED + 1;
+          if (nd) {
+            bool covers = false;
+            for (int k = 0; k < nd; k++) {
+              int x = HLM_DIFF_COL(dd, k);
+              if (x >= o && x < o + HLM_SEED) covers = true;
+            }
+            if (!covers) continue;
+          }
           if (!fill) db->seed_off[code + 1]++;
-          else db->seed_ent[cursor[code]++] = ((uint32_t)t << 8) | (uint32_t)o;
+          else db->seed_ent[cursor[code]++] = ((uint32_t)o << 24) | (uint32_t)t;
         }
       }
     }
@@ -289,5 +362,20 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   db->seed_ent.resize(db->seed_off[HLM_SEED_CODES]);
   cursor.assign(db->seed_off.begin(), db->seed_off.end() - 1);
   scan(true, cursor);
+  // entries of one 12-mer sorted by (column, tile): a read seed at offset 12q can only use columns
+  // [OFF_MIN + 12q, OFF_MIN + 32 + 12q), which the kernel finds by binary search
+  {
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; k++)
+      th.emplace_back([&, k]() {
+        size_t lo = (size_t)HLM_SEED_CODES * k / nt, hi = (size_t)HLM_SEED_CODES * (k + 1) / nt;
+        for (size_t c = lo; c < hi; c++) {
+          uint32_t a = db->seed_off[c], b = db->seed_off[c + 1];
+          if (b - a > 1) std::sort(db->seed_ent.begin() + a, db->seed_ent.begin() + b);
+        }
+      });
+    for (auto& t : th) t.join();
+  }
   return db;
 }

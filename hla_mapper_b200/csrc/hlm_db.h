@@ -27,11 +27,20 @@ struct hlm_db {
   std::vector<uint32_t> seed_ent;
   int64_t n_alleles = 0, n_bases = 0, n_tiles_raw = 0;
 
+  // tile hierarchy: a tile within HLM_KMAX differing columns of an earlier tile of the same
+  // locus and window index is stored as a "child" of that representative ("rep") tile
+  std::vector<uint32_t> tile_parent;  // rep: own id
+  std::vector<uint32_t> tile_diff;    // ndiff << 24 | col2 << 16 | col1 << 8 | col0 (0 for reps)
+  std::vector<uint32_t> child_off;    // CSR over tiles: children of rep t = child_ent[child_off[t] .. child_off[t+1])
+  std::vector<uint32_t> child_ent;    // child tile ids
+  std::vector<uint32_t> child_diff;   // tile_diff of that child (parallel to child_ent)
+  int64_t n_reps = 0;
+
   // device copies, one per CUDA device that has a context on this DB
   struct Dev {
     int device;
     HlmDevDB view;
-    void* ptrs[5];
+    void* ptrs[9];
     int refs;
   };
   std::vector<Dev> devs;

@@ -394,10 +394,7 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
 __global__ void k_clear_tasks(HlmChunk ck, int64_t n_tasks) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  if (i == 0) {
-    ck.counters[0] = 0; ck.counters[1] = 0; ck.counters[2] = 0; ck.counters[3] = 0;
-    ck.counters[4] = 0; ck.counters[5] = 0; ck.counters[6] = 0; ck.counters[7] = 0;
-  }
+  if (i < HLM_N_COUNTERS) ck.counters[i] = 0;
   for (; i < n_tasks; i += stride) {
     ck.task_emin[i] = 0xFFFFFFFFu;
     ck.task_best[i] = HLM_BEST_NONE;
@@ -433,14 +430,29 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * 36 + 32 + lane];
     __syncwarp();
     int Q = n / HLM_SEED;
-    // lane (strand*16 + q) owns seed q of that strand
+    // lane (strand*16 + q) owns seed q of that strand: CSR range of its 12-mer narrowed to the
+    // entries whose column lies in [OFF_MIN + 12q, OFF_MIN + 32 + 12q) (entries are sorted by
+    // column), i.e. to the windows in which read base 0 falls on a column in [OFF_MIN, OFF_MIN+32)
     int my_q = lane & 15, my_strand = lane >> 4;
     uint32_t my_a = 0, my_b = 0;
     if (my_q < Q) {
       uint32_t code;
       if (hlm_seed_code(rd + 18 * my_strand, my_q, &code)) {
-        my_a = __ldg(db.seed_off + code);
-        my_b = __ldg(db.seed_off + code + 1);
+        uint32_t a = __ldg(db.seed_off + code), b = __ldg(db.seed_off + code + 1);
+        uint32_t klo = (uint32_t)(HLM_OFF_MIN + my_q * HLM_SEED) << 24;
+        uint32_t khi = (uint32_t)(HLM_OFF_MIN + HLM_TILE_STRIDE + my_q * HLM_SEED) << 24;
+        uint32_t lo = a, hi = b;
+        while (lo < hi) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(db.seed_ent + mid) < klo) lo = mid + 1; else hi = mid;
+        }
+        my_a = lo;
+        hi = b;
+        while (lo < hi) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(db.seed_ent + mid) < khi) lo = mid + 1; else hi = mid;
+        }
+        my_b = lo;
       }
     }
     for (int strand = 0; strand < 2; strand++) {
@@ -455,19 +467,17 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
           int off = 0;
           if (idx < b) {
             uint32_t e = __ldg(db.seed_ent + idx);
-            tile = e >> 8;
-            off = (int)(e & 0xFFu) - q * HLM_SEED;
-            if (off >= HLM_OFF_MIN && off < HLM_OFF_MIN + HLM_TILE_STRIDE) {
-              int g = tile_locus(db, tile);
-              if ((umask >> g) & 1u) {
-                // candidate (tile, off) belongs to the FIRST read seed that matches it
-                const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-                own = true;
-                for (int qq = 0; qq < q; qq++) {
-                  if (hlm_seed_match(R, T, off, qq)) {
-                    own = false;
-                    break;
-                  }
+            tile = e & 0xFFFFFFu;
+            off = (int)(e >> 24) - q * HLM_SEED;
+            int g = tile_locus(db, tile);
+            if ((umask >> g) & 1u) {
+              // candidate (tile, off) belongs to the FIRST read seed that matches it
+              const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+              own = true;
+              for (int qq = 0; qq < q; qq++) {
+                if (hlm_seed_match(R, T, off, qq)) {
+                  own = false;
+                  break;
                 }
               }
             }
@@ -482,7 +492,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
               if ((int64_t)at < ck.cand_cap)
                 ck.cand[at] = HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF);
               else
-                ck.counters[2] = 1;  // overflow: the host re-runs the chunk in two halves
+                ck.counters[2] = 1;  // overflow: reported by the host
             }
           }
         }
@@ -491,32 +501,158 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   }
 }
 
+// counters[8 + which] = number of candidates appended so far (phase boundaries)
+__global__ void k_snapshot(HlmChunk ck, int which) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long n = ck.counters[0];
+    if ((int64_t)n > ck.cand_cap) n = (unsigned long long)ck.cand_cap;
+    ck.counters[8 + which] = n;
+  }
+}
+
+// phase 0: seed-index candidates; 1 / 2: children appended by expansion round 0 / 1
+__device__ __forceinline__ void cand_range(const HlmChunk& ck, int phase, int64_t& a, int64_t& b) {
+  a = phase == 0 ? 0 : (int64_t)ck.counters[8 + phase - 1];
+  b = (int64_t)ck.counters[8 + phase];
+}
+
 // ------------------------------------------------------------------ k_myers
 __global__ void __launch_bounds__(256)
-k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
-  int64_t ncand = (int64_t)ck.counters[0];
-  if (ncand > ck.cand_cap) ncand = ck.cand_cap;
+k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
+  int64_t first, ncand;
+  cand_range(ck, phase, first, ncand);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long rows = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
+  for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
     uint64_t c = ck.cand[i];
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
     const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-    int lb = hlm_myers_lb(rd, n, T, off);
-    if (lb > 254) lb = 254;
+    int lb;
+    bool dead = false;
+    if (phase != 0) {
+      // a child reached by expanding its rep: it is this path's candidate only when its first
+      // matching seed does not cover a differing column (otherwise the seed index emitted it)
+      uint32_t diff = __ldg(db.tile_diff + tile);
+      int owner = -1, Q = n / HLM_SEED;
+      for (int q = 0; q < Q; q++)
+        if (hlm_seed_match(rd, T, off, q)) {
+          owner = q;
+          break;
+        }
+      dead = owner < 0;
+      if (!dead) {
+        int o = off + owner * HLM_SEED;
+        for (int k = 0; k < HLM_DIFF_N(diff); k++) {
+          int x = HLM_DIFF_COL(diff, k);
+          if (x >= o && x < o + HLM_SEED) dead = true;
+        }
+      }
+    }
+    if (dead) {
+      lb = 254;
+    } else {
+      lb = hlm_myers_lb(rd, n, T, off);
+      if (lb > 253) lb = 253;
+      rows += n;
+    }
     ck.cand[i] = (c & ~0xFFull) | (uint64_t)lb;
     if (lb <= kp.mm_max) {
       int g = tile_locus(db, tile);
       atomicMin(&ck.task_emin[(int64_t)unit * n_targets + g], (uint32_t)lb);
     }
-    rows += n;
   }
   // one atomic per warp
   for (int o = 16; o; o >>= 1) rows += __shfl_xor_sync(FULL, rows, o);
   if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&ck.counters[5], rows);
+}
+
+// ------------------------------------------------------------------ k_expand
+// Children of the rep candidates.  A child differs from its rep in nd <= KMAX columns, so its
+// lower bound is >= lbd = max(0, lb_rep - nd) (one changed reference column changes the banded
+// unit-cost distance by at most one).  Round 0 appends the children with lbd <= min(emin0, mm_max)
+// (emin0 = task minimum over the seed-index candidates): every child left out has lb > emin0.
+// Round 1 appends those with emin0 < lbd <= min(cost(best), mm_max).  Children whose differing
+// columns all lie outside the DP footprint [off - BAND, off + n + BAND) align exactly like the rep
+// and are never materialised.
+__global__ void __launch_bounds__(256)
+k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
+  int64_t nA = (int64_t)ck.counters[8];
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int lane = threadIdx.x & 31;
+  int64_t nloop = (nA + stride - 1) / stride;
+  for (int64_t it = 0; it < nloop; it++) {
+    int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    uint64_t c = 0;
+    int lb = 0, thr_lo = -1, thr_hi = -1;
+    if (i < nA) {
+      c = ck.cand[i];
+      uint32_t tile = HLM_CAND_TILE(c);
+      lb = (int)HLM_CAND_LB(c);
+      if (lb < 254 && __ldg(db.child_off + tile + 1) > __ldg(db.child_off + tile)) {
+        int g = tile_locus(db, tile);
+        int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
+        uint32_t e0 = ck.task_emin0[task];
+        int e0c = e0 > (uint32_t)kp.mm_max ? kp.mm_max : (int)e0;
+        if (round == 0) {
+          thr_hi = e0c;
+          pass = lb - HLM_KMAX <= thr_hi;
+        } else {
+          unsigned long long b = ck.task_best[task];
+          if (b != HLM_BEST_NONE && e0 <= (uint32_t)kp.mm_max) {
+            thr_lo = e0c;
+            thr_hi = HLM_BEST_COST(b) < kp.mm_max ? HLM_BEST_COST(b) : kp.mm_max;
+            pass = lb > thr_lo && lb - HLM_KMAX <= thr_hi;
+          }
+        }
+      }
+    }
+    uint32_t bal = __ballot_sync(FULL, pass);
+    while (bal) {
+      int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      uint64_t cc = __shfl_sync(FULL, c, src);
+      int lbr = __shfl_sync(FULL, lb, src), lo = __shfl_sync(FULL, thr_lo, src),
+          hi = __shfl_sync(FULL, thr_hi, src);
+      uint32_t unit = HLM_CAND_UNIT(cc), tile = HLM_CAND_TILE(cc);
+      int off = (int)HLM_CAND_OFFM(cc) + HLM_OFF_MIN;
+      int n = ck.unit_len[unit];
+      uint32_t a = __ldg(db.child_off + tile), b = __ldg(db.child_off + tile + 1);
+      for (uint32_t base = a; base < b; base += 32) {
+        uint32_t k = base + lane;
+        bool take = false;
+        uint32_t child = 0;
+        if (k < b) {
+          uint32_t diff = __ldg(db.child_diff + k);
+          int nd = HLM_DIFF_N(diff);
+          int lbd = lbr - nd < 0 ? 0 : lbr - nd;
+          if (lbd > lo && lbd <= hi) {
+            for (int x = 0; x < nd; x++) {
+              int col = HLM_DIFF_COL(diff, x);
+              if (col >= off - HLM_BAND && col < off + n + HLM_BAND) take = true;
+            }
+            if (take) child = __ldg(db.child_ent + k);
+          }
+        }
+        uint32_t tb = __ballot_sync(FULL, take);
+        if (tb) {
+          unsigned long long pos = 0;
+          if (lane == 0) pos = atomicAdd(&ck.counters[0], (unsigned long long)__popc(tb));
+          pos = __shfl_sync(FULL, pos, 0);
+          if (take) {
+            unsigned long long at = pos + __popc(tb & ((1u << lane) - 1u));
+            if ((int64_t)at < ck.cand_cap)
+              ck.cand[at] = HLM_CAND(unit, child, HLM_CAND_OFFM(cc), HLM_CAND_STRAND(cc), 0xFF);
+            else
+              ck.counters[2] = 1;
+          }
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ k_select
@@ -540,8 +676,16 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         int g = tile_locus(db, HLM_CAND_TILE(c));
         int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
         int emin = (int)ck.task_emin[task];
-        if (round == 0) take = (lb == emin);
-        else {
+        if (round == 0) {
+          take = (lb == emin);
+          if (take && lb == 0) {
+            // a zero bound is an exact match of the whole read on a band diagonal: the DP result
+            // is known (S = n, no edits, no clips) and nothing can beat or tie-break it
+            take = false;
+            atomicMin(&ck.task_best[task],
+                      (unsigned long long)HLM_BEST_PACK(0, (int)ck.unit_len[HLM_CAND_UNIT(c)], 0, 0));
+          }
+        } else {
           unsigned long long b = ck.task_best[task];
           take = (lb > emin) && b != HLM_BEST_NONE && lb <= HLM_BEST_COST(b);
         }
@@ -820,8 +964,16 @@ void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& c
   k_seed<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(db, kp, ck);
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
-                      int sms, cudaStream_t st) {
-  k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets);
+                      int phase, int sms, cudaStream_t st) {
+  k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, phase);
+}
+void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st) {
+  k_snapshot<<<1, 32, 0, st>>>(ck, which);
+}
+void hlm_launch_expand(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                       int round, int sms, cudaStream_t st) {
+  k_expand<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, round);
+  k_snapshot<<<1, 32, 0, st>>>(ck, 1 + round);
 }
 void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st) {

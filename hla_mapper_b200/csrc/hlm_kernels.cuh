@@ -29,8 +29,11 @@ struct HlmChunk {
   uint32_t* dp_list;     // indices into cand
   int64_t dp_cap;
   unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
-                                 // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total, [7] spare
-  uint32_t* task_emin;   // units * n_targets
+                                 // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total,
+                                 // [7] read too long, [8] n_cand after the seed index,
+                                 // [9] / [10] after expansion round 0 / 1
+  uint32_t* task_emin;   // units * n_targets: minimum lower bound over evaluated candidates
+  uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
   unsigned long long* task_best;
   // outputs
   uint16_t *s1, *s2;
@@ -39,6 +42,8 @@ struct HlmChunk {
   uint32_t *target_mask, *visible_mask;
   uint16_t *min_sum, *others_s1, *others_s2;
 };
+
+#define HLM_N_COUNTERS 16
 
 struct HlmKParams {
   int rna, paired, screen_variant, v_size, minhit, mm_max, clip_mode, skip_screen;
@@ -54,7 +59,10 @@ void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStre
 void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                      cudaStream_t st);
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
-                      int sms, cudaStream_t st);
+                      int phase, int sms, cudaStream_t st);
+void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st);
+void hlm_launch_expand(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
+                       int round, int sms, cudaStream_t st);
 void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st);
 void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,

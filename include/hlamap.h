@@ -147,8 +147,9 @@ typedef struct hlm_assign_out {
 /* per-stage device time of the last hlm_run*, CUDA events on the library's own
  * streams (ms), plus work counters used for GCUPS / roofline accounting */
 typedef struct hlm_profile {
-  double ms_h2d, ms_screen, ms_seed, ms_myers, ms_select, ms_dp, ms_assign, ms_d2h, ms_total;
-  int64_t n_pairs, n_kept, n_tasks, n_candidates, n_dp, n_dp_cells, n_myers_cols;
+  double ms_h2d, ms_screen, ms_seed, ms_myers, ms_expand, ms_select, ms_dp, ms_assign, ms_d2h,
+      ms_total;
+  int64_t n_pairs, n_kept, n_seed_candidates, n_candidates, n_dp, n_dp_cells, n_myers_cols;
   int64_t launches;
   int64_t h2d_bytes, d2h_bytes;
   int64_t bases_bytes; /* bases+quals streamed by the screen kernel               */
@@ -163,7 +164,7 @@ void hlm_db_close(hlm_db* db);
 int hlm_db_n_loci(const hlm_db* db);
 const char* hlm_db_locus_name(const hlm_db* db, int i); /* i == n_loci -> "others" */
 int hlm_db_size(const hlm_db* db);                      /* SIZE: line, or 50      */
-int64_t hlm_db_stat(const hlm_db* db, const char* key); /* "alleles","bases","tiles","kmers","seed_entries" */
+int64_t hlm_db_stat(const hlm_db* db, const char* key); /* "alleles","bases","tiles","reps","children","kmers","seed_entries" */
 
 /* one context per GPU; not thread-safe; distinct contexts may run concurrently */
 hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* params, char* err,

@@ -61,19 +61,10 @@ def hostsim():
     L.hs_db_kmer.restype = C.c_uint32
     L.hs_db_kmer.argtypes = [C.c_void_p, C.c_char_p]
     L.hs_db_candidates.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int]
+    L.hs_db_candidates_brute.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int]
+    L.hs_db_tile_info.restype = C.c_uint32
+    L.hs_db_tile_info.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
     L.hs_db_eval.argtypes = [C.c_void_p, u8p, C.c_int, C.c_uint32, C.POINTER(C.c_int)]
     return L
 
 
-def have_gpu():
-    try:
-        import ctypes as C
-
-        from hla_mapper_b200 import api
-
-        n = C.c_int(0)
-        cudart = C.CDLL("libcudart.so", mode=C.RTLD_GLOBAL) if False else None  # noqa: F841
-        v = [C.c_double(0)] * 4
-        return api.lib().hlm_int32_peak(0, None, None, None, None) == 0
-    except Exception:
-        return False

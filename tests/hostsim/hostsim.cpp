@@ -71,6 +71,8 @@ int64_t hs_db_stat(void* p, int what) {
     case 5: return db->n_alleles;
     case 6: return db->v_size;
     case 7: return db->n_kmers_skipped;
+    case 8: return db->n_reps;
+    case 9: return (int64_t)db->child_ent.size();
     default: return -1;
   }
 }
@@ -90,18 +92,29 @@ uint32_t hs_db_kmer(void* p, const char* kmer20) {
     h = (h + 1) & mask;
   }
 }
-// all (tile, off) candidates of one locus for a read strand, straight from the seed index
+// does seed q of a read placed at tile column off cover one of the child's differing columns?
+static bool seed_covers(uint32_t diff, int off, int q) {
+  for (int k = 0; k < HLM_DIFF_N(diff); k++) {
+    int x = HLM_DIFF_COL(diff, k), o = off + q * HLM_SEED;
+    if (x >= o && x < o + HLM_SEED) return true;
+  }
+  return false;
+}
+// all (tile, off) candidates of one locus for a read strand: seed-index hits (first matching
+// seed owns the candidate) plus the children of every rep hit (same ownership rule; children
+// whose differing columns all lie outside the DP footprint are identical to the rep: skipped)
 int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* out, int cap) {
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
   pack_read(read, n, rd);
-  int cnt = 0;
-  for (int q = 0; q < n / HLM_SEED; q++) {
+  int cnt = 0, Q = n / HLM_SEED;
+  int n_index = 0;
+  for (int q = 0; q < Q; q++) {
     uint32_t code;
     if (!hlm_seed_code(rd, q, &code)) continue;
     for (uint32_t i = db->seed_off[code]; i < db->seed_off[code + 1]; i++) {
-      uint32_t e = db->seed_ent[i], tile = e >> 8;
-      int off = (int)(e & 0xFF) - q * HLM_SEED;
+      uint32_t e = db->seed_ent[i], tile = e & 0xFFFFFFu;
+      int off = (int)(e >> 24) - q * HLM_SEED;
       if (off < HLM_OFF_MIN || off >= HLM_OFF_MIN + HLM_TILE_STRIDE) continue;
       if (tile < db->tile_start[locus] || tile >= db->tile_start[locus + 1]) continue;
       bool first = true;
@@ -112,7 +125,48 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
       cnt++;
     }
   }
+  n_index = cnt;
+  for (int c = 0; c < n_index && c < cap; c++) {
+    uint32_t tile = out[c] >> 8;
+    int off = out[c] & 0xFF;
+    for (uint32_t k = db->child_off[tile]; k < db->child_off[tile + 1]; k++) {
+      uint32_t ch = db->child_ent[k], diff = db->child_diff[k];
+      bool inside = false;
+      for (int x = 0; x < HLM_DIFF_N(diff); x++) {
+        int col = HLM_DIFF_COL(diff, x);
+        if (col >= off - HLM_BAND && col < off + n + HLM_BAND) inside = true;
+      }
+      if (!inside) continue;
+      int owner = -1;
+      for (int q = 0; q < Q && owner < 0; q++)
+        if (hlm_seed_match(rd, &db->tiles[(size_t)ch * HLM_TILE_WORDS], off, q)) owner = q;
+      if (owner < 0 || seed_covers(diff, off, owner)) continue;
+      if (cnt < cap) out[cnt] = (ch << 8) | (uint32_t)off;
+      cnt++;
+    }
+  }
   return cnt;
+}
+// every (tile, off) with at least one matching seed, by brute force over all tiles of the locus
+int hs_db_candidates_brute(void* p, const uint8_t* read, int n, int locus, uint32_t* out, int cap) {
+  hlm_db* db = (hlm_db*)p;
+  uint32_t rd[18];
+  pack_read(read, n, rd);
+  int cnt = 0, Q = n / HLM_SEED;
+  for (uint32_t tile = db->tile_start[locus]; tile < db->tile_start[locus + 1]; tile++)
+    for (int off = HLM_OFF_MIN; off < HLM_OFF_MIN + HLM_TILE_STRIDE; off++) {
+      bool any = false;
+      for (int q = 0; q < Q && !any; q++)
+        any = hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, q);
+      if (!any) continue;
+      if (cnt < cap) out[cnt] = (tile << 8) | (uint32_t)off;
+      cnt++;
+    }
+  return cnt;
+}
+uint32_t hs_db_tile_info(void* p, uint32_t tile, int what) {
+  hlm_db* db = (hlm_db*)p;
+  return what == 0 ? db->tile_parent[tile] : db->tile_diff[tile];
 }
 int hs_db_eval(void* p, const uint8_t* read, int n, uint32_t cand, int* out5) {
   hlm_db* db = (hlm_db*)p;

@@ -184,3 +184,45 @@ def test_tile_candidates_reproduce_exhaustive_oracle(orc, hostsim, small_db, sma
             checked += 1
     assert checked > 50
     hostsim.hs_db_close(h)
+
+
+def test_rep_child_hierarchy_covers_every_seed_candidate(orc, hostsim, tmp_path_factory):
+    """a database with many near-identical alleles: the reduced seed index + child expansion must
+    produce exactly the brute-force candidate set, minus children that are identical to their
+    (present) rep inside the DP footprint"""
+    from hla_mapper_b200 import synth
+
+    d = tmp_path_factory.mktemp("db_dense")
+    db = synth.make_db(str(d / "db"), seed=5, n_loci=3, total_alleles=900, len_range=(500, 600),
+                       n_others=5, n_lineages=4)
+    err = C.create_string_buffer(256)
+    h = hostsim.hs_db_open(db.path.encode(), 0, err, 256)
+    assert h, err.value
+    n_tiles, n_reps, n_child = (hostsim.hs_db_stat(h, 2), hostsim.hs_db_stat(h, 8), hostsim.hs_db_stat(h, 9))
+    assert n_reps + n_child == n_tiles and n_child > 2 * n_reps  # the hierarchy is real here
+    rb = synth.make_reads(db, 40, read_len=150, seed=3, on_target=1.0, frag_mu=300, frag_sd=20)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    a = (C.c_uint32 * 200000)()
+    b = (C.c_uint32 * 200000)()
+    skipped = expanded = 0
+    for i in range(rb.n_pairs):
+        raw = rb.bases1[150 * i:150 * i + int(np.random.default_rng(i).integers(60, 151))]
+        fwd = np.ascontiguousarray(np.array([code.get(int(c), 4) for c in raw], dtype=np.uint8))
+        n = len(fwd)
+        for g in range(3):
+            na = hostsim.hs_db_candidates(h, _p(fwd), n, g, a, 200000)
+            nb = hostsim.hs_db_candidates_brute(h, _p(fwd), n, g, b, 200000)
+            A, B = list(a[:na]), set(b[:nb])
+            assert len(set(A)) == len(A)          # every candidate exactly once
+            assert set(A) <= B
+            for c in B - set(A):
+                tile, off = c >> 8, c & 0xFF
+                parent = hostsim.hs_db_tile_info(h, tile, 0)
+                diff = hostsim.hs_db_tile_info(h, tile, 1)
+                assert parent != tile and ((parent << 8) | off) in set(A)
+                cols = [(diff >> (8 * k)) & 0xFF for k in range(diff >> 24)]
+                assert all(not (off - BAND <= x < off + n + BAND) for x in cols)
+                skipped += 1
+            expanded += sum(1 for c in A if hostsim.hs_db_tile_info(h, c >> 8, 0) != (c >> 8))
+    assert skipped > 0 and expanded > 0
+    hostsim.hs_db_close(h)
