@@ -242,8 +242,8 @@ int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
   float t = ev_ms(ctx->run_start, s.ev[EV_D2H]);
   if (t > pr.ms_total) pr.ms_total = t;
   if (counters_host) {
-    pr.n_candidates += (int64_t)counters_host[0];
-    pr.n_seed_candidates += (int64_t)counters_host[8];
+    pr.n_candidates += (int64_t)counters_host[11];
+    pr.n_seed_candidates += (int64_t)counters_host[12];
     pr.n_kept += (int64_t)counters_host[3];
     pr.n_dp_cells += (int64_t)counters_host[4];
     pr.n_myers_cols += (int64_t)counters_host[5];
@@ -638,6 +638,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   kp.skip_screen = p.skip_screen;
   kp.tolerance = p.tolerance;
   kp.n_loci = db->n_loci;
+  kp.one = 1;
   // mtrim's test, evaluated once per quality byte with the reference's own expression
   // (functions.cpp:99-103): P = pow(10, phred / -10) <= v_mtrim_error, phred = char - 33
   for (int c = 0; c < 256; c++) {

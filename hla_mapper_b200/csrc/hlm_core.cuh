@@ -34,6 +34,19 @@ HLM_HD int hlm_addmax(int a, int b, int c) {  // max(a + b, c)
   return hlm_max(a + b, c);
 #endif
 }
+// a + b issued as a multiply-add (a * one + b, one == 1 at run time but opaque to the compiler):
+// IMAD runs on the FMA pipe, which the DP otherwise leaves idle while the ALU pipe (all min/max
+// and DPX instructions) is the bottleneck
+HLM_HD int hlm_add_fma(int a, int b, int one) {
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+  return d;
+#else
+  (void)one;
+  return a + b;
+#endif
+}
 HLM_HD int hlm_max3(int a, int b, int c) {
 #if defined(__CUDA_ARCH__)
   return __vimax3_s32(a, b, c);
@@ -50,64 +63,101 @@ struct HlmWin {
 HLM_HD uint32_t hlm_tw(const uint32_t* plane, int w) { return plane[w < 8 ? w : 7]; }
 
 // ------------------------------------------------------------------ Myers / Hyyro lower bound
-// Bit-parallel unit-cost distance over the same 41-diagonal band the DP uses.  Row-wise
-// formulation: the 64-bit vectors hold HORIZONTAL deltas of one DP row, bit k = band cell k; going
-// to the next row shifts the band one reference column to the right, so the previous row's
-// vectors are shifted right by one and the entering top cell assumes delta +1, the cell left of
-// the band assumes vertical delta +1.  Those assumptions keep every computed value between the
-// unbanded and the banded (+inf outside) distance, so the result never exceeds the cost field of
-// any alignment the DP can produce: it is a valid lower bound (tested against the
-// oracle in tests/test_core_hostsim.py).
-HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
-                        int off) {
+// Bit-parallel unit-cost distance over the same 41-diagonal band the DP uses (Hyyro's
+// diagonal-band formulation, transposed to rows).  Band cell k of read row i is reference
+// column pos + i + k, c_k its distance value.  Between rows the state is the pair of 64-bit
+// vectors (SP, SN) = the horizontal deltas c_{k+1} - c_k = +1 / -1 of the current row: going to
+// the next row the band moves one column to the right, so exactly these deltas separate the
+// diagonal predecessor (same k) from the vertical predecessor (k + 1) of every new cell and
+// only the diagonal-delta vector D0 has to be shifted:
+//     D0  = (((Eq & SP) + SP) ^ SP) | Eq | SN          c'_k == c_k
+//     VP  = SN | ~(D0 | SP),   VN = D0 & SP            c'_k - c_{k+1}
+//     SP' = VN | ~((D0 >> 1) | VP),   SN' = (D0 >> 1) & VP
+// The cell right of the band (k = 41) is assumed one above its left neighbour (bit 40 of SP is
+// always set) and the cell left of the band is never read.  Those assumptions keep every value
+// between the unbanded and the banded (+inf outside) distance, so the result never exceeds the
+// cost field of any alignment the DP can produce: a valid lower bound (DESIGN.md section 5;
+// tests/test_core_hostsim.py checks it against the oracle).
+//
+// Eq comes from per-candidate match vectors PEQ[b] (bit c = tile column c holds base b; row 4 is
+// all zero for N read bases), kept in shared memory on the device; the read is consumed as
+// 4-bit codes, eight per word, spread from the bit planes with three shift-or-mask steps.
+#define HLM_PEQ_ROWS 41 /* 5 vectors x 8 words + 1 pad word (read when the window ends at word 7) */
+
+HLM_HD uint32_t hlm_spread8(uint32_t x) {  // bit j of x (j < 8) -> bit 4j
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
+// fills PEQ rows from the tile planes; peq(r) is an lvalue for row r
+template <class PEQ>
+HLM_HD void hlm_peq_build(const uint32_t* __restrict__ tile, PEQ peq) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int w = 0; w < 8; w++) {
+    uint32_t p0 = tile[w], p1 = tile[8 + w], nn = ~tile[16 + w];
+    peq(w) = ~p0 & ~p1 & nn;
+    peq(8 + w) = p0 & ~p1 & nn;
+    peq(16 + w) = ~p0 & p1 & nn;
+    peq(24 + w) = p0 & p1 & nn;
+    peq(32 + w) = 0u;
+  }
+  peq(40) = 0u;
+}
+
+template <class PEQ>
+HLM_HD int hlm_myers_core(const uint32_t* __restrict__ rd, int n, int off, PEQ peq) {
   const uint64_t MASK = (1ull << HLM_NB) - 1, TOP = 1ull << (HLM_NB - 1);
-  const uint32_t* T0 = tile;
-  const uint32_t* T1 = tile + 8;
-  const uint32_t* TN = tile + 16;
-  uint64_t HP = 0, HN = 0;
-  int score = 0;  // D(i, k=0)
-  int pos = off - HLM_BAND;
-  int w = pos >> 5, s = pos & 31;
-  HlmWin w0 = {hlm_tw(T0, w), hlm_tw(T0, w + 1), hlm_tw(T0, w + 2)};
-  HlmWin w1 = {hlm_tw(T1, w), hlm_tw(T1, w + 1), hlm_tw(T1, w + 2)};
-  HlmWin wn = {hlm_tw(TN, w), hlm_tw(TN, w + 1), hlm_tw(TN, w + 2)};
-  uint32_t r0 = 0, r1 = 0, rn = 0;
+  uint64_t SP = TOP, SN = 0;
+  int score = 0;  // c_0
+  int p = off - HLM_BAND;
+  uint32_t r0 = 0, r1 = 0, rn = 0, cw = 0;
   for (int i = 0; i < n; i++) {
-    if ((i & 31) == 0) {
-      r0 = rd[i >> 5];
-      r1 = rd[6 + (i >> 5)];
-      rn = rd[12 + (i >> 5)];
+    if ((i & 7) == 0) {
+      if ((i & 31) == 0) {
+        r0 = rd[i >> 5];
+        r1 = rd[6 + (i >> 5)];
+        rn = rd[12 + (i >> 5)];
+      }
+      cw = hlm_spread8(r0 & 0xFFu) | (hlm_spread8(r1 & 0xFFu) << 1) | (hlm_spread8(rn & 0xFFu) << 2);
+      r0 >>= 8;
+      r1 >>= 8;
+      rn >>= 8;
     }
-    uint64_t t0 = (uint64_t)hlm_funnel(w0.a, w0.b, s) | ((uint64_t)hlm_funnel(w0.b, w0.c, s) << 32);
-    uint64_t t1 = (uint64_t)hlm_funnel(w1.a, w1.b, s) | ((uint64_t)hlm_funnel(w1.b, w1.c, s) << 32);
-    uint64_t tn = (uint64_t)hlm_funnel(wn.a, wn.b, s) | ((uint64_t)hlm_funnel(wn.b, wn.c, s) << 32);
-    uint64_t m0 = (uint64_t)0 - (uint64_t)(r0 & 1), m1 = (uint64_t)0 - (uint64_t)(r1 & 1),
-             mn = (uint64_t)0 - (uint64_t)(rn & 1);
-    uint64_t Eq = ~(t0 ^ m0) & ~(t1 ^ m1) & ~(tn | mn) & MASK;
-    r0 >>= 1;
-    r1 >>= 1;
-    rn >>= 1;
-    uint64_t HPa = (HP >> 1) | TOP, HNa = HN >> 1;
-    uint64_t D0 = (((Eq & HPa) + HPa) ^ HPa) | Eq | HNa;
-    uint64_t VP = HNa | ~(D0 | HPa), VN = D0 & HPa;
-    uint64_t X = (VP << 1) | 1ull, Y = VN << 1;
-    HP = (Y | ~(D0 | X)) & MASK;
-    HN = (X & D0) & MASK;
+    int row = (int)(cw & 7u) * 8 + (p >> 5);  // codes 5..7 cannot occur (N clears both code bits)
+    cw >>= 4;
+    uint32_t a = peq(row), b = peq(row + 1), c = peq(row + 2);
+    uint64_t Eq = ((uint64_t)hlm_funnel(a, b, p & 31) | ((uint64_t)hlm_funnel(b, c, p & 31) << 32)) & MASK;
+    p++;
+    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;
+    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;
+    uint64_t D0s = D0 >> 1;
+    SP = VN | ~(D0s | VP) | TOP;
+    SN = D0s & VP;
     score += 1 - (int)(D0 & 1ull);
-    if (++s == 32) {
-      s = 0;
-      w++;
-      w0.a = w0.b; w0.b = w0.c; w0.c = hlm_tw(T0, w + 2);
-      w1.a = w1.b; w1.b = w1.c; w1.c = hlm_tw(T1, w + 2);
-      wn.a = wn.b; wn.b = wn.c; wn.c = hlm_tw(TN, w + 2);
-    }
   }
   int best = score, cur = score;
-  for (int k = 1; k < HLM_NB; k++) {
-    cur += (int)((HP >> k) & 1ull) - (int)((HN >> k) & 1ull);
+  for (int k = 0; k < HLM_NB - 1; k++) {
+    cur += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);
     best = cur < best ? cur : best;
   }
   return best;
+}
+
+// host / generic entry point: PEQ in a local array
+struct HlmPeqLocal {
+  uint32_t* v;
+  HLM_HD uint32_t& operator()(int r) const { return v[r]; }
+};
+HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
+                        int off) {
+  uint32_t buf[HLM_PEQ_ROWS];
+  HlmPeqLocal peq{buf};
+  hlm_peq_build(tile, peq);
+  return hlm_myers_core(rd, n, off, peq);
 }
 
 // ------------------------------------------------------------------ banded affine-gap DP
@@ -119,7 +169,7 @@ struct HlmAln {
 };
 
 HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
-                           int off) {
+                           int off, int one = 1) {
   const uint32_t* T0 = tile;
   const uint32_t* T1 = tile + 8;
   const uint32_t* TN = tile + 16;
@@ -154,21 +204,30 @@ HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_
                      ~(hlm_funnel(wn.b, wn.c, s) | mn);
     start = (i == 1) ? -(HLM_V_CLIP + HLM_CU + 1) : start - (HLM_CU + 1);
     trailpen -= HLM_CU;
-    int f = HLM_V_NEG, hl = HLM_V_NEG, rowmax = HLM_V_NEG;
+    // Cell update, arranged so that the ALU pipe (min/max, DPX) sees 5.5 instructions per cell:
+    //   e  = max(E[k+1] + GAPE, H[k+1] + GAPO)                  VIADDMNMX (+ add)
+    //   f  = max(f + GAPE, h'[k-1] + GAPO)                       VIADDMNMX (+ add)
+    //   h' = max(H[k] + sub, e, start)                           VIMNMX3   (+ predicated add)
+    //   h  = max(h', f)                                          VIMNMX
+    // f may use h' (the cell value without its own f) instead of h: h = max(h', f_prev) and
+    // f_prev + GAPO < f_prev + GAPE, so the dropped term never wins.
+    int f = HLM_V_NEG, hp = HLM_V_NEG, rowmax = HLM_V_NEG, hprev = HLM_V_NEG;
 #pragma unroll
     for (int k = 0; k < HLM_NB; k++) {
-      uint32_t bit = (k < 32) ? ((eq_lo >> k) & 1u) : ((eq_hi >> (k - 32)) & 1u);
-      int sub = bit ? HLM_V_MATCH : HLM_V_MISM;
+      uint32_t bit = (k < 32) ? (eq_lo & (1u << k)) : (eq_hi & (1u << (k - 32)));
       int e = HLM_V_NEG;
-      if (k + 1 < HLM_NB) e = hlm_addmax(E[k + 1], HLM_V_GAPE, H[k + 1] + HLM_V_GAPO);
-      if (k >= 1) f = hlm_addmax(f, HLM_V_GAPE, hl + HLM_V_GAPO);
-      int h = hlm_addmax(H[k], sub, start);
-      h = hlm_max3(h, e, f);
+      if (k + 1 < HLM_NB) e = hlm_addmax(E[k + 1], HLM_V_GAPE, hlm_add_fma(H[k + 1], HLM_V_GAPO, one));
+      if (k >= 1) f = hlm_addmax(f, HLM_V_GAPE, hlm_add_fma(hp, HLM_V_GAPO, one));
+      int hm = hlm_add_fma(H[k], HLM_V_MISM, one);
+      if (bit) hm = hlm_add_fma(H[k], HLM_V_MATCH, one);
+      hp = hlm_max3(hm, e, start);
+      int h = hlm_max(hp, f);
       H[k] = h;
       E[k] = e;
-      hl = h;
-      rowmax = hlm_max(rowmax, h);
+      if (k & 1) rowmax = hlm_max3(rowmax, h, hprev);
+      hprev = h;
     }
+    rowmax = hlm_max(rowmax, hprev);  // NB is odd: the last cell
     int fin = rowmax - (i < n ? trailpen : 0);
     if (fin >= best) {
       best = fin;

@@ -65,6 +65,55 @@ __device__ __forceinline__ void encode8(uint64_t v, uint32_t& pk, uint32_t& b0, 
   }
 }
 
+// Warp-level list appender: a warp reserves HLM_APPEND_BLOCK slots with ONE atomic and fills them
+// from its ballots; unused slots are padded with an invalid record that every consumer skips.
+// (One atomic per ballot on a single counter serialises in L2 at ~10^7 appends per chunk.)
+#define HLM_APPEND_BLOCK 128
+#define HLM_CAND_INVALID 0xFFFFFFFFFFFFFFFFull
+#define HLM_DP_INVALID 0xFFFFFFFFu
+template <class T>
+struct WarpAppender {
+  unsigned long long pos, end, real;
+  T* list;
+  unsigned long long* counter;
+  unsigned long long* overflow;
+  int64_t cap;
+  T invalid;
+  __device__ __forceinline__ WarpAppender(T* l, unsigned long long* c, unsigned long long* ov,
+                                          int64_t cp, T inv)
+      : pos(0), end(0), real(0), list(l), counter(c), overflow(ov), cap(cp), invalid(inv) {}
+  __device__ __forceinline__ void pad(int lane) {
+    for (unsigned long long p = pos + lane; p < end; p += 32)
+      if ((int64_t)p < cap) list[p] = invalid;
+    pos = end;
+  }
+  // called by all 32 lanes (converged)
+  __device__ __forceinline__ void push(bool take, T v, int lane) {
+    uint32_t bal = __ballot_sync(FULL, take);
+    if (!bal) return;
+    int cnt = __popc(bal);
+    if (pos + cnt > end) {
+      pad(lane);
+      unsigned long long np = 0;
+      if (lane == 0) np = atomicAdd(counter, (unsigned long long)HLM_APPEND_BLOCK);
+      np = __shfl_sync(FULL, np, 0);
+      pos = np;
+      end = np + HLM_APPEND_BLOCK;
+    }
+    if (take) {
+      unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
+      if ((int64_t)at < cap) list[at] = v;
+      else *overflow = 1;
+    }
+    pos += cnt;
+    real += cnt;
+  }
+  __device__ __forceinline__ void finish(int lane, unsigned long long* real_counter) {
+    pad(lane);
+    if (lane == 0 && real && real_counter) atomicAdd(real_counter, real);
+  }
+};
+
 struct WarpScratch {
   uint32_t sq[18];    // 2-bit stream of R1 (16 bases / word) + zero padding
   uint32_t p0[9];     // planes of the mate being processed (+1 pad word)
@@ -421,6 +470,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   uint32_t* rd = s_rd[wib];
   int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
   int64_t n_units = ck.n_pairs * ck.units_per_pair;
+  WarpAppender<uint64_t> app(ck.cand, &ck.counters[0], &ck.counters[2], ck.cand_cap, HLM_CAND_INVALID);
   for (int64_t unit = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; unit < n_units; unit += nwarps) {
     int n = ck.unit_len[unit];
     if (n == 0) continue;
@@ -482,23 +532,12 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
               }
             }
           }
-          uint32_t bal = __ballot_sync(FULL, own);
-          if (bal) {
-            unsigned long long pos = 0;
-            if (lane == 0) pos = atomicAdd(&ck.counters[0], (unsigned long long)__popc(bal));
-            pos = __shfl_sync(FULL, pos, 0);
-            if (own) {
-              unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
-              if ((int64_t)at < ck.cand_cap)
-                ck.cand[at] = HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF);
-              else
-                ck.counters[2] = 1;  // overflow: reported by the host
-            }
-          }
+          app.push(own, HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF), lane);
         }
       }
     }
   }
+  app.finish(lane, &ck.counters[11]);
 }
 
 // counters[8 + which] = number of candidates appended so far (phase boundaries)
@@ -507,6 +546,7 @@ __global__ void k_snapshot(HlmChunk ck, int which) {
     unsigned long long n = ck.counters[0];
     if ((int64_t)n > ck.cand_cap) n = (unsigned long long)ck.cand_cap;
     ck.counters[8 + which] = n;
+    if (which == 0) ck.counters[12] = ck.counters[11];
   }
 }
 
@@ -517,14 +557,24 @@ __device__ __forceinline__ void cand_range(const HlmChunk& ck, int phase, int64_
 }
 
 // ------------------------------------------------------------------ k_myers
+// per-thread PEQ rows interleaved across the block: row r of thread t at s_peq[r * 256 + t]
+// (bank = lane: conflict-free whatever row each lane reads)
+struct HlmPeqShared {
+  uint32_t* base;
+  __device__ __forceinline__ uint32_t& operator()(int r) const { return base[r * 256]; }
+};
+
 __global__ void __launch_bounds__(256)
 k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
+  __shared__ uint32_t s_peq[HLM_PEQ_ROWS * 256];
+  HlmPeqShared peq{s_peq + threadIdx.x};
   int64_t first, ncand;
   cand_range(ck, phase, first, ncand);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long rows = 0;
   for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
     uint64_t c = ck.cand[i];
+    if (c == HLM_CAND_INVALID) continue;
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
@@ -554,7 +604,8 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
     if (dead) {
       lb = 254;
     } else {
-      lb = hlm_myers_lb(rd, n, T, off);
+      hlm_peq_build(T, peq);
+      lb = hlm_myers_core(rd, n, off, peq);
       if (lb > 253) lb = 253;
       rows += n;
     }
@@ -583,6 +634,7 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int lane = threadIdx.x & 31;
   int64_t nloop = (nA + stride - 1) / stride;
+  WarpAppender<uint64_t> app(ck.cand, &ck.counters[0], &ck.counters[2], ck.cand_cap, HLM_CAND_INVALID);
   for (int64_t it = 0; it < nloop; it++) {
     int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool pass = false;
@@ -637,22 +689,11 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
             if (take) child = __ldg(db.child_ent + k);
           }
         }
-        uint32_t tb = __ballot_sync(FULL, take);
-        if (tb) {
-          unsigned long long pos = 0;
-          if (lane == 0) pos = atomicAdd(&ck.counters[0], (unsigned long long)__popc(tb));
-          pos = __shfl_sync(FULL, pos, 0);
-          if (take) {
-            unsigned long long at = pos + __popc(tb & ((1u << lane) - 1u));
-            if ((int64_t)at < ck.cand_cap)
-              ck.cand[at] = HLM_CAND(unit, child, HLM_CAND_OFFM(cc), HLM_CAND_STRAND(cc), 0xFF);
-            else
-              ck.counters[2] = 1;
-          }
-        }
+        app.push(take, HLM_CAND(unit, child, HLM_CAND_OFFM(cc), HLM_CAND_STRAND(cc), 0xFF), lane);
       }
     }
   }
+  app.finish(lane, &ck.counters[11]);
 }
 
 // ------------------------------------------------------------------ k_select
@@ -666,6 +707,7 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int lane = threadIdx.x & 31;
   int64_t nloop = (ncand + stride - 1) / stride;
+  unsigned long long n_take = 0;
   for (int64_t it = 0; it < nloop; it++) {
     int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool take = false;
@@ -691,6 +733,7 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         }
       }
     }
+    // the DP list stays dense (no padding): one ballot-aggregated atomic per warp iteration
     uint32_t bal = __ballot_sync(FULL, take);
     if (bal) {
       unsigned long long pos = 0;
@@ -701,8 +744,10 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         if ((int64_t)at < ck.dp_cap) ck.dp_list[at] = (uint32_t)i;
         else ck.counters[2] = 1;
       }
+      n_take += __popc(bal);
     }
   }
+  if (lane == 0 && n_take) atomicAdd(&ck.counters[6], n_take);
 }
 
 // ------------------------------------------------------------------ k_dp
@@ -713,13 +758,15 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long cells = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) {
-    uint64_t c = ck.cand[ck.dp_list[i]];
+    uint32_t di = ck.dp_list[i];
+    if (di == HLM_DP_INVALID) continue;
+    uint64_t c = ck.cand[di];
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
     const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-    HlmAln a = hlm_dp_align(rd, n, T, off);
+    HlmAln a = hlm_dp_align(rd, n, T, off, kp.one);
     int g = tile_locus(db, tile);
     atomicMin(&ck.task_best[(int64_t)unit * n_targets + g],
               (unsigned long long)HLM_BEST_PACK(a.cost, a.S, a.lead, a.trail));
@@ -733,7 +780,6 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
 
 __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    ck.counters[6] += ck.counters[1];
     ck.counters[1] = 0;
   }
 }
@@ -965,6 +1011,11 @@ void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& c
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {
+  static bool once = false;
+  if (!once) {  // 5 blocks x 42 KB of PEQ rows per SM
+    cudaFuncSetAttribute(k_myers, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    once = true;
+  }
   k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, phase);
 }
 void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st) {

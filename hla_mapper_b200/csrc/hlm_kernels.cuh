@@ -31,7 +31,8 @@ struct HlmChunk {
   unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
                                  // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total,
                                  // [7] read too long, [8] n_cand after the seed index,
-                                 // [9] / [10] after expansion round 0 / 1
+                                 // [9] / [10] after expansion round 0 / 1 (slots incl. padding),
+                                 // [11] real candidates, [12] real seed-index candidates
   uint32_t* task_emin;   // units * n_targets: minimum lower bound over evaluated candidates
   uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
   unsigned long long* task_best;
@@ -50,6 +51,7 @@ struct HlmKParams {
   double tolerance;
   uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
   int n_loci;
+  int one;  // == 1; opaque multiplier that keeps the DP's adds on the FMA pipe (hlm_add_fma)
 };
 
 void hlm_launch_screen(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
