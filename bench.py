@@ -45,6 +45,10 @@ from hla_mapper_b200 import _abi, synth  # noqa: E402
 DB_KW = dict(seed=42, n_loci=24, total_alleles=40000, n_others=2000)
 READS_KW = dict(read_len=150, seed=1001, on_target=1.0)
 METRIC = "read pairs/sec scored+assigned"
+# integer instructions of the SASS inner loops (tools/sass_mix.py -> profiles/r1_sass_mix.txt)
+DP_ALU_OPS_PER_CELL = 5.8     # 238 ALU-pipe instructions per 41-cell band row
+DP_INT_OPS_PER_CELL = 10.3    # + 183 IMAD on the FMA pipe
+MYERS_ALU_OPS_PER_ROW = 31.0  # 248 ALU-pipe instructions per 8 band rows
 WORKLOAD = "synthetic 30x WGS MHC-region reads, 2x150bp, 2M pairs/GPU vs 24 loci + others, 40k-allele DB seed 42"
 
 
@@ -197,8 +201,30 @@ def run_b200(args):
     res_dev = m.fetch(h, n)
     m.free(h)
 
+    # ---- per-kernel times: same work, one pipeline slot so that the CUDA events bracketing each
+    # kernel on the launch stream are not stretched by the other slot's kernels (rank 0 only;
+    # outside the timed region of `value`)
+    kstage = {}
+    if rank == 0:
+        ps = _abi.default_params(single_slot=1)
+        if args.chunk:
+            ps.chunk_pairs = args.chunk
+        ms_ = api.Mapper(gdb, local, ps)
+        hs = ms_.upload(rb)
+        ms_.run_device(hs)
+        for _ in range(max(1, min(K, 2))):
+            ms_.run_device(hs)
+            for k, v in ms_.profile().items():
+                kstage[k] = kstage.get(k, 0) + v
+        for k in kstage:
+            kstage[k] /= max(1, min(K, 2))
+        ms_.free(hs)
+        ms_.close()
+
     # ---- end to end through the public call with host buffers
-    buf = _abi.Buffers(n, T)
+    # what hla-mapper consumes downstream: screen flags / trims / locus mask, the (s1, s2) table
+    # and the assignment; the per-alignment diagnostics are not requested
+    buf = _abi.Buffers(n, T, diag=False)
     for _ in range(max(1, min(W, 2))):
         m.run(rb, buffers=buf)
     barrier()
@@ -212,6 +238,8 @@ def run_b200(args):
     wall_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     for k in buf.FIELDS:  # the two arms must agree bit for bit
+        if k[:-1] in ("aln", "nm", "lead", "trail"):
+            continue
         assert np.array_equal(getattr(buf, k), getattr(res_dev, k)), k
     kept = int(((buf.flags & 2) != 0).sum())
     assigned = int((buf.target_mask != 0).sum())
@@ -227,36 +255,43 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- rooflines (rank 0's kernels, live event times of this run)
+    # ---- rooflines (rank 0's kernels; CUDA-event times of the serialised pass above)
     hbm_peak, hbm_src = peaks()
-    per = lambda k: stage[k] / K  # noqa: E731
-    cells = stage["n_dp_cells"] / K
+    per = lambda k: kstage[k]  # noqa: E731
+    cells = kstage["n_dp_cells"]
     dp_ms, my_ms, sc_ms = per("ms_dp"), per("ms_myers"), per("ms_screen")
     gcups = cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
-    # DP: HLM_DP_OPS integer lane-ops per cell in the SASS inner loop against the
-    # measured mixed ALU+FMA-pipe integer issue rate of this GPU
-    ops_per_cell = 6.0
-    dp_peak_gcups = int_peak["mix"] / ops_per_cell
-    screen_bytes = stage["bases_bytes"] / K + 12.0 * n
+    # INT32 roofline.  Every min/max (DPX VIADDMNMX / VIMNMX3) and logic instruction issues on the
+    # ALU pipe only (64 lanes/clk/SM = the measured `viaddmnmx` rate); adds can also go to the FMA
+    # pipe (IMAD).  Instruction counts per cell / per band row are read off the SASS inner loops
+    # (profiles/r1_sass_mix.txt): the ALU pipe is the binding one for both kernels.
+    alu_peak = int_peak["viaddmnmx"]            # G lane-op/s on the ALU pipe
+    dp_alu, dp_all = DP_ALU_OPS_PER_CELL, DP_INT_OPS_PER_CELL
+    dp_peak_gcups = min(alu_peak / dp_alu, int_peak["mix"] / dp_all)
+    screen_bytes = kstage["bases_bytes"] + 12.0 * n
     screen_gbs = screen_bytes / (sc_ms * 1e-3) / 1e9 if sc_ms > 0 else 0.0
-    myers_rows = stage["n_myers_cols"] / K
+    myers_rows = kstage["n_myers_cols"]
+    my_grows = myers_rows / (my_ms * 1e-3) / 1e9 if my_ms > 0 else 0.0
+    my_peak = alu_peak / MYERS_ALU_OPS_PER_ROW
     rooflines = {
         "k_dp": {"bound": "int32", "achieved": round(gcups, 1), "peak": round(dp_peak_gcups, 1),
                  "unit": "GCUPS", "frac": round(gcups / dp_peak_gcups, 4), "traffic": None,
                  "ms_per_step": round(dp_ms, 3), "cells_per_step": int(cells),
                  "int32_peak_glops": {k: round(v, 1) for k, v in int_peak.items()},
-                 "ops_per_cell": ops_per_cell},
-        "k_myers": {"bound": "int32", "achieved": round(myers_rows / (my_ms * 1e-3) / 1e9, 2),
-                    "unit": "G band-rows/s", "ms_per_step": round(my_ms, 3),
-                    "rows_per_step": int(myers_rows)},
+                 "alu_ops_per_cell": dp_alu, "int_ops_per_cell": dp_all,
+                 "peak_source": "hlm_int32_peak micro-kernels measured in this run"},
+        "k_myers": {"bound": "int32", "achieved": round(my_grows, 2), "peak": round(my_peak, 2),
+                    "unit": "G band-rows/s", "frac": round(my_grows / my_peak, 4), "traffic": None,
+                    "ms_per_step": round(my_ms, 3), "rows_per_step": int(myers_rows),
+                    "alu_ops_per_row": MYERS_ALU_OPS_PER_ROW},
         "k_screen": {"bound": "hbm", "achieved": round(screen_gbs, 1), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(screen_gbs / hbm_peak, 4), "traffic": None,
                      "ms_per_step": round(sc_ms, 3), "bytes_per_step": int(screen_bytes),
                      "peak_source": hbm_src},
         "k_seed": {"ms_per_step": round(per("ms_seed"), 3),
-                   "candidates_per_step": int(stage["n_candidates"] / K)},
+                   "seed_candidates_per_step": int(kstage["n_seed_candidates"])},
         "k_expand": {"ms_per_step": round(per("ms_expand"), 3),
-                     "seed_candidates_per_step": int(stage["n_seed_candidates"] / K)},
+                     "candidates_per_step": int(kstage["n_candidates"])},
         "k_select": {"ms_per_step": round(per("ms_select"), 3)},
         "k_scores+k_assign": {"ms_per_step": round(per("ms_assign"), 3)},
     }
@@ -264,7 +299,7 @@ def run_b200(args):
     dom = max(times, key=times.get)
     roof = dict(rooflines[dom])
     roof["kernel"] = dom
-    roof["share_of_step"] = round(times[dom] / (dev_ms / K), 3) if world == 1 else None
+    roof["share_of_step"] = round(times[dom] / max(1e-9, kstage["ms_total"]), 3)
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world,
@@ -284,6 +319,7 @@ def run_b200(args):
         "work": {"kept_pairs": kept, "assigned_pairs": assigned,
                  "candidates_per_step": int(stage["n_candidates"] / K),
                  "dp_alignments_per_step": int(stage["n_dp"] / K),
+                 "serialised_ms_per_step": round(kstage["ms_total"], 3),
                  "wall_ms_per_step_device_arm": round(wall_dev * 1e3 / K, 3)},
     }
     if not args.no_cpu and world >= 1:

@@ -28,7 +28,7 @@ class HlmParams(C.Structure):
         ("screen_variant", C.c_int32), ("v_size", C.c_int32), ("minhit", C.c_int32),
         ("mm_max", C.c_int32), ("clip_mode", C.c_int32), ("tolerance", C.c_double),
         ("mtrim_error", C.c_double), ("chunk_pairs", C.c_int32), ("skip_screen", C.c_int32),
-        ("cand_capacity", C.c_int64),
+        ("cand_capacity", C.c_int64), ("single_slot", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -80,6 +80,8 @@ def default_params(rna=0, **kw):
     p.chunk_pairs = 0
     p.skip_screen = 0
     p.cand_capacity = 0
+    p.single_slot = 0
+    p.reserved0 = 0
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -92,7 +94,9 @@ def _ptr(a, typ):
 class Buffers:
     """numpy-backed output arrays + the ctypes structs that point into them"""
 
-    def __init__(self, n_pairs, n_targets):
+    def __init__(self, n_pairs, n_targets, diag=True):
+        """diag=False: no per-alignment diagnostics (aln / nm / lead / trail): the score struct
+        carries NULL for them and the library neither copies nor returns those arrays"""
         n, T = int(n_pairs), int(n_targets)
         self.n, self.T = n, T
         self.flags = np.zeros(n, np.uint8)
@@ -110,10 +114,13 @@ class Buffers:
         self.scr = HlmScreenOut(_ptr(self.flags, u8p), _ptr(self.trim_lo1, u16p),
                                 _ptr(self.trim_len1, u16p), _ptr(self.trim_lo2, u16p),
                                 _ptr(self.trim_len2, u16p), _ptr(self.locus_mask, u32p))
-        self.sc = HlmScoreOut(_ptr(self.s1, u16p), _ptr(self.s2, u16p), _ptr(self.aln1, i16p),
-                              _ptr(self.aln2, i16p), _ptr(self.nm1, u8p), _ptr(self.nm2, u8p),
-                              _ptr(self.lead1, u8p), _ptr(self.lead2, u8p),
-                              _ptr(self.trail1, u8p), _ptr(self.trail2, u8p))
+        if diag:
+            self.sc = HlmScoreOut(_ptr(self.s1, u16p), _ptr(self.s2, u16p), _ptr(self.aln1, i16p),
+                                  _ptr(self.aln2, i16p), _ptr(self.nm1, u8p), _ptr(self.nm2, u8p),
+                                  _ptr(self.lead1, u8p), _ptr(self.lead2, u8p),
+                                  _ptr(self.trail1, u8p), _ptr(self.trail2, u8p))
+        else:
+            self.sc = HlmScoreOut(_ptr(self.s1, u16p), _ptr(self.s2, u16p))
         self.asg = HlmAssignOut(_ptr(self.target_mask, u32p), _ptr(self.visible_mask, u32p),
                                 _ptr(self.min_sum, u16p), _ptr(self.others_s1, u16p),
                                 _ptr(self.others_s2, u16p))

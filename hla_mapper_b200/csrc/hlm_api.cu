@@ -22,6 +22,7 @@
 #define HLM_STAGE_SCREEN 1
 #define HLM_STAGE_SCORE 2
 #define HLM_STAGE_ASSIGN 4
+#define HLM_MAX_SLOTS 3
 
 namespace {
 
@@ -63,9 +64,9 @@ struct hlm_ctx {
   HlmKParams kp;
   HlmDevDB ddb;
   int device = 0, sms = 148;
-  int n_targets = 0, units_per_pair = 2;
+  int n_targets = 0, units_per_pair = 2, n_slots = 2;
   int64_t chunk_pairs = 0, cand_cap = 0;
-  Slot slot[2];
+  Slot slot[HLM_MAX_SLOTS];
   std::string err;
   hlm_profile prof;
   cudaEvent_t run_start = nullptr;
@@ -346,11 +347,11 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
   int64_t N = in->n_pairs, C = ctx->chunk_pairs;
   auto t0 = std::chrono::steady_clock::now();
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
-  CU(cudaStreamWaitEvent(ctx->slot[1].st, ctx->run_start, 0));
+  for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
   int rc = 0;
   int64_t k = 0;
   for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
-    Slot& s = ctx->slot[k & 1];
+    Slot& s = ctx->slot[k % ctx->n_slots];
     int64_t n = std::min(C, N - first);
     // drain the slot's previous chunk
     if (s.busy) {
@@ -452,14 +453,29 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     launch_stages(ctx, s, stages);
     CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 8 * HLM_N_COUNTERS,
                        cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(s.h_out.p, s.d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-    ctx->prof.d2h_bytes += (int64_t)out_bytes;
+    {  // copy back only the result groups the caller asked for (+ the counters)
+      auto d2h = [&](int a, int b) {  // sections [a, b)
+        size_t lo = s.out_off[a], hi = (b < O_COUNT) ? s.out_off[b] : out_bytes;
+        cudaMemcpyAsync((uint8_t*)s.h_out.p + lo, (uint8_t*)s.d_out.p + lo, hi - lo,
+                        cudaMemcpyDeviceToHost, st);
+        ctx->prof.d2h_bytes += (int64_t)(hi - lo);
+      };
+      if (io.scr) d2h(O_FLAGS, O_S1);
+      if (io.sc) {
+        d2h(O_S1, O_ALN1);
+        if (io.sc->aln1 || io.sc->aln2 || io.sc->nm1 || io.sc->nm2 || io.sc->lead1 || io.sc->lead2 ||
+            io.sc->trail1 || io.sc->trail2)
+          d2h(O_ALN1, O_TARGET);
+      }
+      if (io.asg) d2h(O_TARGET, O_COUNTERS);
+      d2h(O_COUNTERS, O_COUNT);
+    }
     CU(cudaEventRecord(s.ev[EV_D2H], st));
     s.busy = true;
     ctx->prof.bases_bytes += (int64_t)(q ? 2 : 1) * (int64_t)(b1 + b2);
   }
-  for (int i = 0; i < 2; i++) {
-    Slot& s = ctx->slot[(k + i) & 1];
+  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
+    Slot& s = ctx->slot[(k + i) % HLM_MAX_SLOTS];
     if (s.busy) {
       int r2 = finish_slot(ctx, s, (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]));
       if (r2 == 0) scatter_results(ctx, s, io);
@@ -498,6 +514,8 @@ void hlm_params_default(hlm_params* p, int rna) {
   p->chunk_pairs = 0;
   p->skip_screen = 0;
   p->cand_capacity = 0;
+  p->single_slot = 0;
+  p->reserved0 = 0;
 }
 
 hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen) {
@@ -619,6 +637,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   ctx->sms = prop.multiProcessorCount;
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
+  ctx->n_slots = p.single_slot ? 1 : HLM_MAX_SLOTS;
   ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 32768;
   ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 2048;
   if (ctx->cand_cap >= (1ll << 32)) ctx->cand_cap = (1ll << 32) - 1;
@@ -651,7 +670,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
     delete ctx;
     return fail(m);
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
     cudaStreamCreateWithFlags(&ctx->slot[i].st, cudaStreamNonBlocking);
     for (int e = 0; e < EV_COUNT; e++) cudaEventCreate(&ctx->slot[i].ev[e]);
     memset(&ctx->slot[i].ck, 0, sizeof(HlmChunk));
@@ -665,7 +684,7 @@ void hlm_ctx_destroy(hlm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
     Slot& s = ctx->slot[i];
     for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters})
       if (b->p) cudaFree(b->p);
@@ -778,12 +797,12 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   int64_t N = b->n_pairs, C = ctx->chunk_pairs;
   uint8_t* d = (uint8_t*)b->in.p;
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
-  CU(cudaStreamWaitEvent(ctx->slot[1].st, ctx->run_start, 0));
+  for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
   int rc = 0;
   int64_t k = 0;
   unsigned long long cnt[8];
   for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
-    Slot& s = ctx->slot[k & 1];
+    Slot& s = ctx->slot[k % ctx->n_slots];
     int64_t n = std::min(C, N - first);
     if (s.busy) {
       if ((rc = ensure_pinned(ctx, s.h_out, 4096))) break;
@@ -817,8 +836,8 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
     (void)nb;
   }
   (void)cnt;
-  for (int i = 0; i < 2; i++) {
-    Slot& s = ctx->slot[(k + i) & 1];
+  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
+    Slot& s = ctx->slot[(k + i) % HLM_MAX_SLOTS];
     if (s.busy) {
       int r2 = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
       if (rc == 0) rc = r2;

@@ -115,30 +115,47 @@ HLM_HD int hlm_myers_core(const uint32_t* __restrict__ rd, int n, int off, PEQ p
   int score = 0;  // c_0
   int p = off - HLM_BAND;
   uint32_t r0 = 0, r1 = 0, rn = 0, cw = 0;
-  for (int i = 0; i < n; i++) {
-    if ((i & 7) == 0) {
-      if ((i & 31) == 0) {
-        r0 = rd[i >> 5];
-        r1 = rd[6 + (i >> 5)];
-        rn = rd[12 + (i >> 5)];
-      }
-      cw = hlm_spread8(r0 & 0xFFu) | (hlm_spread8(r1 & 0xFFu) << 1) | (hlm_spread8(rn & 0xFFu) << 2);
-      r0 >>= 8;
-      r1 >>= 8;
-      rn >>= 8;
-    }
-    int row = (int)(cw & 7u) * 8 + (p >> 5);  // codes 5..7 cannot occur (N clears both code bits)
-    cw >>= 4;
-    uint32_t a = peq(row), b = peq(row + 1), c = peq(row + 2);
-    uint64_t Eq = ((uint64_t)hlm_funnel(a, b, p & 31) | ((uint64_t)hlm_funnel(b, c, p & 31) << 32)) & MASK;
-    p++;
-    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;
-    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;
-    uint64_t D0s = D0 >> 1;
-    SP = VN | ~(D0s | VP) | TOP;
-    SN = D0s & VP;
-    score += 1 - (int)(D0 & 1ull);
+#define HLM_MYERS_REFILL(i)                                                                       \
+  {                                                                                               \
+    if (((i) & 31) == 0) {                                                                        \
+      r0 = rd[(i) >> 5];                                                                          \
+      r1 = rd[6 + ((i) >> 5)];                                                                    \
+      rn = rd[12 + ((i) >> 5)];                                                                   \
+    }                                                                                             \
+    cw = hlm_spread8(r0 & 0xFFu) | (hlm_spread8(r1 & 0xFFu) << 1) | (hlm_spread8(rn & 0xFFu) << 2); \
+    r0 >>= 8;                                                                                     \
+    r1 >>= 8;                                                                                     \
+    rn >>= 8;                                                                                     \
   }
+#define HLM_MYERS_ROW()                                                                            \
+  {                                                                                               \
+    int row = (int)(cw & 7u) * 8 + (p >> 5); /* codes 5..7 cannot occur (N clears the code bits) */ \
+    cw >>= 4;                                                                                     \
+    uint32_t a = peq(row), b = peq(row + 1), c = peq(row + 2);                                    \
+    uint64_t Eq =                                                                                 \
+        ((uint64_t)hlm_funnel(a, b, p & 31) | ((uint64_t)hlm_funnel(b, c, p & 31) << 32)) & MASK; \
+    p++;                                                                                          \
+    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;                                     \
+    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;                                                  \
+    uint64_t D0s = D0 >> 1;                                                                       \
+    SP = VN | ~(D0s | VP) | TOP;                                                                  \
+    SN = D0s & VP;                                                                                \
+    score += 1 - (int)(D0 & 1ull);                                                                \
+  }
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {  // eight rows per code word, no per-row bookkeeping
+    HLM_MYERS_REFILL(i)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int r = 0; r < 8; r++) HLM_MYERS_ROW()
+  }
+  if (i < n) {
+    HLM_MYERS_REFILL(i)
+    for (; i < n; i++) HLM_MYERS_ROW()
+  }
+#undef HLM_MYERS_REFILL
+#undef HLM_MYERS_ROW
   int best = score, cur = score;
   for (int k = 0; k < HLM_NB - 1; k++) {
     cur += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);

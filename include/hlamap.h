@@ -84,6 +84,9 @@ typedef struct hlm_params {
   int32_t chunk_pairs;    /* pairs per pipeline chunk (0 = default)              */
   int32_t skip_screen;    /* 1: treat every pair as screened (scoring-only runs) */
   int64_t cand_capacity;  /* device candidate slots per chunk (0 = default)      */
+  int32_t single_slot;    /* 1: one pipeline slot, chunks strictly serialised (per-kernel
+                             timing runs; the default two slots overlap copies and kernels) */
+  int32_t reserved0;
 } hlm_params;
 
 /* SoA batch of read pairs.  bases/quals are the FASTQ lines as read (ASCII),
