@@ -165,8 +165,11 @@ def run_b200(args):
     db = get_db(args.db, local == 0, barrier)
     t = time.time()
     # weak scaling: every rank draws its own BLOCK-aligned shard of the pair stream
+    from hla_mapper_b200 import shard
+
     per_rank = -(-n // synth.BLOCK) * synth.BLOCK
-    rb = synth.make_reads(db, n, first_pair=rank * per_rank, **READS_KW)
+    lo, _ = shard.shard_bounds(per_rank * world, world, synth.BLOCK)[rank]
+    rb = synth.make_reads(db, n, first_pair=lo, **READS_KW)
     log(f"[bench r{rank}] {n} pairs generated in {time.time() - t:.1f}s")
     t = time.time()
     gdb = api.Database(args.db)
@@ -411,7 +414,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--db", default=os.environ.get("HLM_BENCH_DB", "/tmp/hlm_bench/db_seed42_40k"))
     ap.add_argument("--cpu-pairs", type=int, default=4000)
-    ap.add_argument("--ref-pairs", type=int, default=2000)
+    ap.add_argument("--ref-pairs", type=int, default=6000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -466,8 +466,11 @@ __device__ __forceinline__ int tile_locus(const HlmDevDB& db, uint32_t tile) {
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   __shared__ uint32_t s_rd[WARPS_PER_BLOCK][36];
+  __shared__ uint32_t s_pre[WARPS_PER_BLOCK][32], s_beg[WARPS_PER_BLOCK][32];
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* rd = s_rd[wib];
+  uint32_t* pre = s_pre[wib];
+  uint32_t* beg = s_beg[wib];
   int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
   int64_t n_units = ck.n_pairs * ck.units_per_pair;
   WarpAppender<uint64_t> app(ck.cand, &ck.counters[0], &ck.counters[2], ck.cand_cap, HLM_CAND_INVALID);
@@ -505,36 +508,48 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         my_b = lo;
       }
     }
-    for (int strand = 0; strand < 2; strand++) {
-      const uint32_t* R = rd + 18 * strand;
-      for (int q = 0; q < Q; q++) {
-        uint32_t a = __shfl_sync(FULL, my_a, strand * 16 + q);
-        uint32_t b = __shfl_sync(FULL, my_b, strand * 16 + q);
-        for (uint32_t base = a; base < b; base += 32) {
-          uint32_t idx = base + lane;
-          bool own = false;
-          uint32_t tile = 0;
-          int off = 0;
-          if (idx < b) {
-            uint32_t e = __ldg(db.seed_ent + idx);
-            tile = e & 0xFFFFFFu;
-            off = (int)(e >> 24) - q * HLM_SEED;
-            int g = tile_locus(db, tile);
-            if ((umask >> g) & 1u) {
-              // candidate (tile, off) belongs to the FIRST read seed that matches it
-              const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-              own = true;
-              for (int qq = 0; qq < q; qq++) {
-                if (hlm_seed_match(R, T, off, qq)) {
-                  own = false;
-                  break;
-                }
-              }
+    // flatten the 2 x Q entry ranges over the lanes (load-balanced expansion): entry t of the
+    // concatenation belongs to the lane j with pre[j] <= t < pre[j + 1]
+    uint32_t cnt = my_b - my_a, inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += v;
+    }
+    uint32_t total = __shfl_sync(FULL, inc, 31);
+    pre[lane] = inc - cnt;  // exclusive prefix
+    beg[lane] = my_a;
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32) {
+      uint32_t t = base + lane;
+      bool own = false;
+      uint32_t tile = 0;
+      int off = 0, strand = 0;
+      if (t < total) {
+        int j = 0;  // last lane with pre[j] <= t
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+          if (j + o < 32 && pre[j + o] <= t) j += o;
+        int q = j & 15;
+        strand = j >> 4;
+        uint32_t e = __ldg(db.seed_ent + beg[j] + (t - pre[j]));
+        tile = e & 0xFFFFFFu;
+        off = (int)(e >> 24) - q * HLM_SEED;
+        int g = tile_locus(db, tile);
+        if ((umask >> g) & 1u) {
+          // candidate (tile, off) belongs to the FIRST read seed that matches it
+          const uint32_t* R = rd + 18 * strand;
+          const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+          own = true;
+          for (int qq = 0; qq < q; qq++) {
+            if (hlm_seed_match(R, T, off, qq)) {
+              own = false;
+              break;
             }
           }
-          app.push(own, HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF), lane);
         }
       }
+      app.push(own, HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF), lane);
     }
   }
   app.finish(lane, &ck.counters[11]);

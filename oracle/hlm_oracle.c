@@ -979,12 +979,80 @@ int orc_sam_score_rna(const char* line, int clip_mode, char* qname, size_t qlen)
 struct orc_ref {
   olocus L;
 };
+/* index cache next to the FASTA (what `bwa index` files are to the real bwa: the reference's
+ * database ships prebuilt aligner indexes, so rebuilding ours per process would not be a fair
+ * stand-in).  Layout: magic, n_al, n_seeds, lens[n_al], codes (concatenated), seeds[n_seeds]. */
+#include <sys/stat.h>
+#include <unistd.h>
+static int cache_load(olocus* L, const char* fasta) {
+  char path[4200];
+  snprintf(path, sizeof path, "%s.orcidx", fasta);
+  struct stat sf, sc;
+  if (stat(fasta, &sf) != 0 || stat(path, &sc) != 0 || sc.st_mtime < sf.st_mtime) return -1;
+  FILE* f = fopen(path, "rb");
+  if (!f) return -1;
+  int64_t hdr[3];
+  if (fread(hdr, 8, 3, f) != 3 || hdr[0] != 0x4F52434944583031LL) {
+    fclose(f);
+    return -1;
+  }
+  L->n_al = hdr[1];
+  L->n_seeds = hdr[2];
+  int32_t* lens = (int32_t*)malloc((size_t)(L->n_al + 1) * 4);
+  int ok = fread(lens, 4, (size_t)L->n_al, f) == (size_t)L->n_al;
+  int64_t tot = 0;
+  for (int64_t a = 0; ok && a < L->n_al; a++) tot += lens[a];
+  uint8_t* codes = (uint8_t*)malloc((size_t)tot + 8);
+  ok = ok && fread(codes, 1, (size_t)tot, f) == (size_t)tot;
+  L->seeds = (oseed*)malloc((size_t)(L->n_seeds + 1) * sizeof(oseed));
+  ok = ok && fread(L->seeds, sizeof(oseed), (size_t)L->n_seeds, f) == (size_t)L->n_seeds;
+  fclose(f);
+  if (!ok) {
+    free(lens);
+    free(codes);
+    free(L->seeds);
+    memset(L, 0, sizeof *L);
+    return -1;
+  }
+  L->al = (oseq*)malloc((size_t)(L->n_al + 1) * sizeof(oseq));
+  int64_t o = 0;
+  for (int64_t a = 0; a < L->n_al; a++) {
+    L->al[a].len = lens[a];
+    L->al[a].codes = (uint8_t*)malloc((size_t)lens[a] + 8); /* orc_ref_close frees per allele */
+    memcpy(L->al[a].codes, codes + o, (size_t)lens[a]);
+    o += lens[a];
+  }
+  free(lens);
+  free(codes);
+  return 0;
+}
+static void cache_store(const olocus* L, const char* fasta) {
+  char path[4200], tmp[4300];
+  snprintf(path, sizeof path, "%s.orcidx", fasta);
+  snprintf(tmp, sizeof tmp, "%s.tmp%d", path, (int)getpid());
+  FILE* f = fopen(tmp, "wb");
+  if (!f) return; /* read-only database: just no cache */
+  int64_t hdr[3] = {0x4F52434944583031LL, L->n_al, L->n_seeds};
+  int ok = fwrite(hdr, 8, 3, f) == 3;
+  for (int64_t a = 0; ok && a < L->n_al; a++) {
+    int32_t l = L->al[a].len;
+    ok = fwrite(&l, 4, 1, f) == 1;
+  }
+  for (int64_t a = 0; ok && a < L->n_al; a++)
+    ok = fwrite(L->al[a].codes, 1, (size_t)L->al[a].len, f) == (size_t)L->al[a].len;
+  ok = ok && fwrite(L->seeds, sizeof(oseed), (size_t)L->n_seeds, f) == (size_t)L->n_seeds;
+  fclose(f);
+  if (ok) rename(tmp, path);
+  else remove(tmp);
+}
 orc_ref* orc_ref_open(const char* fasta) {
   orc_ref* r = (orc_ref*)calloc(1, sizeof(orc_ref));
+  if (cache_load(&r->L, fasta) == 0) return r;
   if (load_fasta(&r->L, fasta) != 0) {
     free(r);
     return NULL;
   }
+  cache_store(&r->L, fasta);
   return r;
 }
 void orc_ref_close(orc_ref* r) {
@@ -1014,4 +1082,38 @@ int orc_ref_align(const orc_ref* r, const uint8_t* ascii, int len, int mode, int
   *lead = a.lead;
   *trail = a.trail;
   return 1;
+}
+
+/* many reads at once on nthreads host threads (what `bwa aln -t T` does); out[4*i..] = S, cost,
+ * lead, trail and ok[i] = 1 when an alignment with cost <= mm_max exists */
+void orc_ref_align_batch(const orc_ref* r, const uint8_t* const* reads, const int* lens, int64_t n,
+                         int mode, int mm_max, int nthreads, int32_t* out, uint8_t* ok) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    scratch sc;
+    memset(&sc, 0, sizeof sc);
+    uint8_t codes[HLM_MAX_READ + 8];
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; i++) {
+      ok[i] = 0;
+      if (lens[i] > HLM_MAX_READ) continue;
+      int64_t cells = 0;
+      to_codes(reads[i], lens[i], codes);
+      ares a = mode ? score_fast(&r->L, codes, lens[i], &sc, mm_max, &cells)
+                    : score_exhaustive(&r->L, codes, lens[i], &sc, &cells);
+      if (!a.valid || a.cost > mm_max) continue;
+      ok[i] = 1;
+      out[4 * i] = a.S;
+      out[4 * i + 1] = a.cost;
+      out[4 * i + 2] = a.lead;
+      out[4 * i + 3] = a.trail;
+    }
+    free(sc.buf);
+    free(sc.fh);
+    free(sc.fidx);
+    free(sc.lb);
+  }
 }

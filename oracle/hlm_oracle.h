@@ -63,6 +63,8 @@ orc_ref* orc_ref_open(const char* fasta);
 void orc_ref_close(orc_ref* r);
 int orc_ref_align(const orc_ref* r, const uint8_t* ascii, int len, int mode, int mm_max, int* S,
                   int* cost, int* lead, int* trail);
+void orc_ref_align_batch(const orc_ref* r, const uint8_t* const* reads, const int* lens, int64_t n,
+                         int mode, int mm_max, int nthreads, int32_t* out, uint8_t* ok);
 
 #ifdef __cplusplus
 }
