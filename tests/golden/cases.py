@@ -10,6 +10,8 @@ DB_PARALOG = dict(seed=20240813, n_loci=9, total_alleles=300, len_range=(700, 90
 DB_TIES = dict(seed=99, n_loci=6, total_alleles=90, len_range=(600, 800), n_others=12,
                paralog_div=(0.002, 0.01), others_div=(0.002, 0.02))
 
+DB_RNA = dict(seed=17, n_loci=5, total_alleles=80, len_range=(500, 700), n_others=10, kind="rna")
+
 CASES = {
     # name: (db kwargs, reads kwargs, mode)
     "dna_paired": (DB_SMALL, dict(n_pairs=1500, read_len=150, seed=11, on_target=0.7, frag_mu=300,
@@ -20,6 +22,8 @@ CASES = {
                                frag_sd=40, lowq_tail=0.2), "paired"),
     "dna_ragged": (DB_SMALL, dict(n_pairs=800, read_len=120, seed=12, on_target=0.8, frag_mu=260,
                                   frag_sd=30, ragged=True), "paired"),
+    "rna_paired": (DB_RNA, dict(n_pairs=800, read_len=100, seed=1004, on_target=0.8, frag_mu=220,
+                                 frag_sd=25), "rna"),
     "dna_single": (DB_SMALL, dict(n_pairs=800, read_len=120, seed=13, on_target=0.8, frag_mu=260,
                                   frag_sd=30, ragged=True), "single"),
 }
@@ -34,17 +38,34 @@ def inputs(name, root):
     rk = dict(rk)
     n = rk.pop("n_pairs")
     rb = synth.make_reads(db, n, **rk)
-    p = _abi.default_params(paired=1 if mode == "paired" else 0)
+    p = _abi.default_params(rna=1 if mode == "rna" else 0, paired=0 if mode == "single" else 1)
     return db, rb, p, mode
+
+
+def rna_splits(rb, buf):
+    """block split of every kept trimmed mate, by the rule the STAR stand-in applies
+    (oracle/standin_star.py): what map_rna.cpp:748-787 would cut the mate into"""
+    import standin_star
+
+    out = []
+    for bases, offs, lo, ln in ((rb.bases1, rb.offs1, buf.trim_lo1, buf.trim_len1),
+                                (rb.bases2, rb.offs2, buf.trim_lo2, buf.trim_len2)):
+        sp = np.zeros(rb.n_pairs, np.uint16)
+        for i in range(rb.n_pairs):
+            if buf.flags[i] & 2:
+                a = int(offs[i]) + int(lo[i])
+                sp[i] = standin_star.split_point(bases[a:a + int(ln[i])].tobytes())
+        out.append(sp)
+    return out
 
 
 def header_lines(rb, mode):
     """the FASTQ header line of R1/R0 as synth.write_fastq writes it"""
-    return ["@" + i + ("/1" if mode == "paired" else "") for i in rb.ids()]
+    return ["@" + i + ("/1" if mode != "single" else "") for i in rb.ids()]
 
 
 def size_override(rb, mode):
     """single-end: sequence_size_r1 = length of the id line (preselect.cpp:1199)"""
-    if mode == "paired":
+    if mode != "single":
         return None
     return np.array([len(h) for h in header_lines(rb, mode)], dtype=np.int32)

@@ -28,9 +28,11 @@ from hla_mapper_b200 import synth  # noqa: E402
 
 def fastq_records(path):
     out = {}
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):  # `rna` gzips at the end
+        path += ".gz"
     if not os.path.exists(path):
         return out
-    with open(path) as f:
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path)) as f:
         while True:
             h = f.readline()
             if not h:
@@ -48,10 +50,11 @@ def main():
     for name in cases.CASES:
         with tempfile.TemporaryDirectory() as tmp:
             db, rb, p, mode = cases.inputs(name, tmp)
-            if mode == "paired":
+            if mode != "single":
                 r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
                 synth.write_fastq(rb, r1, r2)
-                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2)
+                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2,
+                                       rna=(mode == "rna"))
                 tag = "R1"
             else:
                 r0 = os.path.join(tmp, "r0.fq")
@@ -61,7 +64,7 @@ def main():
             names, rows = rr.parse_addressing_table(out + "G_addressing_table.txt")
             sel = fastq_records(out + f"G_selected.{tag}.fastq")
             trim1 = fastq_records(out + f"G_selected.trim.{tag}.fastq")
-            trim2 = fastq_records(out + "G_selected.trim.R2.fastq") if mode == "paired" else {}
+            trim2 = fastq_records(out + "G_selected.trim.R2.fastq") if mode != "single" else {}
             sorted_ = {g: sorted(fastq_records(out + f"G_sorted_{g}_{tag}.fastq")) for g in names[:-1]}
             emitted = {g: sorted(fastq_records(out + f"G_{g}_{tag}.fastq")) for g in names[:-1]}
             gold = {

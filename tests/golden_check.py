@@ -14,7 +14,7 @@ def load(name):
         return json.loads(f.read().decode())
 
 
-def check(buf, rb, loci, gold, paired):
+def check(buf, rb, loci, gold, paired, rna=False):
     """loci = DB loci + ['others'] in DB order"""
     import run_reference as rr  # table formatting helper (oracle/, test infrastructure)
 
@@ -40,7 +40,7 @@ def check(buf, rb, loci, gold, paired):
         mine = sorted(ids[k] for k in kept if (int(buf.locus_mask[k]) >> g) & 1)
         assert mine == gold["sorted"][name], name
     # a-8 / a-10 / a-11 / a-13: every row of the addressing table
-    rows = rr.expected_table(buf, ids, loci, rna=False, paired=paired)
+    rows = rr.expected_table(buf, ids, loci, rna=rna, paired=paired)
     assert set(rows) == set(gold["table"])
     for rid, (cols, tgt) in rows.items():
         assert [cols, tgt] == gold["table"][rid], rid
