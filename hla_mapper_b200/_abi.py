@@ -64,6 +64,17 @@ class HlmProfile(C.Structure):
                                          "d2h_bytes", "bases_bytes")]
 
 
+class HlmFileOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("downsampling", C.c_int32), ("batch_pairs", C.c_int32),
+                ("write_selected", C.c_int32)]
+
+
+class HlmFileStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_pairs", "n_selected", "n_kept", "n_assigned",
+                                         "read_mean_size")] + \
+               [(k, C.c_double) for k in ("s_total", "s_gpu", "s_wait_input", "s_collect", "s_write")]
+
+
 def default_params(rna=0, **kw):
     """main.cpp:73-86 defaults (the float literal 0.08f widened to double included)"""
     p = HlmParams()

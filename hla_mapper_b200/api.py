@@ -24,6 +24,7 @@ SYMBOLS = [
     "hlm_db_locus_name", "hlm_db_size", "hlm_db_stat", "hlm_ctx_create", "hlm_ctx_destroy",
     "hlm_last_error", "hlm_screen_trim", "hlm_score", "hlm_assign", "hlm_run", "hlm_batch_upload",
     "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
+    "hlm_map_fastq",
 ]
 
 _lib = None
@@ -72,6 +73,8 @@ def lib():
                             C.POINTER(HlmAssignOut)]
     L.hlm_get_profile.argtypes = [C.c_void_p, C.POINTER(HlmProfile)]
     L.hlm_int32_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
+    L.hlm_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
     _lib = L
     return L
 
@@ -160,6 +163,15 @@ class Mapper:
 
     def free(self, dev_batch):
         lib().hlm_batch_free(self.h, dev_batch)
+
+    def map_fastq(self, r1, r2, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1):
+        """hlm_map_fastq: FASTQ(.gz) in, the reference's files around the hot path out"""
+        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected)
+        st = _abi.HlmFileStats()
+        self._check(lib().hlm_map_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None,
+                                        sample.encode(), str(out_dir).encode(), C.byref(o),
+                                        C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
 
     def profile(self):
         p = HlmProfile()

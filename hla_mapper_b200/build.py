@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhlamap.so")
-SOURCES = ["hlm_api.cu", "hlm_kernels.cu", "hlm_db.cpp"]
+SOURCES = ["hlm_api.cu", "hlm_kernels.cu", "hlm_db.cpp", "hlm_files.cpp"]
 HEADERS = ["hlm_common.h", "hlm_core.cuh", "hlm_db.h", "hlm_kernels.cuh", "../../include/hlamap.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         log.append(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"])
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -494,6 +494,11 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
 
 }  // namespace
 
+// accessors for the host file pipeline (hlm_files.cpp)
+void hlm_ctx_set_error(hlm_ctx* ctx, const std::string& msg) { ctx->err = msg; }
+const hlm_db* hlm_ctx_db(const hlm_ctx* ctx) { return ctx->db; }
+const hlm_params* hlm_ctx_params(const hlm_ctx* ctx) { return &ctx->p; }
+
 // =====================================================================================
 extern "C" {
 

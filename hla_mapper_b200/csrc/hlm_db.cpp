@@ -155,6 +155,17 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         if (!g.empty() && db->n_loci < HLM_MAX_LOCI) {
           db->names.push_back(g);
           db->n_loci++;
+          // GENE:name:chr:pos:chrsize:optstart:optend:type
+          std::vector<std::string> f;
+          size_t a = 0;
+          while (a <= line.size()) {
+            size_t b = line.find(':', a);
+            if (b == std::string::npos) b = line.size();
+            f.push_back(line.substr(a, b - a));
+            a = b + 1;
+          }
+          db->gene_opt_start.push_back(f.size() > 5 ? atoi(f[5].c_str()) : 0);
+          db->gene_opt_end.push_back(f.size() > 6 ? atoi(f[6].c_str()) : 0);
         }
       } else if (line.compare(0, 5, "SIZE:") == 0) {
         db->v_size = atoi(line.c_str() + 5);

@@ -12,6 +12,7 @@ struct hlm_db {
   int n_loci = 0;
   int v_size = 50;  // src/main.cpp:79; overridden by SIZE: (map_dna.cpp:351-354)
   std::vector<std::string> names;  // n_loci + "others"
+  std::vector<int> gene_opt_start, gene_opt_end;  // GENE: fields 5, 6 (map_dna.cpp:331-332)
 
   // k-mer screen index
   std::vector<uint64_t> kt;

@@ -362,16 +362,21 @@ def make_reads(db: SynthDB, n_pairs, read_len=150, seed=1001, on_target=1.0, fra
     return ReadBatch(n_pairs, fb1, fq1, o1, fb2, fq2, o2, truth, seed, first_pair)
 
 
-def write_fastq(batch: ReadBatch, path_r1, path_r2=None, prefix="SYN", suffix=True):
+def write_fastq(batch: ReadBatch, path_r1, path_r2=None, prefix="SYN", suffix=True, comment=False,
+                gz=False):
+    """suffix: "/1" "/2" after the id; comment: Illumina-style " 1:N:0:ACGT" field; gz: gzip"""
+    import gzip
+
     ids = batch.ids(prefix)
-    for path, b, q, o, tag in ((path_r1, batch.bases1, batch.quals1, batch.offs1, "/1"),
-                               (path_r2, batch.bases2, batch.quals2, batch.offs2, "/2")):
+    for path, b, q, o, tag, mate in ((path_r1, batch.bases1, batch.quals1, batch.offs1, "/1", b"1"),
+                                     (path_r2, batch.bases2, batch.quals2, batch.offs2, "/2", b"2")):
         if path is None:
             continue
-        with open(path, "wb") as f:
+        with (gzip.open(path, "wb", compresslevel=1) if gz else open(path, "wb")) as f:
             for i in range(batch.n_pairs):
                 a, e = int(o[i]), int(o[i + 1])
-                f.write(b"@" + ids[i].encode() + (tag.encode() if suffix else b"") + b"\n")
+                f.write(b"@" + ids[i].encode() + (tag.encode() if suffix else b"")
+                        + (b" " + mate + b":N:0:ACGT" if comment else b"") + b"\n")
                 f.write(b[a:e].tobytes() + b"\n+\n" + q[a:e].tobytes() + b"\n")
 
 

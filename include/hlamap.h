@@ -195,6 +195,28 @@ int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out*
 
 int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out);
 
+/* ---- file-level front / back end of the dna path ----
+ * Reads r1 (+ r2; NULL for single end) as FASTQ or FASTQ.gz, runs hlm_run batch by batch and
+ * writes what the reference writes around the hot path, byte for byte:
+ *   <out>/<sample>_selected.R{1,2}.fastq, _selected.trim.R{1,2}.fastq  (preselect.cpp:861-877,
+ *                                                                      :1121-1149; R0 single end)
+ *   <out>/<sample>_addressing_table.txt                                (map_dna.cpp:932-1051)
+ *   <out>/<sample>_<gene>_R{1,2}.fastq, _<gene>.trim.R{1,2}.fastq      (map_dna.cpp:1056-1351)
+ * Orders the reference leaves to thread timing (selected.R*.fastq records, table rows) are input
+ * order / id order here. */
+typedef struct hlm_file_opts {
+  int32_t struct_size;
+  int32_t downsampling;   /* main.cpp:86 (30); values < 5 become 5 (main.cpp:434)          */
+  int32_t batch_pairs;    /* pairs per hlm_run call (0 = 1 Mi)                              */
+  int32_t write_selected; /* 0: skip <sample>_selected.R*.fastq                             */
+} hlm_file_opts;
+typedef struct hlm_file_stats {
+  int64_t n_pairs, n_selected, n_kept, n_assigned, read_mean_size;
+  double s_total, s_gpu, s_wait_input, s_collect, s_write;
+} hlm_file_stats;
+int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
+                  const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
+
 /* INT32 micro-benchmark (IADD3 / IMAD / VIADDMNMX chains) used as the DP roofline
  * denominator; returns giga warp-lane ops per second */
 int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,

@@ -59,13 +59,56 @@ def rna_splits(rb, buf):
     return out
 
 
-def header_lines(rb, mode):
+# how the FASTQ files of a case are written (synth.write_fastq keywords)
+FASTQ_KW = {
+    "dna_paired_100": dict(suffix=False, comment=True),
+    "dna_ragged": dict(suffix=True, comment=True),
+    "dna_ties": dict(suffix=True, gz=True),
+    "dna_single": dict(suffix=False),
+}
+
+
+def write_inputs(name, rb, mode, root):
+    """FASTQ files of the case -> (r1, r2 or None)"""
+    import os
+
+    kw = dict(FASTQ_KW.get(name, {}))
+    ext = ".fastq.gz" if kw.get("gz") else ".fastq"
+    if mode == "single":
+        r0 = os.path.join(root, "r0" + ext)
+        synth.write_fastq(rb, r0, None, **kw)
+        return r0, None
+    r1, r2 = os.path.join(root, "r1" + ext), os.path.join(root, "r2" + ext)
+    synth.write_fastq(rb, r1, r2, **kw)
+    return r1, r2
+
+
+def header_lines(rb, mode, name=None):
     """the FASTQ header line of R1/R0 as synth.write_fastq writes it"""
-    return ["@" + i + ("/1" if mode != "single" else "") for i in rb.ids()]
+    kw = FASTQ_KW.get(name, {})
+    return ["@" + i + ("/1" if kw.get("suffix", True) else "") + (" 1:N:0:ACGT" if kw.get("comment") else "")
+            for i in rb.ids()]
 
 
-def size_override(rb, mode):
+def size_override(rb, mode, name=None):
     """single-end: sequence_size_r1 = length of the id line (preselect.cpp:1199)"""
     if mode != "single":
         return None
-    return np.array([len(h) for h in header_lines(rb, mode)], dtype=np.int32)
+    return np.array([len(h) for h in header_lines(rb, mode, name)], dtype=np.int32)
+
+
+def canonical_digest(path):
+    """sha256 of a file the reference wrote, after removing the orders it leaves to thread timing:
+    FASTQ -> 4-line records sorted; addressing table -> header + sorted rows"""
+    import hashlib
+
+    data = open(path, "rb").read()
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    if path.endswith("addressing_table.txt"):
+        body = [lines[0]] + sorted(lines[1:])
+    else:
+        recs = [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines), 4)]
+        body = sorted(recs)
+    return hashlib.sha256(b"\n".join(body)).hexdigest() + f":{len(lines)}"

@@ -50,16 +50,13 @@ def main():
     for name in cases.CASES:
         with tempfile.TemporaryDirectory() as tmp:
             db, rb, p, mode = cases.inputs(name, tmp)
+            r1, r2 = cases.write_inputs(name, rb, mode, tmp)
             if mode != "single":
-                r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
-                synth.write_fastq(rb, r1, r2)
                 out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2,
                                        rna=(mode == "rna"))
                 tag = "R1"
             else:
-                r0 = os.path.join(tmp, "r0.fq")
-                synth.write_fastq(rb, r0, None, suffix=False)
-                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r0=r0)
+                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r0=r1)
                 tag = "R0"
             names, rows = rr.parse_addressing_table(out + "G_addressing_table.txt")
             sel = fastq_records(out + f"G_selected.{tag}.fastq")
@@ -67,8 +64,17 @@ def main():
             trim2 = fastq_records(out + "G_selected.trim.R2.fastq") if mode != "single" else {}
             sorted_ = {g: sorted(fastq_records(out + f"G_sorted_{g}_{tag}.fastq")) for g in names[:-1]}
             emitted = {g: sorted(fastq_records(out + f"G_{g}_{tag}.fastq")) for g in names[:-1]}
+            files = {}
+            if mode != "rna":  # byte-level digests of what the reference wrote (file pipeline)
+                want = [f"G_selected.{tag}.fastq", f"G_selected.trim.{tag}.fastq", "G_addressing_table.txt"]
+                for g in names[:-1]:
+                    want += [f"G_{g}_{tag}.fastq", f"G_{g}.trim.{tag}.fastq"]
+                if mode == "paired":
+                    want += [w.replace(tag, "R2") for w in want if tag in w]
+                for w in want:
+                    files[w] = cases.canonical_digest(out + w)
             gold = {
-                "case": name, "mode": mode, "targets": names,
+                "case": name, "mode": mode, "targets": names, "files": files,
                 "selected": sorted(sel),
                 "trim1": trim1, "trim2": trim2,
                 "sorted": sorted_, "emitted": emitted,
