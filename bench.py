@@ -247,6 +247,30 @@ def run_b200(args):
     kept = int(((buf.flags & 2) != 0).sum())
     assigned = int((buf.target_mask != 0).sum())
 
+    # ---- FASTQ text in, the reference's output files out (hlm_map_fastq), rank 0, one pass:
+    # reported beside the metric, not part of it (text parsing is separate)
+    files = None
+    if rank == 0 and not args.no_files:
+        import shutil
+        import tempfile
+
+        tmp = tempfile.mkdtemp(prefix="hlm_files_", dir=os.path.dirname(args.db.rstrip("/")))
+        try:
+            r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
+            synth.write_fastq_fast(rb, r1, r2)
+            os.makedirs(os.path.join(tmp, "out"))
+            t0 = time.perf_counter()
+            st = m.map_fastq(r1, r2, "B", os.path.join(tmp, "out"))
+            dt = time.perf_counter() - t0
+            files = {"value": round(n / dt, 1), "unit": "pairs/s",
+                     "input_bytes": os.path.getsize(r1) + os.path.getsize(r2),
+                     "what": "hlm_map_fastq: 2 plain FASTQ files -> selected / trim / addressing table / "
+                             "per-gene FASTQ files, one reader thread per file",
+                     **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()}}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    barrier()
+
     total_pairs = sum_over_ranks(float(n)) * K
     value = total_pairs / (dev_ms * 1e-3)
     e2e = total_pairs / wall_e2e
@@ -316,6 +340,7 @@ def run_b200(args):
         "e2e": {"value": round(e2e, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d / K),
                 "d2h_bytes_per_step": int(d2h / K)},
         "gpu_launches": int(stage["launches"]),
+        "file_pipeline": files,
         "clocks": clocks,
         "roofline": roof,
         "rooflines": rooflines,
@@ -416,6 +441,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=4000)
     ap.add_argument("--ref-pairs", type=int, default=6000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-files", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

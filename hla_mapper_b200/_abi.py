@@ -61,7 +61,7 @@ class HlmProfile(C.Structure):
                                           "ms_d2h", "ms_total")] + \
                [(k, C.c_int64) for k in ("n_pairs", "n_kept", "n_seed_candidates", "n_candidates", "n_dp",
                                          "n_dp_cells", "n_myers_cols", "launches", "h2d_bytes",
-                                         "d2h_bytes", "bases_bytes")]
+                                         "d2h_bytes", "bases_bytes", "n_overflow_splits")]
 
 
 class HlmFileOpts(C.Structure):

@@ -106,7 +106,12 @@ class Mapper:
 
     def __init__(self, db: Database, device=0, params: HlmParams | None = None, **kw):
         self.db = db
-        self.params = params or _abi.default_params(db.rna, **kw)
+        if params is None:
+            self.params = _abi.default_params(db.rna, **kw)
+        else:  # a private copy with the keyword overrides applied
+            self.params = HlmParams.from_buffer_copy(params)
+            for k, v in kw.items():
+                setattr(self.params, k, v)
         err = C.create_string_buffer(512)
         self.h = lib().hlm_ctx_create(db.h, int(device), C.byref(self.params), err, 512)
         if not self.h:

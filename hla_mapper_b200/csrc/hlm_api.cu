@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@
 #define HLM_STAGE_SCORE 2
 #define HLM_STAGE_ASSIGN 4
 #define HLM_MAX_SLOTS 3
+#define HLM_E_OVERFLOW -100 /* internal: a chunk produced more candidates than cand_capacity */
 
 namespace {
 
@@ -112,10 +114,10 @@ enum { O_FLAGS, O_LO1, O_LEN1, O_LO2, O_LEN2, O_MASK, O_S1, O_S2, O_ALN1, O_ALN2
        O_LEAD1, O_LEAD2, O_TRAIL1, O_TRAIL2, O_TARGET, O_VISIBLE, O_MINSUM, O_OS1, O_OS2, O_COUNTERS,
        O_COUNT };
 size_t out_layout(int64_t n, int T, size_t* off) {
-  size_t sz[O_COUNT] = {(size_t)n, 2u * n, 2u * n, 2u * n, 2u * n, 4u * n,
-                        2u * n * T, 2u * n * T, 2u * n * T, 2u * n * T,
-                        (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T, (size_t)n * T,
-                        (size_t)n * T, 4u * n, 4u * n, 2u * n, 2u * n, 2u * n, 8 * HLM_N_COUNTERS};
+  size_t z = (size_t)n, zt = (size_t)n * (size_t)T;
+  size_t sz[O_COUNT] = {z, 2 * z, 2 * z, 2 * z, 2 * z, 4 * z, 2 * zt, 2 * zt, 2 * zt, 2 * zt,
+                        zt, zt, zt, zt, zt, zt, 4 * z, 4 * z, 2 * z, 2 * z, 2 * z,
+                        (size_t)8 * HLM_N_COUNTERS};
   size_t o = 0;
   for (int i = 0; i < O_COUNT; i++) {
     off[i] = o;
@@ -250,8 +252,8 @@ int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
     pr.n_myers_cols += (int64_t)counters_host[5];
     pr.n_dp += (int64_t)counters_host[6];
     if (counters_host[2]) {
-      ctx->err = "candidate capacity exceeded in a chunk: raise hlm_params.cand_capacity or lower chunk_pairs";
-      return HLM_E_NOMEM;
+      ctx->err = "candidate capacity exceeded for a single pair: raise hlm_params.cand_capacity";
+      return HLM_E_OVERFLOW;  // the caller re-runs the chunk in two halves
     }
     if (counters_host[7]) {
       ctx->err = "a trimmed read is longer than HLM_MAX_READ (184)";
@@ -348,17 +350,9 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
   auto t0 = std::chrono::steady_clock::now();
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
-  int rc = 0;
-  int64_t k = 0;
-  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
-    Slot& s = ctx->slot[k % ctx->n_slots];
-    int64_t n = std::min(C, N - first);
-    // drain the slot's previous chunk
-    if (s.busy) {
-      rc = finish_slot(ctx, s, (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]));
-      scatter_results(ctx, s, io);
-      if (rc) break;
-    }
+  // stage + copy + launch one chunk on a slot (asynchronous)
+  auto submit = [&](Slot& s, int64_t first, int64_t n) -> int {
+    int rc = 0;
     // ---- stage inputs into pinned memory
     size_t b1 = 0, b2 = 0;
     uint64_t f1 = 0, f2 = 0;
@@ -383,13 +377,13 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     sec(7, in->rna_split1 ? n * 2 : 0);
     sec(8, in->rna_split2 ? n * 2 : 0);
     size_t in_bytes = o;
-    if ((rc = ensure_pinned(ctx, s.h_in, in_bytes))) break;
-    if ((rc = ensure_dev(ctx, s.d_in, in_bytes))) break;
+    if ((rc = ensure_pinned(ctx, s.h_in, in_bytes))) return rc;
+    if ((rc = ensure_dev(ctx, s.d_in, in_bytes))) return rc;
     size_t out_bytes = out_layout(n, T, s.out_off);
     s.out_bytes = out_bytes;
-    if ((rc = ensure_pinned(ctx, s.h_out, out_bytes))) break;
-    if ((rc = ensure_dev(ctx, s.d_out, out_bytes))) break;
-    if ((rc = ensure_work(ctx, s, n))) break;
+    if ((rc = ensure_pinned(ctx, s.h_out, out_bytes))) return rc;
+    if ((rc = ensure_dev(ctx, s.d_out, out_bytes))) return rc;
+    if ((rc = ensure_work(ctx, s, n))) return rc;
     uint8_t* h = (uint8_t*)s.h_in.p;
     uint8_t* d = (uint8_t*)s.d_in.p;
     if (need_reads) {
@@ -473,14 +467,36 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     CU(cudaEventRecord(s.ev[EV_D2H], st));
     s.busy = true;
     ctx->prof.bases_bytes += (int64_t)(q ? 2 : 1) * (int64_t)(b1 + b2);
+    return 0;
+  };
+  auto counters_of = [](Slot& s) { return (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]); };
+  // wait for a slot; a chunk whose candidates overflowed the device lists is re-run in halves
+  std::function<int(Slot&)> complete = [&](Slot& s) -> int {
+    if (!s.busy) return 0;
+    int rc = finish_slot(ctx, s, counters_of(s));
+    if (rc == HLM_E_OVERFLOW && s.n > 1) {
+      int64_t first = s.first, n = s.n, h = n / 2;
+      ctx->prof.n_overflow_splits++;
+      if ((rc = submit(s, first, h))) return rc;
+      if ((rc = complete(s))) return rc;
+      if ((rc = submit(s, first + h, n - h))) return rc;
+      return complete(s);
+    }
+    if (rc == HLM_E_OVERFLOW) rc = HLM_E_NOMEM;
+    if (rc == 0) scatter_results(ctx, s, io);
+    return rc;
+  };
+  int rc = 0;
+  int64_t k = 0;
+  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
+    Slot& s = ctx->slot[k % ctx->n_slots];
+    int64_t n = std::min(C, N - first);
+    if ((rc = complete(s))) break;  // drain the slot's previous chunk
+    rc = submit(s, first, n);
   }
   for (int i = 0; i < HLM_MAX_SLOTS; i++) {
-    Slot& s = ctx->slot[(k + i) % HLM_MAX_SLOTS];
-    if (s.busy) {
-      int r2 = finish_slot(ctx, s, (unsigned long long*)((uint8_t*)s.h_out.p + s.out_off[O_COUNTERS]));
-      if (r2 == 0) scatter_results(ctx, s, io);
-      if (rc == 0) rc = r2;
-    }
+    int r2 = complete(ctx->slot[(k + i) % HLM_MAX_SLOTS]);
+    if (rc == 0) rc = r2;
   }
   ctx->prof.n_pairs = N;
   (void)t0;
@@ -803,19 +819,10 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   uint8_t* d = (uint8_t*)b->in.p;
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
-  int rc = 0;
-  int64_t k = 0;
-  unsigned long long cnt[8];
-  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
-    Slot& s = ctx->slot[k % ctx->n_slots];
-    int64_t n = std::min(C, N - first);
-    if (s.busy) {
-      if ((rc = ensure_pinned(ctx, s.h_out, 4096))) break;
-      rc = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
-      if (rc) break;
-    }
-    if ((rc = ensure_pinned(ctx, s.h_out, 4096))) break;
-    if ((rc = ensure_work(ctx, s, n))) break;
+  auto submit = [&](Slot& s, int64_t first, int64_t n) -> int {
+    int rc = 0;
+    if ((rc = ensure_pinned(ctx, s.h_out, 4096))) return rc;
+    if ((rc = ensure_work(ctx, s, n))) return rc;
     HlmChunk& ck = s.ck;
     ck.n_pairs = n;
     ck.bases1 = d + b->in_off[0] + 16;
@@ -837,16 +844,31 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
     CU(cudaMemcpyAsync(s.h_out.p, ck.counters, 8 * HLM_N_COUNTERS, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev[EV_D2H], st));
     s.busy = true;
-    uint64_t nb = 0;
-    (void)nb;
-  }
-  (void)cnt;
-  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
-    Slot& s = ctx->slot[(k + i) % HLM_MAX_SLOTS];
-    if (s.busy) {
-      int r2 = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
-      if (rc == 0) rc = r2;
+    return 0;
+  };
+  std::function<int(Slot&)> complete = [&](Slot& s) -> int {
+    if (!s.busy) return 0;
+    int rc = finish_slot(ctx, s, (unsigned long long*)s.h_out.p);
+    if (rc == HLM_E_OVERFLOW && s.n > 1) {
+      int64_t first = s.first, n = s.n, h = n / 2;
+      ctx->prof.n_overflow_splits++;
+      if ((rc = submit(s, first, h))) return rc;
+      if ((rc = complete(s))) return rc;
+      if ((rc = submit(s, first + h, n - h))) return rc;
+      return complete(s);
     }
+    return rc == HLM_E_OVERFLOW ? HLM_E_NOMEM : rc;
+  };
+  int rc = 0;
+  int64_t k = 0;
+  for (int64_t first = 0; first < N && rc == 0; first += C, k++) {
+    Slot& s = ctx->slot[k % ctx->n_slots];
+    if ((rc = complete(s))) break;
+    rc = submit(s, first, std::min(C, N - first));
+  }
+  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
+    int r2 = complete(ctx->slot[(k + i) % HLM_MAX_SLOTS]);
+    if (rc == 0) rc = r2;
   }
   ctx->prof.n_pairs = N;
   ctx->prof.bases_bytes = b->read_bytes;

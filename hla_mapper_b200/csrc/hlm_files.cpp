@@ -415,8 +415,10 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   double t0 = now_s();
   // std::map<string, ...> order of the reference (byte-wise on the id)
   std::stable_sort(kept.begin(), kept.end(), [](const Kept& a, const Kept& b) { return a.idgen < b.idgen; });
+  // the four groups of output files are independent: write them on separate host threads
+  std::vector<std::thread> writers;
   // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
-  {
+  writers.emplace_back([&] {
     Out t1, t2;
     t1.open(pre + "selected.trim." + tag + ".fastq");
     if (paired) t2.open(pre + "selected.trim.R2.fastq");
@@ -433,10 +435,10 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
     }
     t1.close();
     t2.close();
-  }
+  });
   // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051)
   int64_t n_assigned = 0;
-  {
+  writers.emplace_back([&] {
     Out tb;
     tb.open(pre + "addressing_table.txt");
     std::string line = "Read";
@@ -464,10 +466,13 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       tb.add(line);
     }
     tb.close();
-  }
+  });
   // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351)
   int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
-  for (int g = 0; g < db->n_loci; g++) {
+  int n_gene_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  for (int w = 0; w < n_gene_threads; w++)
+    writers.emplace_back([&, w] {
+  for (int g = w; g < db->n_loci; g += n_gene_threads) {
     const std::string& gene = db->names[g];
     Out r1, r2, c1, c2;
     r1.open(pre + gene + "_" + tag + ".fastq");
@@ -504,6 +509,8 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
     }
     r1.close(); r2.close(); c1.close(); c2.close();
   }
+    });
+  for (auto& th : writers) th.join();
   double t_write = now_s() - t0;
   if (stats) {
     memset(stats, 0, sizeof *stats);

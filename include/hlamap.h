@@ -156,6 +156,7 @@ typedef struct hlm_profile {
   int64_t launches;
   int64_t h2d_bytes, d2h_bytes;
   int64_t bases_bytes; /* bases+quals streamed by the screen kernel               */
+  int64_t n_overflow_splits; /* chunks re-run in halves because their candidate list overflowed */
 } hlm_profile;
 
 void hlm_params_default(hlm_params* p, int rna);

@@ -78,6 +78,28 @@ def test_chunking_does_not_change_results(orc, odb, gdb, small_db, chunk):
     m.close()
 
 
+def test_candidate_overflow_is_handled_by_splitting_chunks(orc, odb, gdb, small_reads):
+    """a chunk whose candidate list does not fit the device buffer is re-run in halves"""
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params()
+    want, _ = orc.run(odb, p, small_reads, mode=1)
+    m = api.Mapper(gdb, 0, p, chunk_pairs=600, cand_capacity=6000)
+    _same(want, m.run(small_reads))
+    assert m.profile()["n_overflow_splits"] > 0
+    h = m.upload(small_reads)
+    m.run_device(h)
+    _same(want, m.fetch(h, small_reads.n_pairs))
+    assert m.profile()["n_overflow_splits"] > 0
+    m.free(h)
+    m.close()
+    # a capacity that a single pair exceeds is an error, not a wrong answer
+    m = api.Mapper(gdb, 0, p, chunk_pairs=64, cand_capacity=3)
+    with pytest.raises(api.HlmError, match="capacity"):
+        m.run(small_reads)
+    m.close()
+
+
 def test_single_end_with_header_length_quirk(orc, odb, gdb, small_db):
     from hla_mapper_b200 import api
 
