@@ -29,6 +29,17 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
   return v;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// pull the 96-byte tile of a candidate towards L2 while the current candidate is being computed
+__device__ __forceinline__ void prefetch_tile(const HlmDevDB& db, uint64_t c) {
+  if (c == 0xFFFFFFFFFFFFFFFFull) return;
+  const uint8_t* t = (const uint8_t*)(db.tiles + (size_t)HLM_CAND_TILE(c) * HLM_TILE_WORDS);
+  prefetch_l2(t);
+  prefetch_l2(t + 95);
+}
+
 // bytes [8*lane, 8*lane+8) of the byte string p[0..len); zero beyond len.  len <= 256.
 __device__ __forceinline__ uint64_t warp_load8(const uint8_t* p, int len, int lane) {
   uintptr_t a = (uintptr_t)p;
@@ -463,18 +474,27 @@ __device__ __forceinline__ int tile_locus(const HlmDevDB& db, uint32_t tile) {
   return g;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// A (tile, off, strand) hit by several read seeds must become ONE candidate.  Each warp keeps the
+// keys it has emitted for the current unit in a shared-memory hash set (exact: full key
+// compare), so duplicates are dropped without touching the tile data; units with more index hits
+// than the set can hold fall back to testing the earlier seeds against the tile.
+#define SEED_WARPS 4
+#define SEED_HT 2048
+#define SEED_HT_MAX 1400
+__global__ void __launch_bounds__(SEED_WARPS * 32)
 k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
-  __shared__ uint32_t s_rd[WARPS_PER_BLOCK][36];
-  __shared__ uint32_t s_pre[WARPS_PER_BLOCK][32], s_beg[WARPS_PER_BLOCK][32];
+  __shared__ uint32_t s_rd[SEED_WARPS][36];
+  __shared__ uint32_t s_pre[SEED_WARPS][32], s_beg[SEED_WARPS][32];
+  __shared__ uint32_t s_ht[SEED_WARPS][SEED_HT];
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t* rd = s_rd[wib];
   uint32_t* pre = s_pre[wib];
   uint32_t* beg = s_beg[wib];
-  int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+  uint32_t* ht = s_ht[wib];
+  int64_t nwarps = (int64_t)gridDim.x * SEED_WARPS;
   int64_t n_units = ck.n_pairs * ck.units_per_pair;
   WarpAppender<uint64_t> app(ck.cand, &ck.counters[0], &ck.counters[2], ck.cand_cap, HLM_CAND_INVALID);
-  for (int64_t unit = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; unit < n_units; unit += nwarps) {
+  for (int64_t unit = (int64_t)blockIdx.x * SEED_WARPS + wib; unit < n_units; unit += nwarps) {
     int n = ck.unit_len[unit];
     if (n == 0) continue;
     uint32_t umask = ck.unit_mask[unit];
@@ -519,6 +539,9 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     uint32_t total = __shfl_sync(FULL, inc, 31);
     pre[lane] = inc - cnt;  // exclusive prefix
     beg[lane] = my_a;
+    bool use_ht = total <= SEED_HT_MAX;
+    if (use_ht)
+      for (int x = lane; x < SEED_HT; x += 32) ht[x] = 0xFFFFFFFFu;
     __syncwarp();
     for (uint32_t base = 0; base < total; base += 32) {
       uint32_t t = base + lane;
@@ -537,14 +560,33 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         off = (int)(e >> 24) - q * HLM_SEED;
         int g = tile_locus(db, tile);
         if ((umask >> g) & 1u) {
-          // candidate (tile, off) belongs to the FIRST read seed that matches it
-          const uint32_t* R = rd + 18 * strand;
-          const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-          own = true;
-          for (int qq = 0; qq < q; qq++) {
-            if (hlm_seed_match(R, T, off, qq)) {
-              own = false;
-              break;
+          if (use_ht) {
+            uint32_t key = (tile << 6) | ((uint32_t)(off - HLM_OFF_MIN) << 1) | (uint32_t)strand;
+            uint32_t h = (key * 2654435761u) >> 21;
+            for (;;) {
+              uint32_t old = atomicCAS(&ht[h], 0xFFFFFFFFu, key);
+              if (old == 0xFFFFFFFFu) {
+                own = true;
+                break;
+              }
+              if (old == key) break;
+              h = (h + 1) & (SEED_HT - 1);
+            }
+          } else {
+            // fallback: the candidate belongs to the first read seed whose index entry hits it
+            // (children only list the seeds that cover one of their differing columns)
+            const uint32_t* R = rd + 18 * strand;
+            const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
+            uint32_t diff = __ldg(db.tile_diff + tile);
+            own = true;
+            for (int qq = 0; qq < q && own; qq++) {
+              if (!hlm_seed_match(R, T, off, qq)) continue;
+              if (HLM_DIFF_N(diff) == 0) own = false;
+              int o = off + qq * HLM_SEED;
+              for (int k = 0; k < HLM_DIFF_N(diff); k++) {
+                int x = HLM_DIFF_COL(diff, k);
+                if (x >= o && x < o + HLM_SEED) own = false;
+              }
             }
           }
         }
@@ -589,6 +631,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
   unsigned long long rows = 0;
   for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
     uint64_t c = ck.cand[i];
+    if (i + stride < ncand) prefetch_tile(db, ck.cand[i + stride]);
     if (c == HLM_CAND_INVALID) continue;
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
@@ -598,23 +641,22 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
     int lb;
     bool dead = false;
     if (phase != 0) {
-      // a child reached by expanding its rep: it is this path's candidate only when its first
-      // matching seed does not cover a differing column (otherwise the seed index emitted it)
+      // a child reached by expanding its rep: it is this path's candidate only when some seed
+      // matches and none of its matching seeds covers a differing column (a covering seed is in
+      // the seed index, which then emitted the candidate)
       uint32_t diff = __ldg(db.tile_diff + tile);
-      int owner = -1, Q = n / HLM_SEED;
-      for (int q = 0; q < Q; q++)
-        if (hlm_seed_match(rd, T, off, q)) {
-          owner = q;
-          break;
-        }
-      dead = owner < 0;
-      if (!dead) {
-        int o = off + owner * HLM_SEED;
+      int Q = n / HLM_SEED;
+      bool any = false;
+      for (int q = 0; q < Q && !dead; q++) {
+        if (!hlm_seed_match(rd, T, off, q)) continue;
+        any = true;
+        int o = off + q * HLM_SEED;
         for (int k = 0; k < HLM_DIFF_N(diff); k++) {
           int x = HLM_DIFF_COL(diff, k);
-          if (x >= o && x < o + HLM_SEED) dead = true;
+          if (x >= o && x < o + HLM_SEED) dead = true;  // the seed index lists this one
         }
       }
+      if (!any) dead = true;
     }
     if (dead) {
       lb = 254;
@@ -776,6 +818,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     uint32_t di = ck.dp_list[i];
     if (di == HLM_DP_INVALID) continue;
     uint64_t c = ck.cand[di];
+    if (i + stride < nd) prefetch_tile(db, ck.cand[ck.dp_list[i + stride]]);
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
@@ -1022,7 +1065,7 @@ void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStre
 }
 void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                      cudaStream_t st) {
-  k_seed<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(db, kp, ck);
+  k_seed<<<grid_for(sms, 6), SEED_WARPS * 32, 0, st>>>(db, kp, ck);
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {

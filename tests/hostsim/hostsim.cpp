@@ -117,9 +117,14 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
       int off = (int)(e >> 24) - q * HLM_SEED;
       if (off < HLM_OFF_MIN || off >= HLM_OFF_MIN + HLM_TILE_STRIDE) continue;
       if (tile < db->tile_start[locus] || tile >= db->tile_start[locus + 1]) continue;
+      // one candidate per (tile, off) hit through the index: the first index entry that hits
+      // it (children only list the seeds covering one of their differing columns)
+      uint32_t diff = db->tile_diff[tile];
       bool first = true;
       for (int qq = 0; qq < q && first; qq++)
-        if (hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, qq)) first = false;
+        if (hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, qq) &&
+            (HLM_DIFF_N(diff) == 0 || seed_covers(diff, off, qq)))
+          first = false;
       if (!first) continue;
       if (cnt < cap) out[cnt] = (tile << 8) | (uint32_t)off;
       cnt++;
@@ -137,10 +142,15 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
         if (col >= off - HLM_BAND && col < off + n + HLM_BAND) inside = true;
       }
       if (!inside) continue;
-      int owner = -1;
-      for (int q = 0; q < Q && owner < 0; q++)
-        if (hlm_seed_match(rd, &db->tiles[(size_t)ch * HLM_TILE_WORDS], off, q)) owner = q;
-      if (owner < 0 || seed_covers(diff, off, owner)) continue;
+      // the expansion owns the child iff some seed matches and no matching seed covers a
+      // differing column (such a seed is in the index, which then produced the candidate)
+      bool any = false, indexed = false;
+      for (int q = 0; q < Q; q++)
+        if (hlm_seed_match(rd, &db->tiles[(size_t)ch * HLM_TILE_WORDS], off, q)) {
+          any = true;
+          if (seed_covers(diff, off, q)) indexed = true;
+        }
+      if (!any || indexed) continue;
       if (cnt < cap) out[cnt] = (ch << 8) | (uint32_t)off;
       cnt++;
     }
