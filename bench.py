@@ -314,7 +314,11 @@ def run_b200(args):
         "k_screen": {"bound": "hbm", "achieved": round(screen_gbs, 1), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(screen_gbs / hbm_peak, 4), "traffic": None,
                      "ms_per_step": round(sc_ms, 3), "bytes_per_step": int(screen_bytes),
-                     "peak_source": hbm_src},
+                     "peak_source": hbm_src,
+                     "probes_per_s": round(n * 130.0 / (sc_ms * 1e-3), 0) if sc_ms > 0 else None,
+                     "limiter": "130 random 8-byte probes per pair into the 134 MB k-mer table (L2 hit "
+                                "48 % in profiles/r1c_kernels_full.txt), not the streaming of the reads; "
+                                "the kernel is 1 % of the step"},
         "k_seed": {"ms_per_step": round(per("ms_seed"), 3),
                    "seed_candidates_per_step": int(kstage["n_seed_candidates"])},
         "k_expand": {"ms_per_step": round(per("ms_expand"), 3),
