@@ -78,6 +78,24 @@ def test_chunking_does_not_change_results(orc, odb, gdb, small_db, chunk):
     m.close()
 
 
+@pytest.mark.parametrize("kw", [
+    dict(tolerance=0.0), dict(tolerance=0.1), dict(mm_max=5), dict(mm_max=12, clip_mode=1),
+    dict(v_size=30), dict(v_size=70), dict(minhit=1), dict(minhit=5, screen_variant=1),
+    dict(mtrim_error=0.01), dict(mtrim_error=0.2), dict(skip_screen=1),
+])
+def test_parameter_variants(orc, odb, gdb, small_db, kw):
+    """size=, tolerance=, error= and the bwa -n limit (main.cpp:73-86, :304-671) reach the kernels"""
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 800, read_len=150, seed=31, on_target=0.8, frag_mu=300,
+                          frag_sd=40, lowq_tail=0.4)
+    p = _abi.default_params(**kw)
+    want, _ = orc.run(odb, p, rb, mode=1)
+    m = api.Mapper(gdb, 0, p)
+    _same(want, m.run(rb))
+    m.close()
+
+
 def test_candidate_overflow_is_handled_by_splitting_chunks(orc, odb, gdb, small_reads):
     """a chunk whose candidate list does not fit the device buffer is re-run in halves"""
     from hla_mapper_b200 import api
