@@ -24,7 +24,7 @@ SYMBOLS = [
     "hlm_db_locus_name", "hlm_db_size", "hlm_db_stat", "hlm_ctx_create", "hlm_ctx_destroy",
     "hlm_last_error", "hlm_screen_trim", "hlm_score", "hlm_assign", "hlm_run", "hlm_batch_upload",
     "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
-    "hlm_map_fastq",
+    "hlm_map_fastq", "hlm_run_async", "hlm_wait",
 ]
 
 _lib = None
@@ -65,6 +65,8 @@ def lib():
                              C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
     L.hlm_run.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
                           C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
+    L.hlm_run_async.argtypes = L.hlm_run.argtypes
+    L.hlm_wait.argtypes = [C.c_void_p]
     L.hlm_batch_upload.restype = C.c_void_p
     L.hlm_batch_upload.argtypes = [C.c_void_p, C.POINTER(HlmBatch)]
     L.hlm_batch_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -131,6 +133,20 @@ class Mapper:
         self._check(lib().hlm_run(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc),
                                   C.byref(buf.asg)))
         return buf
+
+    def run_async(self, rb, buffers=None, **kw):
+        """hlm_run_async; returns the buffers, valid after wait()"""
+        b = self._batch(rb, **kw)
+        buf = buffers or Buffers(rb.n_pairs, self.T)
+        self._check(lib().hlm_run_async(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc),
+                                        C.byref(buf.asg)))
+        self._inflight = (b, buf)  # keep the arrays alive
+        return buf
+
+    def wait(self):
+        rc = lib().hlm_wait(self.h)
+        self._inflight = None
+        self._check(rc)
 
     def screen_trim(self, rb, buffers=None, **kw):
         b = self._batch(rb, **kw)

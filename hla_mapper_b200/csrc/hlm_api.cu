@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -72,6 +73,7 @@ struct hlm_ctx {
   std::string err;
   hlm_profile prof;
   cudaEvent_t run_start = nullptr;
+  std::future<int> pending;  // hlm_run_async
 };
 
 namespace {
@@ -703,6 +705,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
 
 void hlm_ctx_destroy(hlm_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->pending.valid()) ctx->pending.get();
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < HLM_MAX_SLOTS; i++) {
@@ -760,6 +763,37 @@ int hlm_run(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_ou
   io.sc = sc;
   io.asg = asg;
   return run_host(ctx, io, HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ASSIGN);
+}
+
+// asynchronous form: the pipeline runs on a worker thread, the caller overlaps its own host work
+// (parsing the next batch, writing the previous one) and collects the return code with hlm_wait.
+// The arrays named by the arguments must stay valid and untouched until hlm_wait returns; the
+// small argument structs themselves are copied.
+int hlm_run_async(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+                  hlm_assign_out* asg) {
+  if (!ctx || !in) return HLM_E_ARG;
+  if (ctx->pending.valid()) {
+    ctx->err = "hlm_run_async: a run is already in flight (call hlm_wait first)";
+    return HLM_E_ARG;
+  }
+  hlm_batch b = *in;
+  bool hs = scr != nullptr, hc = sc != nullptr, ha = asg != nullptr;
+  hlm_screen_out s1{};
+  hlm_score_out s2{};
+  hlm_assign_out s3{};
+  if (hs) s1 = *scr;
+  if (hc) s2 = *sc;
+  if (ha) s3 = *asg;
+  ctx->pending = std::async(std::launch::async, [ctx, b, s1, s2, s3, hs, hc, ha]() mutable {
+    return hlm_run(ctx, &b, hs ? &s1 : nullptr, hc ? &s2 : nullptr, ha ? &s3 : nullptr);
+  });
+  return HLM_OK;
+}
+
+int hlm_wait(hlm_ctx* ctx) {
+  if (!ctx) return HLM_E_ARG;
+  if (!ctx->pending.valid()) return HLM_OK;
+  return ctx->pending.get();
 }
 
 // ---------------------------------------------------------------- device-resident batches

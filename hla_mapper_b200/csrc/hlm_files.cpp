@@ -217,15 +217,37 @@ void erase_all(std::string& s, const char* pat) {  // boost::replace_all(s, pat,
   while ((p = s.find(pat, p)) != std::string::npos) s.erase(p, n);
 }
 
+// stable bump allocator for the per-read records that are kept until the end of the run
+class Arena {
+ public:
+  char* put(const char* src, size_t n) {
+    char* d = alloc(n);
+    memcpy(d, src, n);
+    return d;
+  }
+  char* alloc(size_t n) {
+    if (blocks_.empty() || used_ + n > cap_) {
+      cap_ = std::max<size_t>(n, (size_t)64 << 20);
+      blocks_.emplace_back(new char[cap_]);
+      used_ = 0;
+    }
+    char* d = blocks_.back().get() + used_;
+    used_ += n;
+    return d;
+  }
+
+ private:
+  std::vector<std::unique_ptr<char[]>> blocks_;
+  size_t cap_ = 0, used_ = 0;
+};
+
 struct Kept {
-  std::string idgen;      // sequence_size_r1 key
-  std::string tok;        // first blank-separated token of the (normalised) header, with '@'
-  std::string h1, h2;     // header lines as written to selected.R*.fastq
-  std::string s1, q1, s2, q2;  // original (untrimmed) records
+  const char *idgen, *h1, *h2, *s1, *q1, *s2, *q2;  // arena pointers
+  const uint16_t *sc1, *sc2;                        // per target
+  uint32_t idl, tokl, h1l, h2l, l1, l2;             // tok = h1[0 .. tokl)
   uint16_t lo1, n1, lo2, n2;
   uint32_t locus_mask, target, visible;
   uint16_t os1, os2;
-  std::vector<uint16_t> sc1, sc2;  // per target
 };
 
 struct Out {
@@ -240,12 +262,13 @@ struct Out {
     if (f && !buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
     buf.clear();
   }
-  void add(const std::string& s) {
-    buf += s;
-    if (buf.size() > (1u << 22)) flush();
-  }
+  void add(const std::string& s) { add(s.data(), s.size()); }
   void add(const char* s, size_t n) {
     buf.append(s, n);
+    if (buf.size() > (1u << 22)) flush();
+  }
+  void fill(char c, size_t n) {
+    buf.append(n, c);
     if (buf.size() > (1u << 22)) flush();
   }
   void close() {
@@ -259,7 +282,47 @@ double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// result arrays of one batch
+struct Results {
+  std::vector<uint8_t> flags;
+  std::vector<uint16_t> lo1, len1, lo2, len2, s1, s2, minsum, os1, os2;
+  std::vector<uint32_t> lmask, target, visible;
+  std::vector<int32_t> so;
+  hlm_batch hb;
+  hlm_screen_out scr;
+  hlm_score_out sc;
+  hlm_assign_out as;
+  MateBatch *b1 = nullptr, *b2 = nullptr;
+  void bind(MateBatch* m1, MateBatch* m2, int T, bool paired) {
+    b1 = m1;
+    b2 = m2;
+    int64_t n = m1->n;
+    flags.resize(n); lo1.resize(n); len1.resize(n); lo2.resize(n); len2.resize(n);
+    lmask.resize(n); target.resize(n); visible.resize(n); minsum.resize(n); os1.resize(n); os2.resize(n);
+    s1.resize((size_t)n * T); s2.resize((size_t)n * T);
+    memset(&hb, 0, sizeof hb);
+    hb.n_pairs = n;
+    hb.bases1 = m1->bases.data(); hb.quals1 = m1->quals.data(); hb.offs1 = m1->offs.data();
+    if (paired) {
+      hb.bases2 = m2->bases.data(); hb.quals2 = m2->quals.data(); hb.offs2 = m2->offs.data();
+    } else {
+      // single end: sequence_size_r1 = length of the header line (src/preselect.cpp:1199)
+      so.resize(n);
+      for (int64_t i = 0; i < n; i++) so[i] = (int32_t)(m1->hoff[i + 1] - m1->hoff[i]);
+      hb.size_override1 = so.data();
+    }
+    scr = {flags.data(), lo1.data(), len1.data(), lo2.data(), len2.data(), lmask.data()};
+    memset(&sc, 0, sizeof sc);
+    sc.s1 = s1.data();
+    sc.s2 = s2.data();
+    as = {target.data(), visible.data(), minsum.data(), os1.data(), os2.data()};
+  }
+};
+
 }  // namespace
+
+extern "C" int hlm_run_async(hlm_ctx*, const hlm_batch*, hlm_screen_out*, hlm_score_out*, hlm_assign_out*);
+extern "C" int hlm_wait(hlm_ctx*);
 
 extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
                              const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
@@ -279,10 +342,10 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   memset(&o, 0, sizeof o);
   o.struct_size = (int32_t)sizeof o;
   o.downsampling = 30;  // src/main.cpp:86
-  o.batch_pairs = 1 << 20;
+  o.batch_pairs = 1 << 19;
   o.write_selected = 1;
   if (opts_in) memcpy(&o, opts_in, std::min((size_t)opts_in->struct_size, sizeof o));
-  if (o.batch_pairs <= 0) o.batch_pairs = 1 << 20;
+  if (o.batch_pairs <= 0) o.batch_pairs = 1 << 19;
   if (o.downsampling < 5) o.downsampling = 5;  // src/main.cpp:434
   int T = db->n_loci + 1;
   std::string out = std::string(out_dir);
@@ -305,132 +368,141 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       return HLM_E_IO;
     }
   }
+  Arena arena;
   std::vector<Kept> kept;
   int64_t n_pairs = 0, n_selected = 0, sel_bases = 0;
-  std::vector<uint8_t> flags;
-  std::vector<uint16_t> lo1, len1, lo2, len2, s1, s2, minsum, os1, os2;
-  std::vector<uint32_t> lmask, target, visible;
-  std::vector<int32_t> so;
-  int rc = 0;
+  std::string h1, h2, idg;
+
+  // what the reference keeps per selected read, taken from a finished batch
+  auto collect = [&](Results& R) {
+    MateBatch *b1 = R.b1, *b2 = R.b2;
+    int64_t n = b1->n;
+    for (int64_t i = 0; i < n; i++) {
+      if (!(R.flags[i] & HLM_F_SCREENED)) continue;
+      n_selected++;
+      h1.assign(b1->hdr.data() + b1->hoff[i], b1->hoff[i + 1] - b1->hoff[i]);
+      if (paired) {  // src/preselect.cpp:664-665, :675-676
+        h2.assign(b2->hdr.data() + b2->hoff[i], b2->hoff[i + 1] - b2->hoff[i]);
+        if (h1.find('/') != std::string::npos) { erase_all(h1, "/1"); erase_all(h1, "/2"); }
+        if (h2.find('/') != std::string::npos) { erase_all(h2, "/1"); erase_all(h2, "/2"); }
+      }
+      const char* s1p = (const char*)b1->bases.data() + b1->offs[i];
+      const char* q1p = (const char*)b1->quals.data() + b1->offs[i];
+      size_t L1 = b1->offs[i + 1] - b1->offs[i], L2 = 0;
+      const char *s2p = nullptr, *q2p = nullptr;
+      if (paired) {
+        s2p = (const char*)b2->bases.data() + b2->offs[i];
+        q2p = (const char*)b2->quals.data() + b2->offs[i];
+        L2 = b2->offs[i + 1] - b2->offs[i];
+      }
+      sel_bases += (int64_t)L1;
+      if (o.write_selected) {
+        sel1.add(h1); sel1.add("\n", 1); sel1.add(s1p, L1); sel1.add("\n+\n", 3); sel1.add(q1p, L1); sel1.add("\n", 1);
+        if (paired) {
+          sel2.add(h2); sel2.add("\n", 1); sel2.add(s2p, L2); sel2.add("\n+\n", 3); sel2.add(q2p, L2); sel2.add("\n", 1);
+        }
+      }
+      if (!(R.flags[i] & HLM_F_KEPT)) continue;
+      kept.emplace_back();
+      Kept& k = kept.back();
+      size_t sp = h1.find(' ');
+      k.tokl = (uint32_t)(sp == std::string::npos ? h1.size() : sp);
+      idg.assign(h1, k.tokl ? 1 : 0, k.tokl ? k.tokl - 1 : 0);
+      if (idg.find('/') != std::string::npos) {  // src/preselect.cpp:1076-1078, :1170-1172
+        erase_all(idg, "/1");
+        erase_all(idg, "/2");
+      }
+      // one arena record: h1 | h2 | s1 | q1 | s2 | q2 | idgen | scores
+      size_t bytes = h1.size() + h2.size() + 2 * L1 + 2 * L2 + idg.size();
+      char* p = arena.alloc(bytes + 1 + 4 * (size_t)T);
+      k.h1 = p; k.h1l = (uint32_t)h1.size(); memcpy(p, h1.data(), h1.size()); p += h1.size();
+      k.h2 = p; k.h2l = (uint32_t)h2.size(); memcpy(p, h2.data(), h2.size()); p += h2.size();
+      k.s1 = p; k.l1 = (uint32_t)L1; memcpy(p, s1p, L1); p += L1;
+      k.q1 = p; memcpy(p, q1p, L1); p += L1;
+      k.s2 = p; k.l2 = (uint32_t)L2; if (L2) memcpy(p, s2p, L2); p += L2;
+      k.q2 = p; if (L2) memcpy(p, q2p, L2); p += L2;
+      k.idgen = p; k.idl = (uint32_t)idg.size(); memcpy(p, idg.data(), idg.size()); p += idg.size();
+      p += ((uintptr_t)p & 1);
+      uint16_t* sc = (uint16_t*)p;
+      memcpy(sc, R.s1.data() + (size_t)i * T, 2 * (size_t)T);
+      memcpy(sc + T, R.s2.data() + (size_t)i * T, 2 * (size_t)T);
+      k.sc1 = sc; k.sc2 = sc + T;
+      k.lo1 = R.lo1[i]; k.n1 = R.len1[i]; k.lo2 = R.lo2[i]; k.n2 = R.len2[i];
+      k.locus_mask = R.lmask[i]; k.target = R.target[i]; k.visible = R.visible[i];
+      k.os1 = R.os1[i]; k.os2 = R.os2[i];
+    }
+    n_pairs += n;
+    in1.recycle(b1);
+    if (paired) in2->recycle(b2);
+  };
+
+  // batch k+1 runs on the GPU (hlm_run_async) while batch k is collected on this thread and the
+  // reader threads parse batch k+2
+  Results res[2];
+  int cur = 0, rc = 0;
+  bool inflight = false;
   for (;;) {
     double t0 = now_s();
     MateBatch* b1 = in1.next();
     MateBatch* b2 = paired ? in2->next() : nullptr;
     t_wait += now_s() - t0;
-    if (!b1 || (paired && !b2)) {
-      if (paired && ((b1 != nullptr) != (b2 != nullptr))) {
-        hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
-        rc = HLM_E_IO;
-      }
-      break;
-    }
-    if (paired && b1->n != b2->n) {
+    bool end = !b1 || (paired && !b2);
+    if (end && paired && ((b1 != nullptr) != (b2 != nullptr))) {
       hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
       rc = HLM_E_IO;
-      break;
     }
-    int64_t n = b1->n;
-    flags.resize(n); lo1.resize(n); len1.resize(n); lo2.resize(n); len2.resize(n);
-    lmask.resize(n); target.resize(n); visible.resize(n); minsum.resize(n); os1.resize(n); os2.resize(n);
-    s1.resize((size_t)n * T); s2.resize((size_t)n * T);
-    hlm_batch hb;
-    memset(&hb, 0, sizeof hb);
-    hb.n_pairs = n;
-    hb.bases1 = b1->bases.data(); hb.quals1 = b1->quals.data(); hb.offs1 = b1->offs.data();
-    if (paired) {
-      hb.bases2 = b2->bases.data(); hb.quals2 = b2->quals.data(); hb.offs2 = b2->offs.data();
-    } else {
-      // single end: sequence_size_r1 = length of the header line (src/preselect.cpp:1199)
-      so.resize(n);
-      for (int64_t i = 0; i < n; i++) so[i] = (int32_t)(b1->hoff[i + 1] - b1->hoff[i]);
-      hb.size_override1 = so.data();
+    if (!end && paired && b1->n != b2->n) {
+      hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
+      rc = HLM_E_IO;
+      end = true;
     }
-    hlm_screen_out scr = {flags.data(), lo1.data(), len1.data(), lo2.data(), len2.data(), lmask.data()};
-    hlm_score_out sc;
-    memset(&sc, 0, sizeof sc);
-    sc.s1 = s1.data();
-    sc.s2 = s2.data();
-    hlm_assign_out as = {target.data(), visible.data(), minsum.data(), os1.data(), os2.data()};
-    t0 = now_s();
-    rc = hlm_run(ctx, &hb, &scr, &sc, &as);
-    t_gpu += now_s() - t0;
-    if (rc) break;
-    t0 = now_s();
-    for (int64_t i = 0; i < n; i++) {
-      if (!(flags[i] & HLM_F_SCREENED)) continue;
-      n_selected++;
-      std::string h1(b1->hdr.data() + b1->hoff[i], b1->hoff[i + 1] - b1->hoff[i]);
-      std::string h2;
-      if (paired) {  // src/preselect.cpp:664-665, :675-676
-        h2.assign(b2->hdr.data() + b2->hoff[i], b2->hoff[i + 1] - b2->hoff[i]);
-        erase_all(h1, "/1"); erase_all(h1, "/2");
-        erase_all(h2, "/1"); erase_all(h2, "/2");
-      }
-      const char* q1raw = (const char*)b1->quals.data() + b1->offs[i];
-      size_t L1 = b1->offs[i + 1] - b1->offs[i];
-      sel_bases += (int64_t)L1;
-      if (o.write_selected) {
-        sel1.add(h1); sel1.add("\n", 1);
-        sel1.add((const char*)b1->bases.data() + b1->offs[i], L1); sel1.add("\n+\n", 3);
-        sel1.add(q1raw, L1); sel1.add("\n", 1);
-        if (paired) {
-          size_t L2 = b2->offs[i + 1] - b2->offs[i];
-          sel2.add(h2); sel2.add("\n", 1);
-          sel2.add((const char*)b2->bases.data() + b2->offs[i], L2); sel2.add("\n+\n", 3);
-          sel2.add((const char*)b2->quals.data() + b2->offs[i], L2); sel2.add("\n", 1);
-        }
-      }
-      if (!(flags[i] & HLM_F_KEPT)) continue;
-      kept.emplace_back();
-      Kept& k = kept.back();
-      k.h1 = h1;
-      k.h2 = h2;
-      size_t sp = h1.find(' ');
-      k.tok = h1.substr(0, sp);
-      k.idgen = k.tok.size() ? k.tok.substr(1) : std::string();
-      erase_all(k.idgen, "/1");  // src/preselect.cpp:1076-1078, :1170-1172
-      erase_all(k.idgen, "/2");
-      k.s1.assign((const char*)b1->bases.data() + b1->offs[i], L1);
-      k.q1.assign(q1raw, L1);
-      if (paired) {
-        size_t L2 = b2->offs[i + 1] - b2->offs[i];
-        k.s2.assign((const char*)b2->bases.data() + b2->offs[i], L2);
-        k.q2.assign((const char*)b2->quals.data() + b2->offs[i], L2);
-      }
-      k.lo1 = lo1[i]; k.n1 = len1[i]; k.lo2 = lo2[i]; k.n2 = len2[i];
-      k.locus_mask = lmask[i]; k.target = target[i]; k.visible = visible[i];
-      k.os1 = os1[i]; k.os2 = os2[i];
-      k.sc1.assign(s1.begin() + (size_t)i * T, s1.begin() + (size_t)(i + 1) * T);
-      k.sc2.assign(s2.begin() + (size_t)i * T, s2.begin() + (size_t)(i + 1) * T);
+    if (inflight) {  // finish the previous batch on the GPU
+      t0 = now_s();
+      int r2 = hlm_wait(ctx);
+      t_gpu += now_s() - t0;
+      inflight = false;
+      if (rc == 0) rc = r2;
     }
-    n_pairs += n;
-    t_post += now_s() - t0;
-    in1.recycle(b1);
-    if (paired) in2->recycle(b2);
+    int prev = cur ^ 1;  // results of the batch that just finished
+    bool have_prev = res[prev].b1 != nullptr;
+    if (!end && rc == 0) {
+      res[cur].bind(b1, b2, T, paired);
+      rc = hlm_run_async(ctx, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
+      inflight = rc == 0;
+    }
+    if (have_prev && rc == 0) {
+      t0 = now_s();
+      collect(res[prev]);
+      t_post += now_s() - t0;
+    }
+    res[prev].b1 = nullptr;
+    if (end || rc) break;
+    cur ^= 1;
   }
+  if (inflight) hlm_wait(ctx);
   sel1.close();
   sel2.close();
   if (rc) return rc;
 
   double t0 = now_s();
   // std::map<string, ...> order of the reference (byte-wise on the id)
-  std::stable_sort(kept.begin(), kept.end(), [](const Kept& a, const Kept& b) { return a.idgen < b.idgen; });
-  // the four groups of output files are independent: write them on separate host threads
+  std::stable_sort(kept.begin(), kept.end(), [](const Kept& a, const Kept& b) {
+    int c = memcmp(a.idgen, b.idgen, std::min(a.idl, b.idl));
+    return c < 0 || (c == 0 && a.idl < b.idl);
+  });
+  // the groups of output files are independent: write them on separate host threads
   std::vector<std::thread> writers;
   // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
   writers.emplace_back([&] {
     Out t1, t2;
     t1.open(pre + "selected.trim." + tag + ".fastq");
     if (paired) t2.open(pre + "selected.trim.R2.fastq");
-    std::string qa;
     for (const Kept& k : kept) {
-      t1.add(k.h1); t1.add("\n", 1);
-      t1.add(k.s1.data() + k.lo1, k.n1); t1.add("\n+\n", 3);
-      qa.assign(k.n1, 'A'); t1.add(qa); t1.add("\n", 1);
+      t1.add(k.h1, k.h1l); t1.add("\n", 1); t1.add(k.s1 + k.lo1, k.n1); t1.add("\n+\n", 3);
+      t1.fill('A', k.n1); t1.add("\n", 1);
       if (paired) {
-        t2.add(k.h2); t2.add("\n", 1);
-        t2.add(k.s2.data() + k.lo2, k.n2); t2.add("\n+\n", 3);
-        qa.assign(k.n2, 'A'); t2.add(qa); t2.add("\n", 1);
+        t2.add(k.h2, k.h2l); t2.add("\n", 1); t2.add(k.s2 + k.lo2, k.n2); t2.add("\n+\n", 3);
+        t2.fill('A', k.n2); t2.add("\n", 1);
       }
     }
     t1.close();
@@ -445,24 +517,30 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
     for (int g = 0; g < T; g++) line += "\t" + db->names[g];
     line += "\tTarget\n";
     tb.add(line);
+    char num[32];
     for (const Kept& k : kept) {
-      line = k.idgen;
+      line.assign(k.idgen, k.idl);
       for (int g = 0; g < T; g++) {
-        line += "\t";
+        line += '\t';
         if (!((k.visible >> g) & 1u)) {
-          line += "-";
+          line += '-';
           continue;
         }
         int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
-        line += std::to_string(a);
-        if (paired) line += "," + std::to_string(b);
+        int m = paired ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
+        line.append(num, m);
       }
-      std::string tg;
+      line += '\t';
+      bool any = false;
       for (int g = 0; g < T; g++)
-        if ((k.target >> g) & 1u) tg += (tg.empty() ? "" : ",") + db->names[g];
-      if (tg.empty()) tg = "-";
+        if ((k.target >> g) & 1u) {
+          if (any) line += ',';
+          line += db->names[g];
+          any = true;
+        }
+      if (!any) line += '-';
       else n_assigned++;
-      line += "\t" + tg + "\n";
+      line += '\n';
       tb.add(line);
     }
     tb.close();
@@ -472,43 +550,40 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   int n_gene_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
   for (int w = 0; w < n_gene_threads; w++)
     writers.emplace_back([&, w] {
-  for (int g = w; g < db->n_loci; g += n_gene_threads) {
-    const std::string& gene = db->names[g];
-    Out r1, r2, c1, c2;
-    r1.open(pre + gene + "_" + tag + ".fastq");
-    c1.open(pre + gene + ".trim." + tag + ".fastq");
-    if (paired) {
-      r2.open(pre + gene + "_R2.fastq");
-      c2.open(pre + gene + ".trim.R2.fastq");
-    }
-    int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
-    int64_t downS = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
-    int64_t counter = 0;
-    std::string qa;
-    for (const Kept& k : kept) {
-      if (!((k.locus_mask >> g) & 1u)) continue;   // was in sorted_<gene>_R1.fastq
-      if (!((k.target >> g) & 1u)) continue;        // sequence_address[(gene, id)]
-      // the lookup key is the header token minus '@' (:1225): it only equals the id when the
-      // token carries no /1 /2 (always true for paired input, whose headers were normalised)
-      if (k.tok.size() < 1 || k.tok.compare(1, std::string::npos, k.idgen) != 0) continue;
-      r1.add(k.h1); r1.add("\n", 1); r1.add(k.s1); r1.add("\n+\n", 3); r1.add(k.q1); r1.add("\n", 1);
-      if (paired) {
-        r2.add(k.h2); r2.add("\n", 1); r2.add(k.s2); r2.add("\n+\n", 3); r2.add(k.q2); r2.add("\n", 1);
-      }
-      if (counter < downS) {
-        c1.add(k.tok); c1.add(" 1:trim\n", 8);
-        c1.add(k.s1.data() + k.lo1, k.n1); c1.add("\n+\n", 3);
-        qa.assign(k.n1, 'A'); c1.add(qa); c1.add("\n", 1);
+      for (int g = w; g < db->n_loci; g += n_gene_threads) {
+        const std::string& gene = db->names[g];
+        Out r1, r2, c1, c2;
+        r1.open(pre + gene + "_" + tag + ".fastq");
+        c1.open(pre + gene + ".trim." + tag + ".fastq");
         if (paired) {
-          c2.add(k.tok); c2.add(" 2:trim\n", 8);
-          c2.add(k.s2.data() + k.lo2, k.n2); c2.add("\n+\n", 3);
-          qa.assign(k.n2, 'A'); c2.add(qa); c2.add("\n", 1);
+          r2.open(pre + gene + "_R2.fastq");
+          c2.open(pre + gene + ".trim.R2.fastq");
         }
+        int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
+        int64_t downS = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
+        int64_t counter = 0;
+        for (const Kept& k : kept) {
+          if (!((k.locus_mask >> g) & 1u)) continue;  // was in sorted_<gene>_R1.fastq
+          if (!((k.target >> g) & 1u)) continue;       // sequence_address[(gene, id)]
+          // the lookup key is the header token minus '@' (:1225): it only equals the id when the
+          // token carries no /1 /2 (always true for paired input, whose headers were normalised)
+          if (k.tokl < 1 || k.tokl - 1 != k.idl || memcmp(k.h1 + 1, k.idgen, k.idl) != 0) continue;
+          r1.add(k.h1, k.h1l); r1.add("\n", 1); r1.add(k.s1, k.l1); r1.add("\n+\n", 3); r1.add(k.q1, k.l1); r1.add("\n", 1);
+          if (paired) {
+            r2.add(k.h2, k.h2l); r2.add("\n", 1); r2.add(k.s2, k.l2); r2.add("\n+\n", 3); r2.add(k.q2, k.l2); r2.add("\n", 1);
+          }
+          if (counter < downS) {
+            c1.add(k.h1, k.tokl); c1.add(" 1:trim\n", 8); c1.add(k.s1 + k.lo1, k.n1); c1.add("\n+\n", 3);
+            c1.fill('A', k.n1); c1.add("\n", 1);
+            if (paired) {
+              c2.add(k.h1, k.tokl); c2.add(" 2:trim\n", 8); c2.add(k.s2 + k.lo2, k.n2); c2.add("\n+\n", 3);
+              c2.fill('A', k.n2); c2.add("\n", 1);
+            }
+          }
+          counter++;
+        }
+        r1.close(); r2.close(); c1.close(); c2.close();
       }
-      counter++;
-    }
-    r1.close(); r2.close(); c1.close(); c2.close();
-  }
     });
   for (auto& th : writers) th.join();
   double t_write = now_s() - t0;

@@ -187,6 +187,12 @@ int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr,
 int hlm_run(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
             hlm_assign_out* asg);
 
+/* asynchronous form of hlm_run: the pipeline runs on a library thread; hlm_wait returns its code.
+ * One run in flight per context; the arrays must stay valid until hlm_wait returns. */
+int hlm_run_async(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+                  hlm_assign_out* asg);
+int hlm_wait(hlm_ctx* ctx);
+
 /* device-resident variant: upload once, run many times (kernel-only timing) */
 hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in);
 void hlm_batch_free(hlm_ctx* ctx, hlm_devbatch* b);
