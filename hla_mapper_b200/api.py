@@ -185,9 +185,11 @@ class Mapper:
     def free(self, dev_batch):
         lib().hlm_batch_free(self.h, dev_batch)
 
-    def map_fastq(self, r1, r2, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1):
+    def map_fastq(self, r1, r2, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1,
+                  select_only=0):
         """hlm_map_fastq: FASTQ(.gz) in, the reference's files around the hot path out"""
-        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected)
+        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
+                             select_only)
         st = _abi.HlmFileStats()
         self._check(lib().hlm_map_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None,
                                         sample.encode(), str(out_dir).encode(), C.byref(o),

@@ -10,8 +10,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhlamap.so")
+CLI = os.path.join(HERE, "hla-mapper-b200")
 SOURCES = ["hlm_api.cu", "hlm_kernels.cu", "hlm_db.cpp", "hlm_files.cpp"]
-HEADERS = ["hlm_common.h", "hlm_core.cuh", "hlm_db.h", "hlm_kernels.cuh", "../../include/hlamap.h"]
+HEADERS = ["hlm_cli.cpp", "hlm_common.h", "hlm_core.cuh", "hlm_db.h", "hlm_kernels.cuh", "../../include/hlamap.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 
@@ -48,6 +49,9 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
     subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"])
+    # the thin `hla-mapper dna|select` command line over the library
+    subprocess.check_call([nvcc(), "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "hlm_cli.cpp"),
+                           "-L" + HERE, "-lhlamap", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

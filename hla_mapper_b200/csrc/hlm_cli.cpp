@@ -1,0 +1,122 @@
+// hlm_cli.cpp — thin command line over libhlamap that keeps the reference's `hla-mapper dna` /
+// `select` key=value interface (src/main.cpp:304-671) for the part of the run the hot path
+// covers.  It is not a re-implementation of hla-mapper's control plane: no setup wizard, no
+// typing, no realignment - it ends where src/map_dna.cpp:1367 begins, leaving the files the
+// downstream steps read (selected*.fastq, addressing_table.txt, per-gene FASTQs).
+//
+//   hla-mapper-b200 dna    r1=R1.fastq[.gz] r2=R2.fastq[.gz] sample=NAME [db=DIR] [output=DIR] ...
+//   hla-mapper-b200 dna    r0=R0.fastq[.gz] sample=NAME ...
+//   hla-mapper-b200 select ...           (screen + trim only: selected*.fastq)
+//
+// Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= --quiet
+// (threads= and buffer= are accepted and ignored: there is no host thread pool to size).
+// db defaults to the `db=` line of ~/.hla-mapper (home from getpwuid, src/main.cpp:266-273).
+#include <pwd.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+
+#include "../../include/hlamap.h"
+
+static bool starts(const std::string& s, const char* k) { return s.compare(0, strlen(k), k) == 0; }
+
+static std::string config_db() {
+  struct passwd* pw = getpwuid(getuid());
+  if (!pw) return "";
+  std::ifstream f(std::string(pw->pw_dir) + "/.hla-mapper");
+  for (std::string line; std::getline(f, line);)
+    if (starts(line, "db=")) return line.substr(3);
+  return "";
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2 || (strcmp(argv[1], "dna") != 0 && strcmp(argv[1], "select") != 0)) {
+    fprintf(stderr,
+            "Usage:     hla-mapper-b200 dna r1=R1.gz r2=R2.gz sample=your_sample_name <options>\n"
+            "           hla-mapper-b200 dna r0=R0.gz sample=your_sample_name <options>\n"
+            "           hla-mapper-b200 select r1=... r2=... sample=... <options>\n"
+            "Options:   db= output= size= tolerance= error= downsample= gpu= --quiet\n");
+    return 1;
+  }
+  bool select_only = strcmp(argv[1], "select") == 0, quiet = false;
+  std::string r0, r1, r2, sample, db, output;
+  double tolerance = -1, error = -1;
+  int size = 0, downsample = 30, gpu = 0;
+  for (int i = 2; i < argc; i++) {
+    std::string a = argv[i];
+    if (starts(a, "r0=")) r0 = a.substr(3);
+    else if (starts(a, "r1=")) r1 = a.substr(3);
+    else if (starts(a, "r2=")) r2 = a.substr(3);
+    else if (starts(a, "sample=")) sample = a.substr(7);
+    else if (starts(a, "db=")) db = a.substr(3);
+    else if (starts(a, "output=")) output = a.substr(7);
+    else if (starts(a, "size=")) size = atoi(a.c_str() + 5);
+    else if (starts(a, "tolerance=")) tolerance = atof(a.c_str() + 10);
+    else if (starts(a, "error=")) error = std::stod(a.substr(6));  // stod, src/main.cpp:658-662
+    else if (starts(a, "downsample=")) downsample = atoi(a.c_str() + 11);
+    else if (starts(a, "gpu=")) gpu = atoi(a.c_str() + 4);
+    else if (a == "--quiet") quiet = true;
+    else if (starts(a, "threads=") || starts(a, "buffer=") || starts(a, "--")) continue;
+    else if (starts(a, "bam=")) {
+      fprintf(stderr, "bam= input needs samtools (src/preselect.cpp:315-418) and is not part of this build\n");
+      return 2;
+    }
+  }
+  bool paired = r0.empty();
+  if (sample.empty() || (paired && (r1.empty() || r2.empty()))) {
+    fprintf(stderr, "You must indicate r1 and r2, or r0, and a sample name.\n");
+    return 2;
+  }
+  if (db.empty()) db = config_db();
+  if (db.empty()) {
+    fprintf(stderr, "No database: pass db= or set it in ~/.hla-mapper\n");
+    return 2;
+  }
+  const std::string& first = paired ? r1 : r0;
+  if (output.empty()) {  // src/map_dna.cpp:404-409
+    size_t sl = first.find_last_of('/');
+    output = (sl == std::string::npos ? std::string(".") : first.substr(0, sl)) + "/hla-mapper/";
+  }
+  mkdir(output.c_str(), 0777);
+  char err[512];
+  hlm_db* D = hlm_db_open(db.c_str(), 0, err, sizeof err);
+  if (!D) {
+    fprintf(stderr, "%s\n", err);
+    return 3;
+  }
+  hlm_params p;
+  hlm_params_default(&p, 0);
+  p.paired = paired ? 1 : 0;
+  if (size > 0) p.v_size = size;
+  if (tolerance >= 0) p.tolerance = tolerance;
+  if (error >= 0) p.mtrim_error = error;
+  hlm_ctx* C = hlm_ctx_create(D, gpu, &p, err, sizeof err);
+  if (!C) {
+    fprintf(stderr, "%s\n", err);
+    hlm_db_close(D);
+    return 3;
+  }
+  hlm_file_opts fo;
+  memset(&fo, 0, sizeof fo);
+  fo.struct_size = (int32_t)sizeof fo;
+  fo.downsampling = downsample;
+  fo.write_selected = 1;
+  fo.select_only = select_only ? 1 : 0;
+  hlm_file_stats st;
+  int rc = hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
+  if (rc != HLM_OK) fprintf(stderr, "hla-mapper-b200: %s\n", hlm_last_error(C));
+  else if (!quiet)
+    fprintf(stderr,
+            "%lld pairs, %lld selected, %lld kept, %lld addressed; %.2fs (gpu wait %.2fs, input wait %.2fs, "
+            "collect %.2fs, write %.2fs) -> %s\n",
+            (long long)st.n_pairs, (long long)st.n_selected, (long long)st.n_kept, (long long)st.n_assigned,
+            st.s_total, st.s_gpu, st.s_wait_input, st.s_collect, st.s_write, output.c_str());
+  hlm_ctx_destroy(C);
+  hlm_db_close(D);
+  return rc == HLM_OK ? 0 : 4;
+}

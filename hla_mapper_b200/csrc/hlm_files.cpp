@@ -321,6 +321,7 @@ struct Results {
 
 }  // namespace
 
+extern "C" int hlm_screen_trim(hlm_ctx*, const hlm_batch*, hlm_screen_out*);
 extern "C" int hlm_run_async(hlm_ctx*, const hlm_batch*, hlm_screen_out*, hlm_score_out*, hlm_assign_out*);
 extern "C" int hlm_wait(hlm_ctx*);
 
@@ -467,8 +468,16 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
     bool have_prev = res[prev].b1 != nullptr;
     if (!end && rc == 0) {
       res[cur].bind(b1, b2, T, paired);
-      rc = hlm_run_async(ctx, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
-      inflight = rc == 0;
+      if (o.select_only) {  // `hla-mapper select`: main_preselect() only
+        double tg = now_s();
+        rc = hlm_screen_trim(ctx, &res[cur].hb, &res[cur].scr);
+        t_gpu += now_s() - tg;
+        std::fill(res[cur].target.begin(), res[cur].target.end(), 0u);
+        std::fill(res[cur].visible.begin(), res[cur].visible.end(), 0u);
+      } else {
+        rc = hlm_run_async(ctx, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
+        inflight = rc == 0;
+      }
     }
     if (have_prev && rc == 0) {
       t0 = now_s();
@@ -510,7 +519,7 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   });
   // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051)
   int64_t n_assigned = 0;
-  writers.emplace_back([&] {
+  if (!o.select_only) writers.emplace_back([&] {
     Out tb;
     tb.open(pre + "addressing_table.txt");
     std::string line = "Read";
@@ -548,7 +557,7 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351)
   int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
   int n_gene_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
-  for (int w = 0; w < n_gene_threads; w++)
+  for (int w = 0; w < n_gene_threads && !o.select_only; w++)
     writers.emplace_back([&, w] {
       for (int g = w; g < db->n_loci; g += n_gene_threads) {
         const std::string& gene = db->names[g];

@@ -216,6 +216,7 @@ typedef struct hlm_file_opts {
   int32_t downsampling;   /* main.cpp:86 (30); values < 5 become 5 (main.cpp:434)          */
   int32_t batch_pairs;    /* pairs per hlm_run call (0 = 1 Mi)                              */
   int32_t write_selected; /* 0: skip <sample>_selected.R*.fastq                             */
+  int32_t select_only;    /* 1: `hla-mapper select`: screen + trim, only selected*.fastq      */
 } hlm_file_opts;
 typedef struct hlm_file_stats {
   int64_t n_pairs, n_selected, n_kept, n_assigned, read_mean_size;
