@@ -24,7 +24,8 @@ SYMBOLS = [
     "hlm_db_locus_name", "hlm_db_size", "hlm_db_stat", "hlm_ctx_create", "hlm_ctx_destroy",
     "hlm_last_error", "hlm_screen_trim", "hlm_score", "hlm_assign", "hlm_run", "hlm_batch_upload",
     "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
-    "hlm_map_fastq", "hlm_run_async", "hlm_wait",
+    "hlm_map_fastq", "hlm_run_async", "hlm_wait", "hlm_multi_create", "hlm_multi_destroy",
+    "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run",
 ]
 
 _lib = None
@@ -67,6 +68,15 @@ def lib():
                           C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
     L.hlm_run_async.argtypes = L.hlm_run.argtypes
     L.hlm_wait.argtypes = [C.c_void_p]
+    L.hlm_multi_create.restype = C.c_void_p
+    L.hlm_multi_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(HlmParams),
+                                   C.c_char_p, C.c_size_t]
+    L.hlm_multi_destroy.argtypes = [C.c_void_p]
+    L.hlm_multi_n_devices.argtypes = [C.c_void_p]
+    L.hlm_multi_last_error.restype = C.c_char_p
+    L.hlm_multi_last_error.argtypes = [C.c_void_p]
+    L.hlm_multi_run.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
+                                C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
     L.hlm_batch_upload.restype = C.c_void_p
     L.hlm_batch_upload.argtypes = [C.c_void_p, C.POINTER(HlmBatch)]
     L.hlm_batch_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -204,6 +214,37 @@ class Mapper:
     def close(self):
         if self.h:
             lib().hlm_ctx_destroy(self.h)
+            self.h = None
+
+
+class MultiMapper:
+    """hlm_multi: every GPU of the box (or the listed ones), pairs sharded by contiguous range"""
+
+    def __init__(self, db: Database, devices=None, params: HlmParams | None = None, **kw):
+        self.db = db
+        self.params = HlmParams.from_buffer_copy(params) if params is not None else _abi.default_params(db.rna)
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        err = C.create_string_buffer(512)
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        self.h = lib().hlm_multi_create(db.h, arr, len(devices) if devices else 0,
+                                        C.byref(self.params), err, 512)
+        if not self.h:
+            raise HlmError(err.value.decode())
+        self.n_devices = lib().hlm_multi_n_devices(self.h)
+        self.T = db.n_loci + 1
+
+    def run(self, rb, buffers=None, **kw):
+        b = _abi.make_batch(rb, paired=bool(self.params.paired), **kw)
+        buf = buffers or Buffers(rb.n_pairs, self.T)
+        rc = lib().hlm_multi_run(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc), C.byref(buf.asg))
+        if rc != 0:
+            raise HlmError(f"libhlamap rc={rc}: {lib().hlm_multi_last_error(self.h).decode()}")
+        return buf
+
+    def close(self):
+        if self.h:
+            lib().hlm_multi_destroy(self.h)
             self.h = None
 
 

@@ -16,6 +16,7 @@
 #include <functional>
 #include <future>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hlm_db.h"
@@ -946,6 +947,92 @@ int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out*
   }
   if (rc) ctx->err = "cudaMemcpy (fetch) failed";
   return rc ? HLM_E_CUDA : 0;
+}
+
+// ---------------------------------------------------------------- all GPUs of the box
+// Pairs are independent (src/map_dna.cpp:917-1029 only touches keys of its own read id): the batch
+// is cut into one contiguous range per GPU, each range runs through its own context on its own
+// host thread, and because outputs are caller-owned arrays the gather is pointer arithmetic.
+// No collective, no peer traffic; the database is replicated.
+struct hlm_multi {
+  std::vector<hlm_ctx*> ctx;
+  int n_targets = 0;
+  std::string err;
+};
+
+hlm_multi* hlm_multi_create(const hlm_db* db, const int* devices, int n_devices, const hlm_params* params,
+                            char* err, size_t errlen) {
+  int ndev = 0;
+  cudaGetDeviceCount(&ndev);
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+  else
+    for (int d = 0; d < ndev; d++) devs.push_back(d);
+  if (devs.empty()) {
+    if (err && errlen) snprintf(err, errlen, "libhlamap needs a CUDA device: there is no CPU path (no device found)");
+    return nullptr;
+  }
+  hlm_multi* m = new hlm_multi();
+  for (int d : devs) {  // sequential: the per-device copy of the database is made here
+    hlm_ctx* c = hlm_ctx_create(db, d, params, err, errlen);
+    if (!c) {
+      for (hlm_ctx* x : m->ctx) hlm_ctx_destroy(x);
+      delete m;
+      return nullptr;
+    }
+    m->ctx.push_back(c);
+  }
+  m->n_targets = db->n_loci + 1;
+  return m;
+}
+
+void hlm_multi_destroy(hlm_multi* m) {
+  if (!m) return;
+  for (hlm_ctx* c : m->ctx) hlm_ctx_destroy(c);
+  delete m;
+}
+
+int hlm_multi_n_devices(const hlm_multi* m) { return m ? (int)m->ctx.size() : 0; }
+const char* hlm_multi_last_error(const hlm_multi* m) { return m ? m->err.c_str() : "null"; }
+
+int hlm_multi_run(hlm_multi* m, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+                  hlm_assign_out* asg) {
+  if (!m || !in) return HLM_E_ARG;
+  int G = (int)m->ctx.size(), T = m->n_targets;
+  int64_t N = in->n_pairs, per = (N + G - 1) / G;
+  std::vector<int> rcs(G, 0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; g++) {
+    int64_t lo = std::min(N, (int64_t)g * per), hi = std::min(N, lo + per);
+    if (lo >= hi) continue;
+    th.emplace_back([=, &rcs]() {
+      hlm_batch b = *in;  // offsets stay absolute: only the offset arrays and per-pair arrays move
+      b.n_pairs = hi - lo;
+      b.offs1 = in->offs1 + lo;
+      if (in->offs2) b.offs2 = in->offs2 + lo;
+      if (in->size_override1) b.size_override1 = in->size_override1 + lo;
+      if (in->rna_split1) b.rna_split1 = in->rna_split1 + lo;
+      if (in->rna_split2) b.rna_split2 = in->rna_split2 + lo;
+      hlm_screen_out s1{};
+      hlm_score_out s2{};
+      hlm_assign_out s3{};
+      auto at = [&](auto* p, int64_t per_pair) { return p ? p + lo * per_pair : p; };
+      if (scr) s1 = {at(scr->flags, 1), at(scr->trim_lo1, 1), at(scr->trim_len1, 1), at(scr->trim_lo2, 1),
+                     at(scr->trim_len2, 1), at(scr->locus_mask, 1)};
+      if (sc) s2 = {at(sc->s1, T), at(sc->s2, T), at(sc->aln1, T), at(sc->aln2, T), at(sc->nm1, T),
+                    at(sc->nm2, T), at(sc->lead1, T), at(sc->lead2, T), at(sc->trail1, T), at(sc->trail2, T)};
+      if (asg) s3 = {at(asg->target_mask, 1), at(asg->visible_mask, 1), at(asg->min_sum, 1),
+                     at(asg->others_s1, 1), at(asg->others_s2, 1)};
+      rcs[g] = hlm_run(m->ctx[g], &b, scr ? &s1 : nullptr, sc ? &s2 : nullptr, asg ? &s3 : nullptr);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < G; g++)
+    if (rcs[g]) {
+      m->err = hlm_last_error(m->ctx[g]);
+      return rcs[g];
+    }
+  return HLM_OK;
 }
 
 int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out) {

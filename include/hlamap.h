@@ -200,6 +200,18 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b);
 int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out* sc,
               hlm_assign_out* asg);
 
+/* all GPUs of one box: one context + host thread per device, the batch cut into one contiguous
+ * range per device, results written straight into the caller's arrays (the pairs
+ * are independent, src/map_dna.cpp:917-1029, so there is no collective).  devices == NULL: all. */
+typedef struct hlm_multi hlm_multi;
+hlm_multi* hlm_multi_create(const hlm_db* db, const int* devices, int n_devices,
+                            const hlm_params* params, char* err, size_t errlen);
+void hlm_multi_destroy(hlm_multi* m);
+int hlm_multi_n_devices(const hlm_multi* m);
+const char* hlm_multi_last_error(const hlm_multi* m);
+int hlm_multi_run(hlm_multi* m, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
+                  hlm_assign_out* asg);
+
 int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out);
 
 /* ---- file-level front / back end of the dna path ----

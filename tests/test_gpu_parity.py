@@ -118,6 +118,42 @@ def test_candidate_overflow_is_handled_by_splitting_chunks(orc, odb, gdb, small_
     m.close()
 
 
+def test_multi_context_sharding_gathers_in_order(orc, odb, gdb, small_db):
+    """hlm_multi_run: contiguous pair ranges on one context per listed device (here the same
+    device three times, or every GPU of the box when there are several), results gathered by
+    pointer arithmetic into the caller's arrays"""
+    import ctypes as C
+
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 1001, read_len=120, seed=12, on_target=0.8, frag_mu=260,
+                          frag_sd=30, ragged=True)
+    p = _abi.default_params()
+    want, _ = orc.run(odb, p, rb, mode=1)
+    mm = api.MultiMapper(gdb, devices=[0, 0, 0], params=p, chunk_pairs=100)
+    assert mm.n_devices == 3
+    _same(want, mm.run(rb))
+    mm.close()
+    mm = api.MultiMapper(gdb, params=p)  # all GPUs of the box
+    assert mm.n_devices >= 1
+    _same(want, mm.run(rb))
+    mm.close()
+
+
+def test_async_run_overlaps_host_work(orc, odb, gdb, small_reads):
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params()
+    want, _ = orc.run(odb, p, small_reads, mode=1)
+    m = api.Mapper(gdb, 0, p)
+    buf = m.run_async(small_reads)
+    with pytest.raises(api.HlmError, match="already in flight"):
+        m.run_async(small_reads)
+    m.wait()
+    _same(want, buf)
+    m.close()
+
+
 def test_single_end_with_header_length_quirk(orc, odb, gdb, small_db):
     from hla_mapper_b200 import api
 
