@@ -9,6 +9,8 @@
 #include "hlm_db.h"
 
 #include <algorithm>
+#include <chrono>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -47,26 +49,43 @@ void load_motifs(const std::string& path, uint32_t bit,
                  std::vector<std::pair<uint64_t, uint32_t>>& out, int64_t& skipped) {
   std::vector<char> buf;
   if (!read_file(path, buf)) return;
-  size_t i = 0, n = buf.size();
-  while (i < n) {
-    size_t e = i;
-    while (e < n && buf[e] != '\n') e++;
-    if (e - i == HLM_MOTIF) {
-      uint64_t key = 0;
-      bool ok = true;
-      for (int x = 0; x < HLM_MOTIF; x++) {
-        unsigned char c = (unsigned char)buf[i + x];
-        int code = (c == 'A') ? 0 : (c == 'C') ? 1 : (c == 'G') ? 2 : (c == 'T') ? 3 : 4;
-        if (code > 3) {
-          ok = false;
-          break;
-        }
-        key |= (uint64_t)code << (2 * x);
-      }
-      if (ok) out.emplace_back(key, bit);
-      else skipped++;
+  size_t n = buf.size();
+  unsigned nt = n > (8u << 20) ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+  std::vector<std::vector<std::pair<uint64_t, uint32_t>>> part(nt);
+  std::vector<int64_t> skip(nt, 0);
+  auto work = [&](unsigned k) {
+    size_t i = n * k / nt, end = n * (k + 1) / nt;
+    if (k > 0) {  // start at the first line that begins inside this chunk
+      while (i < n && buf[i - 1] != '\n') i++;
     }
-    i = e + 1;
+    auto& o = part[k];
+    while (i < end) {
+      size_t e = i;
+      while (e < n && buf[e] != '\n') e++;
+      if (e - i == HLM_MOTIF) {
+        uint64_t key = 0;
+        bool ok = true;
+        for (int x = 0; x < HLM_MOTIF; x++) {
+          unsigned char c = (unsigned char)buf[i + x];
+          int code = (c == 'A') ? 0 : (c == 'C') ? 1 : (c == 'G') ? 2 : (c == 'T') ? 3 : 4;
+          if (code > 3) {
+            ok = false;
+            break;
+          }
+          key |= (uint64_t)code << (2 * x);
+        }
+        if (ok) o.emplace_back(key, bit);
+        else skip[k]++;
+      }
+      i = e + 1;
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned k = 0; k < nt; k++) th.emplace_back(work, k);
+  for (auto& t : th) t.join();
+  for (unsigned k = 0; k < nt; k++) {
+    out.insert(out.end(), part[k].begin(), part[k].end());
+    skipped += skip[k];
   }
 }
 
@@ -129,7 +148,17 @@ inline uint64_t mix64(uint64_t h, uint64_t v) {
 
 }  // namespace
 
+static double db_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define DB_T(label)                                                                   \
+  if (getenv("HLM_DB_TIMING")) {                                                      \
+    fprintf(stderr, "[hlm_db] %-28s %.2fs\n", label, db_now() - t_stage);             \
+    t_stage = db_now();                                                               \
+  }
+
 hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
+  double t_stage = db_now();
   std::string base(dir);
   const char* kind = rna ? "rna" : "dna";
   std::vector<char> info;
@@ -220,21 +249,27 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     if (db->mask_tab.empty()) db->mask_tab.push_back(0);
   }
 
+  DB_T("k-mer table")
   // ---- tiles: per locus, distinct 256-column windows at stride 32 of the padded alleles.
   // A new window that differs from an earlier window of the same locus and window index in
   // <= HLM_KMAX columns becomes a "child" of that representative; everything else is a "rep".
-  db->tile_start.assign(db->n_loci + 2, 0);
-  for (int g = 0; g <= db->n_loci; g++) {
-    db->tile_start[g] = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+  // loci are independent: build their tile sets on host threads, then concatenate
+  struct LocusTiles {
+    std::vector<uint32_t> tiles, parent, diff;
+    int64_t n_alleles = 0, n_bases = 0, n_raw = 0, n_reps = 0;
+  };
+  std::vector<LocusTiles> per(db->n_loci + 1);
+  auto build_locus = [&](int g) {
+    LocusTiles& L = per[g];
     std::vector<Planes> al;
     std::string path = g < db->n_loci
                            ? base + "/mapper/" + kind + "/" + db->names[g] + "/" + db->names[g] + ".fas"
                            : base + "/others/" + kind + "/hla_gen_others.fasta";
-    load_fasta(path, al, db->n_bases);
-    db->n_alleles += (int64_t)al.size();
+    load_fasta(path, al, L.n_bases);
+    L.n_alleles += (int64_t)al.size();
     size_t raw = 0;
     for (auto& P : al) raw += (size_t)(HLM_PAD + P.len) / 32 + 1;
-    db->n_tiles_raw += (int64_t)raw;
+    L.n_raw += (int64_t)raw;
     size_t cap = 1024;
     while (cap < raw * 2) cap <<= 1;
     std::vector<uint32_t> slot(cap, 0xFFFFFFFFu);  // tile id per hash slot
@@ -256,16 +291,16 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         size_t s = h & (cap - 1);
         bool found = false;
         while (slot[s] != 0xFFFFFFFFu) {
-          if (memcmp(&db->tiles[(size_t)slot[s] * HLM_TILE_WORDS], w, sizeof w) == 0) {
+          if (memcmp(&L.tiles[(size_t)slot[s] * HLM_TILE_WORDS], w, sizeof w) == 0) {
             found = true;
             break;
           }
           s = (s + 1) & (cap - 1);
         }
         if (found) continue;
-        uint32_t id = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+        uint32_t id = (uint32_t)(L.tiles.size() / HLM_TILE_WORDS);
         slot[s] = id;
-        db->tiles.insert(db->tiles.end(), w, w + HLM_TILE_WORDS);
+        L.tiles.insert(L.tiles.end(), w, w + HLM_TILE_WORDS);
         // nearest representative at this window index
         uint32_t best_rep = id, best_diff = 0;
         int best_n = HLM_KMAX + 1;
@@ -281,7 +316,7 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         std::sort(seen.begin(), seen.end());
         seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
         for (uint32_t r : seen) {
-          const uint32_t* R = &db->tiles[(size_t)r * HLM_TILE_WORDS];
+          const uint32_t* R = &L.tiles[(size_t)r * HLM_TILE_WORDS];
           int n = 0;
           uint32_t dmask[8];
           for (int x = 0; x < 8 && n < best_n; x++) {
@@ -300,12 +335,36 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         }
         if (best_rep == id) {
           for (int x = 0; x < 8; x++) rep_lsh[keys[x]].push_back(id);
-          db->n_reps++;
+          L.n_reps++;
         }
-        db->tile_parent.push_back(best_rep);
-        db->tile_diff.push_back(best_diff);
+        L.parent.push_back(best_rep);
+        L.diff.push_back(best_diff);
       }
     }
+  };
+  {
+    std::atomic<int> next(0);
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), db->n_loci + 1));
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; k++)
+      th.emplace_back([&] {
+        for (int g; (g = next.fetch_add(1)) <= db->n_loci;) build_locus(g);
+      });
+    for (auto& t : th) t.join();
+  }
+  db->tile_start.assign(db->n_loci + 2, 0);
+  for (int g = 0; g <= db->n_loci; g++) {
+    LocusTiles& L = per[g];
+    uint32_t base_id = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
+    db->tile_start[g] = base_id;
+    db->tiles.insert(db->tiles.end(), L.tiles.begin(), L.tiles.end());
+    for (uint32_t pr : L.parent) db->tile_parent.push_back(pr + base_id);
+    db->tile_diff.insert(db->tile_diff.end(), L.diff.begin(), L.diff.end());
+    db->n_alleles += L.n_alleles;
+    db->n_bases += L.n_bases;
+    db->n_tiles_raw += L.n_raw;
+    db->n_reps += L.n_reps;
+    L = LocusTiles();
   }
   size_t n_tiles = db->tiles.size() / HLM_TILE_WORDS;
   db->tile_start[db->n_loci + 1] = (uint32_t)n_tiles;
@@ -314,6 +373,7 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     delete db;
     return nullptr;
   }
+  DB_T("tiles + hierarchy")
   // children CSR
   db->child_off.assign(n_tiles + 1, 0);
   for (size_t t = 0; t < n_tiles; t++)
@@ -331,12 +391,15 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
       }
   }
 
+  DB_T("children CSR")
   // ---- seed index: CSR over 12-mers.  Reps: every seed start column in [OFF_MIN, 256-12];
   // children: only the seeds that cover one of their differing columns (every other seed of a
   // child is also a seed of its rep; such candidates are produced by expanding the rep).
   db->seed_off.assign((size_t)HLM_SEED_CODES + 1, 0);
-  auto scan = [&](bool fill, std::vector<uint32_t>& cursor) {
-    for (size_t t = 0; t < n_tiles; t++) {
+  // both passes run over disjoint tile ranges on host threads; slots are claimed with atomic adds
+  // (the order inside one 12-mer does not matter: every range is sorted afterwards)
+  auto scan_range = [&](bool fill, std::vector<uint32_t>& cursor, size_t t_lo, size_t t_hi) {
+    for (size_t t = t_lo; t < t_hi; t++) {
       const uint32_t* T = &db->tiles[t * HLM_TILE_WORDS];
       uint32_t dd = db->tile_diff[t];
       int nd = HLM_DIFF_N(dd);
@@ -361,11 +424,18 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
             }
             if (!covers) continue;
           }
-          if (!fill) db->seed_off[code + 1]++;
-          else db->seed_ent[cursor[code]++] = ((uint32_t)o << 24) | (uint32_t)t;
+          if (!fill) __atomic_fetch_add(&db->seed_off[code + 1], 1u, __ATOMIC_RELAXED);
+          else db->seed_ent[__atomic_fetch_add(&cursor[code], 1u, __ATOMIC_RELAXED)] = ((uint32_t)o << 24) | (uint32_t)t;
         }
       }
     }
+  };
+  auto scan = [&](bool fill, std::vector<uint32_t>& cursor) {
+    unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; k++)
+      th.emplace_back([&, k] { scan_range(fill, cursor, n_tiles * k / nt, n_tiles * (k + 1) / nt); });
+    for (auto& t : th) t.join();
   };
   std::vector<uint32_t> cursor;
   scan(false, cursor);
@@ -373,6 +443,7 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   db->seed_ent.resize(db->seed_off[HLM_SEED_CODES]);
   cursor.assign(db->seed_off.begin(), db->seed_off.end() - 1);
   scan(true, cursor);
+  DB_T("seed index scan x2")
   // entries of one 12-mer sorted by (column, tile): a read seed at offset 12q can only use columns
   // [OFF_MIN + 12q, OFF_MIN + 32 + 12q), which the kernel finds by binary search
   {
@@ -388,5 +459,6 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
       });
     for (auto& t : th) t.join();
   }
+  DB_T("seed index sort")
   return db;
 }
