@@ -25,7 +25,7 @@ SYMBOLS = [
     "hlm_last_error", "hlm_screen_trim", "hlm_score", "hlm_assign", "hlm_run", "hlm_batch_upload",
     "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
     "hlm_map_fastq", "hlm_run_async", "hlm_wait", "hlm_multi_create", "hlm_multi_destroy",
-    "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run",
+    "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run", "hlm_dp_layout_ab",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def lib():
     L.hlm_multi_last_error.argtypes = [C.c_void_p]
     L.hlm_multi_run.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
                                 C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
+    L.hlm_dp_layout_ab.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.hlm_batch_upload.restype = C.c_void_p
     L.hlm_batch_upload.argtypes = [C.c_void_p, C.POINTER(HlmBatch)]
     L.hlm_batch_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -246,6 +248,20 @@ class MultiMapper:
         if self.h:
             lib().hlm_multi_destroy(self.h)
             self.h = None
+
+
+def dp_layout_ab(device=0, n_cands=1 << 18, read_len=150):
+    """thread-per-candidate vs warp-per-candidate DP on the same synthetic candidates"""
+    a, b = C.c_double(0), C.c_double(0)
+    bad, cells = C.c_int64(0), C.c_int64(0)
+    rc = lib().hlm_dp_layout_ab(int(device), int(n_cands), int(read_len), C.byref(a), C.byref(b),
+                                C.byref(bad), C.byref(cells))
+    if rc != 0:
+        raise HlmError(f"hlm_dp_layout_ab rc={rc}")
+    return {"ms_thread_per_candidate": a.value, "ms_warp_per_candidate": b.value,
+            "mismatching_results": bad.value, "cells": cells.value,
+            "gcups_thread_per_candidate": cells.value / a.value / 1e6,
+            "gcups_warp_per_candidate": cells.value / b.value / 1e6}
 
 
 def int32_peak(device=0):

@@ -1035,6 +1035,94 @@ int hlm_multi_run(hlm_multi* m, const hlm_batch* in, hlm_screen_out* scr, hlm_sc
   return HLM_OK;
 }
 
+// A/B of the two DP work layouts on synthetic candidates (see k_dpab_* in hlm_kernels.cu)
+int hlm_dp_layout_ab(int cuda_device, int n_cands, int read_len, double* ms_thread, double* ms_warp,
+                     int64_t* n_mismatch, int64_t* n_cells) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cuda_device < 0 || cuda_device >= ndev) return HLM_E_NODEVICE;
+  if (n_cands <= 0 || read_len < 20 || read_len > HLM_MAX_READ) return HLM_E_ARG;
+  cudaSetDevice(cuda_device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  int m = n_cands, n = read_len;
+  std::vector<uint32_t> reads((size_t)m * 18), tiles((size_t)m * HLM_TILE_WORDS);
+  std::vector<int> offn((size_t)m * 2);
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (uint32_t)(st >> 32); };
+  std::vector<uint8_t> t(256), r(HLM_MAX_READ + 8);
+  for (int c = 0; c < m; c++) {
+    for (int x = 0; x < 256; x++) t[x] = (uint8_t)(rnd() & 3);
+    if (rnd() % 8 == 0) t[rnd() % 256] = 4;
+    int off = HLM_OFF_MIN + (int)(rnd() % HLM_TILE_STRIDE), len = n;
+    int shift = (int)(rnd() % 7) - 3, k = 0;
+    for (int x = 0; x < len; x++) r[k++] = t[std::min(255, std::max(0, off + shift + x))];
+    int nerr = rnd() % 16;
+    for (int e = 0; e < nerr; e++) r[rnd() % len] = (uint8_t)(rnd() % 5);
+    if (rnd() % 3 == 0) {  // a small indel
+      int p = 5 + (int)(rnd() % (len - 10)), g = 1 + (int)(rnd() % 3);
+      if (rnd() & 1) memmove(&r[p], &r[p + g], len - p - g);
+      else { memmove(&r[p + g], &r[p], len - p - g); for (int x = 0; x < g; x++) r[p + x] = (uint8_t)(rnd() & 3); }
+    }
+    if (rnd() % 4 == 0) for (int x = 0, j = 1 + (int)(rnd() % 12); x < j; x++) r[x] = (uint8_t)(rnd() & 3);
+    if (rnd() % 4 == 0) for (int x = 0, j = 1 + (int)(rnd() % 12); x < j; x++) r[len - 1 - x] = (uint8_t)(rnd() & 3);
+    uint32_t* R = &reads[(size_t)c * 18];
+    for (int x = 0; x < 18; x++) R[x] = x >= 12 ? 0xFFFFFFFFu : 0u;
+    for (int x = 0; x < len; x++) {
+      if (r[x] > 3) continue;
+      R[12 + (x >> 5)] &= ~(1u << (x & 31));
+      if (r[x] & 1) R[x >> 5] |= 1u << (x & 31);
+      if (r[x] & 2) R[6 + (x >> 5)] |= 1u << (x & 31);
+    }
+    uint32_t* Tt = &tiles[(size_t)c * HLM_TILE_WORDS];
+    for (int x = 0; x < HLM_TILE_WORDS; x++) Tt[x] = 0;
+    for (int x = 0; x < 256; x++) {
+      if (t[x] > 3) { Tt[16 + (x >> 5)] |= 1u << (x & 31); continue; }
+      if (t[x] & 1) Tt[x >> 5] |= 1u << (x & 31);
+      if (t[x] & 2) Tt[8 + (x >> 5)] |= 1u << (x & 31);
+    }
+    offn[2 * c] = off;
+    offn[2 * c + 1] = len;
+  }
+  uint32_t *d_r = nullptr, *d_t = nullptr;
+  int* d_o = nullptr;
+  int4 *d_a = nullptr, *d_b = nullptr;
+  if (cudaMalloc(&d_r, reads.size() * 4) || cudaMalloc(&d_t, tiles.size() * 4) || cudaMalloc(&d_o, offn.size() * 4) ||
+      cudaMalloc(&d_a, (size_t)m * 16) || cudaMalloc(&d_b, (size_t)m * 16))
+    return HLM_E_NOMEM;
+  cudaMemcpy(d_r, reads.data(), reads.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_t, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_o, offn.data(), offn.size() * 4, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double ms[2] = {0, 0};
+  for (int which = 0; which < 2; which++) {
+    int4* out = which ? d_b : d_a;
+    hlm_launch_dpab(which, d_r, d_t, d_o, m, out, prop.multiProcessorCount, 0);
+    cudaEventRecord(e0, 0);
+    for (int rep = 0; rep < 3; rep++) hlm_launch_dpab(which, d_r, d_t, d_o, m, out, prop.multiProcessorCount, 0);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float f = 0;
+    cudaEventElapsedTime(&f, e0, e1);
+    ms[which] = f / 3.0;
+  }
+  std::vector<int> a((size_t)m * 4), b((size_t)m * 4);
+  cudaMemcpy(a.data(), d_a, (size_t)m * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(b.data(), d_b, (size_t)m * 16, cudaMemcpyDeviceToHost);
+  int64_t bad = 0;
+  for (size_t i = 0; i < a.size(); i += 4)
+    if (memcmp(&a[i], &b[i], 16) != 0) bad++;
+  cudaError_t ce = cudaGetLastError();
+  cudaFree(d_r); cudaFree(d_t); cudaFree(d_o); cudaFree(d_a); cudaFree(d_b);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms_thread) *ms_thread = ms[0];
+  if (ms_warp) *ms_warp = ms[1];
+  if (n_mismatch) *n_mismatch = bad;
+  if (n_cells) *n_cells = (int64_t)m * n * HLM_NB;
+  return ce == cudaSuccess ? HLM_OK : HLM_E_CUDA;
+}
+
 int hlm_get_profile(const hlm_ctx* ctx, hlm_profile* out) {
   if (!ctx || !out) return HLM_E_ARG;
   *out = ctx->prof;

@@ -990,6 +990,103 @@ k_assign(HlmKParams kp, HlmChunk ck, int n_targets) {
   }
 }
 
+// ------------------------------------------------------------------ DP layout A/B (evidence)
+// The same banded affine DP in the two work layouts, on flat arrays of (read planes, tile, off):
+//   k_dpab_thread  thread per candidate, band row in registers (what k_dp does)
+//   k_dpab_warp    warp per candidate, band cells across lanes (lane k owns cells k and k + 32),
+//                  neighbours fetched with shuffles, the horizontal-gap recurrence as a warp
+//                  max-plus prefix scan - the "wavefront with warp shuffles" layout
+// Results are bit-identical (tests/test_gpu_parity.py); bench.py reports both cell rates.
+__global__ void __launch_bounds__(128)
+k_dpab_thread(const uint32_t* __restrict__ reads, const uint32_t* __restrict__ tiles,
+              const int* __restrict__ offn, int m, int one, int4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    HlmAln a = hlm_dp_align(reads + (size_t)i * 18, offn[2 * i + 1], tiles + (size_t)i * HLM_TILE_WORDS,
+                            offn[2 * i], one);
+    out[i] = make_int4(a.S, a.cost, a.lead, a.trail);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_dpab_warp(const uint32_t* __restrict__ reads, const uint32_t* __restrict__ tiles,
+            const int* __restrict__ offn, int m, int4* __restrict__ out) {
+  int lane = threadIdx.x & 31;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int GE = -HLM_V_GAPE, GO = -HLM_V_GAPO;
+  bool has1 = lane < HLM_NB - 32;  // lanes 0..8 also own cell lane + 32
+  for (int c = warp; c < m; c += nwarps) {
+    const uint32_t* rd = reads + (size_t)c * 18;
+    const uint32_t* T = tiles + (size_t)c * HLM_TILE_WORDS;
+    int off = offn[2 * c], n = offn[2 * c + 1];
+    int H0 = 0, E0 = HLM_V_NEG, H1 = 0, E1 = HLM_V_NEG;
+    long long best = -(1ll << 60);  // (value << 8 | row) of this lane's cells
+    int start = 0, trailpen = HLM_V_CLIP + n * HLM_CU;
+    for (int i = 1; i <= n; i++) {
+      int pos = off - HLM_BAND + (i - 1), w = pos >> 5, sh = pos & 31;
+      uint32_t r0 = (rd[(i - 1) >> 5] >> ((i - 1) & 31)) & 1u, r1 = (rd[6 + ((i - 1) >> 5)] >> ((i - 1) & 31)) & 1u,
+               rn = (rd[12 + ((i - 1) >> 5)] >> ((i - 1) & 31)) & 1u;
+      uint32_t m0 = 0u - r0, m1 = 0u - r1, mn = 0u - rn;
+      uint32_t eq_lo = ~(hlm_funnel(hlm_tw(T, w), hlm_tw(T, w + 1), sh) ^ m0) &
+                       ~(hlm_funnel(hlm_tw(T + 8, w), hlm_tw(T + 8, w + 1), sh) ^ m1) &
+                       ~(hlm_funnel(hlm_tw(T + 16, w), hlm_tw(T + 16, w + 1), sh) | mn);
+      uint32_t eq_hi = ~(hlm_funnel(hlm_tw(T, w + 1), hlm_tw(T, w + 2), sh) ^ m0) &
+                       ~(hlm_funnel(hlm_tw(T + 8, w + 1), hlm_tw(T + 8, w + 2), sh) ^ m1) &
+                       ~(hlm_funnel(hlm_tw(T + 16, w + 1), hlm_tw(T + 16, w + 2), sh) | mn);
+      start = (i == 1) ? -(HLM_V_CLIP + HLM_CU + 1) : start - (HLM_CU + 1);
+      trailpen -= HLM_CU;
+      // vertical predecessors: cell k + 1 of the previous row
+      int Hu0 = __shfl_down_sync(FULL, H0, 1), Eu0 = __shfl_down_sync(FULL, E0, 1);
+      int Hx = __shfl_sync(FULL, H1, 0), Ex = __shfl_sync(FULL, E1, 0);
+      if (lane == 31) { Hu0 = Hx; Eu0 = Ex; }
+      int Hu1 = __shfl_down_sync(FULL, H1, 1), Eu1 = __shfl_down_sync(FULL, E1, 1);
+      int e0 = hlm_max(Eu0 + HLM_V_GAPE, Hu0 + HLM_V_GAPO);
+      int e1 = (lane < HLM_NB - 33) ? hlm_max(Eu1 + HLM_V_GAPE, Hu1 + HLM_V_GAPO) : HLM_V_NEG;
+      int hp0 = hlm_max3(H0 + (((eq_lo >> lane) & 1u) ? HLM_V_MATCH : HLM_V_MISM), e0, start);
+      int hp1 = has1 ? hlm_max3(H1 + (((eq_hi >> lane) & 1u) ? HLM_V_MATCH : HLM_V_MISM), e1, start) : HLM_V_NEG;
+      // horizontal gaps: f_k = max_{j<k} (hp_j + j*GE) - GO - (k-1)*GE   (max-plus prefix scan)
+      int u0 = hp0 + lane * GE, s0 = u0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(FULL, s0, o);
+        if (lane >= o) s0 = hlm_max(s0, v);
+      }
+      int ex0 = __shfl_up_sync(FULL, s0, 1);  // exclusive
+      int tot0 = __shfl_sync(FULL, s0, 31);
+      int f0 = lane == 0 ? HLM_V_NEG : ex0 - GO - (lane - 1) * GE;
+      int u1 = has1 ? hp1 + (lane + 32) * GE : HLM_V_NEG, s1 = u1;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        int v = __shfl_up_sync(FULL, s1, o);
+        if (lane >= o) s1 = hlm_max(s1, v);
+      }
+      int ex1 = __shfl_up_sync(FULL, s1, 1);
+      ex1 = lane == 0 ? tot0 : hlm_max(ex1, tot0);
+      int f1 = ex1 - GO - (lane + 31) * GE;
+      int h0 = hlm_max(hp0, f0), h1 = has1 ? hlm_max(hp1, f1) : HLM_V_NEG;
+      H0 = h0; E0 = e0; H1 = h1; E1 = e1;
+      int fin = hlm_max(h0, h1) - (i < n ? trailpen : 0);
+      long long key = ((long long)fin << 8) | (long long)i;
+      if (key > best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      long long v = __shfl_xor_sync(FULL, best, o);
+      if (v > best) best = v;
+    }
+    if (lane == 0) {
+      int bv = (int)(best >> 8), bi = (int)(best & 0xFF);
+      int S = (bv + HLM_SC - 1) >> 20, rem = S * HLM_SC - bv;
+      out[c] = make_int4(S, rem >> 9, rem & 511, n - bi);
+    }
+  }
+}
+
+void hlm_launch_dpab(int which, const uint32_t* reads, const uint32_t* tiles, const int* offn, int m,
+                     int4* out, int sms, cudaStream_t st) {
+  if (which == 0) k_dpab_thread<<<sms * 4, 128, 0, st>>>(reads, tiles, offn, m, 1, out);
+  else k_dpab_warp<<<sms * 8, 256, 0, st>>>(reads, tiles, offn, m, out);
+}
+
 // ------------------------------------------------------------------ INT32 peak micro-kernels
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_int_peak(int* out, int iters, int seed) {

@@ -242,6 +242,14 @@ int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const 
 int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,
                    double* giga_viaddmnmx);
 
+/* A/B of the two work layouts of the banded DP on synthetic candidates: thread per candidate with
+ * the band row in registers (the product kernel) versus warp per candidate with the band across
+ * lanes, shuffles and a max-plus prefix scan for the horizontal gaps (the "wavefront with warp
+ * shuffles" layout).  Returns the kernel times, the number of candidates whose results differ
+ * (must be 0) and the algorithmic cells per launch. */
+int hlm_dp_layout_ab(int cuda_device, int n_cands, int read_len, double* ms_thread, double* ms_warp,
+                     int64_t* n_mismatch, int64_t* n_cells);
+
 #ifdef __cplusplus
 }
 #endif

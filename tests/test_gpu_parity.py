@@ -140,6 +140,18 @@ def test_multi_context_sharding_gathers_in_order(orc, odb, gdb, small_db):
     mm.close()
 
 
+def test_dp_layouts_agree_bit_for_bit():
+    """thread-per-candidate (product) and warp-per-candidate (shuffle wavefront) DP kernels"""
+    from hla_mapper_b200 import api
+
+    for n in (150, 100, 57, 184):
+        r = api.dp_layout_ab(0, 40000, n)
+        assert r["mismatching_results"] == 0, r
+    r = api.dp_layout_ab(0, 1 << 18, 150)
+    print(r)
+    assert r["gcups_thread_per_candidate"] > r["gcups_warp_per_candidate"]
+
+
 def test_async_run_overlaps_host_work(orc, odb, gdb, small_reads):
     from hla_mapper_b200 import api
 
