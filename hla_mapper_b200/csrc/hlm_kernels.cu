@@ -603,6 +603,7 @@ __global__ void k_snapshot(HlmChunk ck, int which) {
     unsigned long long n = ck.counters[0];
     if ((int64_t)n > ck.cand_cap) n = (unsigned long long)ck.cand_cap;
     ck.counters[8 + which] = n;
+    ck.counters[15] = 0;  // work counter of the k_myers launch that follows
     if (which == 0) ck.counters[12] = ck.counters[11];
   }
 }
@@ -627,11 +628,20 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
   HlmPeqShared peq{s_peq + threadIdx.x};
   int64_t first, ncand;
   cand_range(ck, phase, first, ncand);
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long rows = 0;
-  for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += stride) {
+  int lane_ = threadIdx.x & 31;
+  // warps pull groups of 32 candidates from a device counter (dead / short candidates make a
+  // static split uneven); the next group's tiles are prefetched towards L2 meanwhile
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane_ == 0) base = atomicAdd(&ck.counters[15], 32ull);
+    base = __shfl_sync(FULL, base, 0);
+    int64_t i = first + (int64_t)base + lane_;
+    if (first + (int64_t)base >= ncand) break;
+    if (i >= ncand) continue;
     uint64_t c = ck.cand[i];
-    if (i + stride < ncand) prefetch_tile(db, ck.cand[i + stride]);
+    if (i + 32 * (int64_t)gridDim.x * (blockDim.x >> 5) < ncand)
+      prefetch_tile(db, ck.cand[i + 32 * (int64_t)gridDim.x * (blockDim.x >> 5)]);
     if (c == HLM_CAND_INVALID) continue;
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
@@ -812,13 +822,20 @@ __global__ void __launch_bounds__(128)
 k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
   int64_t nd = (int64_t)ck.counters[1];
   if (nd > ck.dp_cap) nd = ck.dp_cap;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int lane = threadIdx.x & 31;
   unsigned long long cells = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) {
+  // warps pull groups of 32 list entries from a device counter: a DP takes 50-184 rows depending
+  // on the trimmed read, so a static grid-stride split leaves a long tail
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ck.counters[14], 32ull);
+    base = __shfl_sync(FULL, base, 0);
+    if ((int64_t)base >= nd) break;
+    int64_t i = (int64_t)base + lane;
+    if (i >= nd) continue;
     uint32_t di = ck.dp_list[i];
     if (di == HLM_DP_INVALID) continue;
     uint64_t c = ck.cand[di];
-    if (i + stride < nd) prefetch_tile(db, ck.cand[ck.dp_list[i + stride]]);
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
@@ -831,14 +848,13 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     cells += (unsigned long long)n * HLM_NB;
   }
   for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
-  if ((threadIdx.x & 31) == 0 && cells) {
-    atomicAdd(&ck.counters[4], cells);
-  }
+  if (lane == 0 && cells) atomicAdd(&ck.counters[4], cells);
 }
 
 __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ck.counters[1] = 0;
+    ck.counters[14] = 0;
   }
 }
 
