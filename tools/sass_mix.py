@@ -38,8 +38,10 @@ def loops(fn_prefix):
     return res
 
 
-def report(name, fn_prefix, pick, per, unit):
-    dst, src, c = loops(fn_prefix)[pick]
+def report(name, fn_prefix, marker, min_count, per, unit):
+    # the innermost loop that holds the marker instruction at least min_count times
+    cands = [l for l in loops(fn_prefix) if l[2][marker] >= min_count]
+    dst, src, c = min(cands, key=lambda l: l[1] - l[0])
     tot = sum(c.values())
     fma = sum(v for k, v in c.items() if k in FMA)
     lsu = sum(v for k, v in c.items() if k in LSU)
@@ -52,5 +54,5 @@ def report(name, fn_prefix, pick, per, unit):
 
 if __name__ == "__main__":
     print("# SASS instruction mix of the inner loops (cuobjdump -sass hla_mapper_b200/build/hlm_kernels.cu.o)")
-    report("k_dp row loop (one 41-cell band row)", "_Z4k_dp8", 1, 41, "cells")
-    report("k_myers main loop (8 band rows)", "_Z7k_myers8", 1, 8, "rows")
+    report("k_dp row loop (one 41-cell band row)", "_Z4k_dp8", "VIADDMNMX", 70, 41, "cells")
+    report("k_myers main loop (8 band rows)", "_Z7k_myers8", "LDS", 20, 8, "rows")
