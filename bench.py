@@ -46,8 +46,8 @@ DB_KW = dict(seed=42, n_loci=24, total_alleles=40000, n_others=2000)
 READS_KW = dict(read_len=150, seed=1001, on_target=1.0)
 METRIC = "read pairs/sec scored+assigned"
 # integer instructions of the SASS inner loops (tools/sass_mix.py -> profiles/r1_sass_mix.txt)
-DP_ALU_OPS_PER_CELL = 5.8     # 238 ALU-pipe instructions per 41-cell band row
-DP_INT_OPS_PER_CELL = 10.3    # + 183 IMAD on the FMA pipe
+DP_ALU_OPS_PER_CELL = 5.9     # 243 ALU-pipe instructions per 41-cell band row
+DP_INT_OPS_PER_CELL = 10.3    # + 180 IMAD on the FMA pipe
 MYERS_ALU_OPS_PER_ROW = 31.0  # 248 ALU-pipe instructions per 8 band rows
 WORKLOAD = "synthetic 30x WGS MHC-region reads, 2x150bp, 2M pairs/GPU vs 24 loci + others, 40k-allele DB seed 42"
 
@@ -272,9 +272,11 @@ def run_b200(args):
     barrier()
 
     total_pairs = sum_over_ranks(float(n)) * K
+    h2d_all, d2h_all = sum_over_ranks(float(h2d)), sum_over_ranks(float(d2h))  # all ranks
     value = total_pairs / (dev_ms * 1e-3)
     e2e = total_pairs / wall_e2e
     int_peak = api.int32_peak(local) if rank == 0 else None
+    dp_ab = api.dp_layout_ab(local, 1 << 18, 150) if rank == 0 else None
     m.close()
     gdb.close()
     if rank != 0:
@@ -341,10 +343,11 @@ def run_b200(args):
                    "l2": "inputs (1.2 GB/step) larger than the 126 MB L2; no flush needed",
                    "parallelism": f"pair-sharded x{world}, DB replicated, no collective"},
         "gcups": round(gcups, 1),
-        "e2e": {"value": round(e2e, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d / K),
-                "d2h_bytes_per_step": int(d2h / K)},
+        "e2e": {"value": round(e2e, 1), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_all / K),
+                "d2h_bytes_per_step": int(d2h_all / K)},
         "gpu_launches": int(stage["launches"]),
         "file_pipeline": files,
+        "dp_layout_ab": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in dp_ab.items()},
         "clocks": clocks,
         "roofline": roof,
         "rooflines": rooflines,
