@@ -367,12 +367,8 @@ int orc_screen_trim(const orc_db* db, const hlm_params* p, const hlm_batch* in, 
   for (int64_t i = 0; i < n; i++) {
     const uint8_t* s1 = in->bases1 + in->offs1[i];
     int l1 = (int)(in->offs1[i + 1] - in->offs1[i]);
-    const uint8_t* s2 = NULL;
     int l2 = 0;
-    if (p->paired) {
-      s2 = in->bases2 + in->offs2[i];
-      l2 = (int)(in->offs2[i + 1] - in->offs2[i]);
-    }
+    if (p->paired) l2 = (int)(in->offs2[i + 1] - in->offs2[i]);
     uint8_t fl = 0;
     int lo1 = 0, n1 = 0, lo2 = 0, n2 = 0;
     uint32_t mask = 0;

@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BIN = os.path.join(HERE, "_ref", "hla-mapper-ref")
 BWA_BIN = os.path.join(HERE, "_ref", "bwa")
 STAR_BIN = os.path.join(HERE, "standin_star.py")
+SAMTOOLS_BIN = os.path.join(HERE, "standin_samtools.py")
 
 
 def available():
@@ -34,7 +35,7 @@ def _config(db_path):
         bak = cfg + ".graft-bak"
         shutil.move(cfg, bak)
     with open(cfg, "w") as f:
-        f.write(f"db={db_path}\nsamtools=/bin/true\nbwa={BWA_BIN}\nwhatshap=DISABLED\n"
+        f.write(f"db={db_path}\nsamtools={SAMTOOLS_BIN}\nbwa={BWA_BIN}\nwhatshap=DISABLED\n"
                 f"freebayes=DISABLED\nblast=DISABLED\nstar={STAR_BIN}\n")
     try:
         yield
@@ -44,13 +45,21 @@ def _config(db_path):
             shutil.move(bak, cfg)
 
 
-def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, rna=False, threads=4,
+def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None, rna=False, threads=4,
                   debug=True, exhaustive=False, extra=(), timeout=3600):
     """returns the output directory (with trailing slash, as the reference stores it)"""
     if os.path.exists(out_dir):
         shutil.rmtree(out_dir)
     cmd = [REF_BIN, "rna" if rna else "dna"]
-    if r0:
+    env = dict(os.environ)
+    if bam:  # bam = (r1, r2): the stand-in samtools serves them as the content of a "BAM"
+        os.makedirs(os.path.dirname(out_dir.rstrip("/")) or ".", exist_ok=True)
+        manifest = out_dir.rstrip("/") + ".standin.bam"
+        with open(manifest, "w") as f:
+            f.write(f"{bam[0]}\n{bam[1]}\n")
+        env["HLM_STANDIN_BAM"] = manifest
+        cmd.append(f"bam={manifest}")
+    elif r0:
         cmd.append(f"r0={r0}")
     else:
         cmd += [f"r1={r1}", f"r2={r2}"]
@@ -59,7 +68,6 @@ def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, rna=False
     if debug:
         cmd.append("--debug")
     cmd += list(extra)
-    env = dict(os.environ)
     if exhaustive:
         env["HLM_ORACLE_EXHAUSTIVE"] = "1"
     with _config(db_path):

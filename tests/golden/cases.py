@@ -24,6 +24,10 @@ CASES = {
                                   frag_sd=30, ragged=True), "paired"),
     "rna_paired": (DB_RNA, dict(n_pairs=800, read_len=100, seed=1004, on_target=0.8, frag_mu=220,
                                  frag_sd=25), "rna"),
+    # bam= input: the BAM-derived screen loop (preselect.cpp:484-506), reads served by the samtools
+    # stand-in (oracle/standin_samtools.py)
+    "dna_bam": (DB_SMALL, dict(n_pairs=900, read_len=120, seed=14, on_target=0.8, frag_mu=260,
+                               frag_sd=30, ragged=True), "bam"),
     "dna_single": (DB_SMALL, dict(n_pairs=800, read_len=120, seed=13, on_target=0.8, frag_mu=260,
                                   frag_sd=30, ragged=True), "single"),
 }
@@ -38,7 +42,8 @@ def inputs(name, root):
     rk = dict(rk)
     n = rk.pop("n_pairs")
     rb = synth.make_reads(db, n, **rk)
-    p = _abi.default_params(rna=1 if mode == "rna" else 0, paired=0 if mode == "single" else 1)
+    p = _abi.default_params(rna=1 if mode == "rna" else 0, paired=0 if mode == "single" else 1,
+                            screen_variant=1 if mode == "bam" else 0)
     return db, rb, p, mode
 
 
@@ -65,6 +70,7 @@ FASTQ_KW = {
     "dna_ragged": dict(suffix=True, comment=True),
     "dna_ties": dict(suffix=True, gz=True),
     "dna_single": dict(suffix=False),
+    "dna_bam": dict(suffix=False),
 }
 
 

@@ -51,7 +51,10 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             db, rb, p, mode = cases.inputs(name, tmp)
             r1, r2 = cases.write_inputs(name, rb, mode, tmp)
-            if mode != "single":
+            if mode == "bam":
+                out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", bam=(r1, r2))
+                tag = "R1"
+            elif mode != "single":
                 out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2,
                                        rna=(mode == "rna"))
                 tag = "R1"
@@ -65,7 +68,7 @@ def main():
             sorted_ = {g: sorted(fastq_records(out + f"G_sorted_{g}_{tag}.fastq")) for g in names[:-1]}
             emitted = {g: sorted(fastq_records(out + f"G_{g}_{tag}.fastq")) for g in names[:-1]}
             files = {}
-            if mode != "rna":  # byte-level digests of what the reference wrote (file pipeline)
+            if mode in ("paired", "single"):  # byte-level digests of what the reference wrote (file pipeline)
                 want = [f"G_selected.{tag}.fastq", f"G_selected.trim.{tag}.fastq", "G_addressing_table.txt"]
                 for g in names[:-1]:
                     want += [f"G_{g}_{tag}.fastq", f"G_{g}.trim.{tag}.fastq"]
