@@ -339,7 +339,7 @@ def run_b200(args):
         "steps": K, "warmup": W, "ms_per_step": round(dev_ms / K, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "read_len": 150,
-                   "db": DB_KW, "reads": READS_KW, "chunk_pairs": int(m.params.chunk_pairs) or 32768,
+                   "db": DB_KW, "reads": READS_KW, "chunk_pairs": int(m.params.chunk_pairs) or 65536,
                    "l2": "inputs (1.2 GB/step) larger than the 126 MB L2; no flush needed",
                    "parallelism": f"pair-sharded x{world}, DB replicated, no collective"},
         "gcups": round(gcups, 1),

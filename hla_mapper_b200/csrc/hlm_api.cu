@@ -662,7 +662,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
   ctx->n_slots = p.single_slot ? 1 : HLM_MAX_SLOTS;
-  ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 32768;
+  ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 65536;
   ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 2048;
   if (ctx->cand_cap >= (1ll << 32)) ctx->cand_cap = (1ll << 32) - 1;
   if (ctx->chunk_pairs * ctx->units_per_pair >= (1ll << 26)) {
