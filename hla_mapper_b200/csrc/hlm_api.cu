@@ -652,6 +652,10 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
     delete ctx;
     return fail("params.rna does not match the database kind");
   }
+  if (p.mm_max < 0 || p.mm_max > 100 || p.minhit < 0 || p.tolerance < 0) {
+    delete ctx;
+    return fail("params out of range (0 <= mm_max <= 100; the alignment band is fixed at +-20)");
+  }
   if (cudaSetDevice(cuda_device) != cudaSuccess) {
     delete ctx;
     return fail("cudaSetDevice failed");

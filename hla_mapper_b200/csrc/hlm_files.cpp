@@ -15,6 +15,7 @@
 // Byte formats are the reference's (its std::map iteration orders included); only the orders
 // that the reference itself leaves to thread timing (selected.R*.fastq, table rows) are fixed
 // here to input order / id order.
+#include <sys/mman.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -227,8 +228,11 @@ class Arena {
   }
   char* alloc(size_t n) {
     if (blocks_.empty() || used_ + n > cap_) {
-      cap_ = std::max<size_t>(n, (size_t)64 << 20);
-      blocks_.emplace_back(new char[cap_]);
+      cap_ = (std::max<size_t>(n, (size_t)64 << 20) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+      void* m = aligned_alloc((size_t)2 << 20, cap_);
+      if (!m) throw std::bad_alloc();
+      madvise(m, cap_, MADV_HUGEPAGE);  // first-touch faults dominate the collection otherwise
+      blocks_.emplace_back((char*)m);
       used_ = 0;
     }
     char* d = blocks_.back().get() + used_;
@@ -237,7 +241,10 @@ class Arena {
   }
 
  private:
-  std::vector<std::unique_ptr<char[]>> blocks_;
+  struct Free {
+    void operator()(char* p) const { free(p); }
+  };
+  std::vector<std::unique_ptr<char, Free>> blocks_;
   size_t cap_ = 0, used_ = 0;
 };
 
@@ -369,18 +376,24 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       return HLM_E_IO;
     }
   }
-  Arena arena;
   std::vector<Kept> kept;
   int64_t n_pairs = 0, n_selected = 0, sel_bases = 0;
-  std::string h1, h2, idg;
+  int n_workers = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  std::vector<Arena> arenas(n_workers);
 
-  // what the reference keeps per selected read, taken from a finished batch
-  auto collect = [&](Results& R) {
+  // what the reference keeps per selected read, taken from a finished batch: the batch is cut
+  // into one slice per host thread; slices are concatenated in order, so the output is in input order
+  struct Part {
+    std::vector<Kept> kept;
+    std::string sel1, sel2;
+    int64_t n_selected = 0, sel_bases = 0;
+  };
+  auto collect_slice = [&](Results& R, int64_t lo, int64_t hi, Arena& arena, Part& P) {
     MateBatch *b1 = R.b1, *b2 = R.b2;
-    int64_t n = b1->n;
-    for (int64_t i = 0; i < n; i++) {
+    std::string h1, h2, idg;
+    for (int64_t i = lo; i < hi; i++) {
       if (!(R.flags[i] & HLM_F_SCREENED)) continue;
-      n_selected++;
+      P.n_selected++;
       h1.assign(b1->hdr.data() + b1->hoff[i], b1->hoff[i + 1] - b1->hoff[i]);
       if (paired) {  // src/preselect.cpp:664-665, :675-676
         h2.assign(b2->hdr.data() + b2->hoff[i], b2->hoff[i + 1] - b2->hoff[i]);
@@ -396,16 +409,18 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
         q2p = (const char*)b2->quals.data() + b2->offs[i];
         L2 = b2->offs[i + 1] - b2->offs[i];
       }
-      sel_bases += (int64_t)L1;
+      P.sel_bases += (int64_t)L1;
       if (o.write_selected) {
-        sel1.add(h1); sel1.add("\n", 1); sel1.add(s1p, L1); sel1.add("\n+\n", 3); sel1.add(q1p, L1); sel1.add("\n", 1);
+        P.sel1.append(h1); P.sel1.append("\n", 1); P.sel1.append(s1p, L1); P.sel1.append("\n+\n", 3);
+        P.sel1.append(q1p, L1); P.sel1.append("\n", 1);
         if (paired) {
-          sel2.add(h2); sel2.add("\n", 1); sel2.add(s2p, L2); sel2.add("\n+\n", 3); sel2.add(q2p, L2); sel2.add("\n", 1);
+          P.sel2.append(h2); P.sel2.append("\n", 1); P.sel2.append(s2p, L2); P.sel2.append("\n+\n", 3);
+          P.sel2.append(q2p, L2); P.sel2.append("\n", 1);
         }
       }
       if (!(R.flags[i] & HLM_F_KEPT)) continue;
-      kept.emplace_back();
-      Kept& k = kept.back();
+      P.kept.emplace_back();
+      Kept& k = P.kept.back();
       size_t sp = h1.find(' ');
       k.tokl = (uint32_t)(sp == std::string::npos ? h1.size() : sp);
       idg.assign(h1, k.tokl ? 1 : 0, k.tokl ? k.tokl - 1 : 0);
@@ -432,9 +447,30 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       k.locus_mask = R.lmask[i]; k.target = R.target[i]; k.visible = R.visible[i];
       k.os1 = R.os1[i]; k.os2 = R.os2[i];
     }
+  };
+  std::vector<Part> parts(n_workers);
+  auto collect = [&](Results& R) {
+    int64_t n = R.b1->n;
+    for (Part& P : parts) {  // buffers keep their capacity from batch to batch
+      P.kept.clear();
+      P.sel1.clear();
+      P.sel2.clear();
+      P.n_selected = P.sel_bases = 0;
+    }
+    std::vector<std::thread> th;
+    for (int w = 0; w < n_workers; w++)
+      th.emplace_back([&, w] { collect_slice(R, n * w / n_workers, n * (w + 1) / n_workers, arenas[w], parts[w]); });
+    for (auto& t : th) t.join();
+    for (Part& P : parts) {
+      sel1.add(P.sel1);
+      sel2.add(P.sel2);
+      n_selected += P.n_selected;
+      sel_bases += P.sel_bases;
+      kept.insert(kept.end(), P.kept.begin(), P.kept.end());
+    }
     n_pairs += n;
-    in1.recycle(b1);
-    if (paired) in2->recycle(b2);
+    in1.recycle(R.b1);
+    if (paired) in2->recycle(R.b2);
   };
 
   // batch k+1 runs on the GPU (hlm_run_async) while batch k is collected on this thread and the
@@ -503,18 +539,21 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   std::vector<std::thread> writers;
   // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
   writers.emplace_back([&] {
-    Out t1, t2;
+    Out t1;
     t1.open(pre + "selected.trim." + tag + ".fastq");
-    if (paired) t2.open(pre + "selected.trim.R2.fastq");
     for (const Kept& k : kept) {
       t1.add(k.h1, k.h1l); t1.add("\n", 1); t1.add(k.s1 + k.lo1, k.n1); t1.add("\n+\n", 3);
       t1.fill('A', k.n1); t1.add("\n", 1);
-      if (paired) {
-        t2.add(k.h2, k.h2l); t2.add("\n", 1); t2.add(k.s2 + k.lo2, k.n2); t2.add("\n+\n", 3);
-        t2.fill('A', k.n2); t2.add("\n", 1);
-      }
     }
     t1.close();
+  });
+  if (paired) writers.emplace_back([&] {
+    Out t2;
+    t2.open(pre + "selected.trim.R2.fastq");
+    for (const Kept& k : kept) {
+      t2.add(k.h2, k.h2l); t2.add("\n", 1); t2.add(k.s2 + k.lo2, k.n2); t2.add("\n+\n", 3);
+      t2.fill('A', k.n2); t2.add("\n", 1);
+    }
     t2.close();
   });
   // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051)
