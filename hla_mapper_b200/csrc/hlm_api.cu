@@ -580,6 +580,7 @@ int64_t hlm_db_stat(const hlm_db* db, const char* key) {
 }
 
 static int upload_db(hlm_ctx* ctx, hlm_db* db) {
+  std::lock_guard<std::mutex> guard(db->devs_mutex);
   for (auto& d : db->devs)
     if (d.device == ctx->device) {
       ctx->ddb = d.view;
@@ -602,16 +603,21 @@ static int upload_db(hlm_ctx* ctx, hlm_db* db) {
   };
   HlmDevDB v;
   memset(&v, 0, sizeof v);
-  int rc;
-  if ((rc = up(0, db->kt.data(), db->kt.size() * 8, (const void**)&v.kt))) return rc;
-  if ((rc = up(1, db->mask_tab.data(), db->mask_tab.size() * 4, (const void**)&v.mask_tab))) return rc;
-  if ((rc = up(2, db->tiles.data(), db->tiles.size() * 4, (const void**)&v.tiles))) return rc;
-  if ((rc = up(3, db->seed_off.data(), db->seed_off.size() * 4, (const void**)&v.seed_off))) return rc;
-  if ((rc = up(4, db->seed_ent.data(), db->seed_ent.size() * 4, (const void**)&v.seed_ent))) return rc;
-  if ((rc = up(5, db->tile_diff.data(), db->tile_diff.size() * 4, (const void**)&v.tile_diff))) return rc;
-  if ((rc = up(6, db->child_off.data(), db->child_off.size() * 4, (const void**)&v.child_off))) return rc;
-  if ((rc = up(7, db->child_ent.data(), db->child_ent.size() * 4, (const void**)&v.child_ent))) return rc;
-  if ((rc = up(8, db->child_diff.data(), db->child_diff.size() * 4, (const void**)&v.child_diff))) return rc;
+  int rc = 0;
+  if (!rc) rc = up(0, db->kt.data(), db->kt.size() * 8, (const void**)&v.kt);
+  if (!rc) rc = up(1, db->mask_tab.data(), db->mask_tab.size() * 4, (const void**)&v.mask_tab);
+  if (!rc) rc = up(2, db->tiles.data(), db->tiles.size() * 4, (const void**)&v.tiles);
+  if (!rc) rc = up(3, db->seed_off.data(), db->seed_off.size() * 4, (const void**)&v.seed_off);
+  if (!rc) rc = up(4, db->seed_ent.data(), db->seed_ent.size() * 4, (const void**)&v.seed_ent);
+  if (!rc) rc = up(5, db->tile_diff.data(), db->tile_diff.size() * 4, (const void**)&v.tile_diff);
+  if (!rc) rc = up(6, db->child_off.data(), db->child_off.size() * 4, (const void**)&v.child_off);
+  if (!rc) rc = up(7, db->child_ent.data(), db->child_ent.size() * 4, (const void**)&v.child_ent);
+  if (!rc) rc = up(8, db->child_diff.data(), db->child_diff.size() * 4, (const void**)&v.child_diff);
+  if (rc) {  // nothing half-uploaded stays behind
+    for (void* q : dv.ptrs)
+      if (q) cudaFree(q);
+    return rc;
+  }
   v.kt_bits = db->kt_bits;
   v.n_loci = db->n_loci;
   for (int g = 0; g < db->n_loci + 2; g++) v.tile_start[g] = db->tile_start[g];
@@ -663,6 +669,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cuda_device);
   ctx->sms = prop.multiProcessorCount;
+  hlm_kernels_init();
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
   ctx->n_slots = p.single_slot ? 1 : HLM_MAX_SLOTS;
@@ -724,8 +731,11 @@ void hlm_ctx_destroy(hlm_ctx* ctx) {
   }
   cudaEventDestroy(ctx->run_start);
   hlm_db* db = const_cast<hlm_db*>(ctx->db);
-  for (auto& d : db->devs)
-    if (d.device == ctx->device) d.refs--;
+  {
+    std::lock_guard<std::mutex> guard(db->devs_mutex);
+    for (auto& d : db->devs)
+      if (d.device == ctx->device) d.refs--;
+  }
   delete ctx;
 }
 

@@ -2,6 +2,7 @@
 #ifndef HLM_DB_H
 #define HLM_DB_H
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,7 @@ struct hlm_db {
     int refs;
   };
   std::vector<Dev> devs;
+  std::mutex devs_mutex;  // contexts may be created from several host threads
 };
 
 hlm_db* hlm_db_build(const char* dir, int rna, std::string& err);

@@ -1182,12 +1182,13 @@ void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& c
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {
-  static bool once = false;
-  if (!once) {  // 5 blocks x 42 KB of PEQ rows per SM
-    cudaFuncSetAttribute(k_myers, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    once = true;
-  }
   k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, phase);
+}
+// per-device kernel attributes (call once per context, after cudaSetDevice)
+void hlm_kernels_init() {
+  // k_myers: 5 blocks x 42 KB of PEQ rows per SM; k_seed: 6 blocks x 34 KB of hash sets
+  cudaFuncSetAttribute(k_myers, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_seed, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st) {
   k_snapshot<<<1, 32, 0, st>>>(ck, which);

@@ -73,6 +73,7 @@ void hlm_launch_scores(const HlmKParams& kp, const HlmChunk& ck, int n_targets, 
                        cudaStream_t st);
 void hlm_launch_assign(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
                        cudaStream_t st);
+void hlm_kernels_init();
 double hlm_int_peak_run(int which, int sms, cudaStream_t st);
 void hlm_launch_dpab(int which, const uint32_t* reads, const uint32_t* tiles, const int* offn, int m,
                      int4* out, int sms, cudaStream_t st);
