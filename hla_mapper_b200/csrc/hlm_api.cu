@@ -572,6 +572,7 @@ int64_t hlm_db_stat(const hlm_db* db, const char* key) {
   if (k == "tiles_raw") return db->n_tiles_raw;
   if (k == "kmers") return db->n_kmers;
   if (k == "kmers_skipped") return db->n_kmers_skipped;
+  if (k == "kmers_odd") return (int64_t)db->odd_masks.size();
   if (k == "kt_slots") return (int64_t)db->kt.size();
   if (k == "seed_entries") return (int64_t)db->seed_ent.size();
   if (k == "reps") return db->n_reps;
@@ -613,6 +614,9 @@ static int upload_db(hlm_ctx* ctx, hlm_db* db) {
   if (!rc) rc = up(6, db->child_off.data(), db->child_off.size() * 4, (const void**)&v.child_off);
   if (!rc) rc = up(7, db->child_ent.data(), db->child_ent.size() * 4, (const void**)&v.child_ent);
   if (!rc) rc = up(8, db->child_diff.data(), db->child_diff.size() * 4, (const void**)&v.child_diff);
+  if (!rc) rc = up(9, db->odd_keys.data(), db->odd_keys.size(), (const void**)&v.odd_keys);
+  if (!rc) rc = up(10, db->odd_masks.data(), db->odd_masks.size() * 4, (const void**)&v.odd_masks);
+  v.n_odd = (int)db->odd_masks.size();
   if (rc) {  // nothing half-uploaded stays behind
     for (void* q : dv.ptrs)
       if (q) cudaFree(q);

@@ -69,6 +69,9 @@ HLM_COMMON_HD uint64_t hlm_kt_hash(uint64_t key, int bits) {
 struct HlmDevDB {
   const uint64_t* kt;        /* k-mer table                                  */
   const uint32_t* mask_tab;  /* mask id -> membership mask                   */
+  const uint8_t* odd_keys;   /* motif lines with a non-ACGT byte: 20 raw bytes each, sorted */
+  const uint32_t* odd_masks;
+  int n_odd;
   int kt_bits;
   const uint32_t* tiles;     /* n_tiles * 24 words                           */
   const uint32_t* seed_off;  /* 4^12 + 1                                     */

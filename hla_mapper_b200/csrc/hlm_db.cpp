@@ -43,16 +43,20 @@ inline int base_code(unsigned char c) {
 }
 
 // motif lines -> (key, mask bit).  A line can only ever equal seq.substr(c,20) when it is
-// exactly 20 bytes; a 20-byte line holding a non-ACGT byte is not representable in 2 bits and
-// is counted in n_kmers_skipped (it could only match a read with the same byte in place).
+// exactly 20 bytes.  A 20-byte line holding a non-ACGT byte (N, lower case ...) is not
+// representable in 2 bits: it goes to the small "odd" list of raw strings, which the screen
+// consults only for read windows that themselves hold a non-ACGT byte (the reference compares
+// raw strings, so such a line matches a read with the same bytes in place).
 void load_motifs(const std::string& path, uint32_t bit,
-                 std::vector<std::pair<uint64_t, uint32_t>>& out, int64_t& skipped) {
+                 std::vector<std::pair<uint64_t, uint32_t>>& out, int64_t& skipped,
+                 std::vector<std::pair<std::string, uint32_t>>& odd) {
   std::vector<char> buf;
   if (!read_file(path, buf)) return;
   size_t n = buf.size();
   unsigned nt = n > (8u << 20) ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
   std::vector<std::vector<std::pair<uint64_t, uint32_t>>> part(nt);
   std::vector<int64_t> skip(nt, 0);
+  std::vector<std::vector<std::pair<std::string, uint32_t>>> oddp(nt);
   auto work = [&](unsigned k) {
     size_t i = n * k / nt, end = n * (k + 1) / nt;
     if (k > 0) {  // start at the first line that begins inside this chunk
@@ -75,7 +79,10 @@ void load_motifs(const std::string& path, uint32_t bit,
           key |= (uint64_t)code << (2 * x);
         }
         if (ok) o.emplace_back(key, bit);
-        else skip[k]++;
+        else {
+          skip[k]++;
+          oddp[k].emplace_back(std::string(&buf[i], HLM_MOTIF), bit);
+        }
       }
       i = e + 1;
     }
@@ -86,6 +93,7 @@ void load_motifs(const std::string& path, uint32_t bit,
   for (unsigned k = 0; k < nt; k++) {
     out.insert(out.end(), part[k].begin(), part[k].end());
     skipped += skip[k];
+    odd.insert(odd.end(), oddp[k].begin(), oddp[k].end());
   }
 }
 
@@ -212,10 +220,20 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   // ---- k-mer screen index
   {
     std::vector<std::pair<uint64_t, uint32_t>> kv;
-    load_motifs(base + "/motif/" + kind + "/all/motif_all.txt", 1u << 31, kv, db->n_kmers_skipped);
+    std::vector<std::pair<std::string, uint32_t>> odd;
+    load_motifs(base + "/motif/" + kind + "/all/motif_all.txt", 1u << 31, kv, db->n_kmers_skipped, odd);
     for (int g = 0; g < db->n_loci; g++)
       load_motifs(base + "/motif/" + kind + "/loci/" + db->names[g] + ".txt", 1u << g, kv,
-                  db->n_kmers_skipped);
+                  db->n_kmers_skipped, odd);
+    std::sort(odd.begin(), odd.end());
+    for (size_t i = 0; i < odd.size();) {  // sorted raw strings, masks merged
+      uint32_t m = 0;
+      size_t j = i;
+      while (j < odd.size() && odd[j].first == odd[i].first) m |= odd[j++].second;
+      db->odd_keys.insert(db->odd_keys.end(), odd[i].first.begin(), odd[i].first.end());
+      db->odd_masks.push_back(m);
+      i = j;
+    }
     std::sort(kv.begin(), kv.end());
     std::vector<std::pair<uint64_t, uint32_t>> uniq;
     for (size_t i = 0; i < kv.size();) {

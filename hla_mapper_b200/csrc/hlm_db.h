@@ -20,7 +20,9 @@ struct hlm_db {
   std::vector<uint32_t> mask_tab;
   int kt_bits = 0;
   int64_t n_kmers = 0;
-  int64_t n_kmers_skipped = 0;  // 20-char motif lines holding a non-ACGT byte
+  int64_t n_kmers_skipped = 0;  // 20-char motif lines holding a non-ACGT byte (kept in odd_*)
+  std::vector<uint8_t> odd_keys;    // those lines, 20 raw bytes each, sorted
+  std::vector<uint32_t> odd_masks;  // their membership masks
 
   // tiles + seed index
   std::vector<uint32_t> tiles;
@@ -42,7 +44,7 @@ struct hlm_db {
   struct Dev {
     int device;
     HlmDevDB view;
-    void* ptrs[9];
+    void* ptrs[11];
     int refs;
   };
   std::vector<Dev> devs;

@@ -146,6 +146,19 @@ __device__ __forceinline__ uint32_t probe_kmer(const HlmDevDB& db, uint64_t key)
   }
 }
 
+// motif lines holding a non-ACGT byte: raw 20-byte compare against the read as written
+__device__ __forceinline__ uint32_t probe_odd(const HlmDevDB& db, const uint8_t* w) {
+  int lo = 0, hi = db.n_odd;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1, c = 0;
+    const uint8_t* k = db.odd_keys + (size_t)mid * HLM_MOTIF;
+    for (int x = 0; x < HLM_MOTIF && c == 0; x++) c = (int)__ldg(k + x) - (int)w[x];
+    if (c == 0) return __ldg(db.odd_masks + mid);
+    if (c < 0) lo = mid + 1; else hi = mid;
+  }
+  return 0u;
+}
+
 // first set bit at or after pos (< limit), or -1
 __device__ __forceinline__ int next_one(const uint32_t* m, int pos, int limit) {
   while (pos < limit) {
@@ -282,6 +295,7 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
           key &= HLM_KT_KEYMASK;
           uint32_t nn = hlm_funnel(ws.pn[c >> 5], ws.pn[(c >> 5) + 1], c & 31) & 0xFFFFFu;
           if (nn == 0) val = probe_kmer(db, key);
+          else if (db.n_odd) val = probe_odd(db, ck.bases1 + o1 + c);
         }
         myval[r] = val;
         uint32_t hb = __ballot_sync(FULL, val >> 31);

