@@ -163,3 +163,52 @@ def test_low_complexity_reads_and_huge_candidate_lists(orc, tmp_path):
     _write_db(str(tmp_path / "db"), loci, others, rng, motif_every=1)
     rb = _reads_from(rng, [rep, loci["MIX"][0]], 120, 150, err=0.005, junk=0.05)
     _check(orc, str(tmp_path / "db"), rb)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("HLM_FUZZ_SEEDS", "16"))))
+def test_random_databases_reads_and_parameters(orc, tmp_path, seed):
+    """random database shape x read shape x parameter set, exhaustive oracle"""
+    from hla_mapper_b200 import api
+
+    rng = np.random.default_rng(1000 + seed)
+    rna = int(seed % 4 == 3)
+    lo = int(rng.integers(60, 400))
+    db = synth.make_db(str(tmp_path / "db"), seed=int(rng.integers(1, 10 ** 6)),
+                       n_loci=int(rng.integers(1, 9)), total_alleles=int(rng.integers(8, 160)),
+                       len_range=(lo, lo + int(rng.integers(1, 500))), n_others=int(rng.integers(1, 8)),
+                       n_lineages=int(rng.integers(1, 7)), motif_stride=int(rng.integers(1, 6)),
+                       flank=int(rng.integers(0, 200)), kind="rna" if rna else "dna",
+                       v_size=int(rng.choice([20, 30, 50])),
+                       paralog_div=(0.001, float(rng.choice([0.01, 0.1, 0.3]))),
+                       others_div=(0.001, float(rng.choice([0.02, 0.2]))))
+    L = int(rng.choice([36, 50, 75, 100, 125, 150, 184]))
+    rb = synth.make_reads(db, 400, read_len=L, seed=int(rng.integers(1, 10 ** 6)),
+                          on_target=float(rng.choice([0.5, 0.9, 1.0])), frag_mu=max(L, int(rng.integers(L, 3 * L))),
+                          frag_sd=int(rng.integers(1, 60)), lowq_tail=float(rng.choice([0.0, 0.1, 0.6])),
+                          ragged=bool(rng.integers(0, 2)))
+    kw = dict(rna=rna, paired=int(rng.integers(0, 2)) if not rna else 1,
+              screen_variant=int(rng.integers(0, 2)), clip_mode=int(rng.integers(0, 2)),
+              minhit=int(rng.integers(1, 5)), mm_max=int(rng.choice([3, 10, 20])),
+              tolerance=float(rng.choice([0.0, 0.05, 0.08, 0.2])),
+              mtrim_error=float(rng.choice([0.001, float(np.float32(0.08)), 0.5])),
+              skip_screen=int(rng.integers(0, 4) == 0))
+    p = _abi.default_params(**kw)
+    extra = {}
+    if rna:
+        extra = dict(rna_split1=np.where(rng.random(400) < 0.3, rng.integers(1, L, size=400), 0).astype(np.uint16),
+                     rna_split2=np.where(rng.random(400) < 0.3, rng.integers(1, L, size=400), 0).astype(np.uint16))
+    elif not kw["paired"]:
+        extra = dict(size_override1=rng.integers(1, 300, size=400).astype(np.int32))
+    gdb = api.Database(db.path, rna=rna)
+    m = api.Mapper(gdb, 0, p, chunk_pairs=int(rng.choice([1, 37, 400, 65536])))
+    try:
+        want, _ = orc.run(orc.OracleDB(db.path, rna=rna), p, rb, mode=0, **extra)
+    except RuntimeError as e:  # a trimmed read longer than HLM_MAX_READ: both sides must refuse
+        assert "rc=-6" in str(e)
+        with pytest.raises(api.HlmError, match="longer than HLM_MAX_READ"):
+            m.run(rb, **extra)
+        return
+    got = m.run(rb, **extra)
+    m.close()
+    gdb.close()
+    _same(want, got)
