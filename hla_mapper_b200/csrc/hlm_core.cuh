@@ -132,13 +132,14 @@ HLM_HD int hlm_myers_core(const uint32_t* __restrict__ rd, int n, int off, PEQ p
     int row = (int)(cw & 7u) * 8 + (p >> 5); /* codes 5..7 cannot occur (N clears the code bits) */ \
     cw >>= 4;                                                                                     \
     uint32_t a = peq(row), b = peq(row + 1), c = peq(row + 2);                                    \
-    uint64_t Eq =                                                                                 \
-        ((uint64_t)hlm_funnel(a, b, p & 31) | ((uint64_t)hlm_funnel(b, c, p & 31) << 32)) & MASK; \
+    /* bits above the band (>= 41) of Eq, SP and VP are garbage: the addition only carries */    \
+    /* upwards and D0 is masked, so they never reach a band bit */                                \
+    uint64_t Eq = (uint64_t)hlm_funnel(a, b, p & 31) | ((uint64_t)hlm_funnel(b, c, p & 31) << 32); \
     p++;                                                                                          \
     uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;                                     \
-    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;                                                  \
+    uint64_t VP = SN | ~(D0 | SP), VN = (D0 & SP) | TOP; /* TOP: the cell right of the band */    \
     uint64_t D0s = D0 >> 1;                                                                       \
-    SP = VN | ~(D0s | VP) | TOP;                                                                  \
+    SP = VN | ~(D0s | VP);                                                                        \
     SN = D0s & VP;                                                                                \
     score += 1 - (int)(D0 & 1ull);                                                                \
   }
