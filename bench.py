@@ -310,7 +310,10 @@ def run_b200(args):
                  "alu_ops_per_cell": dp_alu, "int_ops_per_cell": dp_all,
                  "peak_source": "hlm_int32_peak micro-kernels measured in this run"},
         "k_myers": {"bound": "int32", "achieved": round(my_grows, 2), "peak": round(my_peak, 2),
-                    "unit": "G band-rows/s", "frac": round(my_grows / my_peak, 4), "traffic": None,
+                    "unit": "G band-rows/s", "frac": round(my_grows / my_peak, 4),
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one seed-index-phase launch
+                    # (65 536-pair chunk), profiles/r1e_kernels_full.txt; the kernel is ALU-bound
+                    "traffic": 570317056,
                     "ms_per_step": round(my_ms, 3), "rows_per_step": int(myers_rows),
                     "alu_ops_per_row": MYERS_ALU_OPS_PER_ROW},
         "k_screen": {"bound": "hbm", "achieved": round(screen_gbs, 1), "peak": hbm_peak,
