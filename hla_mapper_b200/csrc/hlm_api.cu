@@ -2,7 +2,7 @@
 //
 // Replaces the reference's per-read ThreadPool dispatch (src/ThreadPool.hpp:18-100, one
 // packaged_task + two global-mutex acquisitions per read, preselect.cpp:696-745) with a
-// chunked, double-buffered CUDA-stream pipeline: two slots, each with its own stream, pinned
+// chunked, multi-buffered CUDA-stream pipeline: three slots, each with its own stream, pinned
 // staging buffers and device work buffers; while slot A's kernels run, slot B's inputs are
 // staged and copied, and A's results drain back.  No host<->device synchronisation happens
 // inside a chunk; all kernel grids are persistent (multiples of the SM count) and read their

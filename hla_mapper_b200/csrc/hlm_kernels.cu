@@ -3,15 +3,22 @@
 //   k_screen       warp per pair: 20-mer screen (preselect.cpp:707-731 / :484-506), mtrim
 //                  (functions.cpp:89-145), pair filter (preselect.cpp:1132) and per-locus
 //                  candidate mask (map_dna.cpp:611-627) in one streaming pass over the reads.
-//   k_pack_units   warp per pair: 2-bit/bit-plane packing of the trimmed mates (both strands).
-//   k_seed         warp per unit: 12-mer seed lookups in the tile index -> candidate list.
-//   k_myers        thread per candidate: bit-parallel banded edit distance (lower bound).
+//   k_pack_units   warp per pair: bit-plane packing of the trimmed mates (both strands).
+//   k_seed         warp per unit: 12-mer seed lookups in the column-sorted seed index, hits
+//                  flattened over the lanes, de-duplicated in a shared-memory hash set.
+//   k_myers        thread per candidate: Hyyro diagonal-band bit-parallel edit distance with the
+//                  tile's match vectors in shared memory (lossless lower bound of the DP cost).
+//   k_expand       children of the rep candidates that the one-column Lipschitz bound cannot
+//                  exclude (two rounds).
 //   k_select       thread per candidate: which candidates still need the affine DP.
-//   k_dp           thread per candidate: banded affine-gap DP in registers (DPX min/max).
+//   k_dp           thread per candidate: banded affine-gap DP in registers (DPX min/max on the
+//                  ALU pipe, adds on the FMA pipe).
 //   k_scores       warp per pair, lane per target: SAM-reducer semantics (map_dna.cpp:44-118,
 //                  map_rna.cpp:39-101) on the per-task best alignment.
 //   k_assign       warp per pair, lane per target: others back-fill, tolerance filter, argmin,
 //                  tie set (map_dna.cpp:903-1029, map_rna.cpp:925-1027).
+//   k_dpab_*       the DP in two work layouts (evidence for the layout choice, hlm_dp_layout_ab)
+//   k_int_peak     INT32 issue-rate micro-kernels (roofline denominators)
 //
 // All of it is integer / byte work: HBM-, L2- or INT32-bound, no tensor-core shape anywhere.
 #include "hlm_kernels.cuh"

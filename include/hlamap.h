@@ -85,7 +85,7 @@ typedef struct hlm_params {
   int32_t skip_screen;    /* 1: treat every pair as screened (scoring-only runs) */
   int64_t cand_capacity;  /* device candidate slots per chunk (0 = default)      */
   int32_t single_slot;    /* 1: one pipeline slot, chunks strictly serialised (per-kernel
-                             timing runs; the default two slots overlap copies and kernels) */
+                             timing runs; the default three slots overlap copies and kernels) */
   int32_t reserved0;
 } hlm_params;
 
@@ -182,7 +182,7 @@ int hlm_score(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, hlm_
 int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr,
                const hlm_score_out* sc, hlm_assign_out* out);
 
-/* fused screen -> score -> assign over the context's pinned, double-buffered
+/* fused screen -> score -> assign over the context's pinned, multi-buffered
  * stream pipeline.  Any of scr / sc / asg may be NULL (result not copied back). */
 int hlm_run(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* scr, hlm_score_out* sc,
             hlm_assign_out* asg);
