@@ -15,7 +15,9 @@
 // Byte formats are the reference's (its std::map iteration orders included); only the orders
 // that the reference itself leaves to thread timing (selected.R*.fastq, table rows) are fixed
 // here to input order / id order.
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -52,41 +54,72 @@ struct MateBatch {
   }
 };
 
-// reads 4-line records; returns false at EOF
+// reads 4-line records straight out of a large refill buffer (one memchr per line, one copy per
+// field into the SoA vectors)
 class FastqReader {
  public:
   explicit FastqReader(const char* path) {
-    f_ = gzopen(path, "rb");
-    if (f_) gzbuffer(f_, 1 << 22);
-    buf_.resize(1 << 24);
+    // plain text goes through read(2) directly; only gzip streams pay for zlib
+    fd_ = open(path, O_RDONLY);
+    if (fd_ >= 0) {
+      unsigned char magic[2] = {0, 0};
+      ssize_t r = pread(fd_, magic, 2, 0);
+      if (r == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        close(fd_);
+        fd_ = -1;
+        f_ = gzopen(path, "rb");
+        if (f_) gzbuffer(f_, 1 << 22);
+      } else {
+        posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
+      }
+    }
+    buf_.resize((size_t)32 << 20);
   }
   ~FastqReader() {
     if (f_) gzclose(f_);
+    if (fd_ >= 0) close(fd_);
   }
-  bool ok() const { return f_ != nullptr; }
+  bool ok() const { return f_ != nullptr || fd_ >= 0; }
   // appends up to max_pairs records to b; returns number appended
   int64_t read(MateBatch& b, int64_t max_pairs) {
     int64_t got = 0;
     while (got < max_pairs) {
-      const char* l[4];
-      size_t n[4];
-      bool eof = false;
-      for (int k = 0; k < 4; k++)
-        if (!line(l[k], n[k])) {
-          if (k != 0) b.bad = true;  // the reference would read garbage here; we stop
-          eof = true;
+      // find the four line ends of the next record inside the buffer; refill when incomplete
+      const char* base = buf_.data();
+      size_t e[4], p = pos_;
+      int k = 0;
+      for (; k < 4; k++) {
+        const char* nl = (const char*)memchr(base + p, '\n', have_ - p);
+        if (!nl) break;
+        e[k] = (size_t)(nl - base);
+        p = e[k] + 1;
+      }
+      if (k < 4) {
+        if (!eof_) {
+          refill();
+          continue;
+        }
+        // end of file: a last line without newline completes the record, anything else is dropped
+        if (k == 3 && p < have_) {
+          e[3] = have_;
+          p = have_;
+        } else {
+          if (pos_ < have_ && (k > 0 || have_ - pos_ > 0)) b.bad = b.bad || k > 0;
           break;
         }
-      if (eof) break;
-      b.hdr.insert(b.hdr.end(), l[0], l[0] + n[0]);
+      }
+      size_t h0 = pos_, s0 = e[0] + 1, q0 = e[2] + 1;
+      size_t hl = e[0] - h0, sl = e[1] - s0, ql = e[3] - q0;
+      b.hdr.insert(b.hdr.end(), base + h0, base + h0 + hl);
       b.hoff.push_back(b.hdr.size());
-      b.bases.insert(b.bases.end(), l[1], l[1] + n[1]);
+      b.bases.insert(b.bases.end(), (const uint8_t*)base + s0, (const uint8_t*)base + s0 + sl);
       // the quality line is cut / padded to the sequence length only for the device arrays;
       // hla-mapper itself never checks that they agree
-      size_t q = std::min(n[1], n[3]);
-      b.quals.insert(b.quals.end(), l[3], l[3] + q);
-      b.quals.insert(b.quals.end(), n[1] - q, (uint8_t)'!');
+      size_t q = std::min(sl, ql);
+      b.quals.insert(b.quals.end(), (const uint8_t*)base + q0, (const uint8_t*)base + q0 + q);
+      if (q < sl) b.quals.insert(b.quals.end(), sl - q, (uint8_t)'!');
       b.offs.push_back(b.bases.size());
+      pos_ = p;
       got++;
     }
     b.n += got;
@@ -94,51 +127,23 @@ class FastqReader {
   }
 
  private:
-  // next line (without '\n'); pointers stay valid until the 4th next call at least because a
-  // refill moves the unread tail to the front only when fewer than 4 lines can be pending:
-  // we simply copy the four lines of a record into a small side buffer
-  bool line(const char*& p, size_t& n) {
-    for (;;) {
-      char* nl = (char*)memchr(buf_.data() + pos_, '\n', have_ - pos_);
-      if (nl) {
-        size_t len = nl - (buf_.data() + pos_);
-        keep(buf_.data() + pos_, len, p);
-        n = len;
-        pos_ += len + 1;
-        return true;
-      }
-      if (eof_) {
-        if (pos_ < have_) {  // last line without newline
-          size_t len = have_ - pos_;
-          keep(buf_.data() + pos_, len, p);
-          n = len;
-          pos_ = have_;
-          return true;
-        }
-        return false;
-      }
-      // refill: move the tail to the front
-      size_t tail = have_ - pos_;
-      memmove(buf_.data(), buf_.data() + pos_, tail);
-      pos_ = 0;
-      have_ = tail;
-      if (have_ == buf_.size()) buf_.resize(buf_.size() * 2);
-      int r = gzread(f_, buf_.data() + have_, (unsigned)std::min<size_t>(buf_.size() - have_, 1u << 30));
-      if (r <= 0) eof_ = true;
-      else have_ += (size_t)r;
-    }
-  }
-  void keep(const char* s, size_t len, const char*& out) {
-    std::vector<char>& v = side_[side_i_++ & 3];
-    v.assign(s, s + len);
-    out = v.data();
+  void refill() {  // move the unread tail to the front and read on
+    size_t tail = have_ - pos_;
+    memmove(buf_.data(), buf_.data() + pos_, tail);
+    pos_ = 0;
+    have_ = tail;
+    if (have_ == buf_.size()) buf_.resize(buf_.size() * 2);
+    size_t want = std::min<size_t>(buf_.size() - have_, 1u << 30);
+    long r = f_ ? (long)gzread(f_, buf_.data() + have_, (unsigned)want)
+                : (long)::read(fd_, buf_.data() + have_, want);
+    if (r <= 0) eof_ = true;
+    else have_ += (size_t)r;
   }
   gzFile f_ = nullptr;
+  int fd_ = -1;
   std::vector<char> buf_;
   size_t pos_ = 0, have_ = 0;
   bool eof_ = false;
-  std::vector<char> side_[4];
-  unsigned side_i_ = 0;
 };
 
 // bounded producer queue of batches

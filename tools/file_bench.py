@@ -1,0 +1,36 @@
+"""FASTQ ingest throughput of hlm_map_fastq on decoy-heavy input (the whole-genome case: almost
+nothing passes the screen, so the run is bound by the text path).  Usage (GPU box):
+    python tools/file_bench.py [n_pairs] [on_target]"""
+import os
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hla_mapper_b200 import _abi, api, synth
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+    on = float(sys.argv[2]) if len(sys.argv) > 2 else 0.01
+    with tempfile.TemporaryDirectory(dir="/tmp") as tmp:
+        db = synth.make_db(os.path.join(tmp, "db"), seed=42, n_loci=24, total_alleles=4000, n_others=200)
+        rb = synth.make_reads(db, n, read_len=150, seed=1003, on_target=on)
+        r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
+        synth.write_fastq_fast(rb, r1, r2)
+        size = os.path.getsize(r1) + os.path.getsize(r2)
+        gdb = api.Database(db.path)
+        m = api.Mapper(gdb, 0, _abi.default_params())
+        for rep in range(2):
+            out = os.path.join(tmp, f"out{rep}")
+            os.makedirs(out)
+            t = time.perf_counter()
+            st = m.map_fastq(r1, r2, "W", out)
+            dt = time.perf_counter() - t
+            print(f"rep {rep}: {n} pairs ({size / 1e9:.2f} GB of FASTQ) in {dt:.2f}s = {n / dt / 1e6:.2f} M pairs/s, "
+                  f"{size / dt / 1e9:.2f} GB/s text; stats {st}")
+        m.close()
+
+
+if __name__ == "__main__":
+    main()
