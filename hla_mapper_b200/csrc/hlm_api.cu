@@ -350,7 +350,6 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
   int T = ctx->n_targets;
   bool paired = ctx->p.paired;
   int64_t N = in->n_pairs, C = ctx->chunk_pairs;
-  auto t0 = std::chrono::steady_clock::now();
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
   // stage + copy + launch one chunk on a slot (asynchronous)
@@ -502,7 +501,6 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     if (rc == 0) rc = r2;
   }
   ctx->prof.n_pairs = N;
-  (void)t0;
   cudaError_t e = cudaGetLastError();
   if (rc == 0 && e != cudaSuccess) {
     ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e);

@@ -62,9 +62,10 @@ def test_config2_wgs_2x150_full_size(orc, full_db):
     T = gdb.n_loci + 1
     got = m.run(rb, buffers=_abi.Buffers(n, T))
     # oracle parity on a prefix (the fast CPU port needs ~1 ms per pair at this database size)
-    sub = rb.slice(0, 1500)
+    k = int(os.environ.get("HLM_PREFIX", "4000"))
+    sub = rb.slice(0, k)
     want, _ = orc.run(orc.OracleDB(path), p, sub, mode=1)
-    _same(want, got, 1500)
+    _same(want, got, k)
     # idempotence + chunk invariance over the whole batch (device-resident second pass)
     m2 = api.Mapper(gdb, 0, p, chunk_pairs=50021)
     h = m2.upload(rb)
