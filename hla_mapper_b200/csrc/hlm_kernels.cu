@@ -1203,7 +1203,7 @@ void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& c
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {
-  k_myers<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, phase);
+  k_myers<<<grid_for(sms, 4), 256, 0, st>>>(db, kp, ck, n_targets, phase);
 }
 // per-device kernel attributes (call once per context, after cudaSetDevice)
 void hlm_kernels_init() {
