@@ -315,7 +315,10 @@ void scatter_results(hlm_ctx* ctx, Slot& s, const HostIO& io) {
 }
 
 int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
+  uint64_t longest = 0;
   for (int64_t i = 0; i < in->n_pairs; i++) {
+    longest = std::max(longest, in->offs1[i + 1] - in->offs1[i]);
+    if (ctx->p.paired && in->offs2) longest = std::max(longest, in->offs2[i + 1] - in->offs2[i]);
     if (in->offs1[i + 1] < in->offs1[i] || in->offs1[i + 1] - in->offs1[i] > HLM_RAW_MAX) {
       ctx->err = "read 1 longer than 256 bases (or offsets not ascending)";
       return HLM_E_TOOLONG;
@@ -325,6 +328,8 @@ int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
       return HLM_E_TOOLONG;
     }
   }
+  // DP work is grouped by length: "full length" = within 6 bases of the longest read of the batch
+  ctx->kp.full_len = longest > 6 ? (int)std::min<uint64_t>(longest, HLM_MAX_READ) - 6 : 0;
   return 0;
 }
 
@@ -823,6 +828,7 @@ hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in) {
   bool paired = ctx->p.paired;
   b->n_pairs = n;
   b->paired = paired;
+  b->max_len = ctx->kp.full_len;  // set by check_lengths above
   size_t b1 = (size_t)in->offs1[n], b2 = paired ? (size_t)in->offs2[n] : 0;
   size_t o = 0;
   auto sec = [&](int i, size_t bytes) { b->in_off[i] = o; o += align16(bytes + 32); };
@@ -867,6 +873,7 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   memset(&ctx->prof, 0, sizeof ctx->prof);
   int T = ctx->n_targets;
   int64_t N = b->n_pairs, C = ctx->chunk_pairs;
+  ctx->kp.full_len = (int)b->max_len;
   uint8_t* d = (uint8_t*)b->in.p;
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));

@@ -821,15 +821,26 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         }
       }
     }
-    // the DP list stays dense (no padding): one ballot-aggregated atomic per warp iteration
-    uint32_t bal = __ballot_sync(FULL, take);
+    // the DP list stays dense (no padding) and is two-ended: full-length units grow from the
+    // front, trimmed (shorter) ones from the back, so that the 32 candidates a DP warp pulls
+    // have (almost) the same number of rows
+    bool full = take && (int)ck.unit_len[HLM_CAND_UNIT(ck.cand[i])] >= kp.full_len;
+    uint32_t bal = __ballot_sync(FULL, take), balf = __ballot_sync(FULL, full);
     if (bal) {
-      unsigned long long pos = 0;
-      if (lane == 0) pos = atomicAdd(&ck.counters[1], (unsigned long long)__popc(bal));
-      pos = __shfl_sync(FULL, pos, 0);
+      uint32_t balb = bal & ~balf;
+      unsigned long long pf = 0, pb = 0;
+      if (lane == 0) {
+        if (balf) pf = atomicAdd(&ck.counters[1], (unsigned long long)__popc(balf));
+        if (balb) pb = atomicAdd(&ck.counters[13], (unsigned long long)__popc(balb));
+      }
+      pf = __shfl_sync(FULL, pf, 0);
+      pb = __shfl_sync(FULL, pb, 0);
       if (take) {
-        unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
-        if ((int64_t)at < ck.dp_cap) ck.dp_list[at] = (uint32_t)i;
+        uint32_t below = (1u << lane) - 1u;
+        long long at = full ? (long long)(pf + __popc(balf & below))
+                            : (long long)ck.dp_cap - 1 - (long long)(pb + __popc(balb & below));
+        // the two ends must not meet: checked against the other end's count at the time
+        if (at >= 0 && at < ck.dp_cap) ck.dp_list[at] = (uint32_t)i;
         else ck.counters[2] = 1;
       }
       n_take += __popc(bal);
@@ -841,8 +852,12 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
 // ------------------------------------------------------------------ k_dp
 __global__ void __launch_bounds__(128)
 k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
-  int64_t nd = (int64_t)ck.counters[1];
-  if (nd > ck.dp_cap) nd = ck.dp_cap;
+  int64_t nf = (int64_t)ck.counters[1], nb = (int64_t)ck.counters[13];
+  if (nf + nb > ck.dp_cap) {  // the two ends met: flagged, the host re-runs the chunk in halves
+    if (threadIdx.x == 0 && blockIdx.x == 0) ck.counters[2] = 1;
+    return;
+  }
+  int64_t nf_pad = (nf + 31) & ~(int64_t)31, nd = nf_pad + nb;
   int lane = threadIdx.x & 31;
   unsigned long long cells = 0;
   // warps pull groups of 32 list entries from a device counter: a DP takes 50-184 rows depending
@@ -852,8 +867,14 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     if (lane == 0) base = atomicAdd(&ck.counters[14], 32ull);
     base = __shfl_sync(FULL, base, 0);
     if ((int64_t)base >= nd) break;
-    int64_t i = (int64_t)base + lane;
-    if (i >= nd) continue;
+    int64_t j = (int64_t)base + lane, i;
+    if (j < nf_pad) {
+      if (j >= nf) continue;
+      i = j;  // front: full-length units
+    } else {
+      if (j >= nd) continue;
+      i = ck.dp_cap - nb + (j - nf_pad);  // back: trimmed units
+    }
     uint32_t di = ck.dp_list[i];
     if (di == HLM_DP_INVALID) continue;
     uint64_t c = ck.cand[di];
@@ -875,6 +896,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
 __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ck.counters[1] = 0;
+    ck.counters[13] = 0;
     ck.counters[14] = 0;
   }
 }
