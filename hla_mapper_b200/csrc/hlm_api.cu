@@ -159,7 +159,8 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   if ((rc = ensure_dev(ctx, s.d_units, (size_t)n * U * 36 * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_unit_meta, align16((size_t)n * U * 2) + (size_t)n * U * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_dp, (size_t)ctx->cand_cap * 4))) return rc;
+  int64_t dp_cap = ctx->cand_cap / 2;  // DPs are a fraction of the candidates; overflow splits the chunk
+  if ((rc = ensure_dev(ctx, s.d_dp, (size_t)dp_cap * 9 + 4096))) return rc;
   if ((rc = ensure_dev(ctx, s.d_tasks, 2 * align16((size_t)n * U * T * 4) + (size_t)n * U * T * 8 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
   HlmChunk& ck = s.ck;
@@ -170,7 +171,11 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   ck.cand = (uint64_t*)s.d_cand.p;
   ck.cand_cap = ctx->cand_cap;
   ck.dp_list = (uint32_t*)s.d_dp.p;
-  ck.dp_cap = ctx->cand_cap;
+  ck.dp_sorted = ck.dp_list + dp_cap;
+  ck.dp_hist = ck.dp_sorted + dp_cap;
+  ck.dp_cursor = ck.dp_hist + 256;
+  ck.dp_len = (uint8_t*)(ck.dp_cursor + 256);
+  ck.dp_cap = dp_cap;
   ck.counters = (unsigned long long*)s.d_counters.p;
   ck.task_emin = (uint32_t*)s.d_tasks.p;
   ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16((size_t)n * U * T * 4));
@@ -211,7 +216,7 @@ void launch_stages(hlm_ctx* ctx, Slot& s, int stages) {
     hlm_launch_dp(ctx->ddb, ctx->kp, ck, T, sms, st);
     cudaEventRecord(s.ev[EV_DP1], st);
     hlm_launch_scores(ctx->kp, ck, T, sms, st);
-    ctx->prof.launches += 19;
+    ctx->prof.launches += 23;
   } else {
     for (int e = EV_SEED; e <= EV_DP1; e++) cudaEventRecord(s.ev[e], st);
   }
@@ -328,8 +333,7 @@ int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
       return HLM_E_TOOLONG;
     }
   }
-  // DP work is grouped by length: "full length" = within 6 bases of the longest read of the batch
-  ctx->kp.full_len = longest > 6 ? (int)std::min<uint64_t>(longest, HLM_MAX_READ) - 6 : 0;
+  (void)longest;
   return 0;
 }
 
@@ -828,7 +832,6 @@ hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in) {
   bool paired = ctx->p.paired;
   b->n_pairs = n;
   b->paired = paired;
-  b->max_len = ctx->kp.full_len;  // set by check_lengths above
   size_t b1 = (size_t)in->offs1[n], b2 = paired ? (size_t)in->offs2[n] : 0;
   size_t o = 0;
   auto sec = [&](int i, size_t bytes) { b->in_off[i] = o; o += align16(bytes + 32); };
@@ -873,7 +876,6 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   memset(&ctx->prof, 0, sizeof ctx->prof);
   int T = ctx->n_targets;
   int64_t N = b->n_pairs, C = ctx->chunk_pairs;
-  ctx->kp.full_len = (int)b->max_len;
   uint8_t* d = (uint8_t*)b->in.p;
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));

@@ -476,6 +476,7 @@ __global__ void k_clear_tasks(HlmChunk ck, int64_t n_tasks) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (i < HLM_N_COUNTERS) ck.counters[i] = 0;
+  if (i < 256) ck.dp_hist[i] = 0;
   for (; i < n_tasks; i += stride) {
     ck.task_emin[i] = 0xFFFFFFFFu;
     ck.task_best[i] = HLM_BEST_NONE;
@@ -821,27 +822,26 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         }
       }
     }
-    // the DP list stays dense (no padding) and is two-ended: full-length units grow from the
-    // front, trimmed (shorter) ones from the back, so that the 32 candidates a DP warp pulls
-    // have (almost) the same number of rows
-    bool full = take && (int)ck.unit_len[HLM_CAND_UNIT(ck.cand[i])] >= kp.full_len;
-    uint32_t bal = __ballot_sync(FULL, take), balf = __ballot_sync(FULL, full);
+    // the DP list stays dense (no padding): one ballot-aggregated atomic per warp iteration.  The
+    // number of DP rows (= trimmed length) goes with every entry and into a histogram: the list
+    // is counting-sorted by length before k_dp so that the 32 candidates of a DP warp are alike.
+    int nrows = take ? (int)ck.unit_len[HLM_CAND_UNIT(ck.cand[i])] : 0;
+    uint32_t bal = __ballot_sync(FULL, take);
     if (bal) {
-      uint32_t balb = bal & ~balf;
-      unsigned long long pf = 0, pb = 0;
-      if (lane == 0) {
-        if (balf) pf = atomicAdd(&ck.counters[1], (unsigned long long)__popc(balf));
-        if (balb) pb = atomicAdd(&ck.counters[13], (unsigned long long)__popc(balb));
-      }
-      pf = __shfl_sync(FULL, pf, 0);
-      pb = __shfl_sync(FULL, pb, 0);
+      unsigned long long pos = 0;
+      if (lane == 0) pos = atomicAdd(&ck.counters[1], (unsigned long long)__popc(bal));
+      pos = __shfl_sync(FULL, pos, 0);
+      // one histogram atomic per distinct length in the warp
+      uint32_t peers = __match_any_sync(FULL, nrows);
       if (take) {
-        uint32_t below = (1u << lane) - 1u;
-        long long at = full ? (long long)(pf + __popc(balf & below))
-                            : (long long)ck.dp_cap - 1 - (long long)(pb + __popc(balb & below));
-        // the two ends must not meet: checked against the other end's count at the time
-        if (at >= 0 && at < ck.dp_cap) ck.dp_list[at] = (uint32_t)i;
-        else ck.counters[2] = 1;
+        unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
+        if ((int64_t)at < ck.dp_cap) {
+          ck.dp_list[at] = (uint32_t)i;
+          ck.dp_len[at] = (uint8_t)nrows;
+        } else {
+          ck.counters[2] = 1;
+        }
+        if (lane == __ffs(peers) - 1) atomicAdd(&ck.dp_hist[nrows], (uint32_t)__popc(peers));
       }
       n_take += __popc(bal);
     }
@@ -849,34 +849,65 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
   if (lane == 0 && n_take) atomicAdd(&ck.counters[6], n_take);
 }
 
+// ------------------------------------------------------------------ DP list: counting sort by length
+// dp_hist[n] -> dp_cursor[n] = first slot of length n in descending order of n (long DPs first:
+// the tail of the launch is filled by the short ones); the histogram is cleared for the next round
+__global__ void k_dp_scan(HlmChunk ck) {
+  __shared__ uint32_t s[256];
+  int t = threadIdx.x;  // 256 threads; thread t owns length 255 - t
+  uint32_t v = ck.dp_hist[255 - t];
+  s[t] = v;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    uint32_t x = t >= o ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += x;
+    __syncthreads();
+  }
+  ck.dp_cursor[255 - t] = s[t] - v;
+  ck.dp_hist[255 - t] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_dp_scatter(HlmChunk ck) {
+  if (ck.counters[2]) return;  // a list overflowed: the host re-runs the chunk in halves
+  int64_t nd = (int64_t)ck.counters[1];
+  if (nd > ck.dp_cap) nd = ck.dp_cap;
+  int lane = threadIdx.x & 31;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nloop = (nd + stride - 1) / stride;
+  for (int64_t it = 0; it < nloop; it++) {
+    int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = i < nd;
+    int n = act ? (int)ck.dp_len[i] : -1 - lane;  // inactive lanes never match anyone
+    uint32_t peers = __match_any_sync(FULL, n);
+    if (act) {
+      int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&ck.dp_cursor[n], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      ck.dp_sorted[base + __popc(peers & ((1u << lane) - 1u))] = ck.dp_list[i];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ k_dp
 __global__ void __launch_bounds__(128)
 k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
-  int64_t nf = (int64_t)ck.counters[1], nb = (int64_t)ck.counters[13];
-  if (nf + nb > ck.dp_cap) {  // the two ends met: flagged, the host re-runs the chunk in halves
-    if (threadIdx.x == 0 && blockIdx.x == 0) ck.counters[2] = 1;
-    return;
-  }
-  int64_t nf_pad = (nf + 31) & ~(int64_t)31, nd = nf_pad + nb;
+  if (ck.counters[2]) return;  // a list overflowed: the host re-runs the chunk in halves
+  int64_t nd = (int64_t)ck.counters[1];
+  if (nd > ck.dp_cap) nd = ck.dp_cap;
   int lane = threadIdx.x & 31;
   unsigned long long cells = 0;
-  // warps pull groups of 32 list entries from a device counter: a DP takes 50-184 rows depending
-  // on the trimmed read, so a static grid-stride split leaves a long tail
+  // warps pull groups of 32 entries of the length-sorted list from a device counter
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&ck.counters[14], 32ull);
     base = __shfl_sync(FULL, base, 0);
     if ((int64_t)base >= nd) break;
-    int64_t j = (int64_t)base + lane, i;
-    if (j < nf_pad) {
-      if (j >= nf) continue;
-      i = j;  // front: full-length units
-    } else {
-      if (j >= nd) continue;
-      i = ck.dp_cap - nb + (j - nf_pad);  // back: trimmed units
-    }
-    uint32_t di = ck.dp_list[i];
-    if (di == HLM_DP_INVALID) continue;
+    int64_t i = (int64_t)base + lane;
+    if (i >= nd) continue;
+    uint32_t di = ck.dp_sorted[i];
     uint64_t c = ck.cand[di];
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
@@ -896,7 +927,6 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
 __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ck.counters[1] = 0;
-    ck.counters[13] = 0;
     ck.counters[14] = 0;
   }
 }
@@ -1247,6 +1277,8 @@ void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk&
 }
 void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                    int sms, cudaStream_t st) {
+  k_dp_scan<<<1, 256, 0, st>>>(ck);
+  k_dp_scatter<<<grid_for(sms, 4), 256, 0, st>>>(ck);
   k_dp<<<grid_for(sms, 4), 128, 0, st>>>(db, kp, ck, n_targets);
   k_dp_round_end<<<1, 32, 0, st>>>(ck);
 }

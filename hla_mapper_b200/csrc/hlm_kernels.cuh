@@ -26,14 +26,18 @@ struct HlmChunk {
   // scoring work
   uint64_t* cand;        // candidate records
   int64_t cand_cap;
-  uint32_t* dp_list;     // indices into cand
+  uint32_t* dp_list;     // indices into cand, in selection order
+  uint32_t* dp_sorted;   // ... counting-sorted by DP rows (descending)
+  uint8_t* dp_len;       // DP rows of dp_list[i]
+  uint32_t* dp_hist;     // [256] rows histogram, then ...
+  uint32_t* dp_cursor;   // [256] ... scatter cursors
   int64_t dp_cap;
   unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
                                  // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total,
                                  // [7] read too long, [8] n_cand after the seed index,
                                  // [9] / [10] after expansion round 0 / 1 (slots incl. padding),
                                  // [11] real candidates, [12] real seed-index candidates,
-                                 // [13] DP list entries at the back, [14] / [15] work counters
+                                 // [14] / [15] work counters
   uint32_t* task_emin;   // units * n_targets: minimum lower bound over evaluated candidates
   uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
   unsigned long long* task_best;
@@ -52,7 +56,6 @@ struct HlmKParams {
   double tolerance;
   uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
   int n_loci;
-  int full_len;  // units at least this long go to the front of the DP list (k_select)
   int one;  // == 1; opaque multiplier that keeps the DP's adds on the FMA pipe (hlm_add_fma)
 };
 
