@@ -156,7 +156,7 @@ void bind_outputs(HlmChunk& ck, uint8_t* base, const size_t* off, int64_t first,
 int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   int U = ctx->units_per_pair, T = ctx->n_targets;
   int rc;
-  if ((rc = ensure_dev(ctx, s.d_units, (size_t)n * U * 36 * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_units, (size_t)n * U * HLM_UNIT_STRIDE * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_unit_meta, align16((size_t)n * U * 2) + (size_t)n * U * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
   int64_t dp_cap = ctx->cand_cap / 2;  // DPs are a fraction of the candidates; overflow splits the chunk

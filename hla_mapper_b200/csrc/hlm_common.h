@@ -19,9 +19,10 @@
 //                        seed_ent[], entries (column << 24 | tile_id) sorted by (column, tile).
 //                        Reps list every seed; children only the seeds covering a differing
 //                        column (their other candidates come from expanding the rep).
-// packed reads         a "unit" (trimmed mate, or an RNA block of it) is 18 words: r0[6], r1[6],
-//                        rn[6], base i at bit (i & 31) of word (i >> 5); bits >= len are 0 in
-//                        r0/r1 and 1 in rn.
+// packed reads         a "unit" (trimmed mate, or an RNA block of it) is 18 words per strand: r0[6],
+//                        r1[6], rn[6], base i at bit (i & 31) of word (i >> 5); bits >= len are 0
+//                        in r0/r1 and 1 in rn; plus 24 words per strand of 4-bit codes (code bit 0
+//                        / 1 = r0 / r1, bit 2 = N), eight bases per word, for the Myers kernel.
 #ifndef HLM_COMMON_H
 #define HLM_COMMON_H
 
@@ -36,6 +37,8 @@
 #define HLM_OFF_MIN HLM_BAND        /* candidate column of read base 0: [OFF_MIN, OFF_MIN+32) */
 #define HLM_NB (2 * HLM_BAND + 1)   /* band cells per DP row                               */
 #define HLM_UNIT_WORDS 18
+#define HLM_CODE_WORDS 24            /* 4-bit read codes, 8 per word, per strand               */
+#define HLM_UNIT_STRIDE (2 * HLM_UNIT_WORDS + 2 * HLM_CODE_WORDS) /* planes fwd, planes rc, codes fwd, codes rc */
 #define HLM_READ_WORDS 6
 #define HLM_RAW_MAX 256             /* longest raw read line the screen kernel accepts     */
 #define HLM_SEED_CODES (1u << (2 * HLM_SEED))

@@ -81,7 +81,8 @@ HLM_HD uint32_t hlm_tw(const uint32_t* plane, int w) { return plane[w < 8 ? w : 
 //
 // Eq comes from per-candidate match vectors PEQ[b] (bit c = tile column c holds base b; row 4 is
 // all zero for N read bases), kept in shared memory on the device; the read is consumed as
-// 4-bit codes, eight per word, spread from the bit planes with three shift-or-mask steps.
+// 4-bit codes, eight per word (k_pack_units spreads them from the bit planes with three
+// shift-or-mask steps and stores them next to the planes).
 #define HLM_PEQ_ROWS 41 /* 5 vectors x 8 words + 1 pad word (read when the window ends at word 7) */
 
 HLM_HD uint32_t hlm_spread8(uint32_t x) {  // bit j of x (j < 8) -> bit 4j
@@ -108,25 +109,15 @@ HLM_HD void hlm_peq_build(const uint32_t* __restrict__ tile, PEQ peq) {
   peq(40) = 0u;
 }
 
+// codes: the read as 4-bit codes, 8 per word (code bit 0 / 1 = the base, bit 2 = N -> PEQ row 4)
 template <class PEQ>
-HLM_HD int hlm_myers_core(const uint32_t* __restrict__ rd, int n, int off, PEQ peq) {
+HLM_HD int hlm_myers_core(const uint32_t* __restrict__ codes, int n, int off, PEQ peq) {
   const uint64_t MASK = (1ull << HLM_NB) - 1, TOP = 1ull << (HLM_NB - 1);
   uint64_t SP = TOP, SN = 0;
   int score = 0;  // c_0
   int p = off - HLM_BAND;
-  uint32_t r0 = 0, r1 = 0, rn = 0, cw = 0;
-#define HLM_MYERS_REFILL(i)                                                                       \
-  {                                                                                               \
-    if (((i) & 31) == 0) {                                                                        \
-      r0 = rd[(i) >> 5];                                                                          \
-      r1 = rd[6 + ((i) >> 5)];                                                                    \
-      rn = rd[12 + ((i) >> 5)];                                                                   \
-    }                                                                                             \
-    cw = hlm_spread8(r0 & 0xFFu) | (hlm_spread8(r1 & 0xFFu) << 1) | (hlm_spread8(rn & 0xFFu) << 2); \
-    r0 >>= 8;                                                                                     \
-    r1 >>= 8;                                                                                     \
-    rn >>= 8;                                                                                     \
-  }
+  uint32_t cw = 0;
+#define HLM_MYERS_REFILL(i) cw = codes[(i) >> 3];
 #define HLM_MYERS_ROW()                                                                            \
   {                                                                                               \
     int row = (int)(cw & 7u) * 8 + (p >> 5); /* codes 5..7 cannot occur (N clears the code bits) */ \
@@ -172,10 +163,15 @@ struct HlmPeqLocal {
 };
 HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
                         int off) {
-  uint32_t buf[HLM_PEQ_ROWS];
+  uint32_t buf[HLM_PEQ_ROWS], codes[24];
   HlmPeqLocal peq{buf};
   hlm_peq_build(tile, peq);
-  return hlm_myers_core(rd, n, off, peq);
+  for (int j = 0; j < 24; j++) {
+    int w = j >> 2, sh = 8 * (j & 3);
+    codes[j] = hlm_spread8((rd[w] >> sh) & 0xFFu) | (hlm_spread8((rd[6 + w] >> sh) & 0xFFu) << 1) |
+               (hlm_spread8((rd[12 + w] >> sh) & 0xFFu) << 2);
+  }
+  return hlm_myers_core(codes, n, off, peq);
 }
 
 // ------------------------------------------------------------------ banded affine-gap DP

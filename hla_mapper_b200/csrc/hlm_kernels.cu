@@ -376,7 +376,7 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
 // unit layout per pair: dna: [mate]; rna: [mate*3 + {whole, block A, block B}]
 __device__ __forceinline__ void write_unit(const HlmChunk& ck, int64_t unit, WarpScratch& ws, int lo,
                                            int n, uint32_t tmask, int lane) {
-  uint32_t* out = ck.unit_planes + unit * 36;
+  uint32_t* out = ck.unit_planes + unit * HLM_UNIT_STRIDE;
   // forward planes: bits [lo, lo+n) of the staged planes
   uint32_t f0 = 0, f1 = 0, fn = 0xFFFFFFFFu;
   if (lane < 6) {
@@ -426,6 +426,18 @@ __device__ __forceinline__ void write_unit(const HlmChunk& ck, int64_t unit, War
   if (lane == 0) {
     ck.unit_len[unit] = (uint16_t)n;
     ck.unit_mask[unit] = tmask;
+  }
+  __syncwarp();
+  // 4-bit codes of both strands for k_myers: word j = bases 8j .. 8j+7 (lanes 0-23 one strand each
+  // pass); the planes were just written by this warp
+  for (int strand = 0; strand < 2; strand++) {
+    if (lane < HLM_CODE_WORDS) {
+      const uint32_t* P = out + 18 * strand;
+      int w = lane >> 2, sh = 8 * (lane & 3);
+      uint32_t x0 = (P[w] >> sh) & 0xFFu, x1 = (P[6 + w] >> sh) & 0xFFu, xn = (P[12 + w] >> sh) & 0xFFu;
+      out[2 * HLM_UNIT_WORDS + HLM_CODE_WORDS * strand + lane] =
+          hlm_spread8(x0) | (hlm_spread8(x1) << 1) | (hlm_spread8(xn) << 2);
+    }
   }
   __syncwarp();
 }
@@ -521,8 +533,8 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     if (n == 0) continue;
     uint32_t umask = ck.unit_mask[unit];
     __syncwarp();
-    rd[lane] = ck.unit_planes[unit * 36 + lane];
-    if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * 36 + 32 + lane];
+    rd[lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + lane];
+    if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + 32 + lane];
     __syncwarp();
     int Q = n / HLM_SEED;
     // lane (strand*16 + q) owns seed q of that strand: CSR range of its 12-mer narrowed to the
@@ -668,7 +680,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
-    const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
+    const uint32_t* rd = ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
     int lb;
     bool dead = false;
@@ -694,7 +706,9 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       lb = 254;
     } else {
       hlm_peq_build(T, peq);
-      lb = hlm_myers_core(rd, n, off, peq);
+      lb = hlm_myers_core(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
+                              HLM_CODE_WORDS * strand,
+                          n, off, peq);
       if (lb > 253) lb = 253;
       rows += n;
     }
@@ -912,7 +926,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
     int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
     int n = ck.unit_len[unit];
-    const uint32_t* rd = ck.unit_planes + (size_t)unit * 36 + 18 * strand;
+    const uint32_t* rd = ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
     HlmAln a = hlm_dp_align(rd, n, T, off, kp.one);
     int g = tile_locus(db, tile);
