@@ -75,6 +75,13 @@ class HlmFileStats(C.Structure):
                [(k, C.c_double) for k in ("s_total", "s_gpu", "s_wait_input", "s_collect", "s_write")]
 
 
+class HlmBamStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_records", "n_region", "n_unmapped", "n_names", "n_r0", "n_r1",
+                                         "n_r2", "n_out", "bytes_compressed", "bytes_inflated")] + \
+               [("paired", C.c_int32), ("reserved0", C.c_int32)] + \
+               [(k, C.c_double) for k in ("s_pass1", "s_pass2", "s_total")]
+
+
 def default_params(rna=0, **kw):
     """main.cpp:73-86 defaults (the float literal 0.08f widened to double included)"""
     p = HlmParams()

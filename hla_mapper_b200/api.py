@@ -26,6 +26,8 @@ SYMBOLS = [
     "hlm_batch_free", "hlm_run_device", "hlm_fetch", "hlm_get_profile", "hlm_int32_peak",
     "hlm_map_fastq", "hlm_run_async", "hlm_wait", "hlm_multi_create", "hlm_multi_destroy",
     "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run", "hlm_dp_layout_ab",
+    "hlm_bam_extract", "hlm_reads_paired", "hlm_reads_count", "hlm_reads_free",
+    "hlm_reads_write_fastq", "hlm_map_reads",
 ]
 
 _lib = None
@@ -89,6 +91,16 @@ def lib():
     L.hlm_int32_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
     L.hlm_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                 C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
+    L.hlm_bam_extract.restype = C.c_void_p
+    L.hlm_bam_extract.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                  C.POINTER(_abi.HlmBamStats), C.c_char_p, C.c_size_t]
+    L.hlm_reads_paired.argtypes = [C.c_void_p]
+    L.hlm_reads_count.restype = C.c_int64
+    L.hlm_reads_count.argtypes = [C.c_void_p]
+    L.hlm_reads_free.argtypes = [C.c_void_p]
+    L.hlm_reads_write_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.hlm_map_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p,
+                                C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
     _lib = L
     return L
 
@@ -112,6 +124,32 @@ class Database:
     def close(self):
         if self.h:
             lib().hlm_db_close(self.h)
+            self.h = None
+
+
+class BamReads:
+    """hlm_reads: what the reference's bam= front end (four samtools calls, preselect.cpp:315-447)
+    hands to its screen loop, extracted in-process (host threads only, no GPU involved)"""
+
+    def __init__(self, db: Database, bam, bed=None, skip_unmapped=0, threads=0):
+        err = C.create_string_buffer(512)
+        st = _abi.HlmBamStats()
+        self.h = lib().hlm_bam_extract(db.h, str(bam).encode(), str(bed).encode() if bed else None,
+                                       int(skip_unmapped), int(threads), C.byref(st), err, 512)
+        if not self.h:
+            raise HlmError(err.value.decode())
+        self.stats = {k: getattr(st, k) for k, _ in _abi.HlmBamStats._fields_}
+        self.paired = bool(lib().hlm_reads_paired(self.h))
+        self.n = int(lib().hlm_reads_count(self.h))
+
+    def write_fastq(self, r1, r2=None):
+        rc = lib().hlm_reads_write_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None)
+        if rc != 0:
+            raise HlmError(f"hlm_reads_write_fastq rc={rc}")
+
+    def close(self):
+        if self.h:
+            lib().hlm_reads_free(self.h)
             self.h = None
 
 
@@ -206,6 +244,16 @@ class Mapper:
         self._check(lib().hlm_map_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None,
                                         sample.encode(), str(out_dir).encode(), C.byref(o),
                                         C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
+
+    def map_reads(self, reads: BamReads, sample, out_dir, downsampling=30, batch_pairs=0,
+                  write_selected=1, select_only=0):
+        """hlm_map_reads: reads extracted from a BAM in, the same files as map_fastq out"""
+        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
+                             select_only)
+        st = _abi.HlmFileStats()
+        self._check(lib().hlm_map_reads(self.h, reads.h, sample.encode(), str(out_dir).encode(),
+                                        C.byref(o), C.byref(st)))
         return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
 
     def profile(self):

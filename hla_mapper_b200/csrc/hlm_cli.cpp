@@ -6,10 +6,11 @@
 //
 //   hla-mapper-b200 dna    r1=R1.fastq[.gz] r2=R2.fastq[.gz] sample=NAME [db=DIR] [output=DIR] ...
 //   hla-mapper-b200 dna    r0=R0.fastq[.gz] sample=NAME ...
+//   hla-mapper-b200 dna    bam=ALIGNED.bam sample=NAME [--skip-unmapped] ...   (no samtools needed)
 //   hla-mapper-b200 select ...           (screen + trim only: selected*.fastq)
 //
-// Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= --quiet
-// (threads= and buffer= are accepted and ignored: there is no host thread pool to size).
+// Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= threads= --quiet
+// --skip-unmapped (threads= sizes the BAM reader only; buffer= is accepted and ignored).
 // db defaults to the `db=` line of ~/.hla-mapper (home from getpwuid, src/main.cpp:266-273).
 #include <pwd.h>
 #include <sys/stat.h>
@@ -39,14 +40,15 @@ int main(int argc, char** argv) {
     fprintf(stderr,
             "Usage:     hla-mapper-b200 dna r1=R1.gz r2=R2.gz sample=your_sample_name <options>\n"
             "           hla-mapper-b200 dna r0=R0.gz sample=your_sample_name <options>\n"
+            "           hla-mapper-b200 dna bam=sample.bam sample=your_sample_name <options>\n"
             "           hla-mapper-b200 select r1=... r2=... sample=... <options>\n"
-            "Options:   db= output= size= tolerance= error= downsample= gpu= --quiet\n");
+            "Options:   db= output= size= tolerance= error= downsample= gpu= threads= --quiet --skip-unmapped\n");
     return 1;
   }
   bool select_only = strcmp(argv[1], "select") == 0, quiet = false;
-  std::string r0, r1, r2, sample, db, output;
+  std::string r0, r1, r2, bam, sample, db, output;
   double tolerance = -1, error = -1;
-  int size = 0, downsample = 30, gpu = 0;
+  int size = 0, downsample = 30, gpu = 0, threads = 0, skip_unmapped = 0;
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     if (starts(a, "r0=")) r0 = a.substr(3);
@@ -61,15 +63,14 @@ int main(int argc, char** argv) {
     else if (starts(a, "downsample=")) downsample = atoi(a.c_str() + 11);
     else if (starts(a, "gpu=")) gpu = atoi(a.c_str() + 4);
     else if (a == "--quiet") quiet = true;
-    else if (starts(a, "threads=") || starts(a, "buffer=") || starts(a, "--")) continue;
-    else if (starts(a, "bam=")) {
-      fprintf(stderr, "bam= input needs samtools (src/preselect.cpp:315-418) and is not part of this build\n");
-      return 2;
-    }
+    else if (a == "--skip-unmapped") skip_unmapped = 1;  // src/main.cpp:626-630
+    else if (starts(a, "threads=")) threads = atoi(a.c_str() + 8);
+    else if (starts(a, "bam=")) bam = a.substr(4);
+    else if (starts(a, "buffer=") || starts(a, "--")) continue;
   }
   bool paired = r0.empty();
-  if (sample.empty() || (paired && (r1.empty() || r2.empty()))) {
-    fprintf(stderr, "You must indicate r1 and r2, or r0, and a sample name.\n");
+  if (sample.empty() || (bam.empty() && paired && (r1.empty() || r2.empty()))) {
+    fprintf(stderr, "You must indicate r1 and r2, or r0, or bam, and a sample name.\n");
     return 2;
   }
   if (db.empty()) db = config_db();
@@ -77,7 +78,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "No database: pass db= or set it in ~/.hla-mapper\n");
     return 2;
   }
-  const std::string& first = paired ? r1 : r0;
+  const std::string& first = !bam.empty() ? bam : paired ? r1 : r0;
   if (output.empty()) {  // src/map_dna.cpp:404-409
     size_t sl = first.find_last_of('/');
     output = (sl == std::string::npos ? std::string(".") : first.substr(0, sl)) + "/hla-mapper/";
@@ -89,15 +90,34 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s\n", err);
     return 3;
   }
+  // bam=: the reads come out of the BAM first; whether they are paired is a property of the file
+  // (v_map_type, src/preselect.cpp:420-425)
+  hlm_reads* R = nullptr;
+  hlm_bam_stats bs;
+  if (!bam.empty()) {
+    R = hlm_bam_extract(D, bam.c_str(), nullptr, skip_unmapped, threads, &bs, err, sizeof err);
+    if (!R) {
+      fprintf(stderr, "%s\n", err);
+      hlm_db_close(D);
+      return 3;
+    }
+    paired = hlm_reads_paired(R) != 0;
+    if (!quiet)
+      fprintf(stderr, "%lld BAM records (%.2f GB inflated) in %.2fs: %lld in the regions, %lld unmapped, %lld names -> %lld %s\n",
+              (long long)bs.n_records, bs.bytes_inflated / 1e9, bs.s_total, (long long)bs.n_region,
+              (long long)bs.n_unmapped, (long long)bs.n_names, (long long)bs.n_out, paired ? "pairs" : "reads");
+  }
   hlm_params p;
   hlm_params_default(&p, 0);
   p.paired = paired ? 1 : 0;
+  if (R) p.screen_variant = HLM_SCREEN_BAM;
   if (size > 0) p.v_size = size;
   if (tolerance >= 0) p.tolerance = tolerance;
   if (error >= 0) p.mtrim_error = error;
   hlm_ctx* C = hlm_ctx_create(D, gpu, &p, err, sizeof err);
   if (!C) {
     fprintf(stderr, "%s\n", err);
+    hlm_reads_free(R);
     hlm_db_close(D);
     return 3;
   }
@@ -108,7 +128,9 @@ int main(int argc, char** argv) {
   fo.write_selected = 1;
   fo.select_only = select_only ? 1 : 0;
   hlm_file_stats st;
-  int rc = hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
+  int rc = R ? hlm_map_reads(C, R, sample.c_str(), output.c_str(), &fo, &st)
+             : hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
+  hlm_reads_free(R);
   if (rc != HLM_OK) fprintf(stderr, "hla-mapper-b200: %s\n", hlm_last_error(C));
   else if (!quiet)
     fprintf(stderr,

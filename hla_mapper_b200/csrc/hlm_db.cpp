@@ -177,6 +177,7 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   }
   hlm_db* db = new hlm_db();
   db->rna = rna;
+  db->dir = dir;
   bool version_ok = false;
   {
     size_t i = 0, n = info.size();

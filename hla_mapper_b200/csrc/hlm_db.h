@@ -10,6 +10,7 @@
 
 struct hlm_db {
   int rna = 0;
+  std::string dir;  // database directory as given (bed/select_*.bed is read from it on demand)
   int n_loci = 0;
   int v_size = 50;  // src/main.cpp:79; overridden by SIZE: (map_dna.cpp:351-354)
   std::vector<std::string> names;  // n_loci + "others"

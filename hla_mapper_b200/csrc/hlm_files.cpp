@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "hlm_db.h"
+#include "hlm_files.h"
 
 extern "C" const char* hlm_last_error(const hlm_ctx* ctx);
 void hlm_ctx_set_error(hlm_ctx* ctx, const std::string& msg);
@@ -39,20 +40,6 @@ const hlm_db* hlm_ctx_db(const hlm_ctx* ctx);
 const hlm_params* hlm_ctx_params(const hlm_ctx* ctx);
 
 namespace {
-
-struct MateBatch {
-  std::vector<uint8_t> bases, quals;
-  std::vector<uint64_t> offs;       // n + 1
-  std::vector<char> hdr;            // header lines, no newline, concatenated
-  std::vector<uint64_t> hoff;       // n + 1
-  int64_t n = 0;
-  bool bad = false;                 // truncated / malformed input
-  void clear() {
-    bases.clear(); quals.clear(); hdr.clear();
-    offs.assign(1, 0); hoff.assign(1, 0);
-    n = 0;
-  }
-};
 
 // reads 4-line records straight out of a large refill buffer (one memchr per line, one copy per
 // field into the SoA vectors)
@@ -218,6 +205,35 @@ class BatchStream {
   bool stop_ = false, done_ = false;
 };
 
+// r1 (+ r2) FASTQ files, one reader thread each
+class FileSource : public PairSource {
+ public:
+  FileSource(const char* r1, const char* r2, int64_t batch_pairs) : in1_(r1, batch_pairs) {
+    if (r2) in2_.reset(new BatchStream(r2, batch_pairs));
+  }
+  bool ok1() const { return in1_.ok(); }
+  bool ok2() const { return !in2_ || in2_->ok(); }
+  bool next(MateBatch*& b1, MateBatch*& b2, int& rc, std::string& err) override {
+    b1 = in1_.next();
+    b2 = in2_ ? in2_->next() : nullptr;
+    bool end = !b1 || (in2_ && !b2);
+    if (in2_ && ((end && (b1 != nullptr) != (b2 != nullptr)) || (!end && b1->n != b2->n))) {
+      err = "r1 and r2 hold different numbers of reads";
+      rc = HLM_E_IO;
+      return false;
+    }
+    return !end;
+  }
+  void recycle(MateBatch* b1, MateBatch* b2) override {
+    in1_.recycle(b1);
+    if (in2_) in2_->recycle(b2);
+  }
+
+ private:
+  BatchStream in1_;
+  std::unique_ptr<BatchStream> in2_;
+};
+
 void erase_all(std::string& s, const char* pat) {  // boost::replace_all(s, pat, "")
   size_t n = strlen(pat), p = 0;
   while ((p = s.find(pat, p)) != std::string::npos) s.erase(p, n);
@@ -340,17 +356,30 @@ extern "C" int hlm_wait(hlm_ctx*);
 extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
                              const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
   if (!ctx || !r1_path || !sample || !out_dir) return HLM_E_ARG;
-  const hlm_db* db = hlm_ctx_db(ctx);
   const hlm_params* P = hlm_ctx_params(ctx);
-  if (P->rna) {
-    hlm_ctx_set_error(ctx, "hlm_map_fastq drives the dna path; rna needs the STAR block split as input");
-    return HLM_E_ARG;
-  }
   bool paired = P->paired != 0;
   if (paired != (r2_path != nullptr)) {
     hlm_ctx_set_error(ctx, "paired context needs r1 and r2; single-end context needs r2 == NULL");
     return HLM_E_ARG;
   }
+  int64_t batch = opts_in && opts_in->struct_size >= 12 && opts_in->batch_pairs > 0 ? opts_in->batch_pairs : 1 << 19;
+  FileSource src(r1_path, r2_path, batch);
+  if (!src.ok1() || !src.ok2()) {
+    hlm_ctx_set_error(ctx, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
+    return HLM_E_IO;
+  }
+  return hlm_map_source(ctx, src, paired, sample, out_dir, opts_in, stats);
+}
+
+int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, const char* sample,
+                   const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
+  const hlm_db* db = hlm_ctx_db(ctx);
+  const hlm_params* P = hlm_ctx_params(ctx);
+  if (P->rna) {
+    hlm_ctx_set_error(ctx, "the file pipeline drives the dna path; rna needs the STAR block split as input");
+    return HLM_E_ARG;
+  }
+  bool paired = P->paired != 0;
   hlm_file_opts o;
   memset(&o, 0, sizeof o);
   o.struct_size = (int32_t)sizeof o;
@@ -367,13 +396,6 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   const char* tag = paired ? "R1" : "R0";
 
   double t_start = now_s(), t_gpu = 0, t_post = 0, t_wait = 0;
-  BatchStream in1(r1_path, o.batch_pairs);
-  std::unique_ptr<BatchStream> in2;
-  if (paired) in2.reset(new BatchStream(r2_path, o.batch_pairs));
-  if (!in1.ok() || (paired && !in2->ok())) {
-    hlm_ctx_set_error(ctx, std::string("cannot open ") + (in1.ok() ? r2_path : r1_path));
-    return HLM_E_IO;
-  }
   Out sel1, sel2;
   if (o.write_selected) {
     if (!sel1.open(pre + "selected." + tag + ".fastq") || (paired && !sel2.open(pre + "selected.R2.fastq"))) {
@@ -400,8 +422,8 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       if (!(R.flags[i] & HLM_F_SCREENED)) continue;
       P.n_selected++;
       h1.assign(b1->hdr.data() + b1->hoff[i], b1->hoff[i + 1] - b1->hoff[i]);
-      if (paired) {  // src/preselect.cpp:664-665, :675-676
-        h2.assign(b2->hdr.data() + b2->hoff[i], b2->hoff[i + 1] - b2->hoff[i]);
+      if (paired) h2.assign(b2->hdr.data() + b2->hoff[i], b2->hoff[i + 1] - b2->hoff[i]);
+      if (normalise_pair_headers) {  // src/preselect.cpp:664-665, :675-676
         if (h1.find('/') != std::string::npos) { erase_all(h1, "/1"); erase_all(h1, "/2"); }
         if (h2.find('/') != std::string::npos) { erase_all(h2, "/1"); erase_all(h2, "/2"); }
       }
@@ -474,8 +496,7 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
       kept.insert(kept.end(), P.kept.begin(), P.kept.end());
     }
     n_pairs += n;
-    in1.recycle(R.b1);
-    if (paired) in2->recycle(R.b2);
+    src.recycle(R.b1, R.b2);
   };
 
   // batch k+1 runs on the GPU (hlm_run_async) while batch k is collected on this thread and the
@@ -485,19 +506,11 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   bool inflight = false;
   for (;;) {
     double t0 = now_s();
-    MateBatch* b1 = in1.next();
-    MateBatch* b2 = paired ? in2->next() : nullptr;
+    MateBatch *b1 = nullptr, *b2 = nullptr;
+    std::string src_err;
+    bool end = !src.next(b1, b2, rc, src_err);
+    if (rc) hlm_ctx_set_error(ctx, src_err);
     t_wait += now_s() - t0;
-    bool end = !b1 || (paired && !b2);
-    if (end && paired && ((b1 != nullptr) != (b2 != nullptr))) {
-      hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
-      rc = HLM_E_IO;
-    }
-    if (!end && paired && b1->n != b2->n) {
-      hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
-      rc = HLM_E_IO;
-      end = true;
-    }
     if (inflight) {  // finish the previous batch on the GPU
       t0 = now_s();
       int r2 = hlm_wait(ctx);

@@ -36,6 +36,10 @@ _ALLELE_SHAPE = {
 }
 
 
+# intervals of chr6 written to bed/select_{dna,rna}.bed (0-based, half-open)
+SELECT_BED = ((29000000, 33500000), (31000000, 31002000), (40000000, 40002000))
+
+
 @dataclass
 class SynthDB:
     path: str
@@ -193,6 +197,11 @@ def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000
                 L = len(ancestors[g])
                 f.write(f"GENE:{g}:chr6:{29000000 + gi * 100000}:170805979:1:{L}:HLA\n")
             f.write(f"SIZE:{v_size}\n")
+        # bed/select_<kind>.bed: the regions `samtools view -ML` extracts (preselect.cpp:332-334)
+        os.makedirs(os.path.join(path, "bed"), exist_ok=True)
+        with open(os.path.join(path, "bed", f"select_{kind}.bed"), "w") as f:
+            for b, e in SELECT_BED:
+                f.write(f"chr6\t{b}\t{e}\n")
         os.makedirs(os.path.join(path, "motif", kind, "all"), exist_ok=True)
         os.makedirs(os.path.join(path, "motif", kind, "loci"), exist_ok=True)
         os.makedirs(os.path.join(path, "others", kind), exist_ok=True)

@@ -237,6 +237,35 @@ typedef struct hlm_file_stats {
 int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
                   const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
 
+/* ---- BAM front end of the dna path ----
+ * hlm_bam_extract replaces the four samtools processes of the reference's bam= input
+ * (preselect.cpp:315-418: view -ML <db>/bed/select_{dna,rna}.bed, view -f4, view -N, fastq) with
+ * an in-process reader (BGZF blocks inflated on `threads` host threads, 0 = all): reads that
+ * overlap a BED interval or are unmapped, plus every primary record sharing their names, as the
+ * R0 / R1 / R2 sets `samtools fastq` would write.  The result says whether the reference would
+ * treat the BAM as paired (v_map_type, preselect.cpp:420-425); create the context with that
+ * `paired` and screen_variant = HLM_SCREEN_BAM, then hlm_map_reads runs the same pipeline and
+ * writes the same files as hlm_map_fastq.  bed_path == NULL: the database's own BED.
+ * Errors carry the reference's messages ("Extraction failed!", "There is not enough data ..."). */
+typedef struct hlm_reads hlm_reads;
+typedef struct hlm_bam_stats {
+  int64_t n_records, n_region, n_unmapped, n_names, n_r0, n_r1, n_r2, n_out;
+  int64_t bytes_compressed, bytes_inflated;
+  int32_t paired, reserved0;
+  double s_pass1, s_pass2, s_total;
+} hlm_bam_stats;
+hlm_reads* hlm_bam_extract(const hlm_db* db, const char* bam_path, const char* bed_path,
+                           int skip_unmapped, int threads, hlm_bam_stats* stats, char* err,
+                           size_t errlen);
+int hlm_reads_paired(const hlm_reads* r);
+int64_t hlm_reads_count(const hlm_reads* r); /* pairs (paired) or reads (single end) to be mapped */
+void hlm_reads_free(hlm_reads* r);
+/* the reads as FASTQ, in the order and with the header lines they enter the screen with (paired:
+ * both files; single end: r2_path ignored) */
+int hlm_reads_write_fastq(const hlm_reads* r, const char* r1_path, const char* r2_path);
+int hlm_map_reads(hlm_ctx* ctx, const hlm_reads* reads, const char* sample, const char* out_dir,
+                  const hlm_file_opts* opts, hlm_file_stats* stats);
+
 /* INT32 micro-benchmark (IADD3 / IMAD / VIADDMNMX chains) used as the DP roofline
  * denominator; returns giga warp-lane ops per second */
 int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,

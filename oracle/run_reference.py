@@ -52,7 +52,10 @@ def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None,
         shutil.rmtree(out_dir)
     cmd = [REF_BIN, "rna" if rna else "dna"]
     env = dict(os.environ)
-    if bam:  # bam = (r1, r2): the stand-in samtools serves them as the content of a "BAM"
+    if isinstance(bam, str):  # a real BAM file: parsed by the stand-in samtools (oracle/bamlite.py)
+        env.pop("HLM_STANDIN_BAM", None)
+        cmd.append(f"bam={bam}")
+    elif bam:  # bam = (r1, r2): the stand-in samtools serves them as the content of a "BAM"
         os.makedirs(os.path.dirname(out_dir.rstrip("/")) or ".", exist_ok=True)
         manifest = out_dir.rstrip("/") + ".standin.bam"
         with open(manifest, "w") as f:

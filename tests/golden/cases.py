@@ -32,6 +32,31 @@ CASES = {
                                   frag_sd=30, ragged=True), "single"),
 }
 
+# bam= input from a real BAM file (tests/bam_cases.py writes it): the whole front end of
+# preselect.cpp:315-631 - name, (db kwargs, reads kwargs, make_bam kwargs)
+BAM_CASES = {
+    "dna_bamfile": (DB_SMALL, dict(n_pairs=1400, read_len=120, seed=21, on_target=0.8, frag_mu=260,
+                                   frag_sd=30, ragged=True), dict(seed=31, single=False)),
+    "dna_bamfile_single": (DB_SMALL, dict(n_pairs=1200, read_len=120, seed=22, on_target=0.8, frag_mu=260,
+                                          frag_sd=30, ragged=True), dict(seed=32, single=True)),
+}
+
+
+def bam_inputs(name, root):
+    """(SynthDB written under root, path of the BAM, params)"""
+    import os
+
+    import bam_cases
+
+    dbk, rk, bk = BAM_CASES[name]
+    db = synth.make_db(os.path.join(root, f"db_{dbk['seed']}"), **dbk)
+    rk = dict(rk)
+    rb = synth.make_reads(db, rk.pop("n_pairs"), **rk)
+    bam = os.path.join(root, name + ".bam")
+    bam_cases.make_bam(rb, bam, **bk)
+    p = _abi.default_params(rna=0, paired=0 if bk["single"] else 1, screen_variant=1)
+    return db, bam, p
+
 
 def inputs(name, root):
     """(SynthDB written under root, ReadBatch, params, header lines R1)"""
@@ -101,6 +126,12 @@ def size_override(rb, mode, name=None):
     if mode != "single":
         return None
     return np.array([len(h) for h in header_lines(rb, mode, name)], dtype=np.int32)
+
+
+def raw_digest(path):
+    import hashlib
+
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
 
 
 def canonical_digest(path):

@@ -20,6 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
 
 import cases  # noqa: E402
 import run_reference as rr  # noqa: E402
@@ -45,9 +46,43 @@ def fastq_records(path):
     return out
 
 
+def bam_case(name):
+    """bam=<real BAM>: the reference's whole bam= front end, samtools served by the stand-in"""
+    with tempfile.TemporaryDirectory() as tmp:
+        db, bam, p = cases.bam_inputs(name, tmp)
+        out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", bam=bam)
+        tag = "R1" if p.paired else "R0"
+        names, rows = rr.parse_addressing_table(out + "G_addressing_table.txt")
+        want = [f"G_selected.{tag}.fastq", f"G_selected.trim.{tag}.fastq", "G_addressing_table.txt"]
+        for g in names[:-1]:
+            want += [f"G_{g}_{tag}.fastq", f"G_{g}.trim.{tag}.fastq"]
+        if p.paired:
+            want += [w.replace(tag, "R2") for w in want if tag in w]
+        files = {w: cases.canonical_digest(out + w) for w in want}
+        # the bam= path writes selected.R*.fastq from a std::map: that order is defined
+        exact = {w: cases.raw_digest(out + w) for w in want if w.startswith("G_selected.")}
+        trim1 = fastq_records(out + f"G_selected.trim.{tag}.fastq")
+        sel = fastq_records(out + f"G_selected.{tag}.fastq")
+        gold = {"case": name, "mode": "bamfile", "targets": names, "files": files, "files_exact": exact,
+                "n_selected": len(sel), "n_kept": len(trim1), "n_rows": len(rows),
+                "paired": int(p.paired)}
+        path = os.path.join(HERE, name + ".json.gz")
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(gold, sort_keys=True).encode())
+        multi = sum(1 for v in rows.values() if "," in v[1])
+        print(f"{name}: {len(sel)} selected, {len(trim1)} kept, {len(rows)} rows ({multi} multi-target)"
+              f" -> {os.path.getsize(path)} bytes")
+
+
 def main():
     assert rr.available(), "build oracle/_ref first: make -C oracle ref"
+    only = set(sys.argv[1:])
+    for name in cases.BAM_CASES:
+        if not only or name in only:
+            bam_case(name)
     for name in cases.CASES:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             db, rb, p, mode = cases.inputs(name, tmp)
             r1, r2 = cases.write_inputs(name, rb, mode, tmp)
