@@ -1,7 +1,7 @@
 """BAM ingest throughput of hlm_bam_extract + hlm_map_reads on a whole-genome-shaped BAM: a block of
 records (2 % in the BED regions, 1 % unmapped, the rest elsewhere) written once with
 oracle/bamlite.py and its BGZF blocks repeated K times behind one header.  Usage (GPU box):
-    python tools/bam_bench.py [copies] [threads]"""
+    python tests/bam_bench.py [copies] [threads]"""
 import json
 import os
 import struct
