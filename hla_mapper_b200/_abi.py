@@ -37,7 +37,13 @@ class HlmBatch(C.Structure):
         ("n_pairs", C.c_int64), ("bases1", u8p), ("quals1", u8p), ("offs1", u64p),
         ("bases2", u8p), ("quals2", u8p), ("offs2", u64p), ("size_override1", i32p),
         ("rna_split1", u16p), ("rna_split2", u16p),
+        ("rna_block_off", u64p), ("rna_blocks", C.c_void_p),
     ]
+
+
+# hlm_rna_block as a numpy record
+RNA_BLOCK = np.dtype([("gene", np.uint8), ("mate", np.uint8), ("start", np.uint16), ("len", np.uint16),
+                      ("reserved", np.uint16)])
 
 
 class HlmScreenOut(C.Structure):
@@ -151,8 +157,9 @@ class Buffers:
         return {k: getattr(self, k) for k in self.FIELDS}
 
 
-def make_batch(rb, size_override1=None, rna_split1=None, rna_split2=None, paired=True):
-    """hlm_batch over a synth.ReadBatch (keeps the arrays alive on the returned object)"""
+def make_batch(rb, size_override1=None, rna_split1=None, rna_split2=None, paired=True, rna_blocks=None):
+    """hlm_batch over a synth.ReadBatch (keeps the arrays alive on the returned object);
+    rna_blocks = (offsets uint64[n_pairs + 1], blocks RNA_BLOCK[])"""
     keep = []
 
     def c(a, dt):
@@ -175,5 +182,10 @@ def make_batch(rb, size_override1=None, rna_split1=None, rna_split2=None, paired
         b.rna_split1 = _ptr(c(rna_split1, np.uint16), u16p)
     if rna_split2 is not None:
         b.rna_split2 = _ptr(c(rna_split2, np.uint16), u16p)
+    if rna_blocks is not None:
+        off, blk = rna_blocks
+        b.rna_block_off = _ptr(c(off, np.uint64), u64p)
+        blk = c(blk, RNA_BLOCK)
+        b.rna_blocks = blk.ctypes.data if len(blk) else None
     b._keep = keep
     return b

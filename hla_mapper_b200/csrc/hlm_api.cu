@@ -59,6 +59,7 @@ struct hlm_devbatch {
   int64_t max_len = 0;
   bool paired = true;
   bool has_override = false, has_split1 = false, has_split2 = false;
+  std::vector<uint64_t> blk_off;  // host copy of rna_block_off (chunk slicing); empty = no block list
   int64_t read_bytes = 0;
 };
 
@@ -153,21 +154,28 @@ void bind_outputs(HlmChunk& ck, uint8_t* base, const size_t* off, int64_t first,
   ck.others_s2 = (uint16_t*)(base + off[O_OS2]) + first;
 }
 
-int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
+// n pairs plus n_blocks rna block units
+int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0) {
   int U = ctx->units_per_pair, T = ctx->n_targets;
+  size_t NU = (size_t)n * U + (size_t)n_blocks;
+  if (NU >= (1ull << 26)) {
+    ctx->err = "more than 2^26 units (mates + rna blocks) in one chunk: lower hlm_params.chunk_pairs";
+    return HLM_E_ARG;
+  }
   int rc;
-  if ((rc = ensure_dev(ctx, s.d_units, (size_t)n * U * HLM_UNIT_STRIDE * 4 + 256))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_unit_meta, align16((size_t)n * U * 2) + (size_t)n * U * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_units, NU * HLM_UNIT_STRIDE * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_unit_meta, align16(NU * 2) + NU * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
   int64_t dp_cap = ctx->cand_cap / 2;  // DPs are a fraction of the candidates; overflow splits the chunk
   if ((rc = ensure_dev(ctx, s.d_dp, (size_t)dp_cap * 9 + 4096))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_tasks, 2 * align16((size_t)n * U * T * 4) + (size_t)n * U * T * 8 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_tasks, 2 * align16(NU * T * 4) + NU * T * 8 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
   HlmChunk& ck = s.ck;
   ck.units_per_pair = U;
+  ck.n_units = (int64_t)NU;
   ck.unit_planes = (uint32_t*)s.d_units.p;
   ck.unit_len = (uint16_t*)s.d_unit_meta.p;
-  ck.unit_mask = (uint32_t*)((uint8_t*)s.d_unit_meta.p + align16((size_t)n * U * 2));
+  ck.unit_mask = (uint32_t*)((uint8_t*)s.d_unit_meta.p + align16(NU * 2));
   ck.cand = (uint64_t*)s.d_cand.p;
   ck.cand_cap = ctx->cand_cap;
   ck.dp_list = (uint32_t*)s.d_dp.p;
@@ -178,8 +186,8 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n) {
   ck.dp_cap = dp_cap;
   ck.counters = (unsigned long long*)s.d_counters.p;
   ck.task_emin = (uint32_t*)s.d_tasks.p;
-  ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16((size_t)n * U * T * 4));
-  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 2 * align16((size_t)n * U * T * 4));
+  ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16(NU * T * 4));
+  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 2 * align16(NU * T * 4));
   return 0;
 }
 
@@ -191,7 +199,7 @@ void launch_stages(hlm_ctx* ctx, Slot& s, int stages) {
   if (stages & HLM_STAGE_SCREEN) hlm_launch_screen(ctx->ddb, ctx->kp, ck, sms, st);
   cudaEventRecord(s.ev[EV_SCREEN], st);
   if (stages & HLM_STAGE_SCORE) {
-    size_t n_tasks = (size_t)ck.n_pairs * ck.units_per_pair * T;
+    size_t n_tasks = (size_t)ck.n_units * T;
     hlm_launch_pack(ctx->kp, ck, sms, st);
     hlm_launch_seed(ctx->ddb, ctx->kp, ck, sms, st);
     hlm_launch_snapshot(ck, 0, st);
@@ -319,6 +327,21 @@ void scatter_results(hlm_ctx* ctx, Slot& s, const HostIO& io) {
   }
 }
 
+// the rna block list: CSR offsets ascending, both arrays present
+int check_blocks(hlm_ctx* ctx, const hlm_batch* in) {
+  if (!in->rna_block_off) return 0;
+  for (int64_t i = 0; i < in->n_pairs; i++)
+    if (in->rna_block_off[i + 1] < in->rna_block_off[i]) {
+      ctx->err = "rna_block_off is not ascending";
+      return HLM_E_ARG;
+    }
+  if (in->n_pairs > 0 && in->rna_block_off[in->n_pairs] > in->rna_block_off[0] && !in->rna_blocks) {
+    ctx->err = "rna_block_off without rna_blocks";
+    return HLM_E_ARG;
+  }
+  return 0;
+}
+
 int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
   uint64_t longest = 0;
   for (int64_t i = 0; i < in->n_pairs; i++) {
@@ -353,6 +376,7 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     }
     int rc = check_lengths(ctx, in);
     if (rc) return rc;
+    if (ctx->p.rna && (rc = check_blocks(ctx, in))) return rc;
   }
   CU(cudaSetDevice(ctx->device));
   memset(&ctx->prof, 0, sizeof ctx->prof);
@@ -387,6 +411,11 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     sec(6, in->size_override1 ? n * 4 : 0);
     sec(7, in->rna_split1 ? n * 2 : 0);
     sec(8, in->rna_split2 ? n * 2 : 0);
+    bool blocks = ctx->p.rna && in->rna_block_off && (stages & HLM_STAGE_SCORE);
+    uint64_t bf = blocks ? in->rna_block_off[first] : 0;
+    int64_t nb = blocks ? (int64_t)(in->rna_block_off[first + n] - bf) : 0;
+    sec(9, blocks ? (n + 1) * 8 : 0);
+    sec(10, (size_t)nb * sizeof(hlm_rna_block));
     size_t in_bytes = o;
     if ((rc = ensure_pinned(ctx, s.h_in, in_bytes))) return rc;
     if ((rc = ensure_dev(ctx, s.d_in, in_bytes))) return rc;
@@ -394,9 +423,13 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     s.out_bytes = out_bytes;
     if ((rc = ensure_pinned(ctx, s.h_out, out_bytes))) return rc;
     if ((rc = ensure_dev(ctx, s.d_out, out_bytes))) return rc;
-    if ((rc = ensure_work(ctx, s, n))) return rc;
+    if ((rc = ensure_work(ctx, s, n, nb))) return rc;
     uint8_t* h = (uint8_t*)s.h_in.p;
     uint8_t* d = (uint8_t*)s.d_in.p;
+    if (blocks) {
+      memcpy(h + io_off[9], in->rna_block_off + first, (n + 1) * 8);
+      if (nb) memcpy(h + io_off[10], in->rna_blocks + bf, (size_t)nb * sizeof(hlm_rna_block));
+    }
     if (need_reads) {
       memcpy(h + io_off[0] + 16, in->bases1 + f1, b1);
       if (q) memcpy(h + io_off[1] + 16, in->quals1 + f1, b1);
@@ -422,6 +455,10 @@ int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
     ck.size_override1 = in->size_override1 ? (const int32_t*)(d + io_off[6]) : nullptr;
     ck.rna_split1 = in->rna_split1 ? (const uint16_t*)(d + io_off[7]) : nullptr;
     ck.rna_split2 = in->rna_split2 ? (const uint16_t*)(d + io_off[8]) : nullptr;
+    ck.blk_off = blocks ? (const uint64_t*)(d + io_off[9]) : nullptr;
+    ck.blk = blocks ? (const hlm_rna_block*)(d + io_off[10]) - bf : nullptr;
+    ck.blk_first = (int64_t)bf;
+    ck.n_blocks = nb;
     bind_outputs(ck, (uint8_t*)s.d_out.p, s.out_off, 0, T);
     s.first = first;
     s.n = n;
@@ -840,6 +877,13 @@ hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in) {
   sec(6, in->size_override1 ? n * 4 : 0);
   sec(7, in->rna_split1 ? n * 2 : 0);
   sec(8, in->rna_split2 ? n * 2 : 0);
+  bool blocks = ctx->p.rna && in->rna_block_off;
+  if (blocks) {
+    if (check_blocks(ctx, in)) { delete b; return nullptr; }
+    b->blk_off.assign(in->rna_block_off, in->rna_block_off + n + 1);
+  }
+  sec(9, blocks ? (n + 1) * 8 : 0);
+  sec(10, blocks ? (size_t)(b->blk_off[n] - b->blk_off[0]) * sizeof(hlm_rna_block) : 0);
   if (ensure_dev(ctx, b->in, o)) { delete b; return nullptr; }
   uint8_t* d = (uint8_t*)b->in.p;
   auto cp = [&](int i, const void* src, size_t bytes, size_t lead) {
@@ -852,6 +896,10 @@ hlm_devbatch* hlm_batch_upload(hlm_ctx* ctx, const hlm_batch* in) {
   cp(6, in->size_override1, n * 4, 0);
   cp(7, in->rna_split1, n * 2, 0);
   cp(8, in->rna_split2, n * 2, 0);
+  if (blocks) {
+    cp(9, in->rna_block_off, (n + 1) * 8, 0);
+    cp(10, in->rna_blocks + b->blk_off[0], (size_t)(b->blk_off[n] - b->blk_off[0]) * sizeof(hlm_rna_block), 0);
+  }
   b->read_bytes = 2 * (int64_t)(b1 + b2);
   b->has_override = in->size_override1 != nullptr;
   b->has_split1 = in->rna_split1 != nullptr;
@@ -882,9 +930,15 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   auto submit = [&](Slot& s, int64_t first, int64_t n) -> int {
     int rc = 0;
     if ((rc = ensure_pinned(ctx, s.h_out, 4096))) return rc;
-    if ((rc = ensure_work(ctx, s, n))) return rc;
+    bool blocks = !b->blk_off.empty();
+    int64_t nb = blocks ? (int64_t)(b->blk_off[first + n] - b->blk_off[first]) : 0;
+    if ((rc = ensure_work(ctx, s, n, nb))) return rc;
     HlmChunk& ck = s.ck;
     ck.n_pairs = n;
+    ck.blk_off = blocks ? (const uint64_t*)(d + b->in_off[9]) + first : nullptr;
+    ck.blk = blocks ? (const hlm_rna_block*)(d + b->in_off[10]) - b->blk_off[0] : nullptr;
+    ck.blk_first = blocks ? (int64_t)b->blk_off[first] : 0;
+    ck.n_blocks = nb;
     ck.bases1 = d + b->in_off[0] + 16;
     ck.quals1 = d + b->in_off[1] + 16;
     ck.bases2 = d + b->in_off[2] + 16;
@@ -1038,6 +1092,7 @@ int hlm_multi_run(hlm_multi* m, const hlm_batch* in, hlm_screen_out* scr, hlm_sc
       if (in->size_override1) b.size_override1 = in->size_override1 + lo;
       if (in->rna_split1) b.rna_split1 = in->rna_split1 + lo;
       if (in->rna_split2) b.rna_split2 = in->rna_split2 + lo;
+      if (in->rna_block_off) b.rna_block_off = in->rna_block_off + lo;  // absolute into rna_blocks
       hlm_screen_out s1{};
       hlm_score_out s2{};
       hlm_assign_out s3{};

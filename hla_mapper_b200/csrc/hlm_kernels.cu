@@ -452,6 +452,12 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
   int nm = kp.paired ? 2 : 1;
   for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
     if (lane < U) ck.unit_len[pair * U + lane] = 0;
+    int64_t b0 = 0, b1 = 0;
+    if (kp.rna && ck.blk_off) {
+      b0 = (int64_t)ck.blk_off[pair];
+      b1 = (int64_t)ck.blk_off[pair + 1];
+      for (int64_t b = b0 + lane; b < b1; b += 32) ck.unit_len[ck.n_pairs * U + (b - ck.blk_first)] = 0;
+    }
     __syncwarp();
     if (!(ck.flags[pair] & HLM_F_KEPT)) continue;
     uint32_t lmask = ck.locus_mask[pair];
@@ -468,6 +474,16 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
       stage_bases(p, l, lane, ws, false);
       if (!kp.rna) {
         write_unit(ck, pair * U + m, ws, lo, n, lmask | others, lane);
+      } else if (ck.blk_off) {
+        // the STAR pre-split in full: whole mate vs others only; every block vs its own gene
+        write_unit(ck, pair * U + m * 3, ws, lo, n, others, lane);
+        for (int64_t b = b0; b < b1; b++) {
+          hlm_rna_block blk = ck.blk[b];
+          if (blk.mate != m || blk.gene >= kp.n_loci) continue;
+          int st = blk.start < n ? blk.start : n;
+          int bl = blk.len < n - st ? blk.len : n - st;
+          if (bl > 0) write_unit(ck, ck.n_pairs * U + (b - ck.blk_first), ws, lo + st, bl, 1u << blk.gene, lane);
+        }
       } else {
         const uint16_t* sp = m == 0 ? ck.rna_split1 : ck.rna_split2;
         int split = sp ? sp[pair] : 0;
@@ -526,7 +542,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   uint32_t* beg = s_beg[wib];
   uint32_t* ht = s_ht[wib];
   int64_t nwarps = (int64_t)gridDim.x * SEED_WARPS;
-  int64_t n_units = ck.n_pairs * ck.units_per_pair;
+  int64_t n_units = ck.n_units;
   WarpAppender<uint64_t> app(ck.cand, &ck.counters[0], &ck.counters[2], ck.cand_cap, HLM_CAND_INVALID);
   for (int64_t unit = (int64_t)blockIdx.x * SEED_WARPS + wib; unit < n_units; unit += nwarps) {
     int n = ck.unit_len[unit];
@@ -989,21 +1005,34 @@ k_scores(HlmKParams kp, HlmChunk ck, int n_targets) {
     } else {
       int sum = 0;
       bool any = false;
+      // one record of read_sam_rna: a mapped one adds NM + clips, an unmapped one its length
+      auto record = [&](int64_t unit, int len) {
+        any = true;
+        unsigned long long b = ck.task_best[unit * n_targets + g];
+        if (len > 0 && b != HLM_BEST_NONE && HLM_BEST_COST(b) <= kp.mm_max) {
+          int ld = HLM_BEST_LEAD(b), tr = HLM_BEST_TRAIL(b);
+          int mm = HLM_BEST_COST(b) - ld - tr;
+          if (ld > 0 && mm != len) mm += ld;
+          if (kp.clip_mode == HLM_CLIP_BOTH && tr > 0 && mm != len) mm += tr;
+          sum += mm;
+        } else {
+          sum += len;
+        }
+      };
       if (kept) {
         for (int u = 0; u < U; u++) {
           int64_t unit = pair * U + u;
           int len = ck.unit_len[unit];
           if (!len || !((ck.unit_mask[unit] >> g) & 1u)) continue;
-          any = true;
-          unsigned long long b = ck.task_best[unit * n_targets + g];
-          if (b != HLM_BEST_NONE && HLM_BEST_COST(b) <= kp.mm_max) {
-            int ld = HLM_BEST_LEAD(b), tr = HLM_BEST_TRAIL(b);
-            int mm = HLM_BEST_COST(b) - ld - tr;
-            if (ld > 0 && mm != len) mm += ld;
-            if (kp.clip_mode == HLM_CLIP_BOTH && tr > 0 && mm != len) mm += tr;
-            sum += mm;
-          } else {
-            sum += len;
+          record(unit, len);
+        }
+        if (ck.blk_off && g < kp.n_loci) {
+          int nm_ = kp.paired ? 2 : 1;
+          for (int64_t b = (int64_t)ck.blk_off[pair]; b < (int64_t)ck.blk_off[pair + 1]; b++) {
+            hlm_rna_block blk = ck.blk[b];
+            if (blk.gene != g || blk.mate >= nm_) continue;
+            int64_t unit = ck.n_pairs * U + (b - ck.blk_first);
+            record(unit, ck.unit_len[unit]);  // an empty block is still a record (adds 0)
           }
         }
       }
@@ -1260,7 +1289,7 @@ void hlm_launch_pack(const HlmKParams& kp, const HlmChunk& ck, int sms, cudaStre
   k_pack_units<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(kp, ck);
 }
 void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStream_t st) {
-  int64_t n_tasks = ck.n_pairs * ck.units_per_pair * n_targets;
+  int64_t n_tasks = ck.n_units * n_targets;
   k_clear_tasks<<<grid_for(sms, 8), 256, 0, st>>>(ck, n_tasks);
 }
 void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,

@@ -14,12 +14,18 @@ struct HlmChunk {
   const uint64_t *offs1, *offs2;
   const int32_t* size_override1;
   const uint16_t *rna_split1, *rna_split2;
+  // rna block list (optional): offsets are absolute, `blk` is biased so that they index it
+  // directly; block b is unit n_pairs * units_per_pair + (b - blk_first)
+  const uint64_t* blk_off;
+  const hlm_rna_block* blk;
+  int64_t blk_first, n_blocks;
   // screen outputs
   uint8_t* flags;
   uint16_t *trim_lo1, *trim_len1, *trim_lo2, *trim_len2;
   uint32_t* locus_mask;
-  // units: units_per_pair * n_pairs; 36 words each (fwd planes, rc planes)
+  // units: units_per_pair * n_pairs (+ n_blocks); HLM_UNIT_STRIDE words each
   int units_per_pair;
+  int64_t n_units;
   uint32_t* unit_planes;
   uint16_t* unit_len;    // 0 = inactive
   uint32_t* unit_mask;   // targets this unit is scored against

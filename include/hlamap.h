@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HLM_ABI_VERSION 1
+#define HLM_ABI_VERSION 2
 
 /* limits of this build */
 #define HLM_MAX_LOCI 31   /* loci + "others" must fit a uint32 mask            */
@@ -89,6 +89,19 @@ typedef struct hlm_params {
   int32_t reserved0;
 } hlm_params;
 
+/* One record of the reference's sorted_spliced_<gene>.fastq (map_rna.cpp:740-790): a block of a
+ * trimmed mate that STAR, run on the reads sorted into `gene`, reported between two splice
+ * junctions (or the whole mate when the alignment has none).  start / len are in the trimmed
+ * mate's own orientation; a record STAR printed reverse-complemented covers
+ * [n - start' - len, n - start') of it.  Blocks are clipped to the mate. */
+typedef struct hlm_rna_block {
+  uint8_t gene;      /* DB locus index (< n_loci; others is never spliced)               */
+  uint8_t mate;      /* 0 = R1 / R0, 1 = R2                                              */
+  uint16_t start;
+  uint16_t len;
+  uint16_t reserved; /* 0                                                                */
+} hlm_rna_block;
+
 /* SoA batch of read pairs.  bases/quals are the FASTQ lines as read (ASCII),
  * concatenated; offs has n_pairs+1 entries.  For single-end leave mate 2 NULL.
  * size_override1 (optional, single-end only) replaces len(trimmed R1) in the
@@ -107,6 +120,14 @@ typedef struct hlm_batch {
    * as two blocks that read_sam_rna sums (map_rna.cpp:39-101). */
   const uint16_t* rna_split1;
   const uint16_t* rna_split2;
+  /* RNA only, optional, replaces rna_split*: the STAR pre-split in full, one hlm_rna_block per
+   * record the reference would write to sorted_spliced_<gene>.fastq - per gene, any number of
+   * blocks per mate, one set per reported alignment (multi-mappers included).  Blocks of pair i:
+   * rna_blocks[rna_block_off[i] .. rna_block_off[i+1]).  The loci columns of hlm_score_out.s1
+   * are then exactly read_sam_rna's sums over these records (map_rna.cpp:39-101; a gene without
+   * a record is 0xFFFF); `others` still sees the whole trimmed mates (map_rna.cpp:858-892). */
+  const uint64_t* rna_block_off;
+  const hlm_rna_block* rna_blocks;
 } hlm_batch;
 
 /* one entry per pair */

@@ -731,6 +731,36 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
           const uint16_t* sp = m == 0 ? in->rna_split1 : in->rna_split2;
           if (sp && sp[i] > 0 && sp[i] < len) split = sp[i];
         }
+        if (p->rna && in->rna_block_off) {
+          /* the STAR pre-split in full (map_rna.cpp:740-790): `others` sees the whole mate
+           * (map_rna.cpp:858-892), every gene exactly the records listed for it; each record is
+           * one line of read_sam_rna (map_rna.cpp:39-101) */
+          {
+            int64_t o = i * T + db->n_loci;
+            int sum = out->s1[o] == 0xFFFF ? 0 : out->s1[o];
+            ares a = mode ? score_fast(&db->loc[db->n_loci], codes, len, &sc, p->mm_max, &total_cells)
+                          : score_exhaustive(&db->loc[db->n_loci], codes, len, &sc, &total_cells);
+            if (a.valid && a.cost <= p->mm_max) sum += hla_rna_score(&a, len, p->clip_mode);
+            else sum += len;
+            out->s1[o] = (uint16_t)sum;
+          }
+          for (uint64_t b = in->rna_block_off[i]; b < in->rna_block_off[i + 1]; b++) {
+            hlm_rna_block blk = in->rna_blocks[b];
+            if (blk.mate != m || blk.gene >= db->n_loci) continue;
+            int st = blk.start < len ? blk.start : len;
+            int bl = blk.len < len - st ? blk.len : len - st;
+            int64_t o = i * T + blk.gene;
+            int sum = out->s1[o] == 0xFFFF ? 0 : out->s1[o];
+            if (bl > 0) {
+              ares a = mode ? score_fast(&db->loc[blk.gene], codes + st, bl, &sc, p->mm_max, &total_cells)
+                            : score_exhaustive(&db->loc[blk.gene], codes + st, bl, &sc, &total_cells);
+              if (a.valid && a.cost <= p->mm_max) sum += hla_rna_score(&a, bl, p->clip_mode);
+              else sum += bl;
+            }
+            out->s1[o] = (uint16_t)sum;
+          }
+          continue;
+        }
         for (int g = 0; g < T; g++) {
           /* loci: only pairs sorted into the locus (map_dna.cpp:611-627);
            * others: every trimmed pair (map_dna.cpp:824-860) */

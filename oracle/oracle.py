@@ -89,10 +89,11 @@ class OracleDB:
 
 
 def run(db: OracleDB, params, rb, mode=1, nthreads=0, stages=("screen", "score", "assign"),
-        size_override1=None, rna_split1=None, rna_split2=None, buffers=None):
+        size_override1=None, rna_split1=None, rna_split2=None, buffers=None, rna_blocks=None):
     """screen_trim -> score -> assign with the oracle; returns (_abi.Buffers, n_dp_cells)"""
     L = lib()
-    batch = _abi.make_batch(rb, size_override1, rna_split1, rna_split2, paired=bool(params.paired))
+    batch = _abi.make_batch(rb, size_override1, rna_split1, rna_split2, paired=bool(params.paired),
+                            rna_blocks=rna_blocks)
     buf = buffers or _abi.Buffers(rb.n_pairs, db.n_loci + 1)
     cells = C.c_int64(0)
     if "screen" in stages:

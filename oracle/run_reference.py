@@ -46,7 +46,7 @@ def _config(db_path):
 
 
 def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None, rna=False, threads=4,
-                  debug=True, exhaustive=False, extra=(), timeout=3600):
+                  debug=True, exhaustive=False, extra=(), timeout=3600, star_full=False):
     """returns the output directory (with trailing slash, as the reference stores it)"""
     if os.path.exists(out_dir):
         shutil.rmtree(out_dir)
@@ -73,6 +73,8 @@ def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None,
     cmd += list(extra)
     if exhaustive:
         env["HLM_ORACLE_EXHAUSTIVE"] = "1"
+    if star_full:  # oracle/standin_star.py: gene-dependent splits, multi-mappers, reverse strand
+        env["HLM_STANDIN_STAR"] = "full"
     with _config(db_path):
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env,
                        timeout=timeout, cwd=os.path.dirname(out_dir.rstrip("/")) or ".")

@@ -6,8 +6,56 @@ Honours the one invocation on the hot path (/root/reference/src/map_rna.cpp:728)
 --readFilesIn R1 R2, writes <--outFileNamePrefix>Aligned.out.sam with one record per mate.  A mate
 is reported as spliced (CIGAR aM100NbM, which the reference then cuts into two blocks,
 map_rna.cpp:748-787) by the deterministic rule `split_point()` below, shared with the tests, so
-that the block structure handed to libhlamap (hlm_batch.rna_split{1,2}) is the same."""
+that the block structure handed to libhlamap (hlm_batch.rna_split{1,2}) is the same.
+
+With HLM_STANDIN_STAR=full in the environment the stand-in uses everything the reference's SAM
+loop reacts to instead (`alignments()` below): splits that depend on the gene the run is for
+(--genomeDir .../loci/<gene>/), three-block alignments (whose third block the reference cuts at
+start = size of the second, map_rna.cpp:784), a second (secondary) alignment of the same mate,
+reverse-strand records (SEQ reverse-complemented) and unmapped records (CIGAR "*").  The tests
+turn the same rule into hlm_batch.rna_blocks."""
+import os
 import sys
+import zlib
+
+_COMP = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
+
+
+def alignments(seq: bytes, gene: str):
+    """[(secondary, reverse, unmapped, [block sizes])] reported for one mate in the run for `gene`"""
+    n = len(seq)
+    h = zlib.crc32(seq + b"|" + gene.encode())
+    kind = h % 16
+    if n < 40 or kind < 7:
+        return [(False, False, False, [n])]
+    a = 8 + (h >> 8) % (n - 16)
+    if kind < 10:
+        return [(False, False, False, [a, n - a])]
+    if kind < 12:
+        b = 4 + (h >> 16) % (n - a - 7)
+        return [(False, False, False, [a, b, n - a - b])]
+    if kind == 12:
+        return [(False, False, False, [n]), (True, False, False, [a, n - a])]
+    if kind == 13:
+        return [(False, True, False, [a, n - a])]
+    if kind == 14:
+        return [(False, True, False, [n]), (True, True, False, [n])]
+    return [(False, False, True, [n])]
+
+
+def blocks(seq: bytes, gene: str):
+    """the (start, length) ranges of the mate - in its own orientation - that the reference writes
+    to sorted_spliced_<gene>.fastq for `alignments(seq, gene)`: block k starts where map_rna.cpp:784
+    puts it (0, then the SIZE of the previous block), inside SEQ as printed"""
+    n = len(seq)
+    out = []
+    for _sec, rev, _unm, sizes in alignments(seq, gene):
+        start = 0
+        for sz in sizes:
+            lo, hi = min(start, n), min(start + sz, n)
+            out.append((n - hi, hi - lo) if rev else (lo, hi - lo))
+            start = sz
+    return out
 
 
 def split_point(seq: bytes) -> int:
@@ -52,9 +100,26 @@ def main(argv):
         i += 1
     if prefix is None or not files:
         return 0
+    full = os.environ.get("HLM_STANDIN_STAR") == "full"
+    gene = ""
+    if "--genomeDir" in argv:
+        gene = os.path.basename(argv[argv.index("--genomeDir") + 1].rstrip("/"))
     with open(prefix + "Aligned.out.sam", "wb") as out:
         out.write(b"@HD\tVN:1.4\n")
         mates = [list(records(p)) for p in files]
+        if full:
+            for k in range(len(mates[0])):
+                for m, flag in zip(mates, (99, 147)):
+                    name, s, q = m[k]
+                    for sec, rev, unm, sizes in alignments(s, gene):
+                        f = (flag ^ 0x10 if rev else flag) | (256 if sec else 0)
+                        cigar = b"100N".join(b"%dM" % z for z in sizes)
+                        ss, qq = (s.translate(_COMP)[::-1], q[::-1]) if rev else (s, q)
+                        if unm:
+                            f, cigar = (77 if flag == 99 else 141), b"*"
+                        out.write(b"\t".join([name, b"%d" % f, b"*" if unm else b"standin", b"1", b"255", cigar,
+                                               b"=", b"1", b"0", ss, qq]) + b"\n")
+            return 0
         for k in range(len(mates[0])):
             for m, flag in zip(mates, (b"99", b"147")):
                 name, s, q = m[k]

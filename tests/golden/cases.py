@@ -11,6 +11,8 @@ DB_TIES = dict(seed=99, n_loci=6, total_alleles=90, len_range=(600, 800), n_othe
                paralog_div=(0.002, 0.01), others_div=(0.002, 0.02))
 
 DB_RNA = dict(seed=17, n_loci=5, total_alleles=80, len_range=(500, 700), n_others=10, kind="rna")
+DB_RNA_PARALOG = dict(seed=18, n_loci=6, total_alleles=90, len_range=(500, 700), n_others=10, kind="rna",
+                      paralog_div=(0.002, 0.02))
 
 CASES = {
     # name: (db kwargs, reads kwargs, mode)
@@ -24,6 +26,10 @@ CASES = {
                                   frag_sd=30, ragged=True), "paired"),
     "rna_paired": (DB_RNA, dict(n_pairs=800, read_len=100, seed=1004, on_target=0.8, frag_mu=220,
                                  frag_sd=25), "rna"),
+    # the STAR stand-in in its "full" mode: per-gene splits, three-block and secondary alignments,
+    # reverse-strand and unmapped records -> hlm_batch.rna_blocks
+    "rna_blocks": (DB_RNA_PARALOG, dict(n_pairs=900, read_len=100, seed=1005, on_target=0.85, frag_mu=220,
+                                        frag_sd=25, lowq_tail=0.2), "rna_full"),
     # bam= input: the BAM-derived screen loop (preselect.cpp:484-506), reads served by the samtools
     # stand-in (oracle/standin_samtools.py)
     "dna_bam": (DB_SMALL, dict(n_pairs=900, read_len=120, seed=14, on_target=0.8, frag_mu=260,
@@ -67,7 +73,7 @@ def inputs(name, root):
     rk = dict(rk)
     n = rk.pop("n_pairs")
     rb = synth.make_reads(db, n, **rk)
-    p = _abi.default_params(rna=1 if mode == "rna" else 0, paired=0 if mode == "single" else 1,
+    p = _abi.default_params(rna=1 if mode in ("rna", "rna_full") else 0, paired=0 if mode == "single" else 1,
                             screen_variant=1 if mode == "bam" else 0)
     return db, rb, p, mode
 
@@ -87,6 +93,26 @@ def rna_splits(rb, buf):
                 sp[i] = standin_star.split_point(bases[a:a + int(ln[i])].tobytes())
         out.append(sp)
     return out
+
+
+def rna_blocks(rb, buf, n_loci, loci):
+    """hlm_batch.rna_blocks of every kept pair, by the rule the STAR stand-in applies in its full
+    mode (oracle/standin_star.py): one run per gene of the pair's locus mask, both mates"""
+    import standin_star
+
+    off, out = [0], []
+    for i in range(rb.n_pairs):
+        if buf.flags[i] & 2:
+            for g in range(n_loci):
+                if not (int(buf.locus_mask[i]) >> g) & 1:
+                    continue
+                for m, (bases, offs, lo, ln) in enumerate(((rb.bases1, rb.offs1, buf.trim_lo1, buf.trim_len1),
+                                                           (rb.bases2, rb.offs2, buf.trim_lo2, buf.trim_len2))):
+                    a = int(offs[i]) + int(lo[i])
+                    seq = bases[a:a + int(ln[i])].tobytes()
+                    out += [(g, m, st, bl, 0) for st, bl in standin_star.blocks(seq, loci[g])]
+        off.append(len(out))
+    return np.array(off, np.uint64), np.array(out, dtype=_abi.RNA_BLOCK)
 
 
 # how the FASTQ files of a case are written (synth.write_fastq keywords)

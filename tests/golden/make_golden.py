@@ -91,7 +91,7 @@ def main():
                 tag = "R1"
             elif mode != "single":
                 out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r1=r1, r2=r2,
-                                       rna=(mode == "rna"))
+                                       rna=mode in ("rna", "rna_full"), star_full=(mode == "rna_full"))
                 tag = "R1"
             else:
                 out = rr.run_reference(db.path, os.path.join(tmp, "out"), "G", r0=r1)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = api.lib()
     for n in names:
         assert getattr(L, n) is not None
-    assert L.hlm_abi_version() == 1
+    assert L.hlm_abi_version() == 2  # 2: hlm_batch gained rna_block_off / rna_blocks
 
 
 def test_struct_layouts_match_the_header():
@@ -41,6 +41,9 @@ def test_struct_layouts_match_the_header():
     assert p.mtrim_error == float(__import__("numpy").float32(0.08))
     api.lib().hlm_params_default(C.byref(p), 1)
     assert p.tolerance == 0.08 and p.rna == 1  # map_rna.cpp:116
+    # hlm_batch: 12 pointer-sized fields; hlm_rna_block: 8 bytes, (gene, mate, start, len, reserved)
+    assert C.sizeof(_abi.HlmBatch) == 12 * 8
+    assert _abi.RNA_BLOCK.itemsize == 8 and _abi.RNA_BLOCK.fields["start"][1] == 2
 
 
 def test_db_open_error_messages(tmp_path):

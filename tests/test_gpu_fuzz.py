@@ -194,7 +194,14 @@ def test_random_databases_reads_and_parameters(orc, tmp_path, seed):
               skip_screen=int(rng.integers(0, 4) == 0))
     p = _abi.default_params(**kw)
     extra = {}
-    if rna:
+    if rna and rng.random() < 0.5:  # the STAR pre-split as a full block list
+        from test_rna_blocks import random_blocks
+
+        class Lens:
+            flags = np.zeros(400, np.uint8)
+            trim_len1 = trim_len2 = np.full(400, L, np.uint16)
+        extra = dict(rna_blocks=random_blocks(rng, Lens, len(db.loci)))
+    elif rna:
         extra = dict(rna_split1=np.where(rng.random(400) < 0.3, rng.integers(1, L, size=400), 0).astype(np.uint16),
                      rna_split2=np.where(rng.random(400) < 0.3, rng.integers(1, L, size=400), 0).astype(np.uint16))
     elif not kw["paired"]:
