@@ -48,7 +48,7 @@ METRIC = "read pairs/sec scored+assigned"
 # integer instructions of the SASS inner loops (tools/sass_mix.py -> profiles/r1_sass_mix.txt)
 DP_ALU_OPS_PER_CELL = 5.9     # 243 ALU-pipe instructions per 41-cell band row
 DP_INT_OPS_PER_CELL = 10.3    # + 180 IMAD on the FMA pipe
-MYERS_ALU_OPS_PER_ROW = 27.6  # 221 ALU-pipe instructions per 8 band rows
+MYERS_ALU_OPS_PER_ROW = 23.6  # 189 ALU-pipe instructions per 8 band rows (profiles/r1_sass_mix.txt)
 WORKLOAD = "synthetic 30x WGS MHC-region reads, 2x150bp, 2M pairs/GPU vs 24 loci + others, 40k-allele DB seed 42"
 
 

@@ -156,6 +156,86 @@ HLM_HD int hlm_myers_core(const uint32_t* __restrict__ codes, int n, int off, PE
   return best;
 }
 
+#ifdef __CUDACC__
+// ---- the same recurrence as hlm_myers_core, arranged for the sm_100a pipes (k_myers is bound by
+// the INT32 ALU pipe: profiles/r1g_k_myers_regions.txt).  What can run as a plain 32-bit
+// multiply-add goes to the FMA pipe, which is otherwise idle: the column counter, the byte
+// address of the PEQ row, the times-eight of the read codes.  (High-half multiplies - a way to
+// express right shifts on that pipe - were measured and are too slow to pay.)  The "| TOP" of the
+// generic form is dropped: with D0 cut to the band, bit 40 of SP regenerates itself
+// (VP_40 = 0 -> SP'_40 = ~D0_41 = 1) and nothing above the band is ever set.  The score is not
+// updated per row: bit 0 of D0 is shifted into an accumulator and counted once per eight rows.
+// `one` == 1 at run time, opaque to the compiler.
+__device__ __forceinline__ uint32_t hlm_fma_mad(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// peq_addr: shared-memory byte address of this thread's PEQ row 0; rows are ROW_BYTES apart
+template <int ROW_BYTES>
+__device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ codes, int n, int off,
+                                                  uint32_t peq_addr, uint32_t one) {
+  const uint64_t MASK = (1ull << HLM_NB) - 1;
+  uint64_t SP = 1ull << (HLM_NB - 1), SN = 0;
+  uint32_t p = (uint32_t)(off - HLM_BAND);
+  uint32_t acc = 0;
+  int zeros = 0;
+  const uint32_t krow = one * ROW_BYTES;
+  asm volatile("" ::: "memory");  // the PEQ rows were written with plain stores
+  // C8: eight times the read code of the row; S: its first band column (the funnel shift wraps)
+#define HLM_MYERS_DEV_ROW(C8, S)                                                                    \
+  {                                                                                               \
+    uint32_t ad = hlm_fma_mad((C8) + ((S) >> 5), krow, peq_addr);                                  \
+    uint32_t a, b, c;                                                                             \
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(ad));                                   \
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(b) : "r"(ad), "n"(ROW_BYTES));                \
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(c) : "r"(ad), "n"(2 * ROW_BYTES));            \
+    uint64_t Eq = (uint64_t)__funnelshift_r(a, b, S) | ((uint64_t)__funnelshift_r(b, c, S) << 32); \
+    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;                                     \
+    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;                                                  \
+    uint64_t D0s = D0 >> 1;                                                                       \
+    SP = VN | ~(D0s | VP);                                                                        \
+    SN = D0s & VP;                                                                                \
+    acc = __funnelshift_r(acc, (uint32_t)D0, 1); /* (acc >> 1) | (bit 0 of D0) << 31 */           \
+  }
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint32_t cw = codes[i >> 3];
+    // codes of the even / odd rows, one per byte, times eight
+    uint32_t ev = hlm_fma_mad(cw & 0x07070707u, 8u * one, 0u), od = hlm_fma_mad((cw >> 4) & 0x07070707u, 8u * one, 0u);
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4440), p)
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4440), hlm_fma_mad(one, 1u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4441), hlm_fma_mad(one, 2u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4441), hlm_fma_mad(one, 3u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4442), hlm_fma_mad(one, 4u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4442), hlm_fma_mad(one, 5u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4443), hlm_fma_mad(one, 6u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4443), hlm_fma_mad(one, 7u, p))
+    zeros += __popc(acc >> 24);
+    p = hlm_fma_mad(one, 8u, p);
+  }
+  if (i < n) {
+    uint32_t cw = codes[i >> 3];
+    int rem = n - i;
+    for (int r = 0; r < rem; r++) {
+      HLM_MYERS_DEV_ROW((cw << 3) & 0x38u, p)
+      cw >>= 4;
+      p++;
+    }
+    zeros += __popc(acc >> (32 - rem));
+  }
+#undef HLM_MYERS_DEV_ROW
+  asm volatile("" ::: "memory");  // the next candidate overwrites the PEQ rows
+  int score = n - zeros;
+  int best = score, cur = score;
+  for (int k = 0; k < HLM_NB - 1; k++) {
+    cur += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);
+    best = cur < best ? cur : best;
+  }
+  return best;
+}
+#endif
+
 // host / generic entry point: PEQ in a local array
 struct HlmPeqLocal {
   uint32_t* v;

@@ -722,9 +722,9 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       lb = 254;
     } else {
       hlm_peq_build(T, peq);
-      lb = hlm_myers_core(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
-                              HLM_CODE_WORDS * strand,
-                          n, off, peq);
+      lb = hlm_myers_core_dev<256 * 4>(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
+                                           HLM_CODE_WORDS * strand,
+                                       n, off, (uint32_t)__cvta_generic_to_shared(s_peq + threadIdx.x), (uint32_t)kp.one);
       if (lb > 253) lb = 253;
       rows += n;
     }
