@@ -361,7 +361,16 @@ int check_lengths(hlm_ctx* ctx, const hlm_batch* in) {
 }
 
 // host-buffer pipeline over chunks
+int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages);
 int run_host(hlm_ctx* ctx, const HostIO& io, int stages) {
+  try {  // no exception crosses the C ABI
+    return run_host_unguarded(ctx, io, stages);
+  } catch (const std::exception& x) {
+    ctx->err = std::string("libhlamap: ") + x.what();
+    return HLM_E_NOMEM;
+  }
+}
+int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
   const hlm_batch* in = io.in;
   if (!in || in->n_pairs < 0) {
     ctx->err = "bad batch";
@@ -588,7 +597,12 @@ void hlm_params_default(hlm_params* p, int rna) {
 
 hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen) {
   std::string e;
-  hlm_db* db = db_dir ? hlm_db_build(db_dir, rna, e) : nullptr;
+  hlm_db* db = nullptr;
+  try {  // no exception crosses the C ABI
+    db = db_dir ? hlm_db_build(db_dir, rna, e) : nullptr;
+  } catch (const std::exception& x) {
+    e = std::string("hlm_db_open: ") + x.what();
+  }
   if (!db && err && errlen) snprintf(err, errlen, "%s", e.empty() ? "bad db_dir" : e.c_str());
   return db;
 }

@@ -196,6 +196,7 @@ class BamScanner {
         b.in_len = total - 12 - xlen - 8;
         b.crc = le32(d_ + pos + total - 8);
         b.isize = le32(d_ + pos + total - 4);
+        if (b.isize > 65536) return fail("BGZF block larger than 64 KiB at byte " + std::to_string(pos));
         b.out = out;
         out += b.isize;
         blks.push_back(b);
@@ -450,9 +451,9 @@ void append_read(MateBatch& dst, const MateBatch& src, int64_t i) {
 
 }  // namespace
 
-extern "C" hlm_reads* hlm_bam_extract(const hlm_db* db, const char* bam_path, const char* bed_path,
-                                      int skip_unmapped, int threads, hlm_bam_stats* stats, char* err,
-                                      size_t errlen) {
+static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char* bed_path,
+                              int skip_unmapped, int threads, hlm_bam_stats* stats, char* err,
+                              size_t errlen) {
   if (!db || !bam_path) {
     set_err(err, errlen, "hlm_bam_extract: db and bam_path are required");
     return nullptr;
@@ -634,6 +635,17 @@ extern "C" hlm_reads* hlm_bam_extract(const hlm_db* db, const char* bam_path, co
   return out.release();
 }
 
+extern "C" hlm_reads* hlm_bam_extract(const hlm_db* db, const char* bam_path, const char* bed_path,
+                                      int skip_unmapped, int threads, hlm_bam_stats* stats, char* err,
+                                      size_t errlen) {
+  try {  // no exception crosses the C ABI
+    return bam_extract(db, bam_path, bed_path, skip_unmapped, threads, stats, err, errlen);
+  } catch (const std::exception& e) {
+    set_err(err, errlen, std::string("hlm_bam_extract: ") + e.what());
+    return nullptr;
+  }
+}
+
 extern "C" int hlm_reads_paired(const hlm_reads* r) { return r ? r->paired : 0; }
 extern "C" int64_t hlm_reads_count(const hlm_reads* r) { return r ? r->m1.n : 0; }
 extern "C" void hlm_reads_free(hlm_reads* r) { delete r; }
@@ -674,6 +686,11 @@ extern "C" int hlm_map_reads(hlm_ctx* ctx, const hlm_reads* reads, const char* s
     return HLM_E_ARG;
   }
   int64_t batch = opts && opts->struct_size >= 12 && opts->batch_pairs > 0 ? opts->batch_pairs : 1 << 19;
-  MemSource src(reads, batch);
-  return hlm_map_source(ctx, src, /*normalise_pair_headers=*/false, sample, out_dir, opts, stats);
+  try {
+    MemSource src(reads, batch);
+    return hlm_map_source(ctx, src, /*normalise_pair_headers=*/false, sample, out_dir, opts, stats);
+  } catch (const std::exception& e) {
+    hlm_ctx_set_error(ctx, std::string("hlm_map_reads: ") + e.what());
+    return HLM_E_NOMEM;
+  }
 }

@@ -363,12 +363,17 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
     return HLM_E_ARG;
   }
   int64_t batch = opts_in && opts_in->struct_size >= 12 && opts_in->batch_pairs > 0 ? opts_in->batch_pairs : 1 << 19;
-  FileSource src(r1_path, r2_path, batch);
-  if (!src.ok1() || !src.ok2()) {
-    hlm_ctx_set_error(ctx, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
-    return HLM_E_IO;
+  try {  // no exception crosses the C ABI
+    FileSource src(r1_path, r2_path, batch);
+    if (!src.ok1() || !src.ok2()) {
+      hlm_ctx_set_error(ctx, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
+      return HLM_E_IO;
+    }
+    return hlm_map_source(ctx, src, paired, sample, out_dir, opts_in, stats);
+  } catch (const std::exception& e) {
+    hlm_ctx_set_error(ctx, std::string("hlm_map_fastq: ") + e.what());
+    return HLM_E_NOMEM;
   }
-  return hlm_map_source(ctx, src, paired, sample, out_dir, opts_in, stats);
 }
 
 int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, const char* sample,
