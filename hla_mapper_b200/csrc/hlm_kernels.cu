@@ -821,61 +821,109 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
 // After round 1 no unevaluated candidate can tie or beat the best (cost >= lb).
 __global__ void __launch_bounds__(256)
 k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ int s_wcnt[8];
+  __shared__ unsigned long long s_base;
   int64_t ncand = (int64_t)ck.counters[0];
   if (ncand > ck.cand_cap) ncand = ck.cand_cap;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int lane = threadIdx.x & 31;
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int64_t nloop = (ncand + stride - 1) / stride;
   unsigned long long n_take = 0;
-  for (int64_t it = 0; it < nloop; it++) {
-    int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool take = false;
-    if (i < ncand) {
-      uint64_t c = ck.cand[i];
-      int lb = (int)HLM_CAND_LB(c);
-      if (lb <= kp.mm_max) {
-        int g = tile_locus(db, HLM_CAND_TILE(c));
-        int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
-        int emin = (int)ck.task_emin[task];
+  s_hist[threadIdx.x] = 0;  // blockDim.x == 256
+  __syncthreads();
+  // the kernel is a chain of dependent loads per candidate (record -> locus -> task minimum ->
+  // best): two candidates per thread are in flight at a time (more cost occupancy)
+  constexpr int UN = 2;
+  for (int64_t it = 0; it < nloop; it += UN) {
+    int64_t idx[UN];
+    uint64_t c[UN];
+    int lb[UN], g[UN];
+    bool live[UN], take[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      idx[u] = (it + u) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      c[u] = idx[u] < ncand ? ck.cand[idx[u]] : HLM_CAND_INVALID;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      lb[u] = (int)HLM_CAND_LB(c[u]);
+      live[u] = lb[u] <= kp.mm_max;  // padding and dead candidates carry lb >= 254
+      g[u] = live[u] ? tile_locus(db, HLM_CAND_TILE(c[u])) : 0;
+    }
+    uint32_t emin[UN];
+    unsigned long long best[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      int64_t task = (int64_t)HLM_CAND_UNIT(c[u]) * n_targets + g[u];
+      emin[u] = live[u] ? ck.task_emin[task] : 0u;
+      best[u] = (live[u] && (round != 0 || lb[u] == 0)) ? ck.task_best[task] : HLM_BEST_NONE;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      take[u] = false;
+      if (live[u]) {
+        int64_t task = (int64_t)HLM_CAND_UNIT(c[u]) * n_targets + g[u];
         if (round == 0) {
-          take = (lb == emin);
-          if (take && lb == 0) {
+          take[u] = (lb[u] == (int)emin[u]);
+          if (take[u] && lb[u] == 0) {
             // a zero bound is an exact match of the whole read on a band diagonal: the DP result
             // is known (S = n, no edits, no clips) and nothing can beat or tie-break it
-            take = false;
-            atomicMin(&ck.task_best[task],
-                      (unsigned long long)HLM_BEST_PACK(0, (int)ck.unit_len[HLM_CAND_UNIT(c)], 0, 0));
+            take[u] = false;
+            unsigned long long exact = HLM_BEST_PACK(0, (int)ck.unit_len[HLM_CAND_UNIT(c[u])], 0, 0);
+            if (best[u] > exact) atomicMin(&ck.task_best[task], exact);  // most tasks hold it already
           }
         } else {
-          unsigned long long b = ck.task_best[task];
-          take = (lb > emin) && b != HLM_BEST_NONE && lb <= HLM_BEST_COST(b);
+          take[u] = (lb[u] > (int)emin[u]) && best[u] != HLM_BEST_NONE && lb[u] <= HLM_BEST_COST(best[u]);
         }
       }
     }
-    // the DP list stays dense (no padding): one ballot-aggregated atomic per warp iteration.  The
-    // number of DP rows (= trimmed length) goes with every entry and into a histogram: the list
-    // is counting-sorted by length before k_dp so that the 32 candidates of a DP warp are alike.
-    int nrows = take ? (int)ck.unit_len[HLM_CAND_UNIT(ck.cand[i])] : 0;
-    uint32_t bal = __ballot_sync(FULL, take);
-    if (bal) {
-      unsigned long long pos = 0;
-      if (lane == 0) pos = atomicAdd(&ck.counters[1], (unsigned long long)__popc(bal));
-      pos = __shfl_sync(FULL, pos, 0);
-      // one histogram atomic per distinct length in the warp
-      uint32_t peers = __match_any_sync(FULL, nrows);
-      if (take) {
-        unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
+    // the DP list stays dense (no padding).  List slots are claimed once per BLOCK per iteration
+    // (warp ballots -> shared-memory prefix -> one global atomic): a per-warp atomic on the one
+    // list counter was what bounded this kernel.  The number of DP rows (= trimmed length) goes
+    // with every entry and into a histogram - per block in shared memory, flushed at the end:
+    // the list is counting-sorted by length before k_dp so that the 32 candidates of a DP warp
+    // are alike.
+    uint32_t bal[UN];
+    int wcnt = 0;
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      bal[u] = __ballot_sync(FULL, take[u]);
+      wcnt += __popc(bal[u]);
+    }
+    if (lane == 0) s_wcnt[wib] = wcnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; w++) {
+        int cw = s_wcnt[w];
+        s_wcnt[w] = tot;
+        tot += cw;
+      }
+      s_base = tot ? atomicAdd(&ck.counters[1], (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long pos = s_base + (unsigned long long)s_wcnt[wib];
+    __syncthreads();  // s_wcnt / s_base are rewritten by the next iteration
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (take[u]) {
+        int nrows = (int)ck.unit_len[HLM_CAND_UNIT(c[u])];
+        unsigned long long at = pos + __popc(bal[u] & ((1u << lane) - 1u));
         if ((int64_t)at < ck.dp_cap) {
-          ck.dp_list[at] = (uint32_t)i;
+          ck.dp_list[at] = (uint32_t)idx[u];
           ck.dp_len[at] = (uint8_t)nrows;
         } else {
           ck.counters[2] = 1;
         }
-        if (lane == __ffs(peers) - 1) atomicAdd(&ck.dp_hist[nrows], (uint32_t)__popc(peers));
+        atomicAdd(&s_hist[nrows], 1u);
       }
-      n_take += __popc(bal);
+      pos += __popc(bal[u]);
     }
+    n_take += wcnt;
   }
+  __syncthreads();
+  if (s_hist[threadIdx.x]) atomicAdd(&ck.dp_hist[threadIdx.x], s_hist[threadIdx.x]);
   if (lane == 0 && n_take) atomicAdd(&ck.counters[6], n_take);
 }
 
