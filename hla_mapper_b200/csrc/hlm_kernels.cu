@@ -589,15 +589,21 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     uint32_t total = __shfl_sync(FULL, inc, 31);
     pre[lane] = inc - cnt;  // exclusive prefix
     beg[lane] = my_a;
-    bool use_ht = total <= SEED_HT_MAX;
-    if (use_ht)
-      for (int x = lane; x < SEED_HT; x += 32) ht[x] = 0xFFFFFFFFu;
+    // The set holds one key per candidate emitted so far (distinct keys, not index hits: a unit
+    // with thousands of hits has a few hundred candidates).  While it has room a hit is a
+    // candidate iff its key is new.  Once SEED_HT_MAX keys are in, new keys are no longer stored:
+    // a hit whose key is not in the set is then tested the slow way - it is the candidate's first
+    // hit iff no earlier read seed matches the tile (hits arrive in seed order, so both rules
+    // name the same owner).
+    for (int x = lane; x < SEED_HT; x += 32) ht[x] = 0xFFFFFFFFu;
+    int n_keys = 0;  // warp-uniform
     __syncwarp();
     for (uint32_t base = 0; base < total; base += 32) {
       uint32_t t = base + lane;
       bool own = false;
       uint32_t tile = 0;
       int off = 0, strand = 0;
+      bool insert = n_keys + 32 <= SEED_HT_MAX;
       if (t < total) {
         int j = 0;  // last lane with pre[j] <= t
 #pragma unroll
@@ -610,21 +616,23 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         off = (int)(e >> 24) - q * HLM_SEED;
         int g = tile_locus(db, tile);
         if ((umask >> g) & 1u) {
-          if (use_ht) {
-            uint32_t key = (tile << 6) | ((uint32_t)(off - HLM_OFF_MIN) << 1) | (uint32_t)strand;
-            uint32_t h = (key * 2654435761u) >> 21;
-            for (;;) {
-              uint32_t old = atomicCAS(&ht[h], 0xFFFFFFFFu, key);
-              if (old == 0xFFFFFFFFu) {
-                own = true;
-                break;
-              }
-              if (old == key) break;
-              h = (h + 1) & (SEED_HT - 1);
+          uint32_t key = (tile << 6) | ((uint32_t)(off - HLM_OFF_MIN) << 1) | (uint32_t)strand;
+          uint32_t h = (key * 2654435761u) >> 21;
+          bool found = false;
+          for (;;) {
+            uint32_t old = insert ? atomicCAS(&ht[h], 0xFFFFFFFFu, key) : ht[h];
+            if (old == 0xFFFFFFFFu) break;  // not in the set (and now stored, when inserting)
+            if (old == key) {
+              found = true;
+              break;
             }
-          } else {
-            // fallback: the candidate belongs to the first read seed whose index entry hits it
-            // (children only list the seeds that cover one of their differing columns)
+            h = (h + 1) & (SEED_HT - 1);
+          }
+          if (!found && insert) {
+            own = true;
+          } else if (!found) {
+            // the set is full: the candidate belongs to the first read seed whose index entry
+            // hits it (children only list the seeds that cover one of their differing columns)
             const uint32_t* R = rd + 18 * strand;
             const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
             uint32_t diff = __ldg(db.tile_diff + tile);
@@ -641,6 +649,8 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
           }
         }
       }
+      if (insert) n_keys += __popc(__ballot_sync(FULL, own));
+      __syncwarp();
       app.push(own, HLM_CAND(unit, tile, off - HLM_OFF_MIN, strand, 0xFF), lane);
     }
   }
