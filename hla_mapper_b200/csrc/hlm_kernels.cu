@@ -716,16 +716,16 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       // the seed index, which then emitted the candidate)
       uint32_t diff = __ldg(db.tile_diff + tile);
       int Q = n / HLM_SEED;
-      bool any = false;
-      for (int q = 0; q < Q && !dead; q++) {
-        if (!hlm_seed_match(rd, T, off, q)) continue;
-        any = true;
-        int o = off + q * HLM_SEED;
-        for (int k = 0; k < HLM_DIFF_N(diff); k++) {
-          int x = HLM_DIFF_COL(diff, k);
-          if (x >= o && x < o + HLM_SEED) dead = true;  // the seed index lists this one
-        }
+      // all seed tests first (independent loads, no early exit), then the covering seeds of the
+      // differing columns are looked up in the match mask
+      uint32_t mm = 0;
+#pragma unroll 4
+      for (int q = 0; q < Q; q++) mm |= (uint32_t)hlm_seed_match(rd, T, off, q) << q;
+      for (int k = 0; k < HLM_DIFF_N(diff); k++) {
+        int r = HLM_DIFF_COL(diff, k) - off;  // read position on the diagonal
+        if (r >= 0 && r < Q * HLM_SEED && ((mm >> (r / HLM_SEED)) & 1u)) dead = true;  // the seed index lists this one
       }
+      bool any = mm != 0;
       if (!any) dead = true;
     }
     if (dead) {
