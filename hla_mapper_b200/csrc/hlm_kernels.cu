@@ -716,16 +716,18 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       // the seed index, which then emitted the candidate)
       uint32_t diff = __ldg(db.tile_diff + tile);
       int Q = n / HLM_SEED;
-      // all seed tests first (independent loads, no early exit), then the covering seeds of the
-      // differing columns are looked up in the match mask
-      uint32_t mm = 0;
-#pragma unroll 4
-      for (int q = 0; q < Q; q++) mm |= (uint32_t)hlm_seed_match(rd, T, off, q) << q;
+      // the (at most KMAX) seeds that cover a differing column decide ownership; after them the
+      // first matching seed settles "some seed matches": two to four tests, not Q
+      uint32_t cover = 0;
       for (int k = 0; k < HLM_DIFF_N(diff); k++) {
         int r = HLM_DIFF_COL(diff, k) - off;  // read position on the diagonal
-        if (r >= 0 && r < Q * HLM_SEED && ((mm >> (r / HLM_SEED)) & 1u)) dead = true;  // the seed index lists this one
+        if (r >= 0 && r < Q * HLM_SEED) cover |= 1u << (r / HLM_SEED);
       }
-      bool any = mm != 0;
+      for (uint32_t m = cover; m && !dead; m &= m - 1)
+        dead = hlm_seed_match(rd, T, off, __ffs(m) - 1);  // the seed index lists this one
+      bool any = dead;
+      for (int q = 0; q < Q && !any; q++)
+        if (!((cover >> q) & 1u)) any = hlm_seed_match(rd, T, off, q);
       if (!any) dead = true;
     }
     if (dead) {
