@@ -564,18 +564,22 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         uint32_t a = __ldg(db.seed_off + code), b = __ldg(db.seed_off + code + 1);
         uint32_t klo = (uint32_t)(HLM_OFF_MIN + my_q * HLM_SEED) << 24;
         uint32_t khi = (uint32_t)(HLM_OFF_MIN + HLM_TILE_STRIDE + my_q * HLM_SEED) << 24;
-        uint32_t lo = a, hi = b;
-        while (lo < hi) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(db.seed_ent + mid) < klo) lo = mid + 1; else hi = mid;
+        // both bounds at once: two independent chains of dependent loads instead of one after
+        // the other (this part of the kernel is pure memory latency)
+        uint32_t lo1 = a, hi1 = b, lo2 = a, hi2 = b;
+        while (lo1 < hi1 || lo2 < hi2) {
+          uint32_t m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1;
+          uint32_t e1 = lo1 < hi1 ? __ldg(db.seed_ent + m1) : 0u;
+          uint32_t e2 = lo2 < hi2 ? __ldg(db.seed_ent + m2) : 0u;
+          if (lo1 < hi1) {
+            if (e1 < klo) lo1 = m1 + 1; else hi1 = m1;
+          }
+          if (lo2 < hi2) {
+            if (e2 < khi) lo2 = m2 + 1; else hi2 = m2;
+          }
         }
-        my_a = lo;
-        hi = b;
-        while (lo < hi) {
-          uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(db.seed_ent + mid) < khi) lo = mid + 1; else hi = mid;
-        }
-        my_b = lo;
+        my_a = lo1;
+        my_b = lo2;
       }
     }
     // flatten the 2 x Q entry ranges over the lanes (load-balanced expansion): entry t of the
