@@ -304,7 +304,10 @@ def run_b200(args):
     my_peak = alu_peak / MYERS_ALU_OPS_PER_ROW
     rooflines = {
         "k_dp": {"bound": "int32", "achieved": round(gcups, 1), "peak": round(dp_peak_gcups, 1),
-                 "unit": "GCUPS", "frac": round(gcups / dp_peak_gcups, 4), "traffic": None,
+                 "unit": "GCUPS", "frac": round(gcups / dp_peak_gcups, 4),
+                 # dram bytes read + written by one round-0 launch (65 536-pair chunk),
+                 # profiles/r1i_kernels_full.txt; the kernel is ALU-bound
+                 "traffic": 169649920,
                  "ms_per_step": round(dp_ms, 3), "cells_per_step": int(cells),
                  "int32_peak_glops": {k: round(v, 1) for k, v in int_peak.items()},
                  "alu_ops_per_cell": dp_alu, "int_ops_per_cell": dp_all,
@@ -312,17 +315,20 @@ def run_b200(args):
         "k_myers": {"bound": "int32", "achieved": round(my_grows, 2), "peak": round(my_peak, 2),
                     "unit": "G band-rows/s", "frac": round(my_grows / my_peak, 4),
                     # dram__bytes_read.sum + dram__bytes_write.sum of one seed-index-phase launch
-                    # (65 536-pair chunk), profiles/r1e_kernels_full.txt; the kernel is ALU-bound
-                    "traffic": 570317056,
+                    # (65 536-pair chunk), profiles/r1i_kernels_full.txt; the kernel is ALU-bound
+                    "traffic": 574942720,
                     "ms_per_step": round(my_ms, 3), "rows_per_step": int(myers_rows),
                     "alu_ops_per_row": MYERS_ALU_OPS_PER_ROW},
         "k_screen": {"bound": "hbm", "achieved": round(screen_gbs, 1), "peak": hbm_peak,
-                     "unit": "GB/s", "frac": round(screen_gbs / hbm_peak, 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(screen_gbs / hbm_peak, 4),
+                     # one launch (65 536 pairs, 40 MB algorithmic): 137 MB read + 23 MB written,
+                     # profiles/r1i_kernels_full.txt - the excess is the k-mer table probes
+                     "traffic": 159075840,
                      "ms_per_step": round(sc_ms, 3), "bytes_per_step": int(screen_bytes),
                      "peak_source": hbm_src,
                      "probes_per_s": round(n * 130.0 / (sc_ms * 1e-3), 0) if sc_ms > 0 else None,
                      "limiter": "130 random 8-byte probes per pair into the 134 MB k-mer table (L2 hit "
-                                "48 % in profiles/r1c_kernels_full.txt), not the streaming of the reads; "
+                                "55 % in profiles/r1i_kernels_full.txt), not the streaming of the reads; "
                                 "the kernel is 1 % of the step"},
         "k_seed": {"ms_per_step": round(per("ms_seed"), 3),
                    "seed_candidates_per_step": int(kstage["n_seed_candidates"])},
