@@ -174,7 +174,8 @@ __device__ __forceinline__ uint32_t hlm_fma_mad(uint32_t a, uint32_t b, uint32_t
 // peq_addr: shared-memory byte address of this thread's PEQ row 0; rows are ROW_BYTES apart
 template <int ROW_BYTES>
 __device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ codes, int n, int off,
-                                                  uint32_t peq_addr, uint32_t one) {
+                                                  uint32_t peq_addr, uint32_t one,
+                                                  const uint16_t* __restrict__ mintab) {
   const uint64_t MASK = (1ull << HLM_NB) - 1;
   uint64_t SP = 1ull << (HLM_NB - 1), SN = 0;
   uint32_t p = (uint32_t)(off - HLM_BAND);
@@ -226,13 +227,42 @@ __device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ c
   }
 #undef HLM_MYERS_DEV_ROW
   asm volatile("" ::: "memory");  // the next candidate overwrites the PEQ rows
-  int score = n - zeros;
-  int best = score, cur = score;
-  for (int k = 0; k < HLM_NB - 1; k++) {
-    cur += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);
-    best = cur < best ? cur : best;
+  // minimum over the last band row: prefix sums of the vertical deltas, four columns per look-up
+  // in a 256-entry table (hlm_band_min_entry) instead of forty single steps
+  int best = n - zeros, cur8 = best - 8;
+  uint32_t spl = (uint32_t)SP, sph = (uint32_t)(SP >> 32), snl = (uint32_t)SN, snh = (uint32_t)(SN >> 32);
+  // bytes of ev / od: (SP nibble << 4 | SN nibble) of the even / odd nibbles of a word
+  uint32_t ev = ((spl & 0x0F0F0F0Fu) << 4) | (snl & 0x0F0F0F0Fu);
+  uint32_t od = (spl & 0xF0F0F0F0u) | ((snl >> 4) & 0x0F0F0F0Fu);
+  uint32_t hi = ((sph & 0x0Fu) << 4) | (snh & 0x0Fu) | ((sph & 0xF0u) << 8) | ((snh & 0xF0u) << 4);
+#define HLM_BAND_MIN_STEP(IDX)                                                \
+  {                                                                           \
+    uint32_t e = mintab[IDX];                                                 \
+    best = __viaddmin_s32(cur8, (int)(e >> 8), best);                         \
+    cur8 += (int)(e & 0xFFu) - 8;                                             \
   }
+  HLM_BAND_MIN_STEP(__byte_perm(ev, 0u, 0x4440))
+  HLM_BAND_MIN_STEP(__byte_perm(od, 0u, 0x4440))
+  HLM_BAND_MIN_STEP(__byte_perm(ev, 0u, 0x4441))
+  HLM_BAND_MIN_STEP(__byte_perm(od, 0u, 0x4441))
+  HLM_BAND_MIN_STEP(__byte_perm(ev, 0u, 0x4442))
+  HLM_BAND_MIN_STEP(__byte_perm(od, 0u, 0x4442))
+  HLM_BAND_MIN_STEP(__byte_perm(ev, 0u, 0x4443))
+  HLM_BAND_MIN_STEP(__byte_perm(od, 0u, 0x4443))
+  HLM_BAND_MIN_STEP(hi & 0xFFu)   // columns 32..35
+  HLM_BAND_MIN_STEP(hi >> 8)      // columns 36..39
+#undef HLM_BAND_MIN_STEP
   return best;
+}
+// entry t = (SP nibble << 4 | SN nibble): low byte = sum of the four deltas + 8, high byte = the
+// smallest of the four prefix sums + 8
+__host__ __device__ inline uint16_t hlm_band_min_entry(int t) {
+  int sp = t >> 4, sn = t & 15, cur = 0, mn = 8;
+  for (int k = 0; k < 4; k++) {
+    cur += ((sp >> k) & 1) - ((sn >> k) & 1);
+    mn = cur < mn ? cur : mn;
+  }
+  return (uint16_t)((cur + 8) | ((mn + 8) << 8));
 }
 #endif
 

@@ -689,6 +689,9 @@ struct HlmPeqShared {
 __global__ void __launch_bounds__(256)
 k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
   __shared__ uint32_t s_peq[HLM_PEQ_ROWS * 256];
+  __shared__ uint16_t s_mintab[256];
+  s_mintab[threadIdx.x] = hlm_band_min_entry((int)threadIdx.x);  // blockDim.x == 256
+  __syncthreads();
   HlmPeqShared peq{s_peq + threadIdx.x};
   int64_t first, ncand;
   cand_range(ck, phase, first, ncand);
@@ -740,7 +743,8 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       hlm_peq_build(T, peq);
       lb = hlm_myers_core_dev<256 * 4>(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
                                            HLM_CODE_WORDS * strand,
-                                       n, off, (uint32_t)__cvta_generic_to_shared(s_peq + threadIdx.x), (uint32_t)kp.one);
+                                       n, off, (uint32_t)__cvta_generic_to_shared(s_peq + threadIdx.x), (uint32_t)kp.one,
+                                       s_mintab);
       if (lb > 253) lb = 253;
       rows += n;
     }
