@@ -22,6 +22,10 @@
  *   others back-fill, compare, src/map_dna.cpp:903-1029,
  *   argmin, tie set            src/map_rna.cpp:925-1027                    hlm_assign
  *   ThreadPool dispatch        src/ThreadPool.hpp:18-100                   hlm_run (stream pipeline)
+ *   FASTQ(.gz) loops, writers  src/preselect.cpp:652-1203,
+ *                              src/map_dna.cpp:1036-1351                   hlm_map_fastq
+ *   bam= input (4 x samtools)  src/preselect.cpp:315-631                   hlm_bam_extract, hlm_map_reads
+ *   rna: STAR SAM -> blocks    src/map_rna.cpp:740-790                     hlm_batch.rna_blocks (input)
  */
 #ifndef HLAMAP_H
 #define HLAMAP_H
