@@ -38,6 +38,7 @@
 #include <unordered_set>
 #include <vector>
 
+#include "hlm_bgzf.h"
 #include "hlm_db.h"
 #include "hlm_files.h"
 
@@ -164,73 +165,19 @@ class BamScanner {
 
   template <class Fn>
   bool scan(BamHeader& hdr, Fn&& fn) {
-    size_t pos = 0;
-    std::vector<uint8_t> buf;
+    HlmBgzf bg(d_, n_, threads_);
+    bg.verify_crc = verify_crc;
+    std::vector<uint8_t> buf((size_t)kChunkBlocks * 65536 + (1u << 20));
     size_t carry = 0;
     bool first = true;
-    struct Blk { size_t in, in_len, out; uint32_t isize, crc; };
-    std::vector<Blk> blks;
     std::vector<Rec> recs;
-    while (pos < n_) {
-      // ---- block boundaries of the next chunk (RFC 1952 member with the BC extra subfield)
-      blks.clear();
-      size_t out = carry;
-      while (pos < n_ && blks.size() < (size_t)kChunkBlocks) {
-        if (n_ - pos < 18 || d_[pos] != 0x1f || d_[pos + 1] != 0x8b || d_[pos + 2] != 8 || !(d_[pos + 3] & 4))
-          return fail("not a BGZF block at byte " + std::to_string(pos));
-        uint32_t xlen = le16(d_ + pos + 10), bsize = 0;
-        bool found = false;
-        for (size_t x = pos + 12; x + 4 <= pos + 12 + xlen && x + 4 <= n_;) {
-          uint32_t slen = le16(d_ + x + 2);
-          if (d_[x] == 'B' && d_[x + 1] == 'C' && slen == 2 && x + 6 <= n_) {
-            bsize = le16(d_ + x + 4);
-            found = true;
-            break;
-          }
-          x += 4 + slen;
-        }
-        size_t total = (size_t)bsize + 1;
-        if (!found || total < 12 + xlen + 8 || pos + total > n_) return fail("truncated BGZF block at byte " + std::to_string(pos));
-        Blk b;
-        b.in = pos + 12 + xlen;
-        b.in_len = total - 12 - xlen - 8;
-        b.crc = le32(d_ + pos + total - 8);
-        b.isize = le32(d_ + pos + total - 4);
-        if (b.isize > 65536) return fail("BGZF block larger than 64 KiB at byte " + std::to_string(pos));
-        b.out = out;
-        out += b.isize;
-        blks.push_back(b);
-        pos += total;
-      }
-      // ---- inflate the chunk behind the bytes carried over from the previous one
-      if (buf.size() < out) buf.resize(out + (out >> 2));
-      std::atomic<size_t> next{0};
-      std::atomic<int> bad{0};
-      run_parallel([&](int) {
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-        for (;;) {
-          size_t i = next.fetch_add(1);
-          if (i >= blks.size()) break;
-          const Blk& b = blks[i];
-          if (b.isize == 0) continue;
-          inflateReset(&zs);
-          zs.next_in = const_cast<Bytef*>(d_ + b.in);
-          zs.avail_in = (uInt)b.in_len;
-          zs.next_out = buf.data() + b.out;
-          zs.avail_out = b.isize;
-          int r = inflate(&zs, Z_FINISH);
-          if (r != Z_STREAM_END || zs.avail_out != 0 ||
-              (verify_crc && (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf.data() + b.out, b.isize) != b.crc)) {
-            bad = 1;
-            break;
-          }
-        }
-        inflateEnd(&zs);
-      });
-      if (bad) return fail("corrupt BGZF block (inflate / CRC)");
-      bytes_inflated += (int64_t)(out - carry);
+    while (!bg.at_end()) {
+      // ---- inflate the next chunk of blocks behind the bytes carried over from the previous one
+      if (buf.size() < carry + (size_t)kChunkBlocks * 65536) buf.resize(carry + (size_t)kChunkBlocks * 65536);
+      long got = bg.fill(buf.data() + carry, buf.size() - carry, kChunkBlocks);
+      if (got < 0) return fail(bg.err);
+      size_t out = carry + (size_t)got;
+      bytes_inflated += got;
       // ---- header (first chunk), then the record boundaries
       size_t p = 0;
       if (first) {
@@ -345,28 +292,6 @@ void set_err(char* err, size_t errlen, const std::string& m) {
   if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
 }
 
-struct Mapped {
-  const uint8_t* p = nullptr;
-  size_t n = 0;
-  int fd = -1;
-  bool open(const char* path) {
-    fd = ::open(path, O_RDONLY);
-    if (fd < 0) return false;
-    struct stat st;
-    if (fstat(fd, &st) != 0 || st.st_size <= 0) return false;
-    n = (size_t)st.st_size;
-    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
-    if (m == MAP_FAILED) return false;
-    madvise(m, n, MADV_SEQUENTIAL);
-    p = (const uint8_t*)m;
-    return true;
-  }
-  ~Mapped() {
-    if (p) munmap((void*)p, n);
-    if (fd >= 0) close(fd);
-  }
-};
-
 // reads held in memory, served in slices
 class MemSource : public PairSource {
  public:
@@ -466,7 +391,7 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
     set_err(err, errlen, "cannot read " + bed);
     return nullptr;
   }
-  Mapped file;
+  HlmMapped file;
   if (!file.open(bam_path)) {
     set_err(err, errlen, std::string("cannot open ") + bam_path);
     return nullptr;

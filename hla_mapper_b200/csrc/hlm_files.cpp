@@ -31,6 +31,7 @@
 #include <thread>
 #include <vector>
 
+#include "hlm_bgzf.h"
 #include "hlm_db.h"
 #include "hlm_files.h"
 
@@ -46,16 +47,24 @@ namespace {
 class FastqReader {
  public:
   explicit FastqReader(const char* path) {
-    // plain text goes through read(2) directly; only gzip streams pay for zlib
+    // plain text goes through read(2) directly; bgzip-compressed files (BGZF: independent
+    // deflate blocks) are inflated on several host threads; only plain gzip streams are left to
+    // zlib's single-threaded gzread
     fd_ = open(path, O_RDONLY);
     if (fd_ >= 0) {
-      unsigned char magic[2] = {0, 0};
-      ssize_t r = pread(fd_, magic, 2, 0);
-      if (r == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+      unsigned char magic[64];
+      memset(magic, 0, sizeof magic);
+      ssize_t r = pread(fd_, magic, sizeof magic, 0);
+      if (r >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         close(fd_);
         fd_ = -1;
-        f_ = gzopen(path, "rb");
-        if (f_) gzbuffer(f_, 1 << 22);
+        if (hlm_is_bgzf(magic, (size_t)r) && map_.open(path)) {
+          int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
+          bg_.reset(new HlmBgzf(map_.p, map_.n, nt));
+        } else {
+          f_ = gzopen(path, "rb");
+          if (f_) gzbuffer(f_, 1 << 22);
+        }
       } else {
         posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
       }
@@ -66,7 +75,7 @@ class FastqReader {
     if (f_) gzclose(f_);
     if (fd_ >= 0) close(fd_);
   }
-  bool ok() const { return f_ != nullptr || fd_ >= 0; }
+  bool ok() const { return f_ != nullptr || fd_ >= 0 || bg_ != nullptr; }
   // appends up to max_pairs records to b; returns number appended
   int64_t read(MateBatch& b, int64_t max_pairs) {
     int64_t got = 0;
@@ -110,6 +119,7 @@ class FastqReader {
       got++;
     }
     b.n += got;
+    if (corrupt_) b.io_error = true;
     return got;
   }
 
@@ -119,15 +129,28 @@ class FastqReader {
     memmove(buf_.data(), buf_.data() + pos_, tail);
     pos_ = 0;
     have_ = tail;
-    if (have_ == buf_.size()) buf_.resize(buf_.size() * 2);
+    if (buf_.size() - have_ < (1u << 16)) buf_.resize(buf_.size() * 2);  // room for one BGZF block
     size_t want = std::min<size_t>(buf_.size() - have_, 1u << 30);
-    long r = f_ ? (long)gzread(f_, buf_.data() + have_, (unsigned)want)
-                : (long)::read(fd_, buf_.data() + have_, want);
+    long r;
+    if (bg_) {
+      r = bg_->fill((uint8_t*)buf_.data() + have_, want, 512);
+      if (r < 0) corrupt_ = true;
+    } else if (f_) {
+      r = (long)gzread(f_, buf_.data() + have_, (unsigned)want);
+      int en = Z_OK;
+      if (r <= 0) gzerror(f_, &en);
+      if (r < 0 || (en != Z_OK && en != Z_STREAM_END)) corrupt_ = true;  // truncated / damaged gzip stream
+    } else {
+      r = (long)::read(fd_, buf_.data() + have_, want);
+    }
     if (r <= 0) eof_ = true;
     else have_ += (size_t)r;
   }
   gzFile f_ = nullptr;
   int fd_ = -1;
+  HlmMapped map_;
+  std::unique_ptr<HlmBgzf> bg_;
+  bool corrupt_ = false;
   std::vector<char> buf_;
   size_t pos_ = 0, have_ = 0;
   bool eof_ = false;
@@ -184,7 +207,7 @@ class BatchStream {
       b->clear();
       int64_t got = rd_.read(*b, batch_);
       std::lock_guard<std::mutex> g(m_);
-      if (got > 0) q_.push(b);
+      if (got > 0 || b->io_error) q_.push(b);
       else free_.push_back(b);
       if (got < batch_) {
         done_ = true;
@@ -216,6 +239,11 @@ class FileSource : public PairSource {
   bool next(MateBatch*& b1, MateBatch*& b2, int& rc, std::string& err) override {
     b1 = in1_.next();
     b2 = in2_ ? in2_->next() : nullptr;
+    if ((b1 && b1->io_error) || (b2 && b2->io_error)) {
+      err = std::string(b1 && b1->io_error ? "r1" : "r2") + " is corrupt or truncated (gzip / BGZF stream)";
+      rc = HLM_E_IO;
+      return false;
+    }
     bool end = !b1 || (in2_ && !b2);
     if (in2_ && ((end && (b1 != nullptr) != (b2 != nullptr)) || (!end && b1->n != b2->n))) {
       err = "r1 and r2 hold different numbers of reads";

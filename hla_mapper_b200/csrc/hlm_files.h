@@ -15,12 +15,14 @@ struct MateBatch {
   std::vector<char> hdr;            // header lines, no newline, concatenated
   std::vector<uint64_t> hoff;       // n + 1
   int64_t n = 0;
-  bool bad = false;                 // truncated / malformed input
+  bool bad = false;                 // a partial record at the end of the text (dropped, like getline loops do)
+  bool io_error = false;            // the compressed stream is corrupt / truncated
   void clear() {
     bases.clear(); quals.clear(); hdr.clear();
     offs.assign(1, 0); hoff.assign(1, 0);
     n = 0;
     bad = false;
+    io_error = false;
   }
   void push(const char* h, size_t hl, const uint8_t* s, const uint8_t* q, size_t l) {
     hdr.insert(hdr.end(), h, h + hl);

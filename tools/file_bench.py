@@ -1,24 +1,56 @@
 """FASTQ ingest throughput of hlm_map_fastq on decoy-heavy input (the whole-genome case: almost
 nothing passes the screen, so the run is bound by the text path).  Usage (GPU box):
-    python tools/file_bench.py [n_pairs] [on_target]"""
+    python tools/file_bench.py [n_pairs] [on_target] [plain|bgzf|gzip]
+bgzf = the FASTQ files bgzip-compressed (inflated block-parallel by the reader), gzip = plain gzip
+(zlib's single stream per file)."""
 import os
+import struct
 import sys
 import tempfile
 import time
+import zlib
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hla_mapper_b200 import _abi, api, synth
 
 
+def bgzf_write(src, dst, block=0xff00):
+    """bgzip: RFC 1952 members of <= 64 KiB with the BC extra subfield (SAM specification 4.1)"""
+    with open(src, "rb") as f, open(dst, "wb") as o:
+        while True:
+            raw = f.read(block)
+            c = zlib.compressobj(1, zlib.DEFLATED, -15)
+            comp = c.compress(raw) + c.flush()
+            o.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00"
+                    + struct.pack("<H", len(comp) + 25) + comp
+                    + struct.pack("<II", zlib.crc32(raw) & 0xffffffff, len(raw)))
+            if not raw:
+                return
+
+
+def gzip_write(src, dst):
+    import gzip
+    import shutil
+
+    with open(src, "rb") as f, gzip.open(dst, "wb", compresslevel=1) as o:
+        shutil.copyfileobj(f, o, 1 << 24)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
     on = float(sys.argv[2]) if len(sys.argv) > 2 else 0.01
+    kind = sys.argv[3] if len(sys.argv) > 3 else "plain"
     with tempfile.TemporaryDirectory(dir="/tmp") as tmp:
         db = synth.make_db(os.path.join(tmp, "db"), seed=42, n_loci=24, total_alleles=4000, n_others=200)
         rb = synth.make_reads(db, n, read_len=150, seed=1003, on_target=on)
         r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
         synth.write_fastq_fast(rb, r1, r2)
         size = os.path.getsize(r1) + os.path.getsize(r2)
+        if kind != "plain":
+            for src in (r1, r2):
+                (bgzf_write if kind == "bgzf" else gzip_write)(src, src + ".gz")
+                os.remove(src)
+            r1, r2 = r1 + ".gz", r2 + ".gz"
         gdb = api.Database(db.path)
         m = api.Mapper(gdb, 0, _abi.default_params())
         for rep in range(2):
@@ -27,7 +59,7 @@ def main():
             t = time.perf_counter()
             st = m.map_fastq(r1, r2, "W", out)
             dt = time.perf_counter() - t
-            print(f"rep {rep}: {n} pairs ({size / 1e9:.2f} GB of FASTQ) in {dt:.2f}s = {n / dt / 1e6:.2f} M pairs/s, "
+            print(f"rep {rep} [{kind}]: {n} pairs ({size / 1e9:.2f} GB of FASTQ) in {dt:.2f}s = {n / dt / 1e6:.2f} M pairs/s, "
                   f"{size / dt / 1e9:.2f} GB/s text; stats {st}")
         m.close()
 
