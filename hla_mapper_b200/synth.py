@@ -160,7 +160,7 @@ def make_db(path, seed=42, n_loci=24, total_alleles=40000, len_range=(3000, 4000
             s[pos] = (s[pos] + rng.integers(1, 4, size=nsnp, dtype=np.uint8)) & 3
             lo = [int(p) for p in pos]
             if rng.random() < 0.05:  # occasional 1-3 bp indel
-                p = int(rng.integers(50, L - 50))
+                p = int(rng.integers(50, L - 50)) if L > 100 else int(rng.integers(0, max(1, L)))  # short test sequences
                 k = int(rng.integers(1, 4))
                 if rng.random() < 0.5:
                     s = np.concatenate([s[:p], s[p + k:]])
@@ -276,6 +276,9 @@ def _block(db, src, rng, n, read_len, on_target, frag_mu, frag_sd, lowq_tail):
     ar = np.arange(L, dtype=np.int64)
     i1 = (src.starts[hap] + st)[:, None] + ar[None, :]
     i2 = (src.starts[hap] + st + frag - 1)[:, None] - ar[None, :]
+    # sources shorter than a read (tiny test databases): the read runs on into its neighbours
+    i1 = np.minimum(i1, len(src.flat) - 1)
+    i2 = np.maximum(i2, 0)
     r1 = src.flat[i1]
     r2 = _COMP[src.flat[i2]]
     flip = rng.random(n) < 0.5

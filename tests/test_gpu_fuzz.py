@@ -165,7 +165,10 @@ def test_low_complexity_reads_and_huge_candidate_lists(orc, tmp_path):
     _check(orc, str(tmp_path / "db"), rb)
 
 
-@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("HLM_FUZZ_SEEDS", "16"))))
+_FUZZ_FIRST = int(__import__("os").environ.get("HLM_FUZZ_FIRST", "0"))  # HLM_FUZZ_FIRST / HLM_FUZZ_SEEDS: seed window
+
+
+@pytest.mark.parametrize("seed", range(_FUZZ_FIRST, _FUZZ_FIRST + int(__import__("os").environ.get("HLM_FUZZ_SEEDS", "16"))))
 def test_random_databases_reads_and_parameters(orc, tmp_path, seed):
     """random database shape x read shape x parameter set, exhaustive oracle"""
     from hla_mapper_b200 import api
