@@ -19,12 +19,6 @@
 // the half-open BED interval, end from the CIGAR's reference-consuming operations, pos + 1 when
 // there are none; `fastq` drops secondary / supplementary records, reverse-complements records
 // flagged reverse, writes quality 1 ('"') when the BAM holds none).
-#include <fcntl.h>
-#include <sys/mman.h>
-#include <sys/stat.h>
-#include <unistd.h>
-#include <zlib.h>
-
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -154,8 +148,8 @@ uint64_t hash_name(const char* s, size_t n) {
   return h | 1;  // 0 marks an empty slot
 }
 
-// the BGZF scanner: inflates `chunk_blocks` blocks at a time on all threads, walks the records and
-// hands (records of the chunk) to `fn(worker, first, last)` on all threads
+// the BAM scanner: inflates kChunkBlocks BGZF blocks at a time on all threads (hlm_bgzf.h), walks
+// the records and hands (records of the chunk) to `fn(worker, first, last)` on all threads
 class BamScanner {
  public:
   BamScanner(const uint8_t* data, size_t size, int threads) : d_(data), n_(size), threads_(threads) {}
