@@ -84,7 +84,7 @@ class HlmFileStats(C.Structure):
 class HlmBamStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_records", "n_region", "n_unmapped", "n_names", "n_r0", "n_r1",
                                          "n_r2", "n_out", "bytes_compressed", "bytes_inflated")] + \
-               [("paired", C.c_int32), ("reserved0", C.c_int32)] + \
+               [("paired", C.c_int32), ("cached", C.c_int32)] + \
                [(k, C.c_double) for k in ("s_pass1", "s_pass2", "s_total")]
 
 

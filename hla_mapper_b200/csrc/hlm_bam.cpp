@@ -13,16 +13,20 @@
 //   header edits of the screen loops ("/1" resp. "/2": first occurrence removed)            :469-472, :549-552
 //   R1 joined to R2 by id, std::map order                                                   :556-603
 //
-// The BAM is read twice (names, then records); BGZF blocks are independent deflate streams and
-// are inflated on all host threads, a chunk of blocks at a time.  samtools itself is not in the
+// The BAM is scanned twice (names, then records); BGZF blocks are independent deflate streams and
+// are inflated on all host threads, a chunk of blocks at a time; the inflated chunks of the first
+// scan are kept for the second when they fit a memory budget.  samtools itself is not in the
 // sandbox: the record selection restates its documented behaviour (overlap = [pos, end) against
 // the half-open BED interval, end from the CIGAR's reference-consuming operations, pos + 1 when
 // there are none; `fastq` drops secondary / supplementary records, reverse-complements records
 // flagged reverse, writes quality 1 ('"') when the BAM holds none).
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -157,18 +161,40 @@ class BamScanner {
   int64_t n_records = 0, bytes_inflated = 0;
   bool verify_crc = true;  // the second scan of the same mapping skips the check
 
+  // Inflated chunks kept from the first scan so that the second does not inflate again; given
+  // up (and emptied) as soon as it would exceed its budget.
+  struct Cache {
+    struct Chunk {
+      std::unique_ptr<uint8_t[]> buf;
+      size_t begin, end;  // whole records in buf[begin, end)
+    };
+    std::vector<Chunk> chunks;
+    size_t bytes = 0, budget = 0;
+    bool valid = false;
+  };
+
   template <class Fn>
-  bool scan(BamHeader& hdr, Fn&& fn) {
+  bool scan(BamHeader& hdr, Fn&& fn, Cache* keep = nullptr) {
     HlmBgzf bg(d_, n_, threads_);
     bg.verify_crc = verify_crc;
-    std::vector<uint8_t> buf((size_t)kChunkBlocks * 65536 + (1u << 20));
+    const size_t chunk_cap = (size_t)kChunkBlocks * 65536;
+    size_t cap = chunk_cap + (1u << 20);
+    std::unique_ptr<uint8_t[]> buf(new uint8_t[cap]);
+    bool caching = keep != nullptr && keep->budget > 0;
+    if (keep) keep->valid = false;
     size_t carry = 0;
     bool first = true;
     std::vector<Rec> recs;
     while (!bg.at_end()) {
       // ---- inflate the next chunk of blocks behind the bytes carried over from the previous one
-      if (buf.size() < carry + (size_t)kChunkBlocks * 65536) buf.resize(carry + (size_t)kChunkBlocks * 65536);
-      long got = bg.fill(buf.data() + carry, buf.size() - carry, kChunkBlocks);
+      if (cap < carry + chunk_cap) {
+        size_t ncap = carry + chunk_cap;
+        std::unique_ptr<uint8_t[]> nb(new uint8_t[ncap]);
+        memcpy(nb.get(), buf.get(), carry);
+        buf = std::move(nb);
+        cap = ncap;
+      }
+      long got = bg.fill(buf.get() + carry, cap - carry, kChunkBlocks);
       if (got < 0) return fail(bg.err);
       size_t out = carry + (size_t)got;
       bytes_inflated += got;
@@ -176,28 +202,43 @@ class BamScanner {
       size_t p = 0;
       if (first) {
         first = false;
-        if (!parse_header(buf.data(), out, p, hdr)) return false;
+        if (!parse_header(buf.get(), out, p, hdr)) return false;
         on_header();
       }
-      recs.clear();
-      while (p + 4 <= out) {
-        uint32_t bs = le32(buf.data() + p);
-        if (bs < R_FIXED) return fail("malformed BAM record");
-        if (p + 4 + (size_t)bs > out) break;
-        Rec r{buf.data() + p + 4, bs};
-        if (!r.sane()) return fail("malformed BAM record");
-        recs.push_back(r);
-        p += 4 + (size_t)bs;
-      }
-      n_records += (int64_t)recs.size();
-      size_t nr = recs.size();
-      run_parallel([&](int w) { fn(w, recs.data() + nr * w / threads_, recs.data() + nr * (w + 1) / threads_); });
-      on_chunk();
+      size_t begin = p;
+      if (!walk(buf.get(), p, out, recs)) return false;
+      process(recs, fn);
       carry = out - p;
-      memmove(buf.data(), buf.data() + p, carry);
+      if (caching && keep->bytes + cap > keep->budget) {  // does not fit: scan twice after all
+        keep->chunks.clear();
+        keep->bytes = 0;
+        caching = false;
+      }
+      if (caching) {
+        // the chunk stays where it is; the unfinished record moves to the front of a new buffer
+        std::unique_ptr<uint8_t[]> nb(new uint8_t[cap]);
+        memcpy(nb.get(), buf.get() + p, carry);
+        keep->chunks.push_back({std::move(buf), begin, p});
+        keep->bytes += cap;
+        buf = std::move(nb);
+      } else {
+        memmove(buf.get(), buf.get() + p, carry);
+      }
     }
     if (first) return fail("empty BAM file");
     if (carry) return fail("truncated BAM record at end of file");
+    if (keep) keep->valid = caching;
+    return true;
+  }
+  // the second scan over chunks kept by the first
+  template <class Fn>
+  bool scan(const Cache& kept, Fn&& fn) {
+    std::vector<Rec> recs;
+    for (const Cache::Chunk& c : kept.chunks) {
+      size_t p = c.begin;
+      if (!walk(c.buf.get(), p, c.end, recs) || p != c.end) return fail("malformed BAM record");
+      process(recs, fn);
+    }
     return true;
   }
   // both run on the scanning thread: after the header has been parsed; after every chunk (merge
@@ -211,6 +252,27 @@ class BamScanner {
   bool fail(const std::string& m) {
     err = m;
     return false;
+  }
+  // record boundaries of buf[p, out): p ends behind the last whole record
+  bool walk(const uint8_t* buf, size_t& p, size_t out, std::vector<Rec>& recs) {
+    recs.clear();
+    while (p + 4 <= out) {
+      uint32_t bs = le32(buf + p);
+      if (bs < R_FIXED) return fail("malformed BAM record");
+      if (p + 4 + (size_t)bs > out) break;
+      Rec r{buf + p + 4, bs};
+      if (!r.sane()) return fail("malformed BAM record");
+      recs.push_back(r);
+      p += 4 + (size_t)bs;
+    }
+    return true;
+  }
+  template <class Fn>
+  void process(const std::vector<Rec>& recs, Fn& fn) {
+    n_records += (int64_t)recs.size();
+    size_t nr = recs.size();
+    run_parallel([&](int w) { fn(w, recs.data() + nr * w / threads_, recs.data() + nr * (w + 1) / threads_); });
+    on_chunk();
   }
   template <class F>
   void run_parallel(F&& f) {
@@ -391,6 +453,14 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
     return nullptr;
   }
 
+  // the inflated BAM is kept between the two scans when it fits a quarter of the machine's memory,
+  // at most 64 GB (HLM_BAM_CACHE_GB overrides; 0 = always scan twice)
+  BamScanner::Cache cache;
+  {
+    double gb = std::min(64.0, 0.25 * (double)sysconf(_SC_PHYS_PAGES) * (double)sysconf(_SC_PAGE_SIZE) / 1e9);
+    if (const char* e = getenv("HLM_BAM_CACHE_GB")) gb = atof(e);
+    cache.budget = gb > 0 ? (size_t)(gb * 1e9) : 0;
+  }
   // ---- pass 1: names of the records in the BED regions and of the unmapped records
   BamHeader hdr;
   std::unordered_set<std::string> names;
@@ -435,7 +505,7 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
         }
         if (hit) o.names.emplace_back(r->name(), r->name_len());
       }
-    });
+    }, &cache);
     if (!ok) {
       set_err(err, errlen, std::string(bam_path) + ": " + sc.err);
       return nullptr;
@@ -493,7 +563,7 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
         }
     };
     BamHeader again;
-    bool ok = sc.scan(again, [&](int wi, const Rec* a, const Rec* b) {
+    auto emit = [&](int wi, const Rec* a, const Rec* b) {
       W& w = ws[(size_t)wi];
       for (const Rec* r = a; r < b; r++) {
         uint32_t flag = r->flag();
@@ -508,7 +578,8 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
         int which = (r1 && !r2) ? 1 : (r2 && !r1) ? 2 : 0;
         w.bytes[which] += emit_fastq(*r, which, w.out[which], w.h, w.s, w.q);
       }
-    });
+    };
+    bool ok = cache.valid ? sc.scan(cache, emit) : sc.scan(again, emit);
     if (!ok) {
       set_err(err, errlen, std::string(bam_path) + ": " + sc.err);
       return nullptr;
@@ -547,6 +618,7 @@ static hlm_reads* bam_extract(const hlm_db* db, const char* bam_path, const char
     stats->n_r2 = sets[2].n;
     stats->n_out = out->m1.n;
     stats->paired = out->paired;
+    stats->cached = cache.valid ? 1 : 0;
     stats->s_pass1 = t2 - t1;
     stats->s_pass2 = t3 - t2;
     stats->s_total = now_s() - t_start;

@@ -276,7 +276,8 @@ typedef struct hlm_reads hlm_reads;
 typedef struct hlm_bam_stats {
   int64_t n_records, n_region, n_unmapped, n_names, n_r0, n_r1, n_r2, n_out;
   int64_t bytes_compressed, bytes_inflated;
-  int32_t paired, reserved0;
+  int32_t paired;
+  int32_t cached; /* 1: the inflated BAM was kept in memory between the two scans */
   double s_pass1, s_pass2, s_total;
 } hlm_bam_stats;
 hlm_reads* hlm_bam_extract(const hlm_db* db, const char* bam_path, const char* bed_path,

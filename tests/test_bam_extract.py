@@ -36,9 +36,12 @@ def _dump(reads, tmp):
     return [x + y for x, y in zip(a, b)]
 
 
-@pytest.mark.parametrize("single,block,threads", [(False, 0xff00, 0), (False, 900, 3), (True, 4000, 1)])
-def test_extract_matches_the_restated_samtools_calls(dbs, tmp_path, single, block, threads):
+@pytest.mark.parametrize("single,block,threads,cache_gb", [(False, 0xff00, 0, None), (False, 900, 3, "0"),
+                                                          (True, 4000, 1, None), (False, 0xff00, 2, "0.2")])
+def test_extract_matches_the_restated_samtools_calls(dbs, tmp_path, monkeypatch, single, block, threads, cache_gb):
     sdb, db = dbs
+    if cache_gb is not None:  # "0": scan twice; "0.2": one 134 MB chunk fits, a second would not
+        monkeypatch.setenv("HLM_BAM_CACHE_GB", cache_gb)
     rb = synth.make_reads(sdb, 700, read_len=120, seed=5, on_target=0.8, frag_mu=260, frag_sd=30, ragged=True)
     bam = str(tmp_path / "s.bam")
     n_rec = bam_cases.make_bam(rb, bam, seed=3, single=single)
@@ -51,6 +54,7 @@ def test_extract_matches_the_restated_samtools_calls(dbs, tmp_path, single, bloc
         reads = api.BamReads(db, bam, skip_unmapped=skip, threads=threads)
         assert reads.paired == paired == (not single)
         assert reads.stats["n_records"] == n_rec
+        assert reads.stats["cached"] == (0 if cache_gb == "0" else 1)
         got = _dump(reads, tmp_path)
         assert len(got) == reads.n == len(want) > 100
         assert got == want
