@@ -27,7 +27,7 @@ SYMBOLS = [
     "hlm_map_fastq", "hlm_run_async", "hlm_wait", "hlm_multi_create", "hlm_multi_destroy",
     "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run", "hlm_dp_layout_ab",
     "hlm_bam_extract", "hlm_reads_paired", "hlm_reads_count", "hlm_reads_free",
-    "hlm_reads_write_fastq", "hlm_map_reads",
+    "hlm_reads_write_fastq", "hlm_map_reads", "hlm_int32_peaks",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def lib():
                             C.POINTER(HlmAssignOut)]
     L.hlm_get_profile.argtypes = [C.c_void_p, C.POINTER(HlmProfile)]
     L.hlm_int32_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
+    L.hlm_int32_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
     L.hlm_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                 C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
     L.hlm_bam_extract.restype = C.c_void_p
@@ -313,12 +314,13 @@ def dp_layout_ab(device=0, n_cands=1 << 18, read_len=150):
 
 
 def int32_peak(device=0):
-    """measured giga lane-ops/s of IADD3, IMAD, mixed and VIADDMNMX chains"""
-    v = [C.c_double(0) for _ in range(4)]
-    rc = lib().hlm_int32_peak(int(device), *[C.byref(x) for x in v])
+    """measured giga lane-ops/s of IADD3, IMAD, IADD3+IMAD, VIADDMNMX, LOP3, SHF and 3 LOP3 : 1 SHF
+    chains (hlm_int32_peaks)"""
+    v = (C.c_double * 7)()
+    rc = lib().hlm_int32_peaks(int(device), v, 7)
     if rc != 0:
-        raise HlmError(f"hlm_int32_peak rc={rc}")
-    return dict(zip(("iadd3", "imad", "mix", "viaddmnmx"), (x.value for x in v)))
+        raise HlmError(f"hlm_int32_peaks rc={rc}")
+    return dict(zip(("iadd3", "imad", "mix", "viaddmnmx", "lop3", "shf", "lop3_shf_mix"), list(v)))
 
 
 def addressing_table(buf, ids, loci, rna=False, paired=True):

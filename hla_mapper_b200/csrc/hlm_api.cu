@@ -632,6 +632,7 @@ int64_t hlm_db_stat(const hlm_db* db, const char* key) {
   if (k == "kmers_skipped") return db->n_kmers_skipped;
   if (k == "kmers_odd") return (int64_t)db->odd_masks.size();
   if (k == "kt_slots") return (int64_t)db->kt.size();
+  if (k == "bloom_words") return (int64_t)db->kb.size();
   if (k == "seed_entries") return (int64_t)db->seed_ent.size();
   if (k == "reps") return db->n_reps;
   if (k == "children") return (int64_t)db->child_ent.size();
@@ -674,6 +675,8 @@ static int upload_db(hlm_ctx* ctx, hlm_db* db) {
   if (!rc) rc = up(8, db->child_diff.data(), db->child_diff.size() * 4, (const void**)&v.child_diff);
   if (!rc) rc = up(9, db->odd_keys.data(), db->odd_keys.size(), (const void**)&v.odd_keys);
   if (!rc) rc = up(10, db->odd_masks.data(), db->odd_masks.size() * 4, (const void**)&v.odd_masks);
+  if (!rc) rc = up(11, db->kb.data(), db->kb.size() * 8, (const void**)&v.kb);
+  v.kb_words = (uint32_t)db->kb.size();
   v.n_odd = (int)db->odd_masks.size();
   if (rc) {  // nothing half-uploaded stays behind
     for (void* q : dv.ptrs)
@@ -1235,6 +1238,20 @@ int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double
   double* outs[4] = {giga_iadd, giga_imad, giga_mix, giga_viaddmnmx};
   for (int w = 0; w < 4; w++)
     if (outs[w]) *outs[w] = hlm_int_peak_run(w, sms, 0);
+  return 0;
+}
+
+// the same, with the logic / shift chains k_myers is made of: out[0..6] = IADD3, IMAD, IADD3+IMAD mix,
+// VIADDMNMX, LOP3, SHF, 3 LOP3 : 1 SHF mix (giga warp-lane ops per second); n = entries wanted
+int hlm_int32_peaks(int cuda_device, double* out, int n) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cuda_device < 0 || cuda_device >= ndev)
+    return HLM_E_NODEVICE;
+  if (!out || n < 0) return HLM_E_ARG;
+  cudaSetDevice(cuda_device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  for (int w = 0; w < n && w < 7; w++) out[w] = hlm_int_peak_run(w, prop.multiProcessorCount, 0);
   return 0;
 }
 

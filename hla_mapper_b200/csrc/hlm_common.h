@@ -2,7 +2,7 @@
 //
 // Base codes: A=0 C=1 G=2 T=3 (complement = 3-c); everything else is N and never matches.
 //
-// k-mer screen index   open-addressing table of u64 slots:
+// k-mer screen index   Bloom front (kb: 4 bytes per key, L2-resident) + open-addressing table of u64 slots:
 //                        bit 63 = occupied, bits 40..55 = id into mask_tab[], bits 0..39 = 20-mer
 //                        (base i of the k-mer at bits 2i..2i+1).  mask_tab[id] = membership
 //                        mask: bit g = motif/<kind>/loci/<g>.txt, bit 31 = motif_all.txt.
@@ -68,9 +68,22 @@ HLM_COMMON_HD uint64_t hlm_kt_hash(uint64_t key, int bits) {
   return (key * 0x9E3779B97F4A7C15ull) >> (64 - bits);
 }
 
+/* Bloom front of the k-mer table: one 64-bit word per probe, four bits per key.  The word comes
+ * from the high half of the multiplicative hash, the bit positions from its low half.  A key
+ * whose four bits are not all set is in no motif file; the others go on to the exact table. */
+HLM_COMMON_HD uint64_t hlm_kb_probe(uint64_t key, uint32_t n_words, uint32_t* word) {
+  uint64_t h = key * 0x9E3779B97F4A7C15ull;
+  uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h;
+  *word = (uint32_t)(((uint64_t)hi * n_words) >> 32);
+  return (1ull << (lo & 63)) | (1ull << ((lo >> 6) & 63)) | (1ull << ((lo >> 12) & 63)) |
+         (1ull << ((lo >> 18) & 63));
+}
+
 /* device view of the database (all pointers are device pointers) */
 struct HlmDevDB {
   const uint64_t* kt;        /* k-mer table                                  */
+  const uint64_t* kb;        /* its Bloom front: kb_words 64-bit words       */
+  uint32_t kb_words;
   const uint32_t* mask_tab;  /* mask id -> membership mask                   */
   const uint8_t* odd_keys;   /* motif lines with a non-ACGT byte: 20 raw bytes each, sorted */
   const uint32_t* odd_masks;

@@ -190,7 +190,15 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
         size_t q = line.find(':', 5);
         std::string g = line.substr(5, q == std::string::npos ? std::string::npos : q - 5);
         g.erase(std::remove(g.begin(), g.end(), ' '), g.end());
-        if (!g.empty() && db->n_loci < HLM_MAX_LOCI) {
+        if (!g.empty() && db->n_loci >= HLM_MAX_LOCI) {
+          // one uint32 membership / target mask per pair: a 32nd locus cannot be represented,
+          // and dropping it silently would score its reads against the wrong targets
+          err = "db_" + std::string(kind) + ".info lists more than " + std::to_string(HLM_MAX_LOCI) +
+                " GENE: lines (limit of this build: loci + others must fit a 32-bit mask)";
+          delete db;
+          return nullptr;
+        }
+        if (!g.empty()) {
           db->names.push_back(g);
           db->n_loci++;
           // GENE:name:chr:pos:chrsize:optstart:optend:type
@@ -266,6 +274,14 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
       return nullptr;
     }
     if (db->mask_tab.empty()) db->mask_tab.push_back(0);
+    // Bloom front of the table (hlm_common.h): 4 bits per key in one 64-bit word, ~2 keys per
+    // word, so that it stays L2-resident (4 bytes per key) while the exact table does not
+    db->kb.assign(std::max<size_t>(64, (uniq.size() + 1) / 2), 0);
+    for (auto& e : uniq) {
+      uint32_t w;
+      uint64_t m = hlm_kb_probe(e.first, (uint32_t)db->kb.size(), &w);
+      db->kb[w] |= m;
+    }
   }
 
   DB_T("k-mer table")

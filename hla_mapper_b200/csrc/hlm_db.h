@@ -19,6 +19,7 @@ struct hlm_db {
   // k-mer screen index
   std::vector<uint64_t> kt;
   std::vector<uint32_t> mask_tab;
+  std::vector<uint64_t> kb;  // Bloom front of kt (hlm_kb_probe)
   int kt_bits = 0;
   int64_t n_kmers = 0;
   int64_t n_kmers_skipped = 0;  // 20-char motif lines holding a non-ACGT byte (kept in odd_*)
@@ -45,7 +46,7 @@ struct hlm_db {
   struct Dev {
     int device;
     HlmDevDB view;
-    void* ptrs[11];
+    void* ptrs[12];
     int refs;
   };
   std::vector<Dev> devs;

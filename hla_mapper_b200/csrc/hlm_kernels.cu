@@ -138,7 +138,7 @@ struct WarpScratch {
   uint32_t p1[9];
   uint32_t pn[9];
   uint32_t good[9];   // mtrim "good quality" bits
-  uint32_t hits[8];   // global-screen hit bits per R1 position
+  uint32_t hits[8];   // global-screen hit bits: [0..3] even R1 positions (bit j <-> 2j), [4..7] odd
   uint32_t rev[3][8]; // scratch for reverse complement
 };
 
@@ -283,41 +283,74 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     bool ok = !(l1 < HLM_MOTIF || l1 < kp.v_size);
     if (kp.paired && kp.screen_variant == HLM_SCREEN_FASTQ && (l2 < HLM_MOTIF || l2 < kp.v_size))
       ok = false;
-    uint32_t myval[8];
+    // membership masks of the R1 windows at positions 2 * (32 r + lane) (even) and + 1 (odd)
+    uint32_t val_e[4], val_o[4];
 #pragma unroll
-    for (int r = 0; r < 8; r++) myval[r] = 0;
+    for (int r = 0; r < 4; r++) val_e[r] = val_o[r] = 0;
     bool screened = false;
     if (ok) {
       stage_bases(ck.bases1 + o1, l1, lane, ws, true);
       int npos = l1 - HLM_MOTIF;  // positions c < npos are probed (the last window never is)
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        int c = r * 32 + lane;
-        uint32_t val = 0;
-        if (c < npos) {
-          int w = c >> 4, s = 2 * (c & 15);
-          uint64_t lo = (uint64_t)ws.sq[w] | ((uint64_t)ws.sq[w + 1] << 32);
-          uint64_t key = lo >> s;
-          if (s) key |= (uint64_t)ws.sq[w + 2] << (64 - s);
-          key &= HLM_KT_KEYMASK;
-          uint32_t nn = hlm_funnel(ws.pn[c >> 5], ws.pn[(c >> 5) + 1], c & 31) & 0xFFFFFu;
-          if (nn == 0) val = probe_kmer(db, key);
-          else if (db.n_odd) val = probe_odd(db, ck.bases1 + o1 + c);
+      int n_even = (npos + 1) >> 1, n_oddpos = npos >> 1;
+      auto probe_at = [&](int c) -> uint32_t {
+        int w = c >> 4, sh = 2 * (c & 15);
+        uint64_t lo = (uint64_t)ws.sq[w] | ((uint64_t)ws.sq[w + 1] << 32);
+        uint64_t key = lo >> sh;
+        if (sh) key |= (uint64_t)ws.sq[w + 2] << (64 - sh);
+        key &= HLM_KT_KEYMASK;
+        uint32_t nn = hlm_funnel(ws.pn[c >> 5], ws.pn[(c >> 5) + 1], c & 31) & 0xFFFFFu;
+        if (nn == 0) {
+          // Bloom front first: one 8-byte load that hits L2 (4 bytes per key); only windows
+          // it cannot exclude go on to the exact table, which does not fit L2
+          uint32_t bw;
+          uint64_t bm = hlm_kb_probe(key, db.kb_words, &bw);
+          return ((__ldg(db.kb + bw) & bm) == bm) ? probe_kmer(db, key) : 0u;
         }
-        myval[r] = val;
-        uint32_t hb = __ballot_sync(FULL, val >> 31);
+        return db.n_odd ? probe_odd(db, ck.bases1 + o1 + c) : 0u;
+      };
+      // Phase 1: the even positions.  The FASTQ loop (stride 2, one extra step after a hit) only
+      // ever leaves them through a hit, so a read without an even hit is rejected after half
+      // the probes - the common case for off-target input.  Phase 2: the odd positions, for
+      // everything else (the BAM loop has stride 1; a kept pair needs every position for its
+      // locus mask).
+      uint32_t any_e = 0;
+      int nhits = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        uint32_t hb = 0;
+        if (r * 32 < n_even) {
+          int j = r * 32 + lane;
+          uint32_t v = j < n_even ? probe_at(2 * j) : 0u;
+          val_e[r] = v;
+          hb = __ballot_sync(FULL, v >> 31);
+        }
         if (lane == 0) ws.hits[r] = hb;
+        any_e |= hb;
+        nhits += __popc(hb);
+      }
+      bool need_odd = kp.skip_screen || kp.screen_variant != HLM_SCREEN_FASTQ || any_e || kp.minhit <= 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        uint32_t hb = 0;
+        if (need_odd && r * 32 < n_oddpos) {
+          int j = r * 32 + lane;
+          uint32_t v = j < n_oddpos ? probe_at(2 * j + 1) : 0u;
+          val_o[r] = v;
+          hb = __ballot_sync(FULL, v >> 31);
+        }
+        if (lane == 0) ws.hits[4 + r] = hb;
+        nhits += __popc(hb);
       }
       __syncwarp();
       if (kp.skip_screen) {
         screened = true;
-      } else {
+      } else if (nhits >= kp.minhit) {
         // the reference's strided scan: FASTQ loop `if hit {hit++;c++}; ...; c++` inside
         // for(;;c++); BAM loop without the trailing c++.  Uniform across the warp.
         int hitcount = 0;
         int step = kp.screen_variant == HLM_SCREEN_FASTQ ? 2 : 1;
         for (int c = 0; c < npos; c += step) {
-          if ((ws.hits[c >> 5] >> (c & 31)) & 1u) {
+          if ((ws.hits[(c & 1) * 4 + (c >> 6)] >> ((c >> 1) & 31)) & 1u) {
             hitcount++;
             c++;
           }
@@ -349,9 +382,10 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         if (n1 >= HLM_MOTIF && (!kp.paired || n2 >= HLM_MOTIF)) {
           uint32_t m = 0;
 #pragma unroll
-          for (int r = 0; r < 8; r++) {
-            int c = r * 32 + lane;
-            if (c >= lo1 && c < lo1 + n1 - HLM_MOTIF) m |= myval[r];
+          for (int r = 0; r < 4; r++) {
+            int c = 2 * (r * 32 + lane);
+            if (c >= lo1 && c < lo1 + n1 - HLM_MOTIF) m |= val_e[r];
+            if (c + 1 >= lo1 && c + 1 < lo1 + n1 - HLM_MOTIF) m |= val_o[r];
           }
           m = __reduce_or_sync(FULL, m);
           lmask = m & 0x7FFFFFFFu;
@@ -1305,11 +1339,22 @@ __global__ void __launch_bounds__(256) k_int_peak(int* out, int iters, int seed)
       } else if (WHICH == 2) {  // mixed add + mad
         a = a + b + seed; c = c * seed + d; e = e + f + seed; g = g * seed + h;
         b = b + a + seed; d = d * seed + c; f = f + e + seed; h = h * seed + g;
-      } else {  // VIADDMNMX chains (what the DP issues)
+      } else if (WHICH == 3) {  // VIADDMNMX chains (what the DP issues)
         a = __viaddmax_s32(a, seed, b); c = __viaddmax_s32(c, seed, d);
         e = __viaddmax_s32(e, seed, f); g = __viaddmax_s32(g, seed, h);
         b = __viaddmax_s32(b, seed, a); d = __viaddmax_s32(d, seed, c);
         f = __viaddmax_s32(f, seed, e); h = __viaddmax_s32(h, seed, g);
+      } else if (WHICH == 4) {  // LOP3 chains (three-input logic: 119 of the 246 k_myers loop instructions)
+#define HLM_LOP3(x, y) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(seed));
+        HLM_LOP3(a, b) HLM_LOP3(c, d) HLM_LOP3(e, f) HLM_LOP3(g, h)
+        HLM_LOP3(b, a) HLM_LOP3(d, c) HLM_LOP3(f, e) HLM_LOP3(h, g)
+      } else if (WHICH == 5) {  // SHF chains (funnel shifts: 42 of the 246)
+#define HLM_SHF(x, y) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(seed));
+        HLM_SHF(a, b) HLM_SHF(c, d) HLM_SHF(e, f) HLM_SHF(g, h)
+        HLM_SHF(b, a) HLM_SHF(d, c) HLM_SHF(f, e) HLM_SHF(h, g)
+      } else {  // the k_myers row mix: 3 LOP3 : 1 SHF
+        HLM_LOP3(a, b) HLM_LOP3(c, d) HLM_LOP3(e, f) HLM_SHF(g, h)
+        HLM_LOP3(b, a) HLM_LOP3(d, c) HLM_LOP3(f, e) HLM_SHF(h, g)
       }
     }
   }
@@ -1330,7 +1375,10 @@ double hlm_int_peak_run(int which, int sms, cudaStream_t st) {
       case 0: k_int_peak<0><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
       case 1: k_int_peak<1><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
       case 2: k_int_peak<2><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
-      default: k_int_peak<3><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      case 3: k_int_peak<3><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      case 4: k_int_peak<4><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      case 5: k_int_peak<5><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
+      default: k_int_peak<6><<<blocks, threads, 0, st>>>(out, iters, 3 + rep); break;
     }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);

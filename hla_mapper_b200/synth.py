@@ -374,6 +374,57 @@ def make_reads(db: SynthDB, n_pairs, read_len=150, seed=1001, on_target=1.0, fra
     return ReadBatch(n_pairs, fb1, fq1, o1, fb2, fq2, o2, truth, seed, first_pair)
 
 
+_FAST = None
+
+
+def _fast_lib():
+    """tools/libsynthreads.so (tools/synth_reads.c), compiled on first use when missing"""
+    global _FAST
+    if _FAST is None:
+        import ctypes as C
+        import subprocess
+
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        so, src = os.path.join(root, "tools", "libsynthreads.so"), os.path.join(root, "tools", "synth_reads.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", so, src, "-lm"])
+        _FAST = C.CDLL(so)
+        P = C.c_void_p
+        _FAST.synth_reads.argtypes = [P, C.c_int64, P, P, P, C.c_int, C.c_uint64, C.c_int64, C.c_int64,
+                                      C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, P, P, P, P, P, C.c_int]
+    return _FAST
+
+
+def make_reads_fast(db: SynthDB, n_pairs, read_len=150, seed=1001, on_target=1.0, frag_mu=400,
+                    frag_sd=60, lowq_tail=0.10, indel_rate=1e-4, first_pair=0, threads=0):
+    """The read model of make_reads (indel errors included: SURVEY.md section 8d asks for 0.01 %) in
+    C with one random stream per pair keyed by (seed, global pair index): any [first_pair,
+    first_pair + n_pairs) window of a run reproduces independently (config 4's shards), at tens
+    of millions of pairs per second instead of 50 k.  Benchmark inputs only; the tests and golden
+    fixtures keep the numpy generator."""
+    src = _Source(db, np.random.Generator(np.random.Philox(key=[seed, 0x5A])))
+    L = int(read_len)
+    b1 = np.empty(n_pairs * L, dtype=np.uint8)
+    q1 = np.empty(n_pairs * L, dtype=np.uint8)
+    b2 = np.empty(n_pairs * L, dtype=np.uint8)
+    q2 = np.empty(n_pairs * L, dtype=np.uint8)
+    truth = np.empty(n_pairs, dtype=np.int32)
+    flat = np.ascontiguousarray(src.flat)
+    starts = np.ascontiguousarray(src.starts, dtype=np.int64)
+    lens = np.ascontiguousarray(src.lens, dtype=np.int64)
+    locus = np.ascontiguousarray(src.locus, dtype=np.int32)
+    rc = _fast_lib().synth_reads(flat.ctypes.data, len(flat), starts.ctypes.data, lens.ctypes.data,
+                                 locus.ctypes.data, len(lens), int(seed), int(first_pair), int(n_pairs),
+                                 L, float(on_target), float(frag_mu), float(frag_sd), float(lowq_tail),
+                                 float(indel_rate), b1.ctypes.data, q1.ctypes.data, b2.ctypes.data,
+                                 q2.ctypes.data, truth.ctypes.data, int(threads))
+    if rc != 0:
+        raise RuntimeError("synth_reads failed")
+    offs = np.arange(n_pairs + 1, dtype=np.uint64) * np.uint64(L)
+    return ReadBatch(n_pairs, b1, q1, offs, b2, q2, offs.copy(), truth, seed, first_pair)
+
+
 def write_fastq(batch: ReadBatch, path_r1, path_r2=None, prefix="SYN", suffix=True, comment=False,
                 gz=False):
     """suffix: "/1" "/2" after the id; comment: Illumina-style " 1:N:0:ACGT" field; gz: gzip"""

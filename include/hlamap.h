@@ -297,6 +297,10 @@ int hlm_map_reads(hlm_ctx* ctx, const hlm_reads* reads, const char* sample, cons
 int hlm_int32_peak(int cuda_device, double* giga_iadd, double* giga_imad, double* giga_mix,
                    double* giga_viaddmnmx);
 
+/* the same plus the instruction classes k_myers is made of: out[0..6] = IADD3, IMAD, IADD3+IMAD mix,
+ * VIADDMNMX, LOP3, SHF, 3 LOP3 : 1 SHF mix */
+int hlm_int32_peaks(int cuda_device, double* out, int n);
+
 /* A/B of the two work layouts of the banded DP on synthetic candidates: thread per candidate with
  * the band row in registers (the product kernel) versus warp per candidate with the band across
  * lanes, shuffles and a max-plus prefix scan for the horizontal gaps (the "wavefront with warp

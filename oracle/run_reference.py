@@ -5,44 +5,44 @@ from /root/reference/src with a Boost header shim) through `hla-mapper dna|rna`,
 restatements against the reference's own code, and to generate tests/golden/*.
 
 TEST INFRASTRUCTURE ONLY.  The reference reads its config from getpwuid()->pw_dir/.hla-mapper
-(/root/reference/src/main.cpp:266-267), so the harness writes that file and restores it.
+(/root/reference/src/main.cpp:266-267).  Every run gets a private directory for it: the
+binary is started with oracle/_ref/libpwshim.so preloaded (oracle/shim/pwshim.c), which answers
+getpwuid() with pw_dir = $HLM_REF_HOME.  The real ~/.hla-mapper is never touched, so concurrent
+harness processes (pytest-xdist, the bench arm beside a test run) cannot disturb each other.
 """
 from __future__ import annotations
 
 import contextlib
 import os
-import pwd
 import shutil
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BIN = os.path.join(HERE, "_ref", "hla-mapper-ref")
 BWA_BIN = os.path.join(HERE, "_ref", "bwa")
+PWSHIM = os.path.join(HERE, "_ref", "libpwshim.so")
 STAR_BIN = os.path.join(HERE, "standin_star.py")
 SAMTOOLS_BIN = os.path.join(HERE, "standin_samtools.py")
 
 
 def available():
-    return os.path.exists(REF_BIN) and os.path.exists(BWA_BIN)
+    return os.path.exists(REF_BIN) and os.path.exists(BWA_BIN) and os.path.exists(PWSHIM)
 
 
 @contextlib.contextmanager
-def _config(db_path):
-    home = pwd.getpwuid(os.getuid()).pw_dir
-    cfg = os.path.join(home, ".hla-mapper")
-    bak = None
-    if os.path.exists(cfg):
-        bak = cfg + ".graft-bak"
-        shutil.move(cfg, bak)
-    with open(cfg, "w") as f:
+def _config(db_path, env):
+    """a private home directory holding .hla-mapper; env gets LD_PRELOAD + HLM_REF_HOME"""
+    home = tempfile.mkdtemp(prefix="hlm_ref_home_")
+    with open(os.path.join(home, ".hla-mapper"), "w") as f:
         f.write(f"db={db_path}\nsamtools={SAMTOOLS_BIN}\nbwa={BWA_BIN}\nwhatshap=DISABLED\n"
                 f"freebayes=DISABLED\nblast=DISABLED\nstar={STAR_BIN}\n")
+    env["HLM_REF_HOME"] = home
+    env["LD_PRELOAD"] = PWSHIM + (":" + env["LD_PRELOAD"] if env.get("LD_PRELOAD") else "")
     try:
         yield
     finally:
-        os.remove(cfg)
-        if bak:
-            shutil.move(bak, cfg)
+        shutil.rmtree(home, ignore_errors=True)
 
 
 def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None, rna=False, threads=4,
@@ -75,7 +75,7 @@ def run_reference(db_path, out_dir, sample, r1=None, r2=None, r0=None, bam=None,
         env["HLM_ORACLE_EXHAUSTIVE"] = "1"
     if star_full:  # oracle/standin_star.py: gene-dependent splits, multi-mappers, reverse strand
         env["HLM_STANDIN_STAR"] = "full"
-    with _config(db_path):
+    with _config(db_path, env):
         subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env,
                        timeout=timeout, cwd=os.path.dirname(out_dir.rstrip("/")) or ".")
     return out_dir.rstrip("/") + "/"
