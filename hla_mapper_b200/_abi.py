@@ -28,7 +28,7 @@ class HlmParams(C.Structure):
         ("screen_variant", C.c_int32), ("v_size", C.c_int32), ("minhit", C.c_int32),
         ("mm_max", C.c_int32), ("clip_mode", C.c_int32), ("tolerance", C.c_double),
         ("mtrim_error", C.c_double), ("chunk_pairs", C.c_int32), ("skip_screen", C.c_int32),
-        ("cand_capacity", C.c_int64), ("single_slot", C.c_int32), ("reserved0", C.c_int32),
+        ("cand_capacity", C.c_int64), ("single_slot", C.c_int32), ("score_cap", C.c_int32),
     ]
 
 
@@ -105,7 +105,7 @@ def default_params(rna=0, **kw):
     p.skip_screen = 0
     p.cand_capacity = 0
     p.single_slot = 0
-    p.reserved0 = 0
+    p.score_cap = 0
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -6,6 +6,7 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -54,6 +55,9 @@ def build(force=False, verbose=False):
                            "-L" + HERE, "-lhlamap", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
+    # instruction mix of the inner loops of THIS object: bench.py's roofline denominators
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "sass_mix.py"), "--json",
+                           os.path.join(HERE, "build", "sass_mix.json")])
     if verbose:
         print("\n".join(log))
     return LIB

@@ -164,18 +164,19 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0) {
   }
   int rc;
   if ((rc = ensure_dev(ctx, s.d_units, NU * HLM_UNIT_STRIDE * 4 + 256))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_unit_meta, align16(NU * 2) + NU * 4 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_unit_meta, 2 * align16(NU * 2) + NU * 4 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_cand, (size_t)ctx->cand_cap * 8))) return rc;
   int64_t dp_cap = ctx->cand_cap / 2;  // DPs are a fraction of the candidates; overflow splits the chunk
   if ((rc = ensure_dev(ctx, s.d_dp, (size_t)dp_cap * 9 + 4096))) return rc;
-  if ((rc = ensure_dev(ctx, s.d_tasks, 2 * align16(NU * T * 4) + NU * T * 8 + 256))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_tasks, 3 * align16(NU * T * 4) + NU * T * 8 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
   HlmChunk& ck = s.ck;
   ck.units_per_pair = U;
   ck.n_units = (int64_t)NU;
   ck.unit_planes = (uint32_t*)s.d_units.p;
   ck.unit_len = (uint16_t*)s.d_unit_meta.p;
-  ck.unit_mask = (uint32_t*)((uint8_t*)s.d_unit_meta.p + align16(NU * 2));
+  ck.unit_cap = (uint16_t*)((uint8_t*)s.d_unit_meta.p + align16(NU * 2));
+  ck.unit_mask = (uint32_t*)((uint8_t*)s.d_unit_meta.p + 2 * align16(NU * 2));
   ck.cand = (uint64_t*)s.d_cand.p;
   ck.cand_cap = ctx->cand_cap;
   ck.dp_list = (uint32_t*)s.d_dp.p;
@@ -187,7 +188,8 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0) {
   ck.counters = (unsigned long long*)s.d_counters.p;
   ck.task_emin = (uint32_t*)s.d_tasks.p;
   ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16(NU * T * 4));
-  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 2 * align16(NU * T * 4));
+  ck.task_pmin = (uint32_t*)((uint8_t*)s.d_tasks.p + 2 * align16(NU * T * 4));
+  ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 3 * align16(NU * T * 4));
   return 0;
 }
 
@@ -592,7 +594,7 @@ void hlm_params_default(hlm_params* p, int rna) {
   p->skip_screen = 0;
   p->cand_capacity = 0;
   p->single_slot = 0;
-  p->reserved0 = 0;
+  p->score_cap = 0;
 }
 
 hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen) {
@@ -755,6 +757,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   kp.mm_max = p.mm_max;
   kp.clip_mode = p.clip_mode;
   kp.skip_screen = p.skip_screen;
+  kp.score_cap = (p.score_cap && !p.rna) ? 1 : 0;
   kp.tolerance = p.tolerance;
   kp.n_loci = db->n_loci;
   kp.one = 1;

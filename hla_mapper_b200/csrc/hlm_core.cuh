@@ -110,8 +110,10 @@ HLM_HD void hlm_peq_build(const uint32_t* __restrict__ tile, PEQ peq) {
 }
 
 // codes: the read as 4-bit codes, 8 per word (code bit 0 / 1 = the base, bit 2 = N -> PEQ row 4)
+// rstar / plb: see hlm_myers_core_dev (the band minimum after rstar rows, any 0 <= rstar <= n)
 template <class PEQ>
-HLM_HD int hlm_myers_core(const uint32_t* __restrict__ codes, int n, int off, PEQ peq) {
+HLM_HD int hlm_myers_core(const uint32_t* __restrict__ codes, int n, int off, PEQ peq, int rstar = -1,
+                          int* plb = nullptr) {
   const uint64_t MASK = (1ull << HLM_NB) - 1, TOP = 1ull << (HLM_NB - 1);
   uint64_t SP = TOP, SN = 0;
   int score = 0;  // c_0
@@ -134,25 +136,27 @@ HLM_HD int hlm_myers_core(const uint32_t* __restrict__ codes, int n, int off, PE
     SN = D0s & VP;                                                                                \
     score += 1 - (int)(D0 & 1ull);                                                                \
   }
-  int i = 0;
-  for (; i + 8 <= n; i += 8) {  // eight rows per code word, no per-row bookkeeping
-    HLM_MYERS_REFILL(i)
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int r = 0; r < 8; r++) HLM_MYERS_ROW()
+#define HLM_MYERS_BANDMIN(out)                                        \
+  {                                                                   \
+    int best_ = score, cur_ = score;                                  \
+    for (int k = 0; k < HLM_NB - 1; k++) {                            \
+      cur_ += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);     \
+      best_ = cur_ < best_ ? cur_ : best_;                            \
+    }                                                                 \
+    out = best_;                                                      \
   }
-  if (i < n) {
-    HLM_MYERS_REFILL(i)
-    for (; i < n; i++) HLM_MYERS_ROW()
+  int i = 0;
+  if (plb && rstar == 0) *plb = 0;
+  for (; i < n; i++) {
+    if ((i & 7) == 0) HLM_MYERS_REFILL(i)
+    HLM_MYERS_ROW()
+    if (plb && i + 1 == rstar) HLM_MYERS_BANDMIN(*plb)
   }
 #undef HLM_MYERS_REFILL
 #undef HLM_MYERS_ROW
-  int best = score, cur = score;
-  for (int k = 0; k < HLM_NB - 1; k++) {
-    cur += (int)((SP >> k) & 1ull) - (int)((SN >> k) & 1ull);
-    best = cur < best ? cur : best;
-  }
+  int best;
+  HLM_MYERS_BANDMIN(best)
+#undef HLM_MYERS_BANDMIN
   return best;
 }
 
@@ -171,65 +175,10 @@ __device__ __forceinline__ uint32_t hlm_fma_mad(uint32_t a, uint32_t b, uint32_t
   asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-// peq_addr: shared-memory byte address of this thread's PEQ row 0; rows are ROW_BYTES apart
-template <int ROW_BYTES>
-__device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ codes, int n, int off,
-                                                  uint32_t peq_addr, uint32_t one,
-                                                  const uint16_t* __restrict__ mintab) {
-  const uint64_t MASK = (1ull << HLM_NB) - 1;
-  uint64_t SP = 1ull << (HLM_NB - 1), SN = 0;
-  uint32_t p = (uint32_t)(off - HLM_BAND);
-  uint32_t acc = 0;
-  int zeros = 0;
-  const uint32_t krow = one * ROW_BYTES;
-  asm volatile("" ::: "memory");  // the PEQ rows were written with plain stores
-  // C8: eight times the read code of the row; S: its first band column (the funnel shift wraps)
-#define HLM_MYERS_DEV_ROW(C8, S)                                                                    \
-  {                                                                                               \
-    uint32_t ad = hlm_fma_mad((C8) + ((S) >> 5), krow, peq_addr);                                  \
-    uint32_t a, b, c;                                                                             \
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(ad));                                   \
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(b) : "r"(ad), "n"(ROW_BYTES));                \
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(c) : "r"(ad), "n"(2 * ROW_BYTES));            \
-    uint64_t Eq = (uint64_t)__funnelshift_r(a, b, S) | ((uint64_t)__funnelshift_r(b, c, S) << 32); \
-    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;                                     \
-    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;                                                  \
-    uint64_t D0s = D0 >> 1;                                                                       \
-    SP = VN | ~(D0s | VP);                                                                        \
-    SN = D0s & VP;                                                                                \
-    acc = __funnelshift_r(acc, (uint32_t)D0, 1); /* (acc >> 1) | (bit 0 of D0) << 31 */           \
-  }
-  int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    uint32_t cw = codes[i >> 3];
-    // codes of the even / odd rows, one per byte, times eight
-    uint32_t ev = hlm_fma_mad(cw & 0x07070707u, 8u * one, 0u), od = hlm_fma_mad((cw >> 4) & 0x07070707u, 8u * one, 0u);
-    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4440), p)
-    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4440), hlm_fma_mad(one, 1u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4441), hlm_fma_mad(one, 2u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4441), hlm_fma_mad(one, 3u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4442), hlm_fma_mad(one, 4u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4442), hlm_fma_mad(one, 5u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4443), hlm_fma_mad(one, 6u, p))
-    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4443), hlm_fma_mad(one, 7u, p))
-    zeros += __popc(acc >> 24);
-    p = hlm_fma_mad(one, 8u, p);
-  }
-  if (i < n) {
-    uint32_t cw = codes[i >> 3];
-    int rem = n - i;
-    for (int r = 0; r < rem; r++) {
-      HLM_MYERS_DEV_ROW((cw << 3) & 0x38u, p)
-      cw >>= 4;
-      p++;
-    }
-    zeros += __popc(acc >> (32 - rem));
-  }
-#undef HLM_MYERS_DEV_ROW
-  asm volatile("" ::: "memory");  // the next candidate overwrites the PEQ rows
-  // minimum over the last band row: prefix sums of the vertical deltas, four columns per look-up
-  // in a 256-entry table (hlm_band_min_entry) instead of forty single steps
-  int best = n - zeros, cur8 = best - 8;
+// minimum over a band row: c0 + prefix sums of the horizontal deltas (SP / SN), four columns per
+// look-up in a 256-entry table (hlm_band_min_entry) instead of forty single steps
+__device__ __forceinline__ int hlm_band_min(uint64_t SP, uint64_t SN, int c0, const uint16_t* __restrict__ mintab) {
+  int best = c0, cur8 = best - 8;
   uint32_t spl = (uint32_t)SP, sph = (uint32_t)(SP >> 32), snl = (uint32_t)SN, snh = (uint32_t)(SN >> 32);
   // bytes of ev / od: (SP nibble << 4 | SN nibble) of the even / odd nibbles of a word
   uint32_t ev = ((spl & 0x0F0F0F0Fu) << 4) | (snl & 0x0F0F0F0Fu);
@@ -254,6 +203,76 @@ __device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ c
 #undef HLM_BAND_MIN_STEP
   return best;
 }
+// peq_addr: shared-memory byte address of this thread's PEQ row 0; rows are ROW_BYTES apart
+template <int ROW_BYTES>
+// rstar / plb (capped scoring): the band minimum after rstar rows (a multiple of 8, or < 0 for
+// "not wanted") is returned through *plb - a lower bound of cost - trailing clip of every alignment
+// the DP can report (the row minimum never decreases from one row to the next, and a reported
+// alignment clips at most mm_max trailing bases)
+__device__ __forceinline__ int hlm_myers_core_dev(const uint32_t* __restrict__ codes, int n, int off,
+                                                  uint32_t peq_addr, uint32_t one,
+                                                  const uint16_t* __restrict__ mintab, int rstar, int* plb) {
+  const uint64_t MASK = (1ull << HLM_NB) - 1;
+  uint64_t SP = 1ull << (HLM_NB - 1), SN = 0;
+  uint32_t p = (uint32_t)(off - HLM_BAND);
+  uint32_t acc = 0;
+  int zeros = 0;
+  const uint32_t krow = one * ROW_BYTES;
+  asm volatile("" ::: "memory");  // the PEQ rows were written with plain stores
+  // C8: eight times the read code of the row; S: its first band column (the funnel shift wraps)
+#define HLM_MYERS_DEV_ROW(C8, S)                                                                    \
+  {                                                                                               \
+    uint32_t ad = hlm_fma_mad((C8) + ((S) >> 5), krow, peq_addr);                                  \
+    uint32_t a, b, c;                                                                             \
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(ad));                                   \
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(b) : "r"(ad), "n"(ROW_BYTES));                \
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(c) : "r"(ad), "n"(2 * ROW_BYTES));            \
+    uint64_t Eq = (uint64_t)__funnelshift_r(a, b, S) | ((uint64_t)__funnelshift_r(b, c, S) << 32); \
+    uint64_t D0 = ((((Eq & SP) + SP) ^ SP) | Eq | SN) & MASK;                                     \
+    uint64_t VP = SN | ~(D0 | SP), VN = D0 & SP;                                                  \
+    uint64_t D0s = D0 >> 1;                                                                       \
+    SP = VN | ~(D0s | VP);                                                                        \
+    SN = D0s & VP;                                                                                \
+    acc = __funnelshift_r(acc, (uint32_t)D0, 1); /* (acc >> 1) | (bit 0 of D0) << 31 */           \
+  }
+  int i = 0;
+  // two passes over ONE copy of the row loop: rows [0, rstar), the prefix bound, rows [rstar, n)
+  int stop = rstar >= 0 ? rstar : n;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+  for (; i + 8 <= stop; i += 8) {
+    uint32_t cw = codes[i >> 3];
+    // codes of the even / odd rows, one per byte, times eight
+    uint32_t ev = hlm_fma_mad(cw & 0x07070707u, 8u * one, 0u), od = hlm_fma_mad((cw >> 4) & 0x07070707u, 8u * one, 0u);
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4440), p)
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4440), hlm_fma_mad(one, 1u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4441), hlm_fma_mad(one, 2u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4441), hlm_fma_mad(one, 3u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4442), hlm_fma_mad(one, 4u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4442), hlm_fma_mad(one, 5u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(ev, 0u, 0x4443), hlm_fma_mad(one, 6u, p))
+    HLM_MYERS_DEV_ROW(__byte_perm(od, 0u, 0x4443), hlm_fma_mad(one, 7u, p))
+    zeros += __popc(acc >> 24);
+    p = hlm_fma_mad(one, 8u, p);
+  }
+  if (pass == 0 && rstar >= 0) *plb = hlm_band_min(SP, SN, rstar - zeros, mintab);
+  if (stop == n) break;
+  stop = n;
+  }
+  if (i < n) {
+    uint32_t cw = codes[i >> 3];
+    int rem = n - i;
+    for (int r = 0; r < rem; r++) {
+      HLM_MYERS_DEV_ROW((cw << 3) & 0x38u, p)
+      cw >>= 4;
+      p++;
+    }
+    zeros += __popc(acc >> (32 - rem));
+  }
+#undef HLM_MYERS_DEV_ROW
+  asm volatile("" ::: "memory");  // the next candidate overwrites the PEQ rows
+  return hlm_band_min(SP, SN, n - zeros, mintab);  // minimum over the last band row
+}
 // entry t = (SP nibble << 4 | SN nibble): low byte = sum of the four deltas + 8, high byte = the
 // smallest of the four prefix sums + 8
 __host__ __device__ inline uint16_t hlm_band_min_entry(int t) {
@@ -272,7 +291,7 @@ struct HlmPeqLocal {
   HLM_HD uint32_t& operator()(int r) const { return v[r]; }
 };
 HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
-                        int off) {
+                        int off, int rstar = -1, int* plb = nullptr) {
   uint32_t buf[HLM_PEQ_ROWS], codes[24];
   HlmPeqLocal peq{buf};
   hlm_peq_build(tile, peq);
@@ -281,7 +300,7 @@ HLM_HD int hlm_myers_lb(const uint32_t* __restrict__ rd, int n, const uint32_t* 
     codes[j] = hlm_spread8((rd[w] >> sh) & 0xFFu) | (hlm_spread8((rd[6 + w] >> sh) & 0xFFu) << 1) |
                (hlm_spread8((rd[12 + w] >> sh) & 0xFFu) << 2);
   }
-  return hlm_myers_core(codes, n, off, peq);
+  return hlm_myers_core(codes, n, off, peq, rstar, plb);
 }
 
 // ------------------------------------------------------------------ banded affine-gap DP

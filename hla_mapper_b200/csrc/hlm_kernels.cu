@@ -409,7 +409,7 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
 // ------------------------------------------------------------------ k_pack_units
 // unit layout per pair: dna: [mate]; rna: [mate*3 + {whole, block A, block B}]
 __device__ __forceinline__ void write_unit(const HlmChunk& ck, int64_t unit, WarpScratch& ws, int lo,
-                                           int n, uint32_t tmask, int lane) {
+                                           int n, uint32_t tmask, int lane, int cap = 0) {
   uint32_t* out = ck.unit_planes + unit * HLM_UNIT_STRIDE;
   // forward planes: bits [lo, lo+n) of the staged planes
   uint32_t f0 = 0, f1 = 0, fn = 0xFFFFFFFFu;
@@ -460,6 +460,7 @@ __device__ __forceinline__ void write_unit(const HlmChunk& ck, int64_t unit, War
   if (lane == 0) {
     ck.unit_len[unit] = (uint16_t)n;
     ck.unit_mask[unit] = tmask;
+    ck.unit_cap[unit] = (uint16_t)cap;
   }
   __syncwarp();
   // 4-bit codes of both strands for k_myers: word j = bases 8j .. 8j+7 (lanes 0-23 one strand each
@@ -507,7 +508,12 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
       }
       stage_bases(p, l, lane, ws, false);
       if (!kp.rna) {
-        write_unit(ck, pair * U + m, ws, lo, n, lmask | others, lane);
+        // the compare step's tolerance for this mate, map_dna.cpp:948-958 (single end: the length
+        // the reference holds for the read, preselect.cpp:1199)
+        int len = (!kp.paired && ck.size_override1) ? ck.size_override1[pair] : n;
+        int cap = (int)(len * kp.tolerance);
+        cap = cap < 0 ? 0 : (cap > 60000 ? 60000 : cap);
+        write_unit(ck, pair * U + m, ws, lo, n, lmask | others, lane, cap);
       } else if (ck.blk_off) {
         // the STAR pre-split in full: whole mate vs others only; every block vs its own gene
         write_unit(ck, pair * U + m * 3, ws, lo, n, others, lane);
@@ -541,6 +547,7 @@ __global__ void k_clear_tasks(HlmChunk ck, int64_t n_tasks) {
   if (i < 256) ck.dp_hist[i] = 0;
   for (; i < n_tasks; i += stride) {
     ck.task_emin[i] = 0xFFFFFFFFu;
+    ck.task_pmin[i] = 0xFFFFFFFFu;
     ck.task_best[i] = HLM_BEST_NONE;
   }
 }
@@ -749,7 +756,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
     int n = ck.unit_len[unit];
     const uint32_t* rd = ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-    int lb;
+    int lb, plb = 0;
     bool dead = false;
     if (phase != 0) {
       // a child reached by expanding its rep: it is this path's candidate only when some seed
@@ -775,10 +782,15 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       lb = 254;
     } else {
       hlm_peq_build(T, peq);
+      // capped scoring: the bound after the rows a trailing clip (<= mm_max bases of a reported
+      // alignment) cannot reach; with both clips in the score the bound of the whole read
+      int rstar = -1;
+      if (kp.score_cap && kp.clip_mode != HLM_CLIP_BOTH) rstar = n > kp.mm_max ? ((n - kp.mm_max) & ~7) : 0;
       lb = hlm_myers_core_dev<256 * 4>(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
                                            HLM_CODE_WORDS * strand,
                                        n, off, (uint32_t)__cvta_generic_to_shared(s_peq + threadIdx.x), (uint32_t)kp.one,
-                                       s_mintab);
+                                       s_mintab, rstar, &plb);
+      if (rstar < 0) plb = lb;
       if (lb > 253) lb = 253;
       rows += n;
     }
@@ -787,10 +799,33 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       int g = tile_locus(db, tile);
       atomicMin(&ck.task_emin[(int64_t)unit * n_targets + g], (uint32_t)lb);
     }
+    // (a rep up to KMAX above mm_max can still hand a reportable child to the expansion)
+    if (kp.score_cap && lb <= kp.mm_max + HLM_KMAX)
+      atomicMin(&ck.task_pmin[(int64_t)unit * n_targets + tile_locus(db, tile)], (uint32_t)plb);
   }
   // one atomic per warp
   for (int o = 16; o; o >>= 1) rows += __shfl_xor_sync(FULL, rows, o);
   if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&ck.counters[5], rows);
+}
+
+// ------------------------------------------------------------------ capped scoring: task gate
+// hlm_params.score_cap (dna): the compare step (map_dna.cpp:948-958) can only use the score of a
+// (mate, target) when s - 1 = cost - trailing clip <= cap = int(len * tolerance) - for BOTH mates
+// of a pair.  task_pmin = minimum over the task's candidates of a lower bound of cost - trailing
+// clip; a child that is not materialised yet differs from a materialised rep in <= KMAX columns,
+// so  pmin > cap + KMAX  proves that no alignment of the task can pass, at every stage of the
+// flow.  Such a task gets no child expansion, no selection and no DP; its score is reported as 0
+// ("none"), which the compare step treats exactly like the failing score it stands for.
+// `others` is different: the mere presence of a score feeds the mate back-fill
+// (map_dna.cpp:903-915), so it stays exact whenever EITHER mate could pass.
+__device__ __forceinline__ bool task_live(const HlmKParams& kp, const HlmChunk& ck, uint32_t unit, int g,
+                                          int n_targets) {
+  if (!kp.score_cap) return true;
+  bool own = ck.task_pmin[(int64_t)unit * n_targets + g] <= (uint32_t)ck.unit_cap[unit] + HLM_KMAX;
+  if (!kp.paired) return own;
+  uint32_t mate = unit ^ 1u;  // dna units: pair * 2 + mate
+  bool other = ck.task_pmin[(int64_t)mate * n_targets + g] <= (uint32_t)ck.unit_cap[mate] + HLM_KMAX;
+  return g < kp.n_loci ? (own && other) : (own || other);
 }
 
 // ------------------------------------------------------------------ k_expand
@@ -822,7 +857,9 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
         uint32_t e0 = ck.task_emin0[task];
         int e0c = e0 > (uint32_t)kp.mm_max ? kp.mm_max : (int)e0;
-        if (round == 0) {
+        if (!task_live(kp, ck, HLM_CAND_UNIT(c), g, n_targets)) {
+          // capped scoring: nothing of this task can pass the tolerance
+        } else if (round == 0) {
           thr_hi = e0c;
           pass = lb - HLM_KMAX <= thr_hi;
         } else {
@@ -904,6 +941,7 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
       lb[u] = (int)HLM_CAND_LB(c[u]);
       live[u] = lb[u] <= kp.mm_max;  // padding and dead candidates carry lb >= 254
       g[u] = live[u] ? tile_locus(db, HLM_CAND_TILE(c[u])) : 0;
+      if (live[u] && kp.score_cap) live[u] = task_live(kp, ck, HLM_CAND_UNIT(c[u]), g[u], n_targets);
     }
     uint32_t emin[UN];
     unsigned long long best[UN];

@@ -29,6 +29,7 @@ struct HlmChunk {
   uint32_t* unit_planes;
   uint16_t* unit_len;    // 0 = inactive
   uint32_t* unit_mask;   // targets this unit is scored against
+  uint16_t* unit_cap;    // capped scoring: int(len * tolerance) of the unit's mate (map_dna.cpp:948-958)
   // scoring work
   uint64_t* cand;        // candidate records
   int64_t cand_cap;
@@ -46,6 +47,7 @@ struct HlmChunk {
                                  // [14] / [15] work counters
   uint32_t* task_emin;   // units * n_targets: minimum lower bound over evaluated candidates
   uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
+  uint32_t* task_pmin;   // capped scoring: minimum prefix bound (rows the trailing clip cannot reach)
   unsigned long long* task_best;
   // outputs
   uint16_t *s1, *s2;
@@ -58,7 +60,7 @@ struct HlmChunk {
 #define HLM_N_COUNTERS 16
 
 struct HlmKParams {
-  int rna, paired, screen_variant, v_size, minhit, mm_max, clip_mode, skip_screen;
+  int rna, paired, screen_variant, v_size, minhit, mm_max, clip_mode, skip_screen, score_cap;
   double tolerance;
   uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
   int n_loci;

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define HLM_ABI_VERSION 2
+#define HLM_ABI_VERSION 3
 
 /* limits of this build */
 #define HLM_MAX_LOCI 31   /* loci + "others" must fit a uint32 mask            */
@@ -90,7 +90,14 @@ typedef struct hlm_params {
   int64_t cand_capacity;  /* device candidate slots per chunk (0 = default)      */
   int32_t single_slot;    /* 1: one pipeline slot, chunks strictly serialised (per-kernel
                              timing runs; the default three slots overlap copies and kernels) */
-  int32_t reserved0;
+  int32_t score_cap;      /* 0 (default): every score up to mm_max is exact, as the reference holds
+                             them in memory.  1: tolerance-capped scoring (dna only; rna ignores
+                             it): scores the compare step cannot use are not computed - a
+                             (pair, target) whose alignment fails (s - 1) <= int(len * tolerance)
+                             for either mate (map_dna.cpp:948-958) may be reported as 0 instead of
+                             its value.  target_mask, visible_mask, min_sum and every score of a
+                             visible target - i.e. the addressing table and the per-gene files -
+                             are identical to the exact mode            */
 } hlm_params;
 
 /* One record of the reference's sorted_spliced_<gene>.fastq (map_rna.cpp:740-790): a block of a

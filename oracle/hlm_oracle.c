@@ -659,6 +659,69 @@ static ares score_fast(const olocus* L, const uint8_t* r, int n, scratch* sc, in
   return best;
 }
 
+/* Seedless check of the aligner definition (mode 2): EVERY diagonal of every allele, both
+ * strands, whose band can hold an alignment of cost <= mm_max - no seed index involved.  Sellers'
+ * unbanded semi-global edit distance finds every reference end position e (reference bases
+ * consumed, N beyond the allele ends) with distance <= mm_max; an alignment of cost <= mm_max
+ * that ends on diagonal e - n lies in the band of every candidate diagonal within BAND of it, so
+ * all of those get the affine DP.  The result is the same lexicographic minimum as
+ * score_exhaustive, taken over this superset of its candidates.  Test infrastructure for the
+ * completeness statement of DESIGN.md section 3 (small databases only: O(n * allele length) per
+ * mate, allele and strand). */
+static ares score_seedless(const olocus* L, const uint8_t* r, int n, int mm_max, int64_t* cells) {
+  ares best = {0, 0, 0, 0, 0};
+  uint8_t rc[HLM_MAX_READ + 8];
+  int D[HLM_MAX_READ + 2];
+  const int P = BAND + mm_max + 1;
+  for (int strand = 0; strand < 2; strand++) {
+    const uint8_t* q = r;
+    if (strand) {
+      revcomp(r, n, rc);
+      q = rc;
+    }
+    for (int al = 0; al < L->n_al; al++) {
+      const oseq* a = &L->al[al];
+      int tlen = a->len;
+      int dlo = -n - P - BAND, nd = tlen + 2 * P + n + 2 * BAND + 4;
+      uint8_t* mark = (uint8_t*)calloc((size_t)nd, 1);
+      for (int i = 0; i <= n; i++) D[i] = i;
+      for (int x = -P; x < tlen + P; x++) {
+        int tb = refc(a->codes, tlen, x);
+        int diag = D[0]; /* D_old[i-1] */
+        D[0] = 0;
+        for (int i = 1; i <= n; i++) {
+          int up = D[i];
+          int v = diag + ((q[i - 1] < 4 && q[i - 1] == tb) ? 0 : 1);
+          if (up + 1 < v) v = up + 1;
+          if (D[i - 1] + 1 < v) v = D[i - 1] + 1;
+          diag = up;
+          D[i] = v;
+        }
+        if (D[n] <= mm_max) {
+          int dc = (x + 1) - n;
+          for (int d = dc - BAND; d <= dc + BAND; d++) mark[d - dlo] = 1;
+        }
+      }
+      for (int k = 0; k < nd; k++) {
+        if (!mark[k]) continue;
+        ares xr;
+        orc_align(q, n, a->codes, tlen, k + dlo, &xr.S, &xr.cost, &xr.lead, &xr.trail);
+        xr.valid = 1;
+        *cells += (int64_t)n * NB;
+        if (ares_better(&xr, &best)) best = xr;
+      }
+      free(mark);
+    }
+  }
+  return best;
+}
+
+static ares score_task(int mode, const olocus* L, const uint8_t* r, int n, scratch* sc, int mm_max,
+                       int64_t* cells) {
+  if (mode == 2) return score_seedless(L, r, n, mm_max, cells);
+  return mode ? score_fast(L, r, n, sc, mm_max, cells) : score_exhaustive(L, r, n, sc, cells);
+}
+
 static void to_codes(const uint8_t* s, int n, uint8_t* out) {
   for (int i = 0; i < n; i++) {
     /* reads are matched as written: only upper-case ACGT are bases */
@@ -738,8 +801,7 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
           {
             int64_t o = i * T + db->n_loci;
             int sum = out->s1[o] == 0xFFFF ? 0 : out->s1[o];
-            ares a = mode ? score_fast(&db->loc[db->n_loci], codes, len, &sc, p->mm_max, &total_cells)
-                          : score_exhaustive(&db->loc[db->n_loci], codes, len, &sc, &total_cells);
+            ares a = score_task(mode, &db->loc[db->n_loci], codes, len, &sc, p->mm_max, &total_cells);
             if (a.valid && a.cost <= p->mm_max) sum += hla_rna_score(&a, len, p->clip_mode);
             else sum += len;
             out->s1[o] = (uint16_t)sum;
@@ -752,8 +814,7 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
             int64_t o = i * T + blk.gene;
             int sum = out->s1[o] == 0xFFFF ? 0 : out->s1[o];
             if (bl > 0) {
-              ares a = mode ? score_fast(&db->loc[blk.gene], codes + st, bl, &sc, p->mm_max, &total_cells)
-                            : score_exhaustive(&db->loc[blk.gene], codes + st, bl, &sc, &total_cells);
+              ares a = score_task(mode, &db->loc[blk.gene], codes + st, bl, &sc, p->mm_max, &total_cells);
               if (a.valid && a.cost <= p->mm_max) sum += hla_rna_score(&a, bl, p->clip_mode);
               else sum += bl;
             }
@@ -767,8 +828,7 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
           if (g < db->n_loci && !((scr->locus_mask[i] >> g) & 1)) continue;
           int64_t o = i * T + g;
           if (!p->rna) {
-            ares a = mode ? score_fast(&db->loc[g], codes, len, &sc, p->mm_max, &total_cells)
-                          : score_exhaustive(&db->loc[g], codes, len, &sc, &total_cells);
+            ares a = score_task(mode, &db->loc[g], codes, len, &sc, p->mm_max, &total_cells);
             if (a.valid && a.cost <= p->mm_max) {
               uint16_t sv = (uint16_t)hla_dna_score(&a, p->clip_mode);
               if (m == 0) {
@@ -793,9 +853,7 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
             for (int b = 0; b < nb; b++) {
               int b0 = (nb == 2 && b == 1) ? split : 0;
               int bl = (nb == 2) ? (b == 0 ? split : len - split) : len;
-              ares a = mode
-                           ? score_fast(&db->loc[g], codes + b0, bl, &sc, p->mm_max, &total_cells)
-                           : score_exhaustive(&db->loc[g], codes + b0, bl, &sc, &total_cells);
+              ares a = score_task(mode, &db->loc[g], codes + b0, bl, &sc, p->mm_max, &total_cells);
               if (a.valid && a.cost <= p->mm_max) sum += hla_rna_score(&a, bl, p->clip_mode);
               else sum += bl; /* unmapped record adds len(SEQ), map_rna.cpp:55-65 */
             }

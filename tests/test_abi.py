@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = api.lib()
     for n in names:
         assert getattr(L, n) is not None
-    assert L.hlm_abi_version() == 2  # 2: hlm_batch gained rna_block_off / rna_blocks
+    assert L.hlm_abi_version() == 3  # 3: hlm_params.score_cap (was reserved0), hlm_int32_peaks
 
 
 def test_struct_layouts_match_the_header():
@@ -53,6 +53,15 @@ def test_db_open_error_messages(tmp_path):
         api.Database(str(tmp_path / "nope"))
     (tmp_path / "db_dna.info").write_text("hla-mapper:3.0\nGENE:HLA-A:chr6:1:2:3:4:HLA\n")
     with pytest.raises(api.HlmError, match="not compatible"):
+        api.Database(str(tmp_path))
+
+
+def test_db_open_refuses_more_loci_than_the_masks_hold(tmp_path):
+    from hla_mapper_b200 import api
+
+    (tmp_path / "db_dna.info").write_text(
+        "hla-mapper:4.3+\n" + "".join(f"GENE:G{i}:chr6:1:2:3:4:HLA\n" for i in range(32)) + "SIZE:50\n")
+    with pytest.raises(api.HlmError, match="more than 31 GENE"):
         api.Database(str(tmp_path))
 
 
