@@ -64,6 +64,13 @@
 #else
 #define HLM_COMMON_HD static inline
 #endif
+/* Read seeds: 12-mers at read offsets 0, st, 2 st, ... <= n - 12.  st = 12
+ * (non-overlapping) for units of HLM_SEED_SHORT bases or more; shorter units - the blocks STAR
+ * cuts an rna mate into - use overlapping seeds, st = 6, so that an error-free 12-mer is found
+ * wherever it lies to within 6 bases (at most 14 seeds per strand either way). */
+HLM_COMMON_HD int hlm_seed_stride(int n) { return n < HLM_SEED_SHORT ? HLM_SEED_STRIDE_SHORT : HLM_SEED; }
+HLM_COMMON_HD int hlm_seed_count(int n) { return n < HLM_SEED ? 0 : (n - HLM_SEED) / hlm_seed_stride(n) + 1; }
+
 HLM_COMMON_HD uint64_t hlm_kt_hash(uint64_t key, int bits) {
   return (key * 0x9E3779B97F4A7C15ull) >> (64 - bits);
 }

@@ -393,10 +393,10 @@ HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_
   return r;
 }
 
-// does read seed q (12 bases at read offset 12q) match the tile exactly at column off + 12q ?
+// does the read seed at read offset rp (12 bases) match the tile exactly at column off + rp ?
 HLM_HD bool hlm_seed_match(const uint32_t* __restrict__ rd, const uint32_t* __restrict__ tile,
-                           int off, int q) {
-  int rp = q * HLM_SEED, tc = off + rp;
+                           int off, int rp) {
+  int tc = off + rp;
   int rw = rp >> 5, rs = rp & 31, tw = tc >> 5, ts = tc & 31;
   uint32_t a0 = hlm_funnel(rd[rw], rw + 1 < 6 ? rd[rw + 1] : 0u, rs);
   uint32_t a1 = hlm_funnel(rd[6 + rw], rw + 1 < 6 ? rd[6 + rw + 1] : 0u, rs);
@@ -407,9 +407,10 @@ HLM_HD bool hlm_seed_match(const uint32_t* __restrict__ rd, const uint32_t* __re
   return (((a0 ^ b0) | (a1 ^ b1) | an | bn) & 0xFFFu) == 0;
 }
 
-// 24-bit seed code (base x at bits 2x) of read seed q; returns false if the seed holds an N
-HLM_HD bool hlm_seed_code(const uint32_t* __restrict__ rd, int q, uint32_t* code) {
-  int rp = q * HLM_SEED, rw = rp >> 5, rs = rp & 31;
+// 24-bit seed code (base x at bits 2x) of the read seed at read offset rp; returns false if the
+// seed holds an N
+HLM_HD bool hlm_seed_code(const uint32_t* __restrict__ rd, int rp, uint32_t* code) {
+  int rw = rp >> 5, rs = rp & 31;
   uint32_t a0 = hlm_funnel(rd[rw], rw + 1 < 6 ? rd[rw + 1] : 0u, rs) & 0xFFFu;
   uint32_t a1 = hlm_funnel(rd[6 + rw], rw + 1 < 6 ? rd[6 + rw + 1] : 0u, rs) & 0xFFFu;
   uint32_t an = hlm_funnel(rd[12 + rw], rw + 1 < 6 ? rd[12 + rw + 1] : 0xFFFFFFFFu, rs) & 0xFFFu;

@@ -593,18 +593,19 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     rd[lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + lane];
     if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + 32 + lane];
     __syncwarp();
-    int Q = n / HLM_SEED;
-    // lane (strand*16 + q) owns seed q of that strand: CSR range of its 12-mer narrowed to the
-    // entries whose column lies in [OFF_MIN + 12q, OFF_MIN + 32 + 12q) (entries are sorted by
-    // column), i.e. to the windows in which read base 0 falls on a column in [OFF_MIN, OFF_MIN+32)
+    int Q = hlm_seed_count(n), st = hlm_seed_stride(n);  // Q <= 15
+    // lane (strand*16 + q) owns seed q of that strand (read offset q * st): CSR range of its
+    // 12-mer narrowed to the entries whose column lies in [OFF_MIN + q st, OFF_MIN + 32 + q st)
+    // (entries are sorted by column), i.e. to the windows in which read base 0 falls on a column
+    // in [OFF_MIN, OFF_MIN+32)
     int my_q = lane & 15, my_strand = lane >> 4;
     uint32_t my_a = 0, my_b = 0;
     if (my_q < Q) {
       uint32_t code;
-      if (hlm_seed_code(rd + 18 * my_strand, my_q, &code)) {
+      if (hlm_seed_code(rd + 18 * my_strand, my_q * st, &code)) {
         uint32_t a = __ldg(db.seed_off + code), b = __ldg(db.seed_off + code + 1);
-        uint32_t klo = (uint32_t)(HLM_OFF_MIN + my_q * HLM_SEED) << 24;
-        uint32_t khi = (uint32_t)(HLM_OFF_MIN + HLM_TILE_STRIDE + my_q * HLM_SEED) << 24;
+        uint32_t klo = (uint32_t)(HLM_OFF_MIN + my_q * st) << 24;
+        uint32_t khi = (uint32_t)(HLM_OFF_MIN + HLM_TILE_STRIDE + my_q * st) << 24;
         // both bounds at once: two independent chains of dependent loads instead of one after
         // the other (this part of the kernel is pure memory latency)
         uint32_t lo1 = a, hi1 = b, lo2 = a, hi2 = b;
@@ -658,7 +659,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         strand = j >> 4;
         uint32_t e = __ldg(db.seed_ent + beg[j] + (t - pre[j]));
         tile = e & 0xFFFFFFu;
-        off = (int)(e >> 24) - q * HLM_SEED;
+        off = (int)(e >> 24) - q * st;
         int g = tile_locus(db, tile);
         if ((umask >> g) & 1u) {
           uint32_t key = (tile << 6) | ((uint32_t)(off - HLM_OFF_MIN) << 1) | (uint32_t)strand;
@@ -683,9 +684,9 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
             uint32_t diff = __ldg(db.tile_diff + tile);
             own = true;
             for (int qq = 0; qq < q && own; qq++) {
-              if (!hlm_seed_match(R, T, off, qq)) continue;
+              if (!hlm_seed_match(R, T, off, qq * st)) continue;
               if (HLM_DIFF_N(diff) == 0) own = false;
-              int o = off + qq * HLM_SEED;
+              int o = off + qq * st;
               for (int k = 0; k < HLM_DIFF_N(diff); k++) {
                 int x = HLM_DIFF_COL(diff, k);
                 if (x >= o && x < o + HLM_SEED) own = false;
@@ -763,19 +764,25 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       // matches and none of its matching seeds covers a differing column (a covering seed is in
       // the seed index, which then emitted the candidate)
       uint32_t diff = __ldg(db.tile_diff + tile);
-      int Q = n / HLM_SEED;
-      // the (at most KMAX) seeds that cover a differing column decide ownership; after them the
-      // first matching seed settles "some seed matches": two to four tests, not Q
+      int Q = hlm_seed_count(n), st = hlm_seed_stride(n);
+      // the seeds that cover a differing column (at most KMAX with non-overlapping seeds, two per
+      // column with the overlapping seeds of short units) decide ownership; after them the first
+      // matching seed settles "some seed matches": a few tests, not Q
       uint32_t cover = 0;
       for (int k = 0; k < HLM_DIFF_N(diff); k++) {
         int r = HLM_DIFF_COL(diff, k) - off;  // read position on the diagonal
-        if (r >= 0 && r < Q * HLM_SEED) cover |= 1u << (r / HLM_SEED);
+        if (r < 0) continue;
+        // seeds q with q st <= r < q st + 12
+        int q1 = r / st, q0 = (r - HLM_SEED + st) / st;  // q0 = ceil((r - 11) / st), >= 0 below
+        if (r < HLM_SEED) q0 = 0;
+        if (q1 > Q - 1) q1 = Q - 1;
+        for (int q = q0; q <= q1; q++) cover |= 1u << q;
       }
       for (uint32_t m = cover; m && !dead; m &= m - 1)
-        dead = hlm_seed_match(rd, T, off, __ffs(m) - 1);  // the seed index lists this one
+        dead = hlm_seed_match(rd, T, off, (__ffs(m) - 1) * st);  // the seed index lists this one
       bool any = dead;
       for (int q = 0; q < Q && !any; q++)
-        if (!((cover >> q) & 1u)) any = hlm_seed_match(rd, T, off, q);
+        if (!((cover >> q) & 1u)) any = hlm_seed_match(rd, T, off, q * st);
       if (!any) dead = true;
     }
     if (dead) {

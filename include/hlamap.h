@@ -44,6 +44,8 @@ extern "C" {
 #define HLM_MAX_READ 184  /* longest trimmed mate the 256-column tiles can hold */
 #define HLM_MOTIF 20      /* motif_size, src/main.cpp:73                        */
 #define HLM_SEED 12       /* aligner seed length (new)           */
+#define HLM_SEED_SHORT 96 /* units shorter than this use overlapping seeds      */
+#define HLM_SEED_STRIDE_SHORT 6
 #define HLM_BAND 20       /* DP half band = v_mm_max, src/main.cpp:77           */
 
 /* error codes */

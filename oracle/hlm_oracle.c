@@ -502,15 +502,17 @@ static int cmp_cand(const void* a, const void* b) {
   return x->d < y->d ? -1 : x->d > y->d;
 }
 
-/* all (allele, diagonal) pairs where some seed (non-overlapping 12-mers at read offsets
- * 0,12,24,...) matches the allele exactly */
+/* all (allele, diagonal) pairs where some seed matches the allele exactly.  Seeds (DESIGN.md
+ * section 3): 12-mers at read offsets 0, st, 2 st, ... <= n - 12; st = 12 (non-overlapping) for
+ * units of HLM_SEED_SHORT (96) bases or more, st = 6 (overlapping) for shorter ones */
 static int64_t collect_cands(const olocus* L, const uint8_t* r, int n, cand** buf, int64_t* cap) {
   int64_t nc = 0;
-  for (int q = 0; (q + 1) * KS <= n; q++) {
+  const int st = n < HLM_SEED_SHORT ? HLM_SEED_STRIDE_SHORT : KS;
+  for (int rp = 0; rp + KS <= n; rp += st) {
     uint32_t code = 0;
     int bad = 0;
     for (int x = 0; x < KS; x++) {
-      int c = r[q * KS + x];
+      int c = r[rp + x];
       if (c > 3) bad = 1;
       code = (code << 2) | (c & 3);
     }
@@ -528,7 +530,7 @@ static int64_t collect_cands(const olocus* L, const uint8_t* r, int n, cand** bu
         *buf = (cand*)realloc(*buf, *cap * sizeof(cand));
       }
       (*buf)[nc].allele = (int32_t)((L->seeds[s].key >> 16) & 0xFFFFFF);
-      (*buf)[nc].d = (int32_t)(L->seeds[s].key & 0xFFFF) - q * KS;
+      (*buf)[nc].d = (int32_t)(L->seeds[s].key & 0xFFFF) - rp;
       nc++;
     }
   }

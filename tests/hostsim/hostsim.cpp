@@ -49,8 +49,8 @@ int hs_seed(const uint8_t* read, int n, const uint8_t* tile_cols, int off, int q
   uint32_t rd[18], t[24];
   pack_read(read, n, rd);
   pack_tile(tile_cols, t);
-  int ok = hlm_seed_code(rd, q, code) ? 1 : 0;
-  return ok | (hlm_seed_match(rd, t, off, q) ? 2 : 0);
+  int ok = hlm_seed_code(rd, q * HLM_SEED, code) ? 1 : 0;
+  return ok | (hlm_seed_match(rd, t, off, q * HLM_SEED) ? 2 : 0);
 }
 // index builder
 void* hs_db_open(const char* dir, int rna, char* err, size_t errlen) {
@@ -92,10 +92,11 @@ uint32_t hs_db_kmer(void* p, const char* kmer20) {
     h = (h + 1) & mask;
   }
 }
-// does seed q of a read placed at tile column off cover one of the child's differing columns?
-static bool seed_covers(uint32_t diff, int off, int q) {
+// does the seed at read offset rp of a read placed at tile column off cover one of the child's
+// differing columns?
+static bool seed_covers(uint32_t diff, int off, int rp) {
   for (int k = 0; k < HLM_DIFF_N(diff); k++) {
-    int x = HLM_DIFF_COL(diff, k), o = off + q * HLM_SEED;
+    int x = HLM_DIFF_COL(diff, k), o = off + rp;
     if (x >= o && x < o + HLM_SEED) return true;
   }
   return false;
@@ -107,14 +108,14 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
   pack_read(read, n, rd);
-  int cnt = 0, Q = n / HLM_SEED;
+  int cnt = 0, Q = hlm_seed_count(n), st = hlm_seed_stride(n);
   int n_index = 0;
   for (int q = 0; q < Q; q++) {
     uint32_t code;
-    if (!hlm_seed_code(rd, q, &code)) continue;
+    if (!hlm_seed_code(rd, q * st, &code)) continue;
     for (uint32_t i = db->seed_off[code]; i < db->seed_off[code + 1]; i++) {
       uint32_t e = db->seed_ent[i], tile = e & 0xFFFFFFu;
-      int off = (int)(e >> 24) - q * HLM_SEED;
+      int off = (int)(e >> 24) - q * st;
       if (off < HLM_OFF_MIN || off >= HLM_OFF_MIN + HLM_TILE_STRIDE) continue;
       if (tile < db->tile_start[locus] || tile >= db->tile_start[locus + 1]) continue;
       // one candidate per (tile, off) hit through the index: the first index entry that hits
@@ -122,8 +123,8 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
       uint32_t diff = db->tile_diff[tile];
       bool first = true;
       for (int qq = 0; qq < q && first; qq++)
-        if (hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, qq) &&
-            (HLM_DIFF_N(diff) == 0 || seed_covers(diff, off, qq)))
+        if (hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, qq * st) &&
+            (HLM_DIFF_N(diff) == 0 || seed_covers(diff, off, qq * st)))
           first = false;
       if (!first) continue;
       if (cnt < cap) out[cnt] = (tile << 8) | (uint32_t)off;
@@ -146,9 +147,9 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
       // differing column (such a seed is in the index, which then produced the candidate)
       bool any = false, indexed = false;
       for (int q = 0; q < Q; q++)
-        if (hlm_seed_match(rd, &db->tiles[(size_t)ch * HLM_TILE_WORDS], off, q)) {
+        if (hlm_seed_match(rd, &db->tiles[(size_t)ch * HLM_TILE_WORDS], off, q * st)) {
           any = true;
-          if (seed_covers(diff, off, q)) indexed = true;
+          if (seed_covers(diff, off, q * st)) indexed = true;
         }
       if (!any || indexed) continue;
       if (cnt < cap) out[cnt] = (ch << 8) | (uint32_t)off;
@@ -162,12 +163,12 @@ int hs_db_candidates_brute(void* p, const uint8_t* read, int n, int locus, uint3
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
   pack_read(read, n, rd);
-  int cnt = 0, Q = n / HLM_SEED;
+  int cnt = 0, Q = hlm_seed_count(n), st = hlm_seed_stride(n);
   for (uint32_t tile = db->tile_start[locus]; tile < db->tile_start[locus + 1]; tile++)
     for (int off = HLM_OFF_MIN; off < HLM_OFF_MIN + HLM_TILE_STRIDE; off++) {
       bool any = false;
       for (int q = 0; q < Q && !any; q++)
-        any = hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, q);
+        any = hlm_seed_match(rd, &db->tiles[(size_t)tile * HLM_TILE_WORDS], off, q * st);
       if (!any) continue;
       if (cnt < cap) out[cnt] = (tile << 8) | (uint32_t)off;
       cnt++;
