@@ -51,6 +51,12 @@ class HlmScreenOut(C.Structure):
                 ("trim_len2", u16p), ("locus_mask", u32p)]
 
 
+class HlmAlleleOut(C.Structure):
+    _fields_ = [("n_alleles", C.c_int32), ("reserved0", C.c_int32),
+                ("nm1", C.POINTER(C.c_uint8)), ("clip1", C.POINTER(C.c_uint8)),
+                ("nm2", C.POINTER(C.c_uint8)), ("clip2", C.POINTER(C.c_uint8))]
+
+
 class HlmScoreOut(C.Structure):
     _fields_ = [("s1", u16p), ("s2", u16p), ("aln1", i16p), ("aln2", i16p), ("nm1", u8p),
                 ("nm2", u8p), ("lead1", u8p), ("lead2", u8p), ("trail1", u8p), ("trail2", u8p)]

@@ -27,7 +27,8 @@ SYMBOLS = [
     "hlm_map_fastq", "hlm_run_async", "hlm_wait", "hlm_multi_create", "hlm_multi_destroy",
     "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run", "hlm_dp_layout_ab",
     "hlm_bam_extract", "hlm_reads_paired", "hlm_reads_count", "hlm_reads_free",
-    "hlm_reads_write_fastq", "hlm_map_reads", "hlm_int32_peaks",
+    "hlm_reads_write_fastq", "hlm_map_reads", "hlm_int32_peaks", "hlm_db_n_alleles",
+    "hlm_db_allele_name", "hlm_score_alleles",
 ]
 
 _lib = None
@@ -66,6 +67,11 @@ def lib():
                             C.POINTER(HlmScoreOut)]
     L.hlm_assign.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
                              C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
+    L.hlm_db_n_alleles.argtypes = [C.c_void_p, C.c_int]
+    L.hlm_db_allele_name.restype = C.c_char_p
+    L.hlm_db_allele_name.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.hlm_score_alleles.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut), C.c_int,
+                                    C.POINTER(_abi.HlmAlleleOut)]
     L.hlm_run.argtypes = [C.c_void_p, C.POINTER(HlmBatch), C.POINTER(HlmScreenOut),
                           C.POINTER(HlmScoreOut), C.POINTER(HlmAssignOut)]
     L.hlm_run_async.argtypes = L.hlm_run.argtypes
@@ -121,6 +127,11 @@ class Database:
 
     def stat(self, key):
         return int(lib().hlm_db_stat(self.h, key.encode()))
+
+    def allele_names(self, locus):
+        """record names of the locus' FASTA in file order (locus == n_loci: others)"""
+        n = lib().hlm_db_n_alleles(self.h, int(locus))
+        return [lib().hlm_db_allele_name(self.h, int(locus), i).decode() for i in range(n)]
 
     def close(self):
         if self.h:
@@ -209,6 +220,20 @@ class Mapper:
         b = self._batch(rb, **kw)
         self._check(lib().hlm_score(self.h, C.byref(b), C.byref(buf.scr), C.byref(buf.sc)))
         return buf
+
+    def score_alleles(self, rb, buf, locus, **kw):
+        """hlm_score_alleles: (nm1, clip1, nm2, clip2) uint8 arrays [n_pairs, n_alleles of locus]"""
+        import numpy as np
+
+        b = self._batch(rb, **kw)
+        na = lib().hlm_db_n_alleles(self.db.h, int(locus))
+        arrs = [np.zeros((rb.n_pairs, na), dtype=np.uint8) for _ in range(4)]
+        out = _abi.HlmAlleleOut()
+        out.n_alleles = na
+        u8p = C.POINTER(C.c_uint8)
+        out.nm1, out.clip1, out.nm2, out.clip2 = [a.ctypes.data_as(u8p) for a in arrs]
+        self._check(lib().hlm_score_alleles(self.h, C.byref(b), C.byref(buf.scr), int(locus), C.byref(out)))
+        return tuple(arrs)
 
     def assign(self, rb, buf, **kw):
         b = self._batch(rb, **kw)

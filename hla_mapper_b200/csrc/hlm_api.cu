@@ -25,6 +25,7 @@
 #define HLM_STAGE_SCREEN 1
 #define HLM_STAGE_SCORE 2
 #define HLM_STAGE_ASSIGN 4
+#define HLM_STAGE_ALLELES 8  /* hlm_score_alleles: needs provided screen results, excludes the others */
 #define HLM_MAX_SLOTS 3
 #define HLM_E_OVERFLOW -100 /* internal: a chunk produced more candidates than cand_capacity */
 
@@ -42,6 +43,7 @@ struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[EV_COUNT];
   Buf h_in, h_out, d_in, d_out, d_units, d_unit_meta, d_cand, d_dp, d_tasks, d_counters;
+  Buf d_cres, d_albest, d_alout;  // hlm_score_alleles only
   HlmChunk ck;
   bool busy = false;
   int64_t first = 0, n = 0;
@@ -155,7 +157,7 @@ void bind_outputs(HlmChunk& ck, uint8_t* base, const size_t* off, int64_t first,
 }
 
 // n pairs plus n_blocks rna block units
-int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0) {
+int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0, int n_al = 0) {
   int U = ctx->units_per_pair, T = ctx->n_targets;
   size_t NU = (size_t)n * U + (size_t)n_blocks;
   if (NU >= (1ull << 26)) {
@@ -190,14 +192,54 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0) {
   ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16(NU * T * 4));
   ck.task_pmin = (uint32_t*)((uint8_t*)s.d_tasks.p + 2 * align16(NU * T * 4));
   ck.task_best = (unsigned long long*)((uint8_t*)s.d_tasks.p + 3 * align16(NU * T * 4));
+  ck.cand_res = nullptr;
+  ck.allele_best = nullptr;
+  ck.n_al = n_al;
+  if (n_al > 0) {
+    if ((rc = ensure_dev(ctx, s.d_cres, (size_t)ctx->cand_cap * 8))) return rc;
+    if ((rc = ensure_dev(ctx, s.d_albest, NU * (size_t)n_al * 8 + 256))) return rc;
+    if ((rc = ensure_dev(ctx, s.d_alout, 4 * (size_t)n * n_al + 256))) return rc;
+    ck.cand_res = (unsigned long long*)s.d_cres.p;
+    ck.allele_best = (unsigned long long*)s.d_albest.p;
+  }
   return 0;
 }
 
-void launch_stages(hlm_ctx* ctx, Slot& s, int stages) {
+void launch_stages(hlm_ctx* ctx, Slot& s, int stages, int allele_locus = -1) {
   const HlmChunk& ck = s.ck;
   int T = ctx->n_targets, sms = ctx->sms;
   cudaStream_t st = s.st;
   hlm_launch_clear_tasks(ck, T, sms, st);
+  if (stages & HLM_STAGE_ALLELES) {
+    // per-allele scoring of one target set: every seed candidate, every child that can hold a
+    // reportable alignment, every live candidate aligned; results gathered per allele
+    HlmKParams kp = ctx->kp;
+    kp.allele_locus = allele_locus;
+    kp.score_cap = 0;
+    size_t nal = (size_t)ck.n_pairs * ck.n_al;
+    uint8_t* o = (uint8_t*)s.d_alout.p;
+    cudaMemsetAsync(ck.cand_res, 0xFF, (size_t)ck.cand_cap * 8, st);
+    cudaMemsetAsync(ck.allele_best, 0xFF, (size_t)ck.n_units * ck.n_al * 8, st);
+    cudaEventRecord(s.ev[EV_SCREEN], st);
+    hlm_launch_pack(kp, ck, sms, st);
+    hlm_launch_seed(ctx->ddb, kp, ck, sms, st);
+    hlm_launch_snapshot(ck, 0, st);
+    cudaEventRecord(s.ev[EV_SEED], st);
+    hlm_launch_myers(ctx->ddb, kp, ck, T, 0, sms, st);
+    cudaEventRecord(s.ev[EV_MYA], st);
+    hlm_launch_expand(ctx->ddb, kp, ck, T, 2, sms, st);
+    cudaEventRecord(s.ev[EV_EX0], st);
+    hlm_launch_myers(ctx->ddb, kp, ck, T, 1, sms, st);
+    cudaEventRecord(s.ev[EV_MYB0], st);
+    hlm_launch_select(ctx->ddb, kp, ck, T, 2, sms, st);
+    cudaEventRecord(s.ev[EV_SEL0], st);
+    hlm_launch_dp(ctx->ddb, kp, ck, T, sms, st);
+    for (int e = EV_DP0; e <= EV_DP1; e++) cudaEventRecord(s.ev[e], st);
+    hlm_launch_allele_gather(ctx->ddb, kp, ck, o, o + nal, o + 2 * nal, o + 3 * nal, sms, st);
+    cudaEventRecord(s.ev[EV_ASSIGN], st);
+    ctx->prof.launches += 16;
+    return;
+  }
   if (stages & HLM_STAGE_SCREEN) hlm_launch_screen(ctx->ddb, ctx->kp, ck, sms, st);
   cudaEventRecord(s.ev[EV_SCREEN], st);
   if (stages & HLM_STAGE_SCORE) {
@@ -288,6 +330,8 @@ struct HostIO {
   hlm_screen_out* scr = nullptr;
   hlm_score_out* sc = nullptr;
   hlm_assign_out* asg = nullptr;
+  hlm_allele_out* al = nullptr;  // hlm_score_alleles
+  int al_locus = -1;
 };
 
 template <class Tp>
@@ -378,7 +422,7 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
     ctx->err = "bad batch";
     return HLM_E_ARG;
   }
-  bool need_reads = stages & (HLM_STAGE_SCREEN | HLM_STAGE_SCORE);
+  bool need_reads = stages & (HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ALLELES);
   if (need_reads) {
     if (!in->bases1 || !in->offs1 || ((stages & HLM_STAGE_SCREEN) && !in->quals1) ||
         (ctx->p.paired && (!in->bases2 || !in->offs2 || ((stages & HLM_STAGE_SCREEN) && !in->quals2)))) {
@@ -394,6 +438,12 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
   int T = ctx->n_targets;
   bool paired = ctx->p.paired;
   int64_t N = in->n_pairs, C = ctx->chunk_pairs;
+  int n_al = 0;
+  if (stages & HLM_STAGE_ALLELES) {
+    // units x alleles x 8 bytes of per-allele minima per chunk: keep it near 1 GB
+    n_al = io.al->n_alleles;
+    C = std::max<int64_t>(32, std::min<int64_t>(C, ((int64_t)1 << 26) / std::max(1, n_al)));
+  }
   CU(cudaEventRecord(ctx->run_start, ctx->slot[0].st));
   for (int i = 1; i < HLM_MAX_SLOTS; i++) CU(cudaStreamWaitEvent(ctx->slot[i].st, ctx->run_start, 0));
   // stage + copy + launch one chunk on a slot (asynchronous)
@@ -434,7 +484,7 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
     s.out_bytes = out_bytes;
     if ((rc = ensure_pinned(ctx, s.h_out, out_bytes))) return rc;
     if ((rc = ensure_dev(ctx, s.d_out, out_bytes))) return rc;
-    if ((rc = ensure_work(ctx, s, n, nb))) return rc;
+    if ((rc = ensure_work(ctx, s, n, nb, n_al))) return rc;
     uint8_t* h = (uint8_t*)s.h_in.p;
     uint8_t* d = (uint8_t*)s.d_in.p;
     if (blocks) {
@@ -503,7 +553,7 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
       ctx->prof.h2d_bytes += (int64_t)(e - a);
     }
     CU(cudaEventRecord(s.ev[EV_H2D], st));
-    launch_stages(ctx, s, stages);
+    launch_stages(ctx, s, stages, io.al_locus);
     CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 8 * HLM_N_COUNTERS,
                        cudaMemcpyDeviceToDevice, st));
     {  // copy back only the result groups the caller asked for (+ the counters)
@@ -543,6 +593,16 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
     }
     if (rc == HLM_E_OVERFLOW) rc = HLM_E_NOMEM;
     if (rc == 0) scatter_results(ctx, s, io);
+    if (rc == 0 && io.al) {  // per-allele bytes straight into the caller's rows (synchronous copies)
+      size_t nal = (size_t)s.n * n_al, at = (size_t)s.first * n_al;
+      const uint8_t* o = (const uint8_t*)s.d_alout.p;
+      uint8_t* dst[4] = {io.al->nm1, io.al->clip1, io.al->nm2, io.al->clip2};
+      for (int k = 0; k < 4; k++)
+        if (dst[k]) {
+          CU(cudaMemcpy(dst[k] + at, o + k * nal, nal, cudaMemcpyDeviceToHost));
+          ctx->prof.d2h_bytes += (int64_t)nal;
+        }
+    }
     return rc;
   };
   int rc = 0;
@@ -623,6 +683,14 @@ const char* hlm_db_locus_name(const hlm_db* db, int i) {
   return (db && i >= 0 && i <= db->n_loci) ? db->names[i].c_str() : nullptr;
 }
 int hlm_db_size(const hlm_db* db) { return db ? db->v_size : 0; }
+int hlm_db_n_alleles(const hlm_db* db, int locus) {
+  return (db && locus >= 0 && locus <= db->n_loci) ? (int)db->allele_names[locus].size() : 0;
+}
+const char* hlm_db_allele_name(const hlm_db* db, int locus, int allele) {
+  if (!db || locus < 0 || locus > db->n_loci) return nullptr;
+  const auto& v = db->allele_names[locus];
+  return (allele >= 0 && (size_t)allele < v.size()) ? v[allele].c_str() : nullptr;
+}
 int64_t hlm_db_stat(const hlm_db* db, const char* key) {
   if (!db || !key) return -1;
   std::string k(key);
@@ -678,6 +746,8 @@ static int upload_db(hlm_ctx* ctx, hlm_db* db) {
   if (!rc) rc = up(9, db->odd_keys.data(), db->odd_keys.size(), (const void**)&v.odd_keys);
   if (!rc) rc = up(10, db->odd_masks.data(), db->odd_masks.size() * 4, (const void**)&v.odd_masks);
   if (!rc) rc = up(11, db->kb.data(), db->kb.size() * 8, (const void**)&v.kb);
+  if (!rc) rc = up(12, db->tile_al_off.data(), db->tile_al_off.size() * 4, (const void**)&v.tile_al_off);
+  if (!rc) rc = up(13, db->tile_al_ent.data(), db->tile_al_ent.size() * 4, (const void**)&v.tile_al_ent);
   v.kb_words = (uint32_t)db->kb.size();
   v.n_odd = (int)db->odd_masks.size();
   if (rc) {  // nothing half-uploaded stays behind
@@ -758,6 +828,7 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   kp.clip_mode = p.clip_mode;
   kp.skip_screen = p.skip_screen;
   kp.score_cap = (p.score_cap && !p.rna) ? 1 : 0;
+  kp.allele_locus = -1;
   kp.tolerance = p.tolerance;
   kp.n_loci = db->n_loci;
   kp.one = 1;
@@ -790,7 +861,8 @@ void hlm_ctx_destroy(hlm_ctx* ctx) {
   cudaDeviceSynchronize();
   for (int i = 0; i < HLM_MAX_SLOTS; i++) {
     Slot& s = ctx->slot[i];
-    for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters})
+    for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters,
+                   &s.d_cres, &s.d_albest, &s.d_alout})
       if (b->p) cudaFree(b->p);
     for (Buf* b : {&s.h_in, &s.h_out})
       if (b->p) cudaFreeHost(b->p);
@@ -824,6 +896,29 @@ int hlm_score(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, hlm_
   io.scr_in = scr;
   io.sc = out;
   return run_host(ctx, io, HLM_STAGE_SCORE);
+}
+
+int hlm_score_alleles(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, int locus,
+                      hlm_allele_out* out) {
+  if (!ctx || !in || !scr || !out) return HLM_E_ARG;
+  if (locus < 0 || locus > ctx->db->n_loci) {
+    ctx->err = "hlm_score_alleles: locus out of range (0 .. n_loci, n_loci = others)";
+    return HLM_E_ARG;
+  }
+  if (out->n_alleles != (int32_t)ctx->db->allele_names[locus].size() || out->n_alleles <= 0) {
+    ctx->err = "hlm_score_alleles: out->n_alleles must equal hlm_db_n_alleles(db, locus)";
+    return HLM_E_ARG;
+  }
+  if (!out->nm1 || (ctx->p.paired && !out->nm2)) {
+    ctx->err = "hlm_score_alleles: nm arrays missing";
+    return HLM_E_ARG;
+  }
+  HostIO io;
+  io.in = in;
+  io.scr_in = scr;
+  io.al = out;
+  io.al_locus = locus;
+  return run_host(ctx, io, HLM_STAGE_ALLELES);
 }
 
 int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, const hlm_score_out* sc,

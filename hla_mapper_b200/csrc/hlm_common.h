@@ -65,11 +65,15 @@
 #define HLM_COMMON_HD static inline
 #endif
 /* Read seeds: 12-mers at read offsets 0, st, 2 st, ... <= n - 12.  st = 12
- * (non-overlapping) for units of HLM_SEED_SHORT bases or more; shorter units - the blocks STAR
- * cuts an rna mate into - use overlapping seeds, st = 6, so that an error-free 12-mer is found
- * wherever it lies to within 6 bases (at most 14 seeds per strand either way). */
-HLM_COMMON_HD int hlm_seed_stride(int n) { return n < HLM_SEED_SHORT ? HLM_SEED_STRIDE_SHORT : HLM_SEED; }
-HLM_COMMON_HD int hlm_seed_count(int n) { return n < HLM_SEED ? 0 : (n - HLM_SEED) / hlm_seed_stride(n) + 1; }
+ * (non-overlapping), except for the units of an `rna` run shorter than HLM_SEED_SHORT bases - the
+ * blocks STAR cuts a mate into - which use overlapping seeds, st = 6, so that an error-free 12-mer
+ * is found wherever it lies to within 6 bases (at most 15 seeds per strand either way). */
+HLM_COMMON_HD int hlm_seed_stride(int n, int rna) {
+  return (rna && n < HLM_SEED_SHORT) ? HLM_SEED_STRIDE_SHORT : HLM_SEED;
+}
+HLM_COMMON_HD int hlm_seed_count(int n, int rna) {
+  return n < HLM_SEED ? 0 : (n - HLM_SEED) / hlm_seed_stride(n, rna) + 1;
+}
 
 HLM_COMMON_HD uint64_t hlm_kt_hash(uint64_t key, int bits) {
   return (key * 0x9E3779B97F4A7C15ull) >> (64 - bits);
@@ -103,6 +107,8 @@ struct HlmDevDB {
   const uint32_t* child_off; /* n_tiles + 1                                           */
   const uint32_t* child_ent; /* child tile ids                                        */
   const uint32_t* child_diff;
+  const uint32_t* tile_al_off; /* n_tiles + 1: alleles (index inside the locus) that hold tile t = */
+  const uint32_t* tile_al_ent; /*   tile_al_ent[tile_al_off[t] .. tile_al_off[t+1])  (hlm_score_alleles) */
   uint32_t tile_start[HLM_MAX_LOCI + 3]; /* first tile id of locus g; [n_loci+1] = n_tiles */
   int n_loci;
 };

@@ -103,7 +103,8 @@ struct Planes {
 };
 
 // FASTA -> bit planes of each N-padded allele
-void load_fasta(const std::string& path, std::vector<Planes>& out, int64_t& n_bases) {
+void load_fasta(const std::string& path, std::vector<Planes>& out, int64_t& n_bases,
+                std::vector<std::string>* names = nullptr) {
   std::vector<char> buf;
   if (!read_file(path, buf)) return;
   std::vector<uint8_t> codes;
@@ -139,6 +140,11 @@ void load_fasta(const std::string& path, std::vector<Planes>& out, int64_t& n_ba
       if (buf[i] == '>') {
         flush(have);
         have = true;
+        if (names) {  // the record's name: the header up to the first blank (what SAM calls RNAME)
+          size_t x = i + 1;
+          while (x < le && buf[x] != ' ' && buf[x] != '\t') x++;
+          names->emplace_back(&buf[i + 1], x - (i + 1));
+        }
       } else if (have) {
         for (size_t x = i; x < le; x++) codes.push_back((uint8_t)base_code((unsigned char)buf[x]));
       }
@@ -291,6 +297,8 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   // loci are independent: build their tile sets on host threads, then concatenate
   struct LocusTiles {
     std::vector<uint32_t> tiles, parent, diff;
+    std::vector<uint32_t> al_tiles;  // tile (local id) of every window of every allele, allele by allele
+    std::vector<std::string> al_names;
     int64_t n_alleles = 0, n_bases = 0, n_raw = 0, n_reps = 0;
   };
   std::vector<LocusTiles> per(db->n_loci + 1);
@@ -300,7 +308,7 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     std::string path = g < db->n_loci
                            ? base + "/mapper/" + kind + "/" + db->names[g] + "/" + db->names[g] + ".fas"
                            : base + "/others/" + kind + "/hla_gen_others.fasta";
-    load_fasta(path, al, L.n_bases);
+    load_fasta(path, al, L.n_bases, &L.al_names);
     L.n_alleles += (int64_t)al.size();
     size_t raw = 0;
     for (auto& P : al) raw += (size_t)(HLM_PAD + P.len) / 32 + 1;
@@ -313,8 +321,10 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     std::unordered_map<uint64_t, std::vector<uint32_t>> rep_lsh;
     std::vector<uint32_t> seen;
     uint32_t w[HLM_TILE_WORDS];
+    uint32_t al_id = 0;
     for (auto& P : al) {
       int jmax = (HLM_PAD + P.len) / 32;
+      uint32_t this_al = al_id++;
       for (int j = 0; j <= jmax; j++) {
         uint64_t h = 0x1234567ull;
         for (int x = 0; x < 8; x++) {
@@ -332,6 +342,8 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
           }
           s = (s + 1) & (cap - 1);
         }
+        L.al_tiles.push_back(this_al);
+        L.al_tiles.push_back(found ? slot[s] : (uint32_t)(L.tiles.size() / HLM_TILE_WORDS));
         if (found) continue;
         uint32_t id = (uint32_t)(L.tiles.size() / HLM_TILE_WORDS);
         slot[s] = id;
@@ -388,10 +400,14 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
     for (auto& t : th) t.join();
   }
   db->tile_start.assign(db->n_loci + 2, 0);
+  db->allele_names.resize(db->n_loci + 1);
+  std::vector<std::pair<uint32_t, uint32_t>> tile_al;  // (global tile, allele index inside its locus)
   for (int g = 0; g <= db->n_loci; g++) {
     LocusTiles& L = per[g];
     uint32_t base_id = (uint32_t)(db->tiles.size() / HLM_TILE_WORDS);
     db->tile_start[g] = base_id;
+    db->allele_names[g] = std::move(L.al_names);
+    for (size_t k = 0; k + 1 < L.al_tiles.size(); k += 2) tile_al.emplace_back(L.al_tiles[k + 1] + base_id, L.al_tiles[k]);
     db->tiles.insert(db->tiles.end(), L.tiles.begin(), L.tiles.end());
     for (uint32_t pr : L.parent) db->tile_parent.push_back(pr + base_id);
     db->tile_diff.insert(db->tile_diff.end(), L.diff.begin(), L.diff.end());
@@ -403,6 +419,15 @@ hlm_db* hlm_db_build(const char* dir, int rna, std::string& err) {
   }
   size_t n_tiles = db->tiles.size() / HLM_TILE_WORDS;
   db->tile_start[db->n_loci + 1] = (uint32_t)n_tiles;
+  // tile -> alleles that hold it (CSR; an allele is listed once per tile), for hlm_score_alleles
+  std::sort(tile_al.begin(), tile_al.end());
+  tile_al.erase(std::unique(tile_al.begin(), tile_al.end()), tile_al.end());
+  db->tile_al_off.assign(n_tiles + 1, 0);
+  for (auto& e : tile_al) db->tile_al_off[e.first + 1]++;
+  for (size_t t = 0; t < n_tiles; t++) db->tile_al_off[t + 1] += db->tile_al_off[t];
+  db->tile_al_ent.resize(tile_al.size());
+  for (size_t k = 0; k < tile_al.size(); k++) db->tile_al_ent[k] = tile_al[k].second;
+  tile_al = {};
   if (n_tiles >= (1u << 24)) {
     err = "too many distinct tiles for the 24-bit tile id";
     delete db;

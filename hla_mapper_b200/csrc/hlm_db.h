@@ -42,11 +42,16 @@ struct hlm_db {
   std::vector<uint32_t> child_diff;   // tile_diff of that child (parallel to child_ent)
   int64_t n_reps = 0;
 
+  // per-allele view (hlm_score_alleles): record names of every target set in file order, and the
+  // alleles that hold each tile (CSR over tiles; allele index inside its locus)
+  std::vector<std::vector<std::string>> allele_names;  // n_loci + 1
+  std::vector<uint32_t> tile_al_off, tile_al_ent;
+
   // device copies, one per CUDA device that has a context on this DB
   struct Dev {
     int device;
     HlmDevDB view;
-    void* ptrs[12];
+    void* ptrs[14];
     int refs;
   };
   std::vector<Dev> devs;

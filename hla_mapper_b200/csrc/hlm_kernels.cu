@@ -507,7 +507,10 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
         continue;
       }
       stage_bases(p, l, lane, ws, false);
-      if (!kp.rna) {
+      if (kp.allele_locus >= 0) {
+        // hlm_score_alleles: the whole mate against one target set, whatever its locus mask
+        write_unit(ck, pair * U + (kp.rna ? m * 3 : m), ws, lo, n, 1u << kp.allele_locus, lane);
+      } else if (!kp.rna) {
         // the compare step's tolerance for this mate, map_dna.cpp:948-958 (single end: the length
         // the reference holds for the read, preselect.cpp:1199)
         int len = (!kp.paired && ck.size_override1) ? ck.size_override1[pair] : n;
@@ -593,7 +596,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
     rd[lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + lane];
     if (lane < 4) rd[32 + lane] = ck.unit_planes[unit * HLM_UNIT_STRIDE + 32 + lane];
     __syncwarp();
-    int Q = hlm_seed_count(n), st = hlm_seed_stride(n);  // Q <= 15
+    int Q = hlm_seed_count(n, kp.rna), st = hlm_seed_stride(n, kp.rna);  // Q <= 15
     // lane (strand*16 + q) owns seed q of that strand (read offset q * st): CSR range of its
     // 12-mer narrowed to the entries whose column lies in [OFF_MIN + q st, OFF_MIN + 32 + q st)
     // (entries are sorted by column), i.e. to the windows in which read base 0 falls on a column
@@ -764,7 +767,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       // matches and none of its matching seeds covers a differing column (a covering seed is in
       // the seed index, which then emitted the candidate)
       uint32_t diff = __ldg(db.tile_diff + tile);
-      int Q = hlm_seed_count(n), st = hlm_seed_stride(n);
+      int Q = hlm_seed_count(n, kp.rna), st = hlm_seed_stride(n, kp.rna);
       // the seeds that cover a differing column (at most KMAX with non-overlapping seeds, two per
       // column with the overlapping seeds of short units) decide ownership; after them the first
       // matching seed settles "some seed matches": a few tests, not Q
@@ -864,7 +867,11 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         int64_t task = (int64_t)HLM_CAND_UNIT(c) * n_targets + g;
         uint32_t e0 = ck.task_emin0[task];
         int e0c = e0 > (uint32_t)kp.mm_max ? kp.mm_max : (int)e0;
-        if (!task_live(kp, ck, HLM_CAND_UNIT(c), g, n_targets)) {
+        if (round == 2) {
+          // per-allele scoring: every child that can hold a reportable alignment
+          thr_hi = kp.mm_max;
+          pass = lb - HLM_KMAX <= thr_hi;
+        } else if (!task_live(kp, ck, HLM_CAND_UNIT(c), g, n_targets)) {
           // capped scoring: nothing of this task can pass the tolerance
         } else if (round == 0) {
           thr_hi = e0c;
@@ -963,7 +970,12 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
       take[u] = false;
       if (live[u]) {
         int64_t task = (int64_t)HLM_CAND_UNIT(c[u]) * n_targets + g[u];
-        if (round == 0) {
+        if (round == 2) {
+          // per-allele scoring: every live candidate is aligned; its result stays with the candidate
+          take[u] = lb[u] > 0;
+          if (lb[u] == 0)
+            ck.cand_res[idx[u]] = HLM_BEST_PACK(0, (int)ck.unit_len[HLM_CAND_UNIT(c[u])], 0, 0);
+        } else if (round == 0) {
           take[u] = (lb[u] == (int)emin[u]);
           if (take[u] && lb[u] == 0) {
             // a zero bound is an exact match of the whole read on a band diagonal: the DP result
@@ -1095,6 +1107,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     int g = tile_locus(db, tile);
     atomicMin(&ck.task_best[(int64_t)unit * n_targets + g],
               (unsigned long long)HLM_BEST_PACK(a.cost, a.S, a.lead, a.trail));
+    if (ck.cand_res) ck.cand_res[di] = (unsigned long long)HLM_BEST_PACK(a.cost, a.S, a.lead, a.trail);
     cells += (unsigned long long)n * HLM_NB;
   }
   for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(FULL, cells, o);
@@ -1105,6 +1118,68 @@ __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ck.counters[1] = 0;
     ck.counters[14] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ per-allele scoring
+// hlm_score_alleles (what `bwa mem -a` against every allele of a gene
+// feeds functions.cpp:347-520).  Every candidate with a result hands it to the alleles that hold
+// its tile (tile_al CSR).  A rep also speaks for those of its children that were never
+// materialised: the ones without a differing column inside the DP footprint align exactly like it.
+// Warp per candidate, lanes over the allele lists; one atomicMin per (unit, allele) incidence.
+__global__ void __launch_bounds__(256)
+k_allele_scatter(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
+  int64_t ncand = (int64_t)ck.counters[0];
+  if (ncand > ck.cand_cap) ncand = ck.cand_cap;
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < ncand; i += nwarps) {
+    unsigned long long r = ck.cand_res[i];
+    if (r == HLM_BEST_NONE || HLM_BEST_COST(r) > kp.mm_max) continue;
+    uint64_t c = ck.cand[i];
+    uint32_t unit = HLM_CAND_UNIT(c), tile = HLM_CAND_TILE(c);
+    int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN;
+    int n = ck.unit_len[unit];
+    unsigned long long* row = ck.allele_best + (size_t)unit * ck.n_al;
+    uint32_t a = __ldg(db.tile_al_off + tile), b = __ldg(db.tile_al_off + tile + 1);
+    for (uint32_t k = a + lane; k < b; k += 32) atomicMin(&row[__ldg(db.tile_al_ent + k)], r);
+    uint32_t ca = __ldg(db.child_off + tile), cb = __ldg(db.child_off + tile + 1);
+    for (uint32_t k = ca; k < cb; k++) {  // (children lists are short next to the allele lists)
+      uint32_t diff = __ldg(db.child_diff + k);
+      bool inside = false;
+      for (int x = 0; x < HLM_DIFF_N(diff); x++) {
+        int col = HLM_DIFF_COL(diff, x);
+        if (col >= off - HLM_BAND && col < off + n + HLM_BAND) inside = true;
+      }
+      if (inside) continue;  // materialised on its own (seed index or expansion) when it is a candidate
+      uint32_t child = __ldg(db.child_ent + k);
+      uint32_t xa = __ldg(db.tile_al_off + child), xb = __ldg(db.tile_al_off + child + 1);
+      for (uint32_t q = xa + lane; q < xb; q += 32) atomicMin(&row[__ldg(db.tile_al_ent + q)], r);
+    }
+  }
+}
+
+// allele_best -> nm / clip bytes per (pair, allele); unit of mate m of a pair: pair * U + (rna ? 3 m : m)
+__global__ void __launch_bounds__(256)
+k_allele_out(HlmKParams kp, HlmChunk ck, uint8_t* nm1, uint8_t* clip1, uint8_t* nm2, uint8_t* clip2) {
+  int64_t total = ck.n_pairs * (int64_t)ck.n_al;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int U = ck.units_per_pair;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t pair = i / ck.n_al;
+    int a = (int)(i - pair * ck.n_al);
+    for (int m = 0; m < (kp.paired ? 2 : 1); m++) {
+      int64_t unit = pair * U + (kp.rna ? 3 * m : m);
+      unsigned long long r = ck.allele_best[(size_t)unit * ck.n_al + a];
+      uint8_t nm = 255, clip = 0;
+      if (r != HLM_BEST_NONE && HLM_BEST_COST(r) <= kp.mm_max) {
+        clip = (uint8_t)(HLM_BEST_LEAD(r) + HLM_BEST_TRAIL(r));
+        nm = (uint8_t)(HLM_BEST_COST(r) - (int)clip);
+      }
+      (m == 0 ? nm1 : nm2)[i] = nm;
+      (m == 0 ? clip1 : clip2)[i] = clip;
+    }
   }
 }
 
@@ -1473,7 +1548,7 @@ void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st) {
 void hlm_launch_expand(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st) {
   k_expand<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, round);
-  k_snapshot<<<1, 32, 0, st>>>(ck, 1 + round);
+  k_snapshot<<<1, 32, 0, st>>>(ck, round == 2 ? 1 : 1 + round);  // round 2 (per-allele): one expansion
 }
 void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st) {
@@ -1485,6 +1560,11 @@ void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck,
   k_dp_scatter<<<grid_for(sms, 4), 256, 0, st>>>(ck);
   k_dp<<<grid_for(sms, 4), 128, 0, st>>>(db, kp, ck, n_targets);
   k_dp_round_end<<<1, 32, 0, st>>>(ck);
+}
+void hlm_launch_allele_gather(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, uint8_t* nm1,
+                              uint8_t* clip1, uint8_t* nm2, uint8_t* clip2, int sms, cudaStream_t st) {
+  k_allele_scatter<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck);
+  k_allele_out<<<grid_for(sms, 8), 256, 0, st>>>(kp, ck, nm1, clip1, nm2, clip2);
 }
 void hlm_launch_scores(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
                        cudaStream_t st) {

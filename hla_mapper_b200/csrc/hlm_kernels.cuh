@@ -49,6 +49,10 @@ struct HlmChunk {
   uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
   uint32_t* task_pmin;   // capped scoring: minimum prefix bound (rows the trailing clip cannot reach)
   unsigned long long* task_best;
+  // per-allele scoring (hlm_score_alleles; null / 0 otherwise)
+  unsigned long long* cand_res;     // per candidate: packed alignment (HLM_BEST_PACK) or HLM_BEST_NONE
+  unsigned long long* allele_best;  // units * n_al: best packed alignment of the unit vs each allele
+  int n_al;
   // outputs
   uint16_t *s1, *s2;
   int16_t *aln1, *aln2;
@@ -61,6 +65,7 @@ struct HlmChunk {
 
 struct HlmKParams {
   int rna, paired, screen_variant, v_size, minhit, mm_max, clip_mode, skip_screen, score_cap;
+  int allele_locus;  // >= 0: per-allele scoring of this target set (hlm_score_alleles); -1 otherwise
   double tolerance;
   uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
   int n_loci;
@@ -82,6 +87,8 @@ void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk&
                        int round, int sms, cudaStream_t st);
 void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                    int sms, cudaStream_t st);
+void hlm_launch_allele_gather(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, uint8_t* nm1,
+                              uint8_t* clip1, uint8_t* nm2, uint8_t* clip2, int sms, cudaStream_t st);
 void hlm_launch_scores(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,
                        cudaStream_t st);
 void hlm_launch_assign(const HlmKParams& kp, const HlmChunk& ck, int n_targets, int sms,

@@ -37,14 +37,14 @@
 extern "C" {
 #endif
 
-#define HLM_ABI_VERSION 3
+#define HLM_ABI_VERSION 4
 
 /* limits of this build */
 #define HLM_MAX_LOCI 31   /* loci + "others" must fit a uint32 mask            */
 #define HLM_MAX_READ 184  /* longest trimmed mate the 256-column tiles can hold */
 #define HLM_MOTIF 20      /* motif_size, src/main.cpp:73                        */
 #define HLM_SEED 12       /* aligner seed length (new)           */
-#define HLM_SEED_SHORT 96 /* units shorter than this use overlapping seeds      */
+#define HLM_SEED_SHORT 96 /* rna: units shorter than this use overlapping seeds */
 #define HLM_SEED_STRIDE_SHORT 6
 #define HLM_BAND 20       /* DP half band = v_mm_max, src/main.cpp:77           */
 
@@ -215,6 +215,27 @@ int hlm_screen_trim(hlm_ctx* ctx, const hlm_batch* in, hlm_screen_out* out);
 int hlm_score(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, hlm_score_out* out);
 int hlm_assign(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr,
                const hlm_score_out* sc, hlm_assign_out* out);
+
+/* Per-allele scoring.  The reference's pseudo-typing step runs
+ * `bwa mem -a` of a gene's reads against a FASTA of all its alleles and reads one NM per
+ * (read, allele) from the SAM (src/functions.cpp:347-520: counterhits / error per allele at
+ * :394-404, nmdata[(allele, read)] at :544-545; rna twin :589-780).  This entry point returns
+ * that matrix from the aligner of DESIGN.md section 3 restricted to one allele at a time: for
+ * every kept pair, each mate and each record i of the locus' FASTA
+ * (mapper/<kind>/<g>/<g>.fas order; locus == n_loci: others), the best alignment over the seed
+ * candidates of that record, both strands - NM (mismatches + gap bases) and the clipped bases
+ * (lead + trail).  nm = 255: no alignment with cost <= mm_max.  Arrays are [n_pairs * n_alleles],
+ * pair-major; rows of pairs that were not kept are 255 / 0.  clip1 / clip2 may be NULL. */
+int hlm_db_n_alleles(const hlm_db* db, int locus);
+const char* hlm_db_allele_name(const hlm_db* db, int locus, int allele); /* FASTA header, first token */
+typedef struct hlm_allele_out {
+  int32_t n_alleles;      /* in: hlm_db_n_alleles(db, locus) - the row length of the arrays */
+  int32_t reserved0;
+  uint8_t *nm1, *clip1;
+  uint8_t *nm2, *clip2;   /* paired only */
+} hlm_allele_out;
+int hlm_score_alleles(hlm_ctx* ctx, const hlm_batch* in, const hlm_screen_out* scr, int locus,
+                      hlm_allele_out* out);
 
 /* fused screen -> score -> assign over the context's pinned, multi-buffered
  * stream pipeline.  Any of scr / sc / asg may be NULL (result not copied back). */

@@ -113,6 +113,7 @@ typedef struct {
   int64_t n_al;
   oseed* seeds; /* sorted: every 12-mer of every allele */
   int64_t n_seeds;
+  int rna; /* target set of an `rna` database: short units use overlapping seeds (collect_cands) */
 } olocus;
 struct orc_db {
   int rna, n_loci, v_size;
@@ -265,9 +266,11 @@ orc_db* orc_db_open(const char* dir, int rna, char* err, size_t errlen) {
     snprintf(path, sizeof path, "%s/mapper/%s/%s/%s.fas", dir, kind, db->loc[g].name,
              db->loc[g].name);
     load_fasta(&db->loc[g], path);
+    db->loc[g].rna = rna;
   }
   snprintf(path, sizeof path, "%s/others/%s/hla_gen_others.fasta", dir, kind);
   load_fasta(&db->loc[db->n_loci], path);
+  db->loc[db->n_loci].rna = rna;
   return db;
 }
 void orc_db_close(orc_db* db) {
@@ -503,11 +506,12 @@ static int cmp_cand(const void* a, const void* b) {
 }
 
 /* all (allele, diagonal) pairs where some seed matches the allele exactly.  Seeds (DESIGN.md
- * section 3): 12-mers at read offsets 0, st, 2 st, ... <= n - 12; st = 12 (non-overlapping) for
- * units of HLM_SEED_SHORT (96) bases or more, st = 6 (overlapping) for shorter ones */
+ * section 3): 12-mers at read offsets 0, st, 2 st, ... <= n - 12; st = 12 (non-overlapping), except
+ * for the units of an `rna` run shorter than HLM_SEED_SHORT (96) bases - the blocks STAR cuts a
+ * mate into - which use st = 6 (overlapping) */
 static int64_t collect_cands(const olocus* L, const uint8_t* r, int n, cand** buf, int64_t* cap) {
   int64_t nc = 0;
-  const int st = n < HLM_SEED_SHORT ? HLM_SEED_STRIDE_SHORT : KS;
+  const int st = (L->rna && n < HLM_SEED_SHORT) ? HLM_SEED_STRIDE_SHORT : KS;
   for (int rp = 0; rp + KS <= n; rp += st) {
     uint32_t code = 0;
     int bad = 0;
@@ -873,6 +877,70 @@ int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const 
   return toolong ? HLM_E_TOOLONG : 0;
 }
 
+/* Per-allele scoring (what `bwa mem -a` of a gene's reads against
+ * every allele feeds src/functions.cpp:347-520).  The aligner definition of DESIGN.md section 3
+ * restricted to ONE allele at a time: for every kept pair, mate and allele of the target set, the
+ * lexicographic minimum (cost, -S, lead, trail) over that allele's seed candidates, both strands.
+ * nm = 255: no candidate, or cost > mm_max.  Arrays [n_pairs * n_alleles], pair-major. */
+int orc_score_alleles(const orc_db* db, const hlm_params* p, const hlm_batch* in,
+                      const hlm_screen_out* scr, int locus, uint8_t* nm1, uint8_t* clip1, uint8_t* nm2,
+                      uint8_t* clip2, int nthreads) {
+  int64_t n = in->n_pairs;
+  const olocus* L = &db->loc[locus];
+  int64_t nA = L->n_al;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    scratch sc;
+    memset(&sc, 0, sizeof sc);
+    uint8_t codes[HLM_MAX_READ + 8], rc[HLM_MAX_READ + 8];
+    ares* best = (ares*)malloc((size_t)nA * sizeof(ares));
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; i++) {
+      for (int m = 0; m < (p->paired ? 2 : 1); m++) {
+        uint8_t* nm = m == 0 ? nm1 : nm2;
+        uint8_t* clip = m == 0 ? clip1 : clip2;
+        for (int64_t a = 0; a < nA; a++) {
+          nm[i * nA + a] = 255;
+          if (clip) clip[i * nA + a] = 0;
+        }
+        if (!(scr->flags[i] & HLM_F_KEPT)) continue;
+        const uint8_t* s = (m == 0 ? in->bases1 + in->offs1[i] + scr->trim_lo1[i]
+                                   : in->bases2 + in->offs2[i] + scr->trim_lo2[i]);
+        int len = m == 0 ? scr->trim_len1[i] : scr->trim_len2[i];
+        if (len > HLM_MAX_READ || len <= 0) continue;
+        to_codes(s, len, codes);
+        memset(best, 0, (size_t)nA * sizeof(ares));
+        for (int strand = 0; strand < 2; strand++) {
+          const uint8_t* q = codes;
+          if (strand) {
+            revcomp(codes, len, rc);
+            q = rc;
+          }
+          int64_t nc = collect_cands(L, q, len, &sc.buf, &sc.cap);
+          for (int64_t c = 0; c < nc; c++) {
+            const oseq* al = &L->al[sc.buf[c].allele];
+            ares x;
+            orc_align(q, len, al->codes, al->len, sc.buf[c].d, &x.S, &x.cost, &x.lead, &x.trail);
+            x.valid = 1;
+            if (ares_better(&x, &best[sc.buf[c].allele])) best[sc.buf[c].allele] = x;
+          }
+        }
+        for (int64_t a = 0; a < nA; a++)
+          if (best[a].valid && best[a].cost <= p->mm_max) {
+            nm[i * nA + a] = (uint8_t)(best[a].cost - best[a].lead - best[a].trail);
+            if (clip) clip[i * nA + a] = (uint8_t)(best[a].lead + best[a].trail);
+          }
+      }
+    }
+    free(best);
+    free(sc.buf);
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ compare / assign */
 /* dna: src/map_dna.cpp:903-1029; rna: src/map_rna.cpp:925-1027 */
 int orc_assign(const orc_db* db, const hlm_params* p, const hlm_batch* in, const hlm_screen_out* scr,
@@ -1133,12 +1201,17 @@ static void cache_store(const olocus* L, const char* fasta) {
 }
 orc_ref* orc_ref_open(const char* fasta) {
   orc_ref* r = (orc_ref*)calloc(1, sizeof(orc_ref));
-  if (cache_load(&r->L, fasta) == 0) return r;
-  if (load_fasta(&r->L, fasta) != 0) {
-    free(r);
-    return NULL;
+  /* the stand-in bwa only sees a FASTA path: the reference keeps the rna target sets under
+   * mapper/rna/ and others/rna/ (map_rna.cpp:833, :858) */
+  int rna = strstr(fasta, "/mapper/rna/") != NULL || strstr(fasta, "/others/rna/") != NULL;
+  if (cache_load(&r->L, fasta) != 0) {
+    if (load_fasta(&r->L, fasta) != 0) {
+      free(r);
+      return NULL;
+    }
+    cache_store(&r->L, fasta);
   }
-  cache_store(&r->L, fasta);
+  r->L.rna = rna;
   return r;
 }
 void orc_ref_close(orc_ref* r) {

@@ -54,6 +54,10 @@ int orc_screen_trim(const orc_db* db, const hlm_params* p, const hlm_batch* in, 
                     int nthreads);
 int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const hlm_screen_out* scr,
               hlm_score_out* out, int mode, int nthreads, int64_t* n_dp_cells);
+/* per-allele matrix of one target set (hlm_score_alleles): exhaustive definition */
+int orc_score_alleles(const orc_db* db, const hlm_params* p, const hlm_batch* in,
+                      const hlm_screen_out* scr, int locus, uint8_t* nm1, uint8_t* clip1, uint8_t* nm2,
+                      uint8_t* clip2, int nthreads);
 int orc_assign(const orc_db* db, const hlm_params* p, const hlm_batch* in, const hlm_screen_out* scr,
                const hlm_score_out* sc, hlm_assign_out* out);
 

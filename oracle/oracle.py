@@ -61,6 +61,8 @@ def lib():
         L.orc_assign.argtypes = [C.c_void_p, C.POINTER(_abi.HlmParams), C.POINTER(_abi.HlmBatch),
                                  C.POINTER(_abi.HlmScreenOut), C.POINTER(_abi.HlmScoreOut),
                                  C.POINTER(_abi.HlmAssignOut)]
+        L.orc_score_alleles.argtypes = [C.c_void_p, C.POINTER(_abi.HlmParams), C.POINTER(_abi.HlmBatch),
+                                        C.POINTER(_abi.HlmScreenOut), C.c_int] + [_abi.u8p] * 4 + [C.c_int]
         _lib = L
     return _lib
 
@@ -109,6 +111,18 @@ def run(db: OracleDB, params, rb, mode=1, nthreads=0, stages=("screen", "score",
                           C.byref(buf.asg))
         assert rc == 0
     return buf, cells.value
+
+
+def score_alleles(db: OracleDB, params, rb, buf, locus, nthreads=0, **kw):
+    """per-allele matrix of one target set: (nm1, clip1, nm2, clip2) uint8 [n_pairs, n_alleles]"""
+    L = lib()
+    batch = _abi.make_batch(rb, paired=bool(params.paired), **kw)
+    na = int(L.orc_db_n_alleles(db.h, int(locus)))
+    arrs = [np.zeros((rb.n_pairs, na), dtype=np.uint8) for _ in range(4)]
+    rc = L.orc_score_alleles(db.h, C.byref(params), C.byref(batch), C.byref(buf.scr), int(locus),
+                             *[a.ctypes.data_as(_abi.u8p) for a in arrs], nthreads)
+    assert rc == 0
+    return tuple(arrs)
 
 
 def mtrim(qual: bytes, err, v_size, slen=None):

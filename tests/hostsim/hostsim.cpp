@@ -108,7 +108,7 @@ int hs_db_candidates(void* p, const uint8_t* read, int n, int locus, uint32_t* o
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
   pack_read(read, n, rd);
-  int cnt = 0, Q = hlm_seed_count(n), st = hlm_seed_stride(n);
+  int cnt = 0, Q = hlm_seed_count(n, db->rna), st = hlm_seed_stride(n, db->rna);
   int n_index = 0;
   for (int q = 0; q < Q; q++) {
     uint32_t code;
@@ -163,7 +163,7 @@ int hs_db_candidates_brute(void* p, const uint8_t* read, int n, int locus, uint3
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
   pack_read(read, n, rd);
-  int cnt = 0, Q = hlm_seed_count(n), st = hlm_seed_stride(n);
+  int cnt = 0, Q = hlm_seed_count(n, db->rna), st = hlm_seed_stride(n, db->rna);
   for (uint32_t tile = db->tile_start[locus]; tile < db->tile_start[locus + 1]; tile++)
     for (int off = HLM_OFF_MIN; off < HLM_OFF_MIN + HLM_TILE_STRIDE; off++) {
       bool any = false;

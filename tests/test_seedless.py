@@ -7,8 +7,10 @@ can hold an alignment of cost <= mm_max gets the affine DP (oracle/hlm_oracle.c 
 Guarantee checked here: an alignment whose cost e (mismatches + gap bases + clipped bases) is
 below G(n) leaves at least one seed untouched, so the seed candidates contain a diagonal whose
 band holds it:
-    n >= 96 (seeds at stride 12):  G = floor(n / 12)               (one cost unit kills <= 1 seed)
-    n <  96 (seeds at stride 6):   G = ceil(Q / 2), Q = (n-12)//6+1 (one cost unit kills <= 2 seeds)
+    seeds at stride 12 (dna; rna units of 96+ bases):  G = floor(n / 12)   (one cost unit kills <= 1 seed)
+    seeds at stride 6 (rna units shorter than 96):     G = max(floor(n / 12), ceil(Q / 2)), Q = (n-12)//6+1
+                                                       (the stride-12 seeds are a subset; one cost unit
+                                                       kills <= 2 of the overlapping seeds)
 Below G the seeded result must EQUAL the seedless one; at and above G the miss rate is printed."""
 import numpy as np
 import pytest
@@ -16,13 +18,13 @@ import pytest
 from hla_mapper_b200 import _abi, synth
 
 
-def guarantee(n):
+def guarantee(n, rna=False):
     if n < 12:
         return 0
-    if n >= 96:
+    if n >= 96 or not rna:
         return n // 12
     q = (n - 12) // 6 + 1
-    return (q + 1) // 2
+    return max(n // 12, (q + 1) // 2)
 
 
 def noisy_reads(db, n_pairs, read_len, seed, rates=(0.0, 0.03, 0.07, 0.12)):
@@ -40,12 +42,12 @@ def noisy_reads(db, n_pairs, read_len, seed, rates=(0.0, 0.03, 0.07, 0.12)):
     return rb
 
 
-def compare(want, got, T, label):
+def compare(want, got, T, label, rna=False):
     """want = seedless, got = seed candidates; scores are cost + 1 (clip_mode = both)"""
     below = above = miss_above = 0
     for s_w, s_g, lens in ((want.s1, got.s1, want.trim_len1), (want.s2, got.s2, want.trim_len2)):
         for i in range(s_w.shape[0]):
-            g_n = guarantee(int(lens[i]))
+            g_n = guarantee(int(lens[i]), rna)
             for t in range(T):
                 w, g = int(s_w[i, t]), int(s_g[i, t])
                 if w == 0:
@@ -124,7 +126,7 @@ def test_rna_short_blocks_below_the_guarantee(orc, tmp_path, split):
         if l1 <= split or l2 <= split:
             continue
         # (a block shorter than 12 bases has no seed and no guarantee: G = 0)
-        g_min = min(guarantee(split), guarantee(l1 - split), guarantee(l2 - split))
+        g_min = min(guarantee(split, True), guarantee(l1 - split, True), guarantee(l2 - split, True))
         for t in range(T):
             w, g = int(want.s1[i, t]), int(got.s1[i, t])
             assert g >= w
