@@ -78,7 +78,8 @@ class HlmProfile(C.Structure):
 
 class HlmFileOpts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("downsampling", C.c_int32), ("batch_pairs", C.c_int32),
-                ("write_selected", C.c_int32), ("select_only", C.c_int32)]
+                ("write_selected", C.c_int32), ("select_only", C.c_int32), ("threads", C.c_int32),
+                ("star_cmd", C.c_char_p)]
 
 
 class HlmFileStats(C.Structure):

@@ -262,10 +262,10 @@ class Mapper:
         lib().hlm_batch_free(self.h, dev_batch)
 
     def map_fastq(self, r1, r2, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1,
-                  select_only=0):
+                  select_only=0, threads=0, star_cmd=None):
         """hlm_map_fastq: FASTQ(.gz) in, the reference's files around the hot path out"""
         o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
-                             select_only)
+                             select_only, threads, str(star_cmd).encode() if star_cmd else None)
         st = _abi.HlmFileStats()
         self._check(lib().hlm_map_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None,
                                         sample.encode(), str(out_dir).encode(), C.byref(o),
@@ -276,7 +276,7 @@ class Mapper:
                   write_selected=1, select_only=0):
         """hlm_map_reads: reads extracted from a BAM in, the same files as map_fastq out"""
         o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
-                             select_only)
+                             select_only, 0, None)
         st = _abi.HlmFileStats()
         self._check(lib().hlm_map_reads(self.h, reads.h, sample.encode(), str(out_dir).encode(),
                                         C.byref(o), C.byref(st)))

@@ -8,6 +8,10 @@
 //   hla-mapper-b200 dna    r0=R0.fastq[.gz] sample=NAME ...
 //   hla-mapper-b200 dna    bam=ALIGNED.bam sample=NAME [--skip-unmapped] ...   (no samtools needed)
 //   hla-mapper-b200 select ...           (screen + trim only: selected*.fastq)
+//   hla-mapper-b200 rna    r1=... r2=... sample=NAME [star=STAR] ...   (src/map_rna.cpp: screen, trim,
+//                          per-gene sort, STAR per gene, block scoring, compare; star defaults to the
+//                          `star=` line of ~/.hla-mapper; star=none: the *_splice_Aligned.out.sam
+//                          files are already in the output directory)
 //
 // Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= threads= --quiet
 // --skip-unmapped (threads= sizes the BAM reader only; buffer= is accepted and ignored).
@@ -26,27 +30,30 @@
 
 static bool starts(const std::string& s, const char* k) { return s.compare(0, strlen(k), k) == 0; }
 
-static std::string config_db() {
+static std::string config_value(const char* key) {
   struct passwd* pw = getpwuid(getuid());
   if (!pw) return "";
   std::ifstream f(std::string(pw->pw_dir) + "/.hla-mapper");
   for (std::string line; std::getline(f, line);)
-    if (starts(line, "db=")) return line.substr(3);
+    if (starts(line, key)) return line.substr(strlen(key));
   return "";
 }
+static std::string config_db() { return config_value("db="); }
 
 int main(int argc, char** argv) {
-  if (argc < 2 || (strcmp(argv[1], "dna") != 0 && strcmp(argv[1], "select") != 0)) {
+  if (argc < 2 || (strcmp(argv[1], "dna") != 0 && strcmp(argv[1], "select") != 0 && strcmp(argv[1], "rna") != 0)) {
     fprintf(stderr,
             "Usage:     hla-mapper-b200 dna r1=R1.gz r2=R2.gz sample=your_sample_name <options>\n"
             "           hla-mapper-b200 dna r0=R0.gz sample=your_sample_name <options>\n"
             "           hla-mapper-b200 dna bam=sample.bam sample=your_sample_name <options>\n"
             "           hla-mapper-b200 select r1=... r2=... sample=... <options>\n"
+            "           hla-mapper-b200 rna r1=R1.gz r2=R2.gz sample=your_sample_name [star=STAR] <options>\n"
             "Options:   db= output= size= tolerance= error= downsample= gpu= threads= --quiet --skip-unmapped\n");
     return 1;
   }
   bool select_only = strcmp(argv[1], "select") == 0, quiet = false;
-  std::string r0, r1, r2, bam, sample, db, output;
+  const int rna = strcmp(argv[1], "rna") == 0 ? 1 : 0;
+  std::string r0, r1, r2, bam, sample, db, output, star;
   double tolerance = -1, error = -1;
   int size = 0, downsample = 30, gpu = 0, threads = 0, skip_unmapped = 0;
   for (int i = 2; i < argc; i++) {
@@ -66,6 +73,7 @@ int main(int argc, char** argv) {
     else if (a == "--skip-unmapped") skip_unmapped = 1;  // src/main.cpp:626-630
     else if (starts(a, "threads=")) threads = atoi(a.c_str() + 8);
     else if (starts(a, "bam=")) bam = a.substr(4);
+    else if (starts(a, "star=")) star = a.substr(5);
     else if (starts(a, "buffer=") || starts(a, "--")) continue;
   }
   bool paired = r0.empty();
@@ -85,7 +93,13 @@ int main(int argc, char** argv) {
   }
   mkdir(output.c_str(), 0777);
   char err[512];
-  hlm_db* D = hlm_db_open(db.c_str(), 0, err, sizeof err);
+  if (rna && !bam.empty()) {
+    fprintf(stderr, "rna: bam= input is not supported by this front end; pass r1= r2= (or r0=)\n");
+    return 2;
+  }
+  if (rna && star.empty()) star = config_value("star=");
+  if (star == "none") star.clear();
+  hlm_db* D = hlm_db_open(db.c_str(), rna, err, sizeof err);
   if (!D) {
     fprintf(stderr, "%s\n", err);
     return 3;
@@ -108,7 +122,7 @@ int main(int argc, char** argv) {
               (long long)bs.n_unmapped, (long long)bs.n_names, (long long)bs.n_out, paired ? "pairs" : "reads");
   }
   hlm_params p;
-  hlm_params_default(&p, 0);
+  hlm_params_default(&p, rna);
   p.paired = paired ? 1 : 0;
   if (R) p.screen_variant = HLM_SCREEN_BAM;
   if (size > 0) p.v_size = size;
@@ -127,6 +141,8 @@ int main(int argc, char** argv) {
   fo.downsampling = downsample;
   fo.write_selected = 1;
   fo.select_only = select_only ? 1 : 0;
+  fo.threads = threads;
+  fo.star_cmd = star.empty() ? nullptr : star.c_str();
   hlm_file_stats st;
   int rc = R ? hlm_map_reads(C, R, sample.c_str(), output.c_str(), &fo, &st)
              : hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);

@@ -21,6 +21,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -309,13 +310,18 @@ struct Kept {
 struct Out {
   FILE* f = nullptr;
   std::string buf;
+  bool bad = false;  // open, a short write or the close failed (ENOSPC, permissions ...)
+  bool used = false;
   bool open(const std::string& p) {
     f = fopen(p.c_str(), "wb");
     buf.reserve(1 << 22);
+    used = true;
+    if (!f) bad = true;
     return f != nullptr;
   }
+  bool failed() const { return used && bad; }
   void flush() {
-    if (f && !buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+    if (f && !buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) bad = true;
     buf.clear();
   }
   void add(const std::string& s) { add(s.data(), s.size()); }
@@ -329,7 +335,7 @@ struct Out {
   }
   void close() {
     flush();
-    if (f) fclose(f);
+    if (f && fclose(f) != 0) bad = true;
     f = nullptr;
   }
 };
@@ -380,6 +386,327 @@ struct Results {
 extern "C" int hlm_screen_trim(hlm_ctx*, const hlm_batch*, hlm_screen_out*);
 extern "C" int hlm_run_async(hlm_ctx*, const hlm_batch*, hlm_screen_out*, hlm_score_out*, hlm_assign_out*);
 extern "C" int hlm_wait(hlm_ctx*);
+extern "C" int hlm_get_profile(const hlm_ctx*, hlm_profile*);
+
+extern "C" int hlm_score(hlm_ctx*, const hlm_batch*, const hlm_screen_out*, hlm_score_out*);
+extern "C" int hlm_assign(hlm_ctx*, const hlm_batch*, const hlm_screen_out*, const hlm_score_out*,
+                          hlm_assign_out*);
+
+namespace {
+
+// ---- rna: STAR between the screen and the scorer (src/map_rna.cpp:648-801) -------------------
+// STAR's per-gene options, src/map_rna.cpp:676-722
+struct StarOpt {
+  const char *mnmax, *readLmax, *mismatchN, *seed;
+};
+StarOpt star_options(const std::string& g) {
+  StarOpt o{"70", "1", "999", "60"};
+  if (g == "HLA-G" || g == "HLA-E" || g == "HLA-F") o = {"30", "0.1", "999", "50"};
+  if (g == "HLA-DMA" || g == "HLA-DMB" || g == "HLA-DOA") o = {"30", "0.1", "10", "50"};
+  if (g == "HLA-DOB" || g == "MICA" || g == "MICB") o = {"30", "0.1", "10", "50"};
+  if (g == "TAP1" || g == "TAP2" || g == "HLA-H") o = {"50", "0.1", "999", "50"};
+  if (g == "HLA-DRA" || g == "HLA-DPA1") o = {"50", "0.1", "999", "50"};
+  return o;
+}
+
+// The (start, size) ranges of SEQ that src/map_rna.cpp:748-787 writes to sorted_spliced_<gene>.fastq
+// for one SAM record: the CIGAR is cut after every N; a piece's size is the sum of its operation
+// lengths except N and D (S, H, I, M, P, X count); piece k starts at the SIZE of piece k-1 (`start =
+// read_size`, :784 - not cumulative), piece 0 at 0.  A CIGAR without N: the whole SEQ.
+void star_record_pieces(const char* cig, size_t cl, size_t seq_len, std::vector<std::pair<int, int>>& out) {
+  out.clear();
+  if (!memchr(cig, 'N', cl)) {
+    out.emplace_back(0, (int)seq_len);
+    return;
+  }
+  int start = 0;
+  size_t p = 0;
+  while (p < cl) {
+    const char* e = (const char*)memchr(cig + p, 'N', cl - p);
+    size_t end = e ? (size_t)(e - cig) + 1 : cl;
+    int read_size = 0;
+    size_t q = p;
+    while (q < end) {  // splitcigar(): a token ends with one of S H M D I N P X
+      size_t t = q;
+      while (t < end && !strchr("SHMDINPX", cig[t])) t++;
+      if (t >= end) break;  // trailing characters without an operation: an unsplit token, no type
+      int v = 0;            // stoi(): the leading digits of the token
+      for (size_t x = q; x < t && cig[x] >= '0' && cig[x] <= '9'; x++) v = v * 10 + (cig[x] - '0');
+      if (cig[t] != 'N' && cig[t] != 'D') read_size += v;
+      q = t + 1;
+    }
+    out.emplace_back(start, read_size);
+    start = read_size;
+    p = end;
+  }
+}
+
+struct RnaBlocks {
+  std::vector<std::vector<hlm_rna_block>> of;  // per kept read
+};
+
+// <pre><gene>_splice_Aligned.out.sam -> blocks of the kept reads + sorted_spliced_<gene>.fastq
+int read_star_sam(const std::string& sam_path, const std::string& spliced_path, int gene,
+                  const std::vector<Kept>& kept, RnaBlocks& rb, std::mutex& mu, std::string& err) {
+  HlmMapped map;
+  Out sp;
+  if (!sp.open(spliced_path)) {
+    err = "cannot write " + spliced_path;
+    return HLM_E_IO;
+  }
+  if (!map.open(sam_path.c_str())) {  // no SAM (STAR wrote nothing): no records for this gene
+    sp.close();
+    return sp.failed() ? HLM_E_IO : 0;
+  }
+  const char* base = (const char*)map.p;
+  size_t n = map.n, p = 0;
+  std::vector<std::pair<int, int>> pieces;
+  std::vector<std::pair<int64_t, hlm_rna_block>> found;
+  char num[32];
+  while (p < n) {
+    const char* nl = (const char*)memchr(base + p, '\n', n - p);
+    size_t e = nl ? (size_t)(nl - base) : n;
+    size_t ls = p;
+    p = e + 1;
+    if (e == ls || base[ls] == '@') continue;
+    // the first eleven tab-separated fields
+    const char* f[12];
+    size_t fl[12];
+    int nf = 0;
+    size_t a = ls;
+    while (nf < 11 && a <= e) {
+      const char* t = (const char*)memchr(base + a, '\t', e - a);
+      size_t b = t ? (size_t)(t - base) : e;
+      f[nf] = base + a;
+      fl[nf] = b - a;
+      nf++;
+      a = b + 1;
+    }
+    if (nf < 11) continue;
+    int flag = atoi(std::string(f[1], fl[1]).c_str());
+    size_t L = fl[9];
+    star_record_pieces(f[5], fl[5], L, pieces);
+    // which kept read: QNAME is the id (first header token, /1 /2 removed)
+    int64_t lo = 0, hi = (int64_t)kept.size();
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      const Kept& k = kept[mid];
+      int c = memcmp(k.idgen, f[0], std::min<size_t>(k.idl, fl[0]));
+      if (c < 0 || (c == 0 && k.idl < fl[0])) lo = mid + 1;
+      else hi = mid;
+    }
+    bool known = lo < (int64_t)kept.size() && kept[lo].idl == fl[0] && memcmp(kept[lo].idgen, f[0], fl[0]) == 0;
+    // Which mate, and in which orientation, SEQ is: by content (SEQ is the trimmed mate as STAR
+    // read it from sorted_<gene>_R*.fastq, or its reverse complement); the FLAG bits 0x80 / 0x10
+    // only break ties and stand in when the content matches neither (clipped / edited SEQ)
+    int mate = (flag & 0x80) ? 1 : 0;
+    bool rev = (flag & 0x10) != 0;
+    if (known) {
+      const Kept& k = kept[lo];
+      auto same = [&](const char* m, size_t ml, bool rc) {
+        if (ml != L) return false;
+        if (!rc) return memcmp(m, f[9], L) == 0;
+        for (size_t x = 0; x < L; x++) {
+          char c = m[L - 1 - x], w;
+          switch (c) {
+            case 'A': w = 'T'; break; case 'C': w = 'G'; break; case 'G': w = 'C'; break; case 'T': w = 'A'; break;
+            case 'a': w = 't'; break; case 'c': w = 'g'; break; case 'g': w = 'c'; break; case 't': w = 'a'; break;
+            default: w = c;
+          }
+          if (w != f[9][x]) return false;
+        }
+        return true;
+      };
+      const char* ms[2] = {k.s1 + k.lo1, k.s2 ? k.s2 + k.lo2 : nullptr};
+      size_t ml[2] = {k.n1, k.n2};
+      bool done = false;
+      for (int pass = 0; pass < 4 && !done; pass++) {
+        int m = (pass & 1) ? 1 - mate : mate;
+        bool r = (pass & 2) ? !rev : rev;
+        if (ms[m] && same(ms[m], ml[m], r)) {
+          mate = m;
+          rev = r;
+          done = true;
+        }
+      }
+    }
+    int blk = 1;
+    for (auto& pc : pieces) {
+      size_t st = std::min<size_t>((size_t)pc.first, L), en = std::min<size_t>((size_t)pc.first + (size_t)pc.second, L);
+      sp.add("@", 1); sp.add(f[0], fl[0]); sp.add("$", 1); sp.add(f[1], fl[1]);
+      int m = snprintf(num, sizeof num, "$%d\n", blk++);
+      sp.add(num, m);
+      sp.add(f[9] + st, en - st); sp.add("\n+\n", 3);
+      size_t qs = std::min<size_t>(st, fl[10]), qe = std::min<size_t>(en, fl[10]);
+      sp.add(f[10] + qs, qe - qs); sp.add("\n", 1);
+      if (!known) continue;
+      hlm_rna_block b;
+      b.gene = (uint8_t)gene;
+      b.mate = (uint8_t)mate;
+      // a record STAR printed reverse-complemented covers [L - en, L - st) of the mate itself
+      b.start = (uint16_t)(rev ? L - en : st);
+      b.len = (uint16_t)(en - st);
+      b.reserved = 0;
+      found.emplace_back(lo, b);
+    }
+  }
+  sp.close();
+  if (sp.failed()) {
+    err = "write error on " + spliced_path;
+    return HLM_E_IO;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  for (auto& fb : found) rb.of[fb.first].push_back(fb.second);
+  return 0;
+}
+
+std::string shq(const std::string& s) {  // single-quoted for sh
+  std::string o = "'";
+  for (char c : s) {
+    if (c == '\'') o += "'\\''";
+    else o += c;
+  }
+  return o + "'";
+}
+
+// the second half of `hla-mapper rna` for the kept reads (already sorted by id): per-gene sorted
+// FASTQs -> STAR (when a command is given) -> block lists -> hlm_score + hlm_assign
+int rna_score_kept(hlm_ctx* ctx, const hlm_db* db, const hlm_file_opts& o, const std::string& pre, bool paired,
+                   std::vector<Kept>& kept) {
+  const char* tag = paired ? "R1" : "R0";
+  int G = db->n_loci, T = G + 1;
+  int nt = o.threads > 0 ? o.threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  nt = std::max(1, std::min(nt, G));
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  RnaBlocks rb;
+  rb.of.resize(kept.size());
+  std::mutex mu;
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int w = 0; w < nt; w++)
+    th.emplace_back([&] {
+      for (int g; (g = next.fetch_add(1)) < G;) {
+        try {
+          const std::string& gene = db->names[g];
+          std::string in1 = pre + "sorted_" + gene + "_" + tag + ".fastq", in2 = pre + "sorted_" + gene + "_R2.fastq";
+          // ---- sorted_<gene>_R*.fastq (src/map_rna.cpp:544-636): the trimmed records of every
+          // kept read that holds a 20-mer of the gene
+          Out s1, s2;
+          if (!s1.open(in1) || (paired && !s2.open(in2))) {
+            rcs[g] = HLM_E_IO;
+            errs[g] = "cannot write " + in1;
+            continue;
+          }
+          for (const Kept& k : kept) {
+            if (!((k.locus_mask >> g) & 1u)) continue;
+            s1.add(k.h1, k.h1l); s1.add("\n", 1); s1.add(k.s1 + k.lo1, k.n1); s1.add("\n+\n", 3);
+            s1.fill('A', k.n1); s1.add("\n", 1);
+            if (paired) {
+              s2.add(k.h2, k.h2l); s2.add("\n", 1); s2.add(k.s2 + k.lo2, k.n2); s2.add("\n+\n", 3);
+              s2.fill('A', k.n2); s2.add("\n", 1);
+            }
+          }
+          s1.close();
+          s2.close();
+          if (s1.failed() || s2.failed()) {
+            rcs[g] = HLM_E_IO;
+            errs[g] = "write error on " + in1;
+            continue;
+          }
+          // ---- STAR, one run per gene with the reference's arguments (src/map_rna.cpp:724-733)
+          if (o.star_cmd && o.star_cmd[0]) {
+            StarOpt so = star_options(gene);
+            std::string sub(pre.begin() + (pre.rfind('/') + 1), pre.end() - 1);  // the sample name
+            std::string prefix = pre + gene + (paired ? "_splice_" : "_");
+            std::string cmd = std::string(o.star_cmd) + " --runThreadN 1 --genomeDir " +
+                              shq(db->dir + "/reference/rna/loci/" + gene + "/") + " --readFilesIn " + shq(in1) +
+                              (paired ? " " + shq(in2) : std::string()) + " --outFileNamePrefix " + shq(prefix) +
+                              " --seedPerWindowNmax " + so.seed + " --outFilterMismatchNmax " + so.mismatchN +
+                              " --outFilterMultimapNmax " + so.mnmax + " --outFilterMismatchNoverReadLmax " +
+                              so.readLmax +
+                              " --outSAMunmapped Within --scoreDelOpen -1 --scoreDelBase -1 --scoreInsOpen -1"
+                              " --scoreInsBase -1 --outSAMattrRGline ID:" + sub + " LB:" + sub + " SM:" + sub +
+                              " > " + shq(pre + gene + ".splice.log") + " 2>&1";
+            int sr = system(cmd.c_str());
+            if (sr != 0) {
+              rcs[g] = HLM_E_IO;
+              errs[g] = "STAR failed for " + gene + " (see " + pre + gene + ".splice.log)";
+              continue;
+            }
+          }
+          // ---- its SAM -> sorted_spliced_<gene>.fastq + the block list (src/map_rna.cpp:735-793;
+          // the reference opens <gene>_splice_Aligned.out.sam for single-end runs too)
+          rcs[g] = read_star_sam(pre + gene + "_splice_Aligned.out.sam", pre + "sorted_spliced_" + gene + ".fastq", g,
+                                 kept, rb, mu, errs[g]);
+        } catch (const std::exception& e) {
+          rcs[g] = HLM_E_NOMEM;
+          errs[g] = e.what();
+        }
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < G; g++)
+    if (rcs[g]) {
+      hlm_ctx_set_error(ctx, errs[g]);
+      return rcs[g];
+    }
+  // ---- score + assign from memory, in chunks of kept reads
+  const int64_t CH = 1 << 18;
+  std::vector<uint8_t> b1, b2, flags;
+  std::vector<uint64_t> o1, o2, boff;
+  std::vector<uint16_t> lo1, n1, lo2, n2, s1, ms, os1, os2;
+  std::vector<uint32_t> lm, tg, vis;
+  std::vector<hlm_rna_block> blocks;
+  for (int64_t a = 0; a < (int64_t)kept.size(); a += CH) {
+    int64_t b = std::min<int64_t>((int64_t)kept.size(), a + CH), n = b - a;
+    b1.clear(); b2.clear(); blocks.clear();
+    o1.assign(1, 0); o2.assign(1, 0); boff.assign(1, 0);
+    flags.assign(n, HLM_F_SCREENED | HLM_F_KEPT);
+    lo1.resize(n); n1.resize(n); lo2.resize(n); n2.resize(n); lm.resize(n);
+    for (int64_t i = a; i < b; i++) {
+      const Kept& k = kept[i];
+      b1.insert(b1.end(), (const uint8_t*)k.s1, (const uint8_t*)k.s1 + k.l1);
+      o1.push_back(b1.size());
+      if (paired) {
+        b2.insert(b2.end(), (const uint8_t*)k.s2, (const uint8_t*)k.s2 + k.l2);
+        o2.push_back(b2.size());
+      }
+      lo1[i - a] = k.lo1; n1[i - a] = k.n1; lo2[i - a] = k.lo2; n2[i - a] = k.n2; lm[i - a] = k.locus_mask;
+      blocks.insert(blocks.end(), rb.of[i].begin(), rb.of[i].end());
+      boff.push_back(blocks.size());
+    }
+    if (blocks.empty()) blocks.resize(1);  // a valid pointer for an empty list
+    hlm_batch hb;
+    memset(&hb, 0, sizeof hb);
+    hb.n_pairs = n;
+    hb.bases1 = b1.data(); hb.offs1 = o1.data();
+    if (paired) { hb.bases2 = b2.data(); hb.offs2 = o2.data(); }
+    hb.rna_block_off = boff.data();
+    hb.rna_blocks = blocks.data();
+    hlm_screen_out scr = {flags.data(), lo1.data(), n1.data(), lo2.data(), n2.data(), lm.data()};
+    s1.assign((size_t)n * T, 0);
+    tg.resize(n); vis.resize(n); ms.resize(n); os1.resize(n); os2.resize(n);
+    hlm_score_out sc;
+    memset(&sc, 0, sizeof sc);
+    sc.s1 = s1.data();
+    hlm_assign_out as = {tg.data(), vis.data(), ms.data(), os1.data(), os2.data()};
+    int rc = hlm_score(ctx, &hb, &scr, &sc);
+    if (rc == 0) rc = hlm_assign(ctx, &hb, &scr, &sc, &as);
+    if (rc) return rc;
+    for (int64_t i = a; i < b; i++) {
+      Kept& k = kept[i];
+      memcpy(const_cast<uint16_t*>(k.sc1), s1.data() + (size_t)(i - a) * T, 2 * (size_t)T);
+      k.target = tg[i - a];
+      k.visible = vis[i - a];
+      k.os1 = os1[i - a];
+      k.os2 = os2[i - a];
+    }
+  }
+  return 0;
+}
+
+}  // namespace
 
 extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
                              const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
@@ -408,11 +735,11 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
                    const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
   const hlm_db* db = hlm_ctx_db(ctx);
   const hlm_params* P = hlm_ctx_params(ctx);
-  if (P->rna) {
-    hlm_ctx_set_error(ctx, "the file pipeline drives the dna path; rna needs the STAR block split as input");
-    return HLM_E_ARG;
-  }
   bool paired = P->paired != 0;
+  // rna (src/map_rna.cpp): the scoring step consumes what STAR made of the per-gene sorted reads,
+  // so the reads are screened + trimmed first, STAR runs per gene between the two halves, and the
+  // kept reads are scored from memory afterwards (rna_score_kept below)
+  const bool rna = P->rna != 0;
   hlm_file_opts o;
   memset(&o, 0, sizeof o);
   o.struct_size = (int32_t)sizeof o;
@@ -518,9 +845,17 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
       P.n_selected = P.sel_bases = 0;
     }
     std::vector<std::thread> th;
+    std::atomic<bool> oom(false);
     for (int w = 0; w < n_workers; w++)
-      th.emplace_back([&, w] { collect_slice(R, n * w / n_workers, n * (w + 1) / n_workers, arenas[w], parts[w]); });
+      th.emplace_back([&, w] {
+        try {
+          collect_slice(R, n * w / n_workers, n * (w + 1) / n_workers, arenas[w], parts[w]);
+        } catch (const std::exception&) {  // bad_alloc in a worker must not reach std::terminate
+          oom = true;
+        }
+      });
     for (auto& t : th) t.join();
+    if (oom) throw std::bad_alloc();
     for (Part& P : parts) {
       sel1.add(P.sel1);
       sel2.add(P.sel2);
@@ -545,9 +880,9 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
     if (rc) hlm_ctx_set_error(ctx, src_err);
     t_wait += now_s() - t0;
     if (inflight) {  // finish the previous batch on the GPU
-      t0 = now_s();
       int r2 = hlm_wait(ctx);
-      t_gpu += now_s() - t0;
+      hlm_profile pr;
+      if (hlm_get_profile(ctx, &pr) == 0) t_gpu += pr.ms_total * 1e-3;  // device time of the batch
       inflight = false;
       if (rc == 0) rc = r2;
     }
@@ -555,7 +890,7 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
     bool have_prev = res[prev].b1 != nullptr;
     if (!end && rc == 0) {
       res[cur].bind(b1, b2, T, paired);
-      if (o.select_only) {  // `hla-mapper select`: main_preselect() only
+      if (o.select_only || rna) {  // `hla-mapper select`: main_preselect() only; rna: scored later
         double tg = now_s();
         rc = hlm_screen_trim(ctx, &res[cur].hb, &res[cur].scr);
         t_gpu += now_s() - tg;
@@ -579,6 +914,10 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
   sel1.close();
   sel2.close();
   if (rc) return rc;
+  if (sel1.failed() || sel2.failed()) {
+    hlm_ctx_set_error(ctx, "cannot write " + pre + "selected.*.fastq");
+    return HLM_E_IO;
+  }
 
   double t0 = now_s();
   // std::map<string, ...> order of the reference (byte-wise on the id)
@@ -586,10 +925,37 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
     int c = memcmp(a.idgen, b.idgen, std::min(a.idl, b.idl));
     return c < 0 || (c == 0 && a.idl < b.idl);
   });
-  // the groups of output files are independent: write them on separate host threads
+  if (rna && !o.select_only) {
+    double tg = now_s();
+    rc = rna_score_kept(ctx, db, o, pre, paired, kept);
+    t_gpu += now_s() - tg;
+    if (rc) return rc;
+  }
+  // the groups of output files are independent: write them on separate host threads.  A failed
+  // open / write / close (ENOSPC, permissions) or an exception inside a writer ends the run with
+  // HLM_E_IO / HLM_E_NOMEM instead of leaving truncated files behind a success code.
   std::vector<std::thread> writers;
+  std::mutex werr_mu;
+  int werr = 0;
+  std::string werr_msg;
+  auto wfail = [&](int code, const std::string& m) {
+    std::lock_guard<std::mutex> g(werr_mu);
+    if (!werr) {
+      werr = code;
+      werr_msg = m;
+    }
+  };
+  auto guarded = [&](auto&& body) {
+    return [&, body]() {
+      try {
+        body();
+      } catch (const std::exception& e) {
+        wfail(HLM_E_NOMEM, std::string("output writer: ") + e.what());
+      }
+    };
+  };
   // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
-  writers.emplace_back([&] {
+  writers.emplace_back(guarded([&] {
     Out t1;
     t1.open(pre + "selected.trim." + tag + ".fastq");
     for (const Kept& k : kept) {
@@ -597,8 +963,9 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
       t1.fill('A', k.n1); t1.add("\n", 1);
     }
     t1.close();
-  });
-  if (paired) writers.emplace_back([&] {
+    if (t1.failed()) wfail(HLM_E_IO, "cannot write " + pre + "selected.trim." + tag + ".fastq");
+  }));
+  if (paired) writers.emplace_back(guarded([&] {
     Out t2;
     t2.open(pre + "selected.trim.R2.fastq");
     for (const Kept& k : kept) {
@@ -606,10 +973,11 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
       t2.fill('A', k.n2); t2.add("\n", 1);
     }
     t2.close();
-  });
+    if (t2.failed()) wfail(HLM_E_IO, "cannot write " + pre + "selected.trim.R2.fastq");
+  }));
   // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051)
   int64_t n_assigned = 0;
-  if (!o.select_only) writers.emplace_back([&] {
+  if (!o.select_only) writers.emplace_back(guarded([&] {
     Out tb;
     tb.open(pre + "addressing_table.txt");
     std::string line = "Read";
@@ -626,7 +994,8 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
           continue;
         }
         int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
-        int m = paired ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
+        if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
+        int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
         line.append(num, m);
       }
       line += '\t';
@@ -643,12 +1012,13 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
       tb.add(line);
     }
     tb.close();
-  });
+    if (tb.failed()) wfail(HLM_E_IO, "cannot write " + pre + "addressing_table.txt");
+  }));
   // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351)
   int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
   int n_gene_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
   for (int w = 0; w < n_gene_threads && !o.select_only; w++)
-    writers.emplace_back([&, w] {
+    writers.emplace_back(guarded([&, w] {
       for (int g = w; g < db->n_loci; g += n_gene_threads) {
         const std::string& gene = db->names[g];
         Out r1, r2, c1, c2;
@@ -682,9 +1052,15 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
           counter++;
         }
         r1.close(); r2.close(); c1.close(); c2.close();
+        if (r1.failed() || r2.failed() || c1.failed() || c2.failed())
+          wfail(HLM_E_IO, "cannot write the per-gene FASTQ files of " + gene + " into " + out);
       }
-    });
+    }));
   for (auto& th : writers) th.join();
+  if (werr) {
+    hlm_ctx_set_error(ctx, werr_msg);
+    return werr;
+  }
   double t_write = now_s() - t0;
   if (stats) {
     memset(stats, 0, sizeof *stats);

@@ -284,6 +284,12 @@ typedef struct hlm_file_opts {
   int32_t batch_pairs;    /* pairs per hlm_run call (0 = 1 Mi)                              */
   int32_t write_selected; /* 0: skip <sample>_selected.R*.fastq                             */
   int32_t select_only;    /* 1: `hla-mapper select`: screen + trim, only selected*.fastq      */
+  int32_t threads;        /* rna: concurrent STAR runs / SAM readers (0 = one per host core)  */
+  const char* star_cmd;   /* rna: the STAR executable.  It is run once per gene on
+                             <sample>_sorted_<gene>_R{1,2}.fastq with the reference's arguments
+                             (map_rna.cpp:676-733).  NULL: STAR is not run - the files
+                             <out>/<sample>_<gene>_splice_Aligned.out.sam must already be there
+                             (a missing one means "no record for this gene")                 */
 } hlm_file_opts;
 typedef struct hlm_file_stats {
   int64_t n_pairs, n_selected, n_kept, n_assigned, read_mean_size;

@@ -163,9 +163,14 @@ def raw_digest(path):
 def canonical_digest(path):
     """sha256 of a file the reference wrote, after removing the orders it leaves to thread timing:
     FASTQ -> 4-line records sorted; addressing table -> header + sorted rows"""
+    import gzip
     import hashlib
+    import os
 
-    data = open(path, "rb").read()
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):  # `rna` gzips some files at the end
+        data = gzip.open(path + ".gz", "rb").read()
+    else:
+        data = open(path, "rb").read()
     lines = data.split(b"\n")
     if lines and lines[-1] == b"":
         lines.pop()

@@ -111,6 +111,15 @@ def main():
                     want += [w.replace(tag, "R2") for w in want if tag in w]
                 for w in want:
                     files[w] = cases.canonical_digest(out + w)
+            if mode in ("rna", "rna_full"):
+                # the rna file pipeline: the same files plus what goes into / comes out of STAR
+                want = ["G_selected.R1.fastq", "G_selected.trim.R1.fastq", "G_addressing_table.txt"]
+                for g in names[:-1]:
+                    want += [f"G_{g}_R1.fastq", f"G_{g}.trim.R1.fastq", f"G_sorted_{g}_R1.fastq"]
+                want += [w.replace("R1", "R2") for w in want if "R1" in w]
+                want += [f"G_sorted_spliced_{g}.fastq" for g in names[:-1]]
+                for w in want:
+                    files[w] = cases.canonical_digest(out + w)
             gold = {
                 "case": name, "mode": mode, "targets": names, "files": files,
                 "selected": sorted(sel),
