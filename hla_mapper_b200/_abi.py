@@ -85,7 +85,7 @@ class HlmFileOpts(C.Structure):
 class HlmFileStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_pairs", "n_selected", "n_kept", "n_assigned",
                                          "read_mean_size")] + \
-               [(k, C.c_double) for k in ("s_total", "s_gpu", "s_wait_input", "s_collect", "s_write")]
+               [(k, C.c_double) for k in ("s_total", "s_gpu", "s_wait_input", "s_collect", "s_write", "s_sort")]
 
 
 class HlmBamStats(C.Structure):

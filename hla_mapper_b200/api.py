@@ -28,7 +28,7 @@ SYMBOLS = [
     "hlm_multi_n_devices", "hlm_multi_last_error", "hlm_multi_run", "hlm_dp_layout_ab",
     "hlm_bam_extract", "hlm_reads_paired", "hlm_reads_count", "hlm_reads_free",
     "hlm_reads_write_fastq", "hlm_map_reads", "hlm_int32_peaks", "hlm_db_n_alleles",
-    "hlm_db_allele_name", "hlm_score_alleles",
+    "hlm_db_allele_name", "hlm_score_alleles", "hlm_multi_map_fastq", "hlm_multi_map_reads",
 ]
 
 _lib = None
@@ -98,6 +98,10 @@ def lib():
     L.hlm_int32_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
     L.hlm_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                 C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
+    L.hlm_multi_map_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                      C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
+    L.hlm_multi_map_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p,
+                                      C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
     L.hlm_bam_extract.restype = C.c_void_p
     L.hlm_bam_extract.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                   C.POINTER(_abi.HlmBamStats), C.c_char_p, C.c_size_t]
@@ -317,6 +321,18 @@ class MultiMapper:
         if rc != 0:
             raise HlmError(f"libhlamap rc={rc}: {lib().hlm_multi_last_error(self.h).decode()}")
         return buf
+
+    def map_fastq(self, r1, r2, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1,
+                  select_only=0, threads=0, star_cmd=None):
+        """hlm_multi_map_fastq: the file pipeline fed to every GPU of the multi-context"""
+        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
+                             select_only, threads, str(star_cmd).encode() if star_cmd else None)
+        st = _abi.HlmFileStats()
+        rc = lib().hlm_multi_map_fastq(self.h, str(r1).encode(), str(r2).encode() if r2 else None,
+                                       sample.encode(), str(out_dir).encode(), C.byref(o), C.byref(st))
+        if rc != 0:
+            raise HlmError(f"libhlamap rc={rc}: {lib().hlm_multi_last_error(self.h).decode()}")
+        return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
 
     def close(self):
         if self.h:

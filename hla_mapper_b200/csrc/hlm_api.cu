@@ -1154,6 +1154,14 @@ struct hlm_multi {
   std::string err;
 };
 
+}  // extern "C"
+hlm_ctx* const* hlm_multi_contexts(const hlm_multi* m, int* n) {
+  *n = (int)m->ctx.size();
+  return m->ctx.data();
+}
+void hlm_multi_set_error(hlm_multi* m, const std::string& msg) { m->err = msg; }
+extern "C" {
+
 hlm_multi* hlm_multi_create(const hlm_db* db, const int* devices, int n_devices, const hlm_params* params,
                             char* err, size_t errlen) {
   int ndev = 0;

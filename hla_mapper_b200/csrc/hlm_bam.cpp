@@ -685,3 +685,29 @@ extern "C" int hlm_map_reads(hlm_ctx* ctx, const hlm_reads* reads, const char* s
     return HLM_E_NOMEM;
   }
 }
+
+extern "C" const char* hlm_last_error(const hlm_ctx* ctx);
+extern "C" int hlm_multi_map_reads(hlm_multi* mm, const hlm_reads* reads, const char* sample, const char* out_dir,
+                                   const hlm_file_opts* opts, hlm_file_stats* stats) {
+  if (!mm || !reads || !sample || !out_dir) return HLM_E_ARG;
+  int n = 0;
+  hlm_ctx* const* cs = hlm_multi_contexts(mm, &n);
+  if (n <= 0) return HLM_E_ARG;
+  const hlm_params* P = hlm_ctx_params(cs[0]);
+  if ((P->paired != 0) != (reads->paired != 0) || P->screen_variant != HLM_SCREEN_BAM) {
+    hlm_multi_set_error(mm, "reads extracted from a BAM need contexts with the BAM's `paired` and "
+                            "screen_variant = HLM_SCREEN_BAM");
+    return HLM_E_ARG;
+  }
+  int64_t batch = opts && opts->struct_size >= 12 && opts->batch_pairs > 0 ? opts->batch_pairs : 1 << 19;
+  int rc;
+  try {
+    MemSource src(reads, batch);
+    rc = hlm_map_source_multi(cs, n, src, /*normalise_pair_headers=*/false, sample, out_dir, opts, stats);
+  } catch (const std::exception& e) {
+    hlm_multi_set_error(mm, std::string("hlm_multi_map_reads: ") + e.what());
+    return HLM_E_NOMEM;
+  }
+  if (rc) hlm_multi_set_error(mm, hlm_last_error(cs[0]));
+  return rc;
+}

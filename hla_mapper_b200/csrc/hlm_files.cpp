@@ -26,6 +26,8 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <queue>
 #include <string>
@@ -731,14 +733,143 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   }
 }
 
+namespace {
+
+// f(t) for t in [0, n) on n host threads; an exception in a worker becomes one in the caller
+template <class F>
+void parallel_for(int n, F f) {
+  if (n <= 1) {
+    f(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::atomic<int> failed(0);
+  for (int t = 0; t < n; t++)
+    th.emplace_back([&, t] {
+      try {
+        f(t);
+      } catch (const std::exception&) {
+        failed = 1;
+      }
+    });
+  for (auto& x : th) x.join();
+  if (failed) throw std::bad_alloc();
+}
+
+// A file whose records are produced by several threads at once: every thread formats a contiguous
+// range of the records into a local buffer and writes it with pwrite() at the offset the ranges
+// before it end at (sizes from a first pass over the same records).
+class ParallelFile {
+ public:
+  bool open(const std::string& p) {
+    fd_ = ::open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    return fd_ >= 0;
+  }
+  ~ParallelFile() {
+    if (fd_ >= 0) ::close(fd_);
+  }
+  bool write_at(const char* d, size_t n, uint64_t off) {
+    while (n) {
+      ssize_t w = pwrite(fd_, d, n, (off_t)off);
+      if (w <= 0) {
+        bad_ = true;
+        return false;
+      }
+      d += w;
+      n -= (size_t)w;
+      off += (uint64_t)w;
+    }
+    return true;
+  }
+  bool close() {
+    if (fd_ >= 0 && ::close(fd_) != 0) bad_ = true;
+    fd_ = -1;
+    return !bad_;
+  }
+  bool bad() const { return bad_; }
+
+ private:
+  int fd_ = -1;
+  std::atomic<bool> bad_{false};
+};
+
+// buffered writer of one thread's range of a ParallelFile
+struct RangeOut {
+  ParallelFile* f = nullptr;
+  uint64_t off = 0;
+  std::string buf;
+  void begin(ParallelFile* file, uint64_t at) {
+    f = file;
+    off = at;
+    buf.clear();
+    buf.reserve(1 << 22);
+  }
+  void add(const char* s, size_t n) {
+    buf.append(s, n);
+    if (buf.size() > (1u << 22)) flush();
+  }
+  void fill(char c, size_t n) {
+    buf.append(n, c);
+    if (buf.size() > (1u << 22)) flush();
+  }
+  void flush() {
+    if (f && !buf.empty()) f->write_at(buf.data(), buf.size(), off);
+    off += buf.size();
+    buf.clear();
+  }
+};
+
+bool id_less(const Kept& a, const Kept& b) {  // std::map<string, ...> order of the reference
+  int c = memcmp(a.idgen, b.idgen, std::min(a.idl, b.idl));
+  return c < 0 || (c == 0 && a.idl < b.idl);
+}
+
+// stable sort of the kept reads by id on nt host threads: sorted runs, then pairwise merges
+void sort_kept(std::vector<Kept>& kept, int nt) {
+  size_t n = kept.size();
+  if (n < (1u << 16) || nt <= 1) {
+    std::stable_sort(kept.begin(), kept.end(), id_less);
+    return;
+  }
+  int runs = 1;
+  while (runs * 2 <= nt && runs < 64) runs *= 2;
+  std::vector<size_t> cut(runs + 1);
+  for (int r = 0; r <= runs; r++) cut[r] = n * (size_t)r / runs;
+  parallel_for(runs, [&](int r) { std::stable_sort(kept.begin() + cut[r], kept.begin() + cut[r + 1], id_less); });
+  std::vector<Kept> tmp(n);
+  std::vector<Kept>*src = &kept, *dst = &tmp;
+  for (int w = 1; w < runs; w *= 2) {
+    int pairs = runs / (2 * w);
+    parallel_for(pairs, [&](int k) {
+      size_t a = cut[2 * w * k], m = cut[2 * w * k + w], b = cut[2 * w * k + 2 * w];
+      std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a, id_less);
+    });
+    std::swap(src, dst);
+  }
+  if (src != &kept) kept.swap(tmp);
+}
+
+}  // namespace
+
 int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, const char* sample,
                    const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
+  return hlm_map_source_multi(&ctx, 1, src, normalise_pair_headers, sample, out_dir, opts_in, stats);
+}
+
+// One driver thread per context pulls batches from the shared source (round robin by arrival),
+// runs them on its GPU (batch k+1 in flight while batch k is collected) and hands the collected
+// batch to an in-order commit, so that whatever the number of GPUs the files are those of a
+// single-GPU run.  Errors are reported on ctxs[0].
+int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool normalise_pair_headers,
+                         const char* sample, const char* out_dir, const hlm_file_opts* opts_in,
+                         hlm_file_stats* stats) {
+  hlm_ctx* ctx = ctxs[0];
   const hlm_db* db = hlm_ctx_db(ctx);
   const hlm_params* P = hlm_ctx_params(ctx);
   bool paired = P->paired != 0;
   // rna (src/map_rna.cpp): the scoring step consumes what STAR made of the per-gene sorted reads,
   // so the reads are screened + trimmed first, STAR runs per gene between the two halves, and the
-  // kept reads are scored from memory afterwards (rna_score_kept below)
+  // kept reads are scored from memory afterwards (rna_score_kept)
   const bool rna = P->rna != 0;
   hlm_file_opts o;
   memset(&o, 0, sizeof o);
@@ -749,33 +880,40 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
   if (opts_in) memcpy(&o, opts_in, std::min((size_t)opts_in->struct_size, sizeof o));
   if (o.batch_pairs <= 0) o.batch_pairs = 1 << 19;
   if (o.downsampling < 5) o.downsampling = 5;  // src/main.cpp:434
+  const bool screen_only = o.select_only || rna;
   int T = db->n_loci + 1;
   std::string out = std::string(out_dir);
   if (out.empty() || out.back() != '/') out += "/";  // src/main.cpp:438-448
   std::string pre = out + sample + "_";               // v_sample = sample + "_" (main.cpp:450-455)
   const char* tag = paired ? "R1" : "R0";
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
 
-  double t_start = now_s(), t_gpu = 0, t_post = 0, t_wait = 0;
-  Out sel1, sel2;
+  double t_start = now_s();
+  ParallelFile sel1, sel2;
   if (o.write_selected) {
     if (!sel1.open(pre + "selected." + tag + ".fastq") || (paired && !sel2.open(pre + "selected.R2.fastq"))) {
       hlm_ctx_set_error(ctx, "cannot write into " + out);
       return HLM_E_IO;
     }
   }
-  std::vector<Kept> kept;
-  int64_t n_pairs = 0, n_selected = 0, sel_bases = 0;
-  int n_workers = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
-  std::vector<Arena> arenas(n_workers);
+  // host threads that collect one finished batch (per driver)
+  const int n_workers = std::max(1, std::min(16, hw / (2 * n_ctx) + 1));
 
   // what the reference keeps per selected read, taken from a finished batch: the batch is cut
-  // into one slice per host thread; slices are concatenated in order, so the output is in input order
+  // into one slice per host thread; slices are committed in order, so the output is in input order
   struct Part {
     std::vector<Kept> kept;
     std::string sel1, sel2;
     int64_t n_selected = 0, sel_bases = 0;
   };
-  auto collect_slice = [&](Results& R, int64_t lo, int64_t hi, Arena& arena, Part& P) {
+  struct BatchOut {
+    int64_t seq = 0, n = 0;
+    std::vector<Part> parts;
+  };
+  // A batch most of whose reads are selected is kept alive instead of being copied read by read
+  // (on-target input: the copy would be the whole batch anyway); the source then hands out a
+  // fresh one.  Sparse batches (whole-genome input) are copied into the arena and recycled.
+  auto collect_slice = [&](Results& R, int64_t lo, int64_t hi, Arena& arena, Part& P, bool retained) {
     MateBatch *b1 = R.b1, *b2 = R.b2;
     std::string h1, h2, idg;
     for (int64_t i = lo; i < hi; i++) {
@@ -815,15 +953,21 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
         erase_all(idg, "/1");
         erase_all(idg, "/2");
       }
-      // one arena record: h1 | h2 | s1 | q1 | s2 | q2 | idgen | scores
-      size_t bytes = h1.size() + h2.size() + 2 * L1 + 2 * L2 + idg.size();
+      // one arena record: h1 | h2 | idgen | scores [| s1 | q1 | s2 | q2 when the batch is not retained]
+      size_t bytes = h1.size() + h2.size() + idg.size() + (retained ? 0 : 2 * L1 + 2 * L2);
       char* p = arena.alloc(bytes + 1 + 4 * (size_t)T);
       k.h1 = p; k.h1l = (uint32_t)h1.size(); memcpy(p, h1.data(), h1.size()); p += h1.size();
       k.h2 = p; k.h2l = (uint32_t)h2.size(); memcpy(p, h2.data(), h2.size()); p += h2.size();
-      k.s1 = p; k.l1 = (uint32_t)L1; memcpy(p, s1p, L1); p += L1;
-      k.q1 = p; memcpy(p, q1p, L1); p += L1;
-      k.s2 = p; k.l2 = (uint32_t)L2; if (L2) memcpy(p, s2p, L2); p += L2;
-      k.q2 = p; if (L2) memcpy(p, q2p, L2); p += L2;
+      k.l1 = (uint32_t)L1;
+      k.l2 = (uint32_t)L2;
+      if (retained) {
+        k.s1 = s1p; k.q1 = q1p; k.s2 = s2p ? s2p : p; k.q2 = q2p ? q2p : p;
+      } else {
+        k.s1 = p; memcpy(p, s1p, L1); p += L1;
+        k.q1 = p; memcpy(p, q1p, L1); p += L1;
+        k.s2 = p; if (L2) memcpy(p, s2p, L2); p += L2;
+        k.q2 = p; if (L2) memcpy(p, q2p, L2); p += L2;
+      }
       k.idgen = p; k.idl = (uint32_t)idg.size(); memcpy(p, idg.data(), idg.size()); p += idg.size();
       p += ((uintptr_t)p & 1);
       uint16_t* sc = (uint16_t*)p;
@@ -835,245 +979,424 @@ int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, c
       k.os1 = R.os1[i]; k.os2 = R.os2[i];
     }
   };
-  std::vector<Part> parts(n_workers);
-  auto collect = [&](Results& R) {
-    int64_t n = R.b1->n;
-    for (Part& P : parts) {  // buffers keep their capacity from batch to batch
-      P.kept.clear();
-      P.sel1.clear();
-      P.sel2.clear();
-      P.n_selected = P.sel_bases = 0;
-    }
-    std::vector<std::thread> th;
-    std::atomic<bool> oom(false);
-    for (int w = 0; w < n_workers; w++)
-      th.emplace_back([&, w] {
-        try {
-          collect_slice(R, n * w / n_workers, n * (w + 1) / n_workers, arenas[w], parts[w]);
-        } catch (const std::exception&) {  // bad_alloc in a worker must not reach std::terminate
-          oom = true;
-        }
-      });
-    for (auto& t : th) t.join();
-    if (oom) throw std::bad_alloc();
-    for (Part& P : parts) {
-      sel1.add(P.sel1);
-      sel2.add(P.sel2);
-      n_selected += P.n_selected;
-      sel_bases += P.sel_bases;
-      kept.insert(kept.end(), P.kept.begin(), P.kept.end());
-    }
-    n_pairs += n;
-    src.recycle(R.b1, R.b2);
-  };
 
-  // batch k+1 runs on the GPU (hlm_run_async) while batch k is collected on this thread and the
-  // reader threads parse batch k+2
-  Results res[2];
-  int cur = 0, rc = 0;
-  bool inflight = false;
-  for (;;) {
-    double t0 = now_s();
-    MateBatch *b1 = nullptr, *b2 = nullptr;
-    std::string src_err;
-    bool end = !src.next(b1, b2, rc, src_err);
-    if (rc) hlm_ctx_set_error(ctx, src_err);
-    t_wait += now_s() - t0;
-    if (inflight) {  // finish the previous batch on the GPU
-      int r2 = hlm_wait(ctx);
-      hlm_profile pr;
-      if (hlm_get_profile(ctx, &pr) == 0) t_gpu += pr.ms_total * 1e-3;  // device time of the batch
-      inflight = false;
-      if (rc == 0) rc = r2;
+  // ---- shared state of the drivers
+  std::mutex src_mu, commit_mu, err_mu;
+  bool src_end = false;
+  int64_t next_seq = 0;
+  int rc_all = 0;
+  std::string err_all;
+  auto fail = [&](int code, const std::string& m) {
+    std::lock_guard<std::mutex> g(err_mu);
+    if (!rc_all) {
+      rc_all = code;
+      err_all = m;
     }
-    int prev = cur ^ 1;  // results of the batch that just finished
-    bool have_prev = res[prev].b1 != nullptr;
-    if (!end && rc == 0) {
-      res[cur].bind(b1, b2, T, paired);
-      if (o.select_only || rna) {  // `hla-mapper select`: main_preselect() only; rna: scored later
-        double tg = now_s();
-        rc = hlm_screen_trim(ctx, &res[cur].hb, &res[cur].scr);
-        t_gpu += now_s() - tg;
-        std::fill(res[cur].target.begin(), res[cur].target.end(), 0u);
-        std::fill(res[cur].visible.begin(), res[cur].visible.end(), 0u);
-      } else {
-        rc = hlm_run_async(ctx, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
-        inflight = rc == 0;
+  };
+  auto failed = [&] {
+    std::lock_guard<std::mutex> g(err_mu);
+    return rc_all != 0;
+  };
+  std::vector<Kept> kept;
+  std::map<int64_t, std::unique_ptr<BatchOut>> pending;
+  int64_t commit_seq = 0, n_pairs = 0, n_selected = 0, sel_bases = 0;
+  uint64_t off1 = 0, off2 = 0;
+  double t_gpu = 0, t_post = 0, t_wait = 0;
+  std::vector<std::vector<Arena>> arenas(n_ctx);
+  for (auto& a : arenas) a = std::vector<Arena>(n_workers);
+
+  // in-order commit: offsets of the selected records and the kept list follow the input order
+  auto commit = [&](std::unique_ptr<BatchOut> bo) {
+    std::vector<std::unique_ptr<BatchOut>> ready;
+    std::vector<std::pair<uint64_t, uint64_t>> offs;  // per ready part
+    {
+      std::lock_guard<std::mutex> g(commit_mu);
+      pending[bo->seq] = std::move(bo);
+      while (!pending.empty() && pending.begin()->first == commit_seq) {
+        std::unique_ptr<BatchOut> b = std::move(pending.begin()->second);
+        pending.erase(pending.begin());
+        commit_seq++;
+        for (Part& P : b->parts) {
+          offs.emplace_back(off1, off2);
+          off1 += P.sel1.size();
+          off2 += P.sel2.size();
+          n_selected += P.n_selected;
+          sel_bases += P.sel_bases;
+          kept.insert(kept.end(), P.kept.begin(), P.kept.end());
+        }
+        n_pairs += b->n;
+        ready.push_back(std::move(b));
       }
     }
-    if (have_prev && rc == 0) {
-      t0 = now_s();
-      collect(res[prev]);
-      t_post += now_s() - t0;
+    if (!o.write_selected) return;
+    size_t k = 0;
+    for (auto& b : ready) {
+      size_t base = k;
+      parallel_for((int)b->parts.size(), [&](int w) {
+        Part& P = b->parts[w];
+        if (!P.sel1.empty()) sel1.write_at(P.sel1.data(), P.sel1.size(), offs[base + w].first);
+        if (!P.sel2.empty()) sel2.write_at(P.sel2.data(), P.sel2.size(), offs[base + w].second);
+      });
+      k += b->parts.size();
     }
-    res[prev].b1 = nullptr;
-    if (end || rc) break;
-    cur ^= 1;
+  };
+
+  auto drive = [&](int di) {
+    hlm_ctx* c = ctxs[di];
+    Results res[2];
+    int64_t seq_of[2] = {0, 0};
+    int cur = 0;
+    bool inflight = false;
+    auto collect = [&](Results& R, int64_t seq) {
+      int64_t n = R.b1->n, nsel = 0;
+      for (int64_t i = 0; i < n; i++) nsel += (R.flags[i] & HLM_F_SCREENED) ? 1 : 0;
+      bool retained = nsel * 2 > n;
+      std::unique_ptr<BatchOut> bo(new BatchOut());
+      bo->seq = seq;
+      bo->n = n;
+      bo->parts.resize(n_workers);
+      parallel_for(n_workers, [&](int w) {
+        collect_slice(R, n * w / n_workers, n * (w + 1) / n_workers, arenas[di][w], bo->parts[w], retained);
+      });
+      if (!retained) {
+        std::lock_guard<std::mutex> g(src_mu);
+        src.recycle(R.b1, R.b2);
+      }
+      commit(std::move(bo));
+    };
+    for (;;) {
+      MateBatch *b1 = nullptr, *b2 = nullptr;
+      bool end = true;
+      int64_t seq = 0;
+      double t0 = now_s();
+      {
+        std::lock_guard<std::mutex> g(src_mu);
+        if (!src_end && !failed()) {
+          int rc = 0;
+          std::string e;
+          end = !src.next(b1, b2, rc, e);
+          if (rc) fail(rc, e);
+          if (end) src_end = true;
+          else seq = next_seq++;
+        }
+      }
+      double dt_wait = now_s() - t0;
+      if (inflight) {  // finish the previous batch on the GPU
+        int r2 = hlm_wait(c);
+        hlm_profile pr;
+        if (hlm_get_profile(c, &pr) == 0) {
+          std::lock_guard<std::mutex> g(err_mu);
+          t_gpu += pr.ms_total * 1e-3;  // device time of the batch
+        }
+        inflight = false;
+        if (r2) fail(r2, hlm_last_error(c));
+      }
+      int prev = cur ^ 1;  // results of the batch that just finished
+      bool have_prev = res[prev].b1 != nullptr;
+      if (!end && !failed()) {
+        res[cur].bind(b1, b2, T, paired);
+        seq_of[cur] = seq;
+        int rc;
+        if (screen_only) {  // `hla-mapper select`: main_preselect() only; rna: scored later
+          rc = hlm_screen_trim(c, &res[cur].hb, &res[cur].scr);
+          hlm_profile pr;
+          if (rc == 0 && hlm_get_profile(c, &pr) == 0) {
+            std::lock_guard<std::mutex> g(err_mu);
+            t_gpu += pr.ms_total * 1e-3;
+          }
+          std::fill(res[cur].target.begin(), res[cur].target.end(), 0u);
+          std::fill(res[cur].visible.begin(), res[cur].visible.end(), 0u);
+        } else {
+          rc = hlm_run_async(c, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
+          inflight = rc == 0;
+        }
+        if (rc) fail(rc, hlm_last_error(c));
+      }
+      double t1 = now_s();
+      if (have_prev && !failed()) collect(res[prev], seq_of[prev]);
+      {
+        std::lock_guard<std::mutex> g(err_mu);
+        t_wait += dt_wait;
+        t_post += now_s() - t1;
+      }
+      res[prev].b1 = nullptr;
+      if (end || failed()) break;
+      cur ^= 1;
+    }
+    if (inflight) hlm_wait(c);
+  };
+  {
+    std::vector<std::thread> drivers;
+    std::atomic<int> oom(0);
+    for (int d = 0; d < n_ctx; d++)
+      drivers.emplace_back([&, d] {
+        try {
+          drive(d);
+        } catch (const std::exception& e) {
+          fail(HLM_E_NOMEM, std::string("file pipeline: ") + e.what());
+          hlm_wait(ctxs[d]);
+        }
+      });
+    for (auto& t : drivers) t.join();
   }
-  if (inflight) hlm_wait(ctx);
-  sel1.close();
-  sel2.close();
-  if (rc) return rc;
-  if (sel1.failed() || sel2.failed()) {
+  bool sel_ok = sel1.close();
+  sel_ok = sel2.close() && sel_ok;
+  if (rc_all) {
+    hlm_ctx_set_error(ctx, err_all);
+    return rc_all;
+  }
+  if (o.write_selected && !sel_ok) {
     hlm_ctx_set_error(ctx, "cannot write " + pre + "selected.*.fastq");
     return HLM_E_IO;
   }
+  if (n_ctx > 1) {  // per-driver times were summed over the drivers
+    t_post /= n_ctx;
+    t_wait /= n_ctx;
+  }
 
   double t0 = now_s();
-  // std::map<string, ...> order of the reference (byte-wise on the id)
-  std::stable_sort(kept.begin(), kept.end(), [](const Kept& a, const Kept& b) {
-    int c = memcmp(a.idgen, b.idgen, std::min(a.idl, b.idl));
-    return c < 0 || (c == 0 && a.idl < b.idl);
-  });
+  const int nt = std::max(1, std::min(32, hw));
+  sort_kept(kept, nt);
+  double t_sort = now_s() - t0;
   if (rna && !o.select_only) {
     double tg = now_s();
-    rc = rna_score_kept(ctx, db, o, pre, paired, kept);
+    int rc = rna_score_kept(ctx, db, o, pre, paired, kept);
     t_gpu += now_s() - tg;
     if (rc) return rc;
   }
-  // the groups of output files are independent: write them on separate host threads.  A failed
-  // open / write / close (ENOSPC, permissions) or an exception inside a writer ends the run with
-  // HLM_E_IO / HLM_E_NOMEM instead of leaving truncated files behind a success code.
-  std::vector<std::thread> writers;
-  std::mutex werr_mu;
+  // ---- the output files.  Every file is written by all host threads at once: a thread formats a
+  // contiguous range of the (id-sorted) kept reads and writes it at the offset the ranges before
+  // it end at.  A failed open / write / close (ENOSPC, permissions) ends the run with HLM_E_IO.
+  const size_t NK = kept.size();
+  std::vector<size_t> cut(nt + 1);
+  for (int t = 0; t <= nt; t++) cut[t] = NK * (size_t)t / nt;
   int werr = 0;
   std::string werr_msg;
-  auto wfail = [&](int code, const std::string& m) {
-    std::lock_guard<std::mutex> g(werr_mu);
+  auto wfail = [&](const std::string& m) {
+    std::lock_guard<std::mutex> g(err_mu);
     if (!werr) {
-      werr = code;
+      werr = HLM_E_IO;
       werr_msg = m;
     }
   };
-  auto guarded = [&](auto&& body) {
-    return [&, body]() {
-      try {
-        body();
-      } catch (const std::exception& e) {
-        wfail(HLM_E_NOMEM, std::string("output writer: ") + e.what());
-      }
-    };
+  // emit(k, rank, out...) style writers share this driver: `sizes(t)` returns the bytes thread t's
+  // range will produce, `body(t, RangeOut&)` produces them
+  auto write_file = [&](const std::string& path, auto&& sizes, auto&& body) {
+    ParallelFile f;
+    if (!f.open(path)) {
+      wfail("cannot write " + path);
+      return;
+    }
+    std::vector<uint64_t> sz(nt + 1, 0);
+    parallel_for(nt, [&](int t) { sz[t + 1] = sizes(t); });
+    for (int t = 0; t < nt; t++) sz[t + 1] += sz[t];
+    parallel_for(nt, [&](int t) {
+      RangeOut ro;
+      ro.begin(&f, sz[t]);
+      body(t, ro);
+      ro.flush();
+    });
+    if (!f.close()) wfail("write error on " + path);
   };
-  // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
-  writers.emplace_back(guarded([&] {
-    Out t1;
-    t1.open(pre + "selected.trim." + tag + ".fastq");
-    for (const Kept& k : kept) {
-      t1.add(k.h1, k.h1l); t1.add("\n", 1); t1.add(k.s1 + k.lo1, k.n1); t1.add("\n+\n", 3);
-      t1.fill('A', k.n1); t1.add("\n", 1);
-    }
-    t1.close();
-    if (t1.failed()) wfail(HLM_E_IO, "cannot write " + pre + "selected.trim." + tag + ".fastq");
-  }));
-  if (paired) writers.emplace_back(guarded([&] {
-    Out t2;
-    t2.open(pre + "selected.trim.R2.fastq");
-    for (const Kept& k : kept) {
-      t2.add(k.h2, k.h2l); t2.add("\n", 1); t2.add(k.s2 + k.lo2, k.n2); t2.add("\n+\n", 3);
-      t2.fill('A', k.n2); t2.add("\n", 1);
-    }
-    t2.close();
-    if (t2.failed()) wfail(HLM_E_IO, "cannot write " + pre + "selected.trim.R2.fastq");
-  }));
-  // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051)
   int64_t n_assigned = 0;
-  if (!o.select_only) writers.emplace_back(guarded([&] {
-    Out tb;
-    tb.open(pre + "addressing_table.txt");
-    std::string line = "Read";
-    for (int g = 0; g < T; g++) line += "\t" + db->names[g];
-    line += "\tTarget\n";
-    tb.add(line);
-    char num[32];
-    for (const Kept& k : kept) {
-      line.assign(k.idgen, k.idl);
-      for (int g = 0; g < T; g++) {
+  try {
+    // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
+    for (int m = 0; m < (paired ? 2 : 1); m++)
+      write_file(pre + "selected.trim." + (m == 0 ? tag : "R2") + ".fastq",
+                 [&](int t) {
+                   uint64_t b = 0;
+                   for (size_t i = cut[t]; i < cut[t + 1]; i++)
+                     b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].n1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].n2 + 5;
+                   return b;
+                 },
+                 [&](int t, RangeOut& w) {
+                   for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+                     const Kept& k = kept[i];
+                     if (m == 0) {
+                       w.add(k.h1, k.h1l); w.add("\n", 1); w.add(k.s1 + k.lo1, k.n1); w.add("\n+\n", 3);
+                       w.fill('A', k.n1); w.add("\n", 1);
+                     } else {
+                       w.add(k.h2, k.h2l); w.add("\n", 1); w.add(k.s2 + k.lo2, k.n2); w.add("\n+\n", 3);
+                       w.fill('A', k.n2); w.add("\n", 1);
+                     }
+                   }
+                 });
+    // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051, src/map_rna.cpp:945-1049)
+    if (!o.select_only) {
+      std::string header = "Read";
+      for (int g = 0; g < T; g++) header += "\t" + db->names[g];
+      header += "\tTarget\n";
+      std::vector<int64_t> assigned(nt, 0);
+      auto row = [&](const Kept& k, std::string& line, bool& any) {
+        char num[32];
+        line.assign(k.idgen, k.idl);
+        for (int g = 0; g < T; g++) {
+          line += '\t';
+          if (!((k.visible >> g) & 1u)) {
+            line += '-';
+            continue;
+          }
+          int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
+          if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
+          int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
+          line.append(num, m);
+        }
         line += '\t';
-        if (!((k.visible >> g) & 1u)) {
-          line += '-';
-          continue;
-        }
-        int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
-        if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
-        int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
-        line.append(num, m);
-      }
-      line += '\t';
-      bool any = false;
-      for (int g = 0; g < T; g++)
-        if ((k.target >> g) & 1u) {
-          if (any) line += ',';
-          line += db->names[g];
-          any = true;
-        }
-      if (!any) line += '-';
-      else n_assigned++;
-      line += '\n';
-      tb.add(line);
+        any = false;
+        for (int g = 0; g < T; g++)
+          if ((k.target >> g) & 1u) {
+            if (any) line += ',';
+            line += db->names[g];
+            any = true;
+          }
+        if (!any) line += '-';
+        line += '\n';
+      };
+      write_file(pre + "addressing_table.txt",
+                 [&](int t) {
+                   uint64_t b = t == 0 ? header.size() : 0;
+                   std::string line;
+                   bool any;
+                   for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+                     row(kept[i], line, any);
+                     b += line.size();
+                   }
+                   return b;
+                 },
+                 [&](int t, RangeOut& w) {
+                   if (t == 0) w.add(header.data(), header.size());
+                   std::string line;
+                   bool any;
+                   for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+                     row(kept[i], line, any);
+                     assigned[t] += any ? 1 : 0;
+                     w.add(line.data(), line.size());
+                   }
+                 });
+      for (int64_t a : assigned) n_assigned += a;
     }
-    tb.close();
-    if (tb.failed()) wfail(HLM_E_IO, "cannot write " + pre + "addressing_table.txt");
-  }));
-  // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351)
-  int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
-  int n_gene_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
-  for (int w = 0; w < n_gene_threads && !o.select_only; w++)
-    writers.emplace_back(guarded([&, w] {
-      for (int g = w; g < db->n_loci; g += n_gene_threads) {
-        const std::string& gene = db->names[g];
-        Out r1, r2, c1, c2;
-        r1.open(pre + gene + "_" + tag + ".fastq");
-        c1.open(pre + gene + ".trim." + tag + ".fastq");
-        if (paired) {
-          r2.open(pre + gene + "_R2.fastq");
-          c2.open(pre + gene + ".trim.R2.fastq");
-        }
-        int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
-        int64_t downS = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
-        int64_t counter = 0;
-        for (const Kept& k : kept) {
-          if (!((k.locus_mask >> g) & 1u)) continue;  // was in sorted_<gene>_R1.fastq
-          if (!((k.target >> g) & 1u)) continue;       // sequence_address[(gene, id)]
-          // the lookup key is the header token minus '@' (:1225): it only equals the id when the
-          // token carries no /1 /2 (always true for paired input, whose headers were normalised)
-          if (k.tokl < 1 || k.tokl - 1 != k.idl || memcmp(k.h1 + 1, k.idgen, k.idl) != 0) continue;
-          r1.add(k.h1, k.h1l); r1.add("\n", 1); r1.add(k.s1, k.l1); r1.add("\n+\n", 3); r1.add(k.q1, k.l1); r1.add("\n", 1);
-          if (paired) {
-            r2.add(k.h2, k.h2l); r2.add("\n", 1); r2.add(k.s2, k.l2); r2.add("\n+\n", 3); r2.add(k.q2, k.l2); r2.add("\n", 1);
-          }
-          if (counter < downS) {
-            c1.add(k.h1, k.tokl); c1.add(" 1:trim\n", 8); c1.add(k.s1 + k.lo1, k.n1); c1.add("\n+\n", 3);
-            c1.fill('A', k.n1); c1.add("\n", 1);
-            if (paired) {
-              c2.add(k.h1, k.tokl); c2.add(" 2:trim\n", 8); c2.add(k.s2 + k.lo2, k.n2); c2.add("\n+\n", 3);
-              c2.fill('A', k.n2); c2.add("\n", 1);
-            }
-          }
-          counter++;
-        }
-        r1.close(); r2.close(); c1.close(); c2.close();
-        if (r1.failed() || r2.failed() || c1.failed() || c2.failed())
-          wfail(HLM_E_IO, "cannot write the per-gene FASTQ files of " + gene + " into " + out);
+    // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351, src/map_rna.cpp:1072-1344)
+    int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
+    for (int g = 0; g < db->n_loci && !o.select_only; g++) {
+      const std::string& gene = db->names[g];
+      int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
+      int64_t downS = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
+      auto member = [&](const Kept& k) {
+        if (!((k.locus_mask >> g) & 1u)) return false;  // was in sorted_<gene>_R1.fastq
+        if (!((k.target >> g) & 1u)) return false;       // sequence_address[(gene, id)]
+        // the lookup key is the header token minus '@' (:1225): it only equals the id when the
+        // token carries no /1 /2 (always true for paired input, whose headers were normalised)
+        return k.tokl >= 1 && k.tokl - 1 == k.idl && memcmp(k.h1 + 1, k.idgen, k.idl) == 0;
+      };
+      // rank of every range's first member: the first downS members also go to the .trim files
+      std::vector<int64_t> rank(nt + 1, 0);
+      parallel_for(nt, [&](int t) {
+        int64_t c = 0;
+        for (size_t i = cut[t]; i < cut[t + 1]; i++) c += member(kept[i]) ? 1 : 0;
+        rank[t + 1] = c;
+      });
+      for (int t = 0; t < nt; t++) rank[t + 1] += rank[t];
+      for (int m = 0; m < (paired ? 2 : 1); m++) {
+        write_file(pre + gene + "_" + (m == 0 ? tag : "R2") + ".fastq",
+                   [&](int t) {
+                     uint64_t b = 0;
+                     for (size_t i = cut[t]; i < cut[t + 1]; i++)
+                       if (member(kept[i]))
+                         b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].l1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].l2 + 5;
+                     return b;
+                   },
+                   [&](int t, RangeOut& w) {
+                     for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+                       const Kept& k = kept[i];
+                       if (!member(k)) continue;
+                       if (m == 0) {
+                         w.add(k.h1, k.h1l); w.add("\n", 1); w.add(k.s1, k.l1); w.add("\n+\n", 3); w.add(k.q1, k.l1);
+                         w.add("\n", 1);
+                       } else {
+                         w.add(k.h2, k.h2l); w.add("\n", 1); w.add(k.s2, k.l2); w.add("\n+\n", 3); w.add(k.q2, k.l2);
+                         w.add("\n", 1);
+                       }
+                     }
+                   });
+        write_file(pre + gene + ".trim." + (m == 0 ? tag : "R2") + ".fastq",
+                   [&](int t) {
+                     uint64_t b = 0;
+                     int64_t r = rank[t];
+                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS; i++)
+                       if (member(kept[i])) {
+                         b += kept[i].tokl + 8 + 2 * (uint64_t)(m == 0 ? kept[i].n1 : kept[i].n2) + 4;
+                         r++;
+                       }
+                     return b;
+                   },
+                   [&](int t, RangeOut& w) {
+                     int64_t r = rank[t];
+                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS; i++) {
+                       const Kept& k = kept[i];
+                       if (!member(k)) continue;
+                       r++;
+                       w.add(k.h1, k.tokl);
+                       if (m == 0) {
+                         w.add(" 1:trim\n", 8); w.add(k.s1 + k.lo1, k.n1); w.add("\n+\n", 3); w.fill('A', k.n1);
+                       } else {
+                         w.add(" 2:trim\n", 8); w.add(k.s2 + k.lo2, k.n2); w.add("\n+\n", 3); w.fill('A', k.n2);
+                       }
+                       w.add("\n", 1);
+                     }
+                   });
       }
-    }));
-  for (auto& th : writers) th.join();
-  if (werr) {
-    hlm_ctx_set_error(ctx, werr_msg);
-    return werr;
-  }
-  double t_write = now_s() - t0;
-  if (stats) {
-    memset(stats, 0, sizeof *stats);
-    stats->n_pairs = n_pairs;
-    stats->n_selected = n_selected;
-    stats->n_kept = (int64_t)kept.size();
-    stats->n_assigned = n_assigned;
-    stats->read_mean_size = read_mean_size;
-    stats->s_total = now_s() - t_start;
-    stats->s_gpu = t_gpu;
-    stats->s_wait_input = t_wait;
-    stats->s_collect = t_post;
-    stats->s_write = t_write;
+    }
+    if (werr) {
+      hlm_ctx_set_error(ctx, werr_msg);
+      return werr;
+    }
+    double t_write = now_s() - t0;
+    if (stats) {
+      memset(stats, 0, sizeof *stats);
+      stats->n_pairs = n_pairs;
+      stats->n_selected = n_selected;
+      stats->n_kept = (int64_t)kept.size();
+      stats->n_assigned = n_assigned;
+      stats->read_mean_size = read_mean_size;
+      stats->s_total = now_s() - t_start;
+      stats->s_gpu = t_gpu;
+      stats->s_wait_input = t_wait;
+      stats->s_collect = t_post;
+      stats->s_write = t_write;
+      stats->s_sort = t_sort;
+    }
+  } catch (const std::exception& e) {
+    hlm_ctx_set_error(ctx, std::string("output writer: ") + e.what());
+    return HLM_E_NOMEM;
   }
   return HLM_OK;
+}
+
+extern "C" int hlm_multi_map_fastq(hlm_multi* mm, const char* r1_path, const char* r2_path, const char* sample,
+                                   const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
+  if (!mm || !r1_path || !sample || !out_dir) return HLM_E_ARG;
+  int n = 0;
+  hlm_ctx* const* cs = hlm_multi_contexts(mm, &n);
+  if (n <= 0) return HLM_E_ARG;
+  const hlm_params* P = hlm_ctx_params(cs[0]);
+  bool paired = P->paired != 0;
+  if (paired != (r2_path != nullptr)) {
+    hlm_multi_set_error(mm, "paired contexts need r1 and r2; single-end contexts need r2 == NULL");
+    return HLM_E_ARG;
+  }
+  int64_t batch = opts_in && opts_in->struct_size >= 12 && opts_in->batch_pairs > 0 ? opts_in->batch_pairs : 1 << 19;
+  int rc;
+  try {  // no exception crosses the C ABI
+    FileSource src(r1_path, r2_path, batch);
+    if (!src.ok1() || !src.ok2()) {
+      hlm_multi_set_error(mm, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
+      return HLM_E_IO;
+    }
+    rc = hlm_map_source_multi(cs, n, src, paired, sample, out_dir, opts_in, stats);
+  } catch (const std::exception& e) {
+    hlm_multi_set_error(mm, std::string("hlm_multi_map_fastq: ") + e.what());
+    return HLM_E_NOMEM;
+  }
+  if (rc) hlm_multi_set_error(mm, hlm_last_error(cs[0]));
+  return rc;
 }

@@ -48,5 +48,13 @@ class PairSource {
 // path's headers arrive already edited (src/preselect.cpp:469-472, :549-552).
 int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, const char* sample,
                    const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
+// the same over several contexts (one per GPU): batches are dealt to the devices as they arrive,
+// results committed in input order - the files do not depend on the number of devices
+int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool normalise_pair_headers,
+                         const char* sample, const char* out_dir, const hlm_file_opts* opts,
+                         hlm_file_stats* stats);
+// the per-device contexts of an hlm_multi (hlm_api.cu)
+hlm_ctx* const* hlm_multi_contexts(const hlm_multi* m, int* n);
+void hlm_multi_set_error(hlm_multi* m, const std::string& msg);
 
 #endif

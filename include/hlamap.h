@@ -294,9 +294,15 @@ typedef struct hlm_file_opts {
 typedef struct hlm_file_stats {
   int64_t n_pairs, n_selected, n_kept, n_assigned, read_mean_size;
   double s_total, s_gpu, s_wait_input, s_collect, s_write;
+  double s_sort;          /* id sort of the kept reads (part of s_write)                      */
 } hlm_file_stats;
 int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const char* sample,
                   const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
+/* the same on every GPU of an hlm_multi: the reader threads' batches are dealt to the devices as
+ * they arrive, results are committed in input order - the files do not depend on the number of
+ * devices */
+int hlm_multi_map_fastq(hlm_multi* m, const char* r1_path, const char* r2_path, const char* sample,
+                        const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
 
 /* ---- BAM front end of the dna path ----
  * hlm_bam_extract replaces the four samtools processes of the reference's bam= input
@@ -327,6 +333,8 @@ void hlm_reads_free(hlm_reads* r);
 int hlm_reads_write_fastq(const hlm_reads* r, const char* r1_path, const char* r2_path);
 int hlm_map_reads(hlm_ctx* ctx, const hlm_reads* reads, const char* sample, const char* out_dir,
                   const hlm_file_opts* opts, hlm_file_stats* stats);
+int hlm_multi_map_reads(hlm_multi* m, const hlm_reads* reads, const char* sample, const char* out_dir,
+                        const hlm_file_opts* opts, hlm_file_stats* stats);
 
 /* INT32 micro-benchmark (IADD3 / IMAD / VIADDMNMX chains) used as the DP roofline
  * denominator; returns giga warp-lane ops per second */

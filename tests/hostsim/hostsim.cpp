@@ -179,6 +179,27 @@ uint32_t hs_db_tile_info(void* p, uint32_t tile, int what) {
   hlm_db* db = (hlm_db*)p;
   return what == 0 ? db->tile_parent[tile] : db->tile_diff[tile];
 }
+// 64-bit hash of the DP footprint (tile columns off - BAND .. off + n + BAND) of a candidate and its
+// Myers bound: statistics of footprint duplicates among the candidates (analysis only)
+uint64_t hs_db_footprint(void* p, uint32_t cand, int n) {
+  hlm_db* db = (hlm_db*)p;
+  const uint32_t* T = &db->tiles[(size_t)(cand >> 8) * HLM_TILE_WORDS];
+  int off = cand & 0xFF;
+  uint64_t h = 1469598103934665603ULL;
+  for (int c = off - HLM_BAND; c < off + n + HLM_BAND; c++) {
+    int v = 4;
+    if (c >= 0 && c < HLM_TILE_COLS && !((T[16 + (c >> 5)] >> (c & 31)) & 1u))
+      v = (int)((T[c >> 5] >> (c & 31)) & 1u) | (int)(((T[8 + (c >> 5)] >> (c & 31)) & 1u) << 1);
+    h = (h ^ (uint64_t)v) * 1099511628211ULL;
+  }
+  return h;
+}
+int hs_db_lb(void* p, const uint8_t* read, int n, uint32_t cand) {
+  hlm_db* db = (hlm_db*)p;
+  uint32_t rd[18];
+  pack_read(read, n, rd);
+  return hlm_myers_lb(rd, n, &db->tiles[(size_t)(cand >> 8) * HLM_TILE_WORDS], cand & 0xFF);
+}
 int hs_db_eval(void* p, const uint8_t* read, int n, uint32_t cand, int* out5) {
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];
