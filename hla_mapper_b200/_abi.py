@@ -29,6 +29,7 @@ class HlmParams(C.Structure):
         ("mm_max", C.c_int32), ("clip_mode", C.c_int32), ("tolerance", C.c_double),
         ("mtrim_error", C.c_double), ("chunk_pairs", C.c_int32), ("skip_screen", C.c_int32),
         ("cand_capacity", C.c_int64), ("single_slot", C.c_int32), ("score_cap", C.c_int32),
+        ("no_dp_dedup", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -113,6 +114,8 @@ def default_params(rna=0, **kw):
     p.cand_capacity = 0
     p.single_slot = 0
     p.score_cap = 0
+    p.no_dp_dedup = 0
+    p.reserved1 = 0
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -44,6 +44,7 @@ struct Slot {
   cudaEvent_t ev[EV_COUNT];
   Buf h_in, h_out, d_in, d_out, d_units, d_unit_meta, d_cand, d_dp, d_tasks, d_counters;
   Buf d_cres, d_albest, d_alout;  // hlm_score_alleles only
+  Buf d_dptab;                    // footprint de-duplication table of the DP list
   HlmChunk ck;
   bool busy = false;
   int64_t first = 0, n = 0;
@@ -172,6 +173,11 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0, int n_al
   if ((rc = ensure_dev(ctx, s.d_dp, (size_t)dp_cap * 9 + 4096))) return rc;
   if ((rc = ensure_dev(ctx, s.d_tasks, 3 * align16(NU * T * 4) + NU * T * 8 + 256))) return rc;
   if ((rc = ensure_dev(ctx, s.d_counters, 256))) return rc;
+  // de-duplication table: 4 slots per DP a chunk typically selects (about 50 per pair per round);
+  // a fuller table only de-duplicates less
+  int tab_bits = 16;
+  while (tab_bits < 26 && ((int64_t)1 << tab_bits) < std::min<int64_t>(dp_cap * 2, (int64_t)n * 256)) tab_bits++;
+  if ((rc = ensure_dev(ctx, s.d_dptab, (size_t)8 << tab_bits))) return rc;
   HlmChunk& ck = s.ck;
   ck.units_per_pair = U;
   ck.n_units = (int64_t)NU;
@@ -187,6 +193,8 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0, int n_al
   ck.dp_cursor = ck.dp_hist + 256;
   ck.dp_len = (uint8_t*)(ck.dp_cursor + 256);
   ck.dp_cap = dp_cap;
+  ck.dp_tab = ctx->p.no_dp_dedup ? nullptr : (unsigned long long*)s.d_dptab.p;
+  ck.dp_tab_bits = tab_bits;
   ck.counters = (unsigned long long*)s.d_counters.p;
   ck.task_emin = (uint32_t*)s.d_tasks.p;
   ck.task_emin0 = (uint32_t*)((uint8_t*)s.d_tasks.p + align16(NU * T * 4));
@@ -655,6 +663,8 @@ void hlm_params_default(hlm_params* p, int rna) {
   p->cand_capacity = 0;
   p->single_slot = 0;
   p->score_cap = 0;
+  p->no_dp_dedup = 0;
+  p->reserved1 = 0;
 }
 
 hlm_db* hlm_db_open(const char* db_dir, int rna, char* err, size_t errlen) {
@@ -862,7 +872,7 @@ void hlm_ctx_destroy(hlm_ctx* ctx) {
   for (int i = 0; i < HLM_MAX_SLOTS; i++) {
     Slot& s = ctx->slot[i];
     for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters,
-                   &s.d_cres, &s.d_albest, &s.d_alout})
+                   &s.d_cres, &s.d_albest, &s.d_alout, &s.d_dptab})
       if (b->p) cudaFree(b->p);
     for (Buf* b : {&s.h_in, &s.h_out})
       if (b->p) cudaFreeHost(b->p);

@@ -26,6 +26,8 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -819,34 +821,53 @@ struct RangeOut {
   }
 };
 
-bool id_less(const Kept& a, const Kept& b) {  // std::map<string, ...> order of the reference
-  int c = memcmp(a.idgen, b.idgen, std::min(a.idl, b.idl));
-  return c < 0 || (c == 0 && a.idl < b.idl);
+// The kept reads, collected slice by slice, into one vector in the reference's std::map order
+// (byte-wise on the id; stable: equal ids keep their input order).  Only 16-byte keys are sorted -
+// runs on nt host threads, then pairwise merges - and the records are gathered once at the end.
+struct IdKey {
+  const char* s;
+  uint32_t l, part;
+  uint32_t idx, pad;
+};
+bool key_less(const IdKey& a, const IdKey& b) {
+  int c = memcmp(a.s, b.s, std::min(a.l, b.l));
+  return c < 0 || (c == 0 && a.l < b.l);
 }
-
-// stable sort of the kept reads by id on nt host threads: sorted runs, then pairwise merges
-void sort_kept(std::vector<Kept>& kept, int nt) {
-  size_t n = kept.size();
-  if (n < (1u << 16) || nt <= 1) {
-    std::stable_sort(kept.begin(), kept.end(), id_less);
-    return;
-  }
+void sort_kept(std::vector<std::vector<Kept>>& parts, std::vector<Kept>& out, int nt) {
+  size_t n = 0;
+  std::vector<size_t> first(parts.size() + 1, 0);
+  for (size_t p = 0; p < parts.size(); p++) first[p + 1] = first[p] + parts[p].size();
+  n = first[parts.size()];
+  std::vector<IdKey> keys(n);
+  nt = std::max(1, nt);
+  parallel_for(nt, [&](int t) {
+    for (size_t p = (size_t)t; p < parts.size(); p += (size_t)nt)
+      for (size_t i = 0; i < parts[p].size(); i++)
+        keys[first[p] + i] = IdKey{parts[p][i].idgen, parts[p][i].idl, (uint32_t)p, (uint32_t)i, 0};
+  });
   int runs = 1;
-  while (runs * 2 <= nt && runs < 64) runs *= 2;
+  while (runs * 2 <= nt && runs < 64 && n >= (size_t)(1u << 14) * (size_t)(runs * 2)) runs *= 2;
   std::vector<size_t> cut(runs + 1);
   for (int r = 0; r <= runs; r++) cut[r] = n * (size_t)r / runs;
-  parallel_for(runs, [&](int r) { std::stable_sort(kept.begin() + cut[r], kept.begin() + cut[r + 1], id_less); });
-  std::vector<Kept> tmp(n);
-  std::vector<Kept>*src = &kept, *dst = &tmp;
-  for (int w = 1; w < runs; w *= 2) {
-    int pairs = runs / (2 * w);
-    parallel_for(pairs, [&](int k) {
-      size_t a = cut[2 * w * k], m = cut[2 * w * k + w], b = cut[2 * w * k + 2 * w];
-      std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a, id_less);
-    });
-    std::swap(src, dst);
+  parallel_for(runs, [&](int r) { std::stable_sort(keys.begin() + cut[r], keys.begin() + cut[r + 1], key_less); });
+  if (runs > 1) {
+    std::vector<IdKey> tmp(n);
+    std::vector<IdKey>*src = &keys, *dst = &tmp;
+    for (int w = 1; w < runs; w *= 2) {
+      int pairs = runs / (2 * w);
+      parallel_for(pairs, [&](int k) {
+        size_t a = cut[2 * w * k], m = cut[2 * w * k + w], b = cut[2 * w * k + 2 * w];
+        std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a, key_less);
+      });
+      std::swap(src, dst);
+    }
+    if (src != &keys) keys.swap(tmp);
   }
-  if (src != &kept) kept.swap(tmp);
+  out.resize(n);
+  parallel_for(nt, [&](int t) {
+    for (size_t j = n * (size_t)t / nt; j < n * (size_t)(t + 1) / nt; j++) out[j] = parts[keys[j].part][keys[j].idx];
+  });
+  std::vector<std::vector<Kept>>().swap(parts);
 }
 
 }  // namespace
@@ -916,6 +937,11 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
   auto collect_slice = [&](Results& R, int64_t lo, int64_t hi, Arena& arena, Part& P, bool retained) {
     MateBatch *b1 = R.b1, *b2 = R.b2;
     std::string h1, h2, idg;
+    if (o.write_selected && retained && hi > lo) {  // most records of the slice will be written out
+      P.sel1.reserve((size_t)(b1->hoff[hi] - b1->hoff[lo]) + 2 * (size_t)(b1->offs[hi] - b1->offs[lo]) + 6 * (size_t)(hi - lo));
+      if (paired)
+        P.sel2.reserve((size_t)(b2->hoff[hi] - b2->hoff[lo]) + 2 * (size_t)(b2->offs[hi] - b2->offs[lo]) + 6 * (size_t)(hi - lo));
+    }
     for (int64_t i = lo; i < hi; i++) {
       if (!(R.flags[i] & HLM_F_SCREENED)) continue;
       P.n_selected++;
@@ -1000,44 +1026,74 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
   std::vector<Kept> kept;
   std::map<int64_t, std::unique_ptr<BatchOut>> pending;
   int64_t commit_seq = 0, n_pairs = 0, n_selected = 0, sel_bases = 0;
-  uint64_t off1 = 0, off2 = 0;
   double t_gpu = 0, t_post = 0, t_wait = 0;
   std::vector<std::vector<Arena>> arenas(n_ctx);
   for (auto& a : arenas) a = std::vector<Arena>(n_workers);
 
-  // in-order commit: offsets of the selected records and the kept list follow the input order
-  auto commit = [&](std::unique_ptr<BatchOut> bo) {
-    std::vector<std::unique_ptr<BatchOut>> ready;
-    std::vector<std::pair<uint64_t, uint64_t>> offs;  // per ready part
-    {
-      std::lock_guard<std::mutex> g(commit_mu);
-      pending[bo->seq] = std::move(bo);
-      while (!pending.empty() && pending.begin()->first == commit_seq) {
-        std::unique_ptr<BatchOut> b = std::move(pending.begin()->second);
-        pending.erase(pending.begin());
-        commit_seq++;
-        for (Part& P : b->parts) {
-          offs.emplace_back(off1, off2);
-          off1 += P.sel1.size();
-          off2 += P.sel2.size();
-          n_selected += P.n_selected;
-          sel_bases += P.sel_bases;
-          kept.insert(kept.end(), P.kept.begin(), P.kept.end());
-        }
-        n_pairs += b->n;
-        ready.push_back(std::move(b));
+  // in-order commit: the selected records and the kept list follow the input order.  The selected
+  // text goes to two writer threads (one per file, plain sequential writes) so that no driver
+  // waits for the page cache; the kept records stay in their per-slice vectors until the sort.
+  std::vector<std::vector<Kept>> kept_parts;
+  std::mutex wq_mu;
+  std::condition_variable wq_cv;
+  std::deque<std::shared_ptr<BatchOut>> wq[2];
+  bool wq_done = false;
+  auto sel_writer = [&](int which) {
+    ParallelFile& f = which == 0 ? sel1 : sel2;
+    uint64_t off = 0;
+    for (;;) {
+      std::shared_ptr<BatchOut> b;
+      {
+        std::unique_lock<std::mutex> g(wq_mu);
+        wq_cv.wait(g, [&] { return wq_done || !wq[which].empty(); });
+        if (wq[which].empty()) return;
+        b = std::move(wq[which].front());
+        wq[which].pop_front();
+      }
+      for (Part& P : b->parts) {
+        std::string& t = which == 0 ? P.sel1 : P.sel2;
+        if (!t.empty()) f.write_at(t.data(), t.size(), off);
+        off += t.size();
+        std::string().swap(t);
       }
     }
-    if (!o.write_selected) return;
-    size_t k = 0;
-    for (auto& b : ready) {
-      size_t base = k;
-      parallel_for((int)b->parts.size(), [&](int w) {
-        Part& P = b->parts[w];
-        if (!P.sel1.empty()) sel1.write_at(P.sel1.data(), P.sel1.size(), offs[base + w].first);
-        if (!P.sel2.empty()) sel2.write_at(P.sel2.data(), P.sel2.size(), offs[base + w].second);
-      });
-      k += b->parts.size();
+  };
+  std::vector<std::thread> sel_threads;
+  struct Joiner {  // the writer threads never outlive this frame, whatever leaves it
+    std::function<void()> f;
+    ~Joiner() { f(); }
+  } sel_joiner{[&] {
+    {
+      std::lock_guard<std::mutex> q(wq_mu);
+      wq_done = true;
+      wq_cv.notify_all();
+    }
+    for (auto& t : sel_threads)
+      if (t.joinable()) t.join();
+  }};
+  if (o.write_selected) {
+    sel_threads.emplace_back(sel_writer, 0);
+    if (paired) sel_threads.emplace_back(sel_writer, 1);
+  }
+  auto commit = [&](std::unique_ptr<BatchOut> bo) {
+    std::lock_guard<std::mutex> g(commit_mu);
+    pending[bo->seq] = std::move(bo);
+    while (!pending.empty() && pending.begin()->first == commit_seq) {
+      std::shared_ptr<BatchOut> b(std::move(pending.begin()->second));
+      pending.erase(pending.begin());
+      commit_seq++;
+      for (Part& P : b->parts) {
+        n_selected += P.n_selected;
+        sel_bases += P.sel_bases;
+        kept_parts.emplace_back(std::move(P.kept));
+      }
+      n_pairs += b->n;
+      if (o.write_selected) {
+        std::lock_guard<std::mutex> q(wq_mu);
+        wq[0].push_back(b);
+        if (paired) wq[1].push_back(b);
+        wq_cv.notify_all();
+      }
     }
   };
 
@@ -1094,6 +1150,21 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
       int prev = cur ^ 1;  // results of the batch that just finished
       bool have_prev = res[prev].b1 != nullptr;
       if (!end && !failed()) {
+        // reads this build cannot hold (HLM_RAW_MAX raw bases) end the run here, with the read named,
+        // before the batch reaches the GPU
+        for (MateBatch* mb : {b1, b2}) {
+          if (!mb) continue;
+          for (int64_t i = 0; i < mb->n; i++)
+            if (mb->offs[i + 1] - mb->offs[i] > HLM_RAW_MAX) {
+              fail(HLM_E_TOOLONG, "read " + std::string(mb->hdr.data() + mb->hoff[i], mb->hoff[i + 1] - mb->hoff[i]) +
+                                      " is " + std::to_string(mb->offs[i + 1] - mb->offs[i]) +
+                                      " bases long: this build holds reads of up to " + std::to_string(HLM_RAW_MAX) +
+                                      " bases (trimmed mates of up to " + std::to_string(HLM_MAX_READ) + ")");
+              break;
+            }
+        }
+      }
+      if (!end && !failed()) {
         res[cur].bind(b1, b2, T, paired);
         seq_of[cur] = seq;
         int rc;
@@ -1139,9 +1210,14 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
       });
     for (auto& t : drivers) t.join();
   }
+  sel_joiner.f();
   bool sel_ok = sel1.close();
   sel_ok = sel2.close() && sel_ok;
-  if (rc_all) {
+  if (rc_all) {  // nothing half-written stays behind a failed run
+    if (o.write_selected) {
+      unlink((pre + "selected." + tag + ".fastq").c_str());
+      if (paired) unlink((pre + "selected.R2.fastq").c_str());
+    }
     hlm_ctx_set_error(ctx, err_all);
     return rc_all;
   }
@@ -1156,7 +1232,7 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
 
   double t0 = now_s();
   const int nt = std::max(1, std::min(32, hw));
-  sort_kept(kept, nt);
+  sort_kept(kept_parts, kept, nt);
   double t_sort = now_s() - t0;
   if (rna && !o.select_only) {
     double tg = now_s();
@@ -1179,37 +1255,68 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
       werr_msg = m;
     }
   };
-  // emit(k, rank, out...) style writers share this driver: `sizes(t)` returns the bytes thread t's
-  // range will produce, `body(t, RangeOut&)` produces them
-  auto write_file = [&](const std::string& path, auto&& sizes, auto&& body) {
-    ParallelFile f;
-    if (!f.open(path)) {
-      wfail("cannot write " + path);
-      return;
+  // Every file is a job: `sizes(t)` returns the bytes range t of the kept reads will produce,
+  // `body(t, RangeOut&)` produces them at the offset the ranges before it end at.  All (file,
+  // range) tasks go through one pool of host threads, ordered so that concurrent tasks belong to
+  // different files (writes into one file serialise on its inode lock).
+  struct Job {
+    std::string path;
+    std::function<uint64_t(int)> sizes;
+    std::function<void(int, RangeOut&)> body;
+    std::vector<uint64_t> sz;
+    std::unique_ptr<ParallelFile> f;
+  };
+  std::vector<Job> jobs;
+  auto write_file = [&](const std::string& path, std::function<uint64_t(int)> sizes,
+                        std::function<void(int, RangeOut&)> body) {
+    jobs.push_back(Job{path, std::move(sizes), std::move(body), {}, nullptr});
+  };
+  auto run_jobs = [&] {
+    const size_t J = jobs.size();
+    for (Job& j : jobs) {
+      j.sz.assign(nt + 1, 0);
+      j.f.reset(new ParallelFile());
+      if (!j.f->open(j.path)) wfail("cannot write " + j.path);
     }
-    std::vector<uint64_t> sz(nt + 1, 0);
-    parallel_for(nt, [&](int t) { sz[t + 1] = sizes(t); });
-    for (int t = 0; t < nt; t++) sz[t + 1] += sz[t];
-    parallel_for(nt, [&](int t) {
-      RangeOut ro;
-      ro.begin(&f, sz[t]);
-      body(t, ro);
-      ro.flush();
+    if (werr) return;
+    std::atomic<size_t> next(0);
+    parallel_for(nt, [&](int) {
+      for (size_t k; (k = next.fetch_add(1)) < J * (size_t)nt;) jobs[k % J].sz[k / J + 1] = jobs[k % J].sizes((int)(k / J));
     });
-    if (!f.close()) wfail("write error on " + path);
+    for (Job& j : jobs)
+      for (int t = 0; t < nt; t++) j.sz[t + 1] += j.sz[t];
+    next = 0;
+    parallel_for(nt, [&](int) {
+      RangeOut ro;
+      for (size_t k; (k = next.fetch_add(1)) < J * (size_t)nt;) {
+        Job& j = jobs[k % J];
+        int t = (int)(k / J);
+        if (j.sz[t + 1] == j.sz[t]) continue;
+        ro.begin(j.f.get(), j.sz[t]);
+        j.body(t, ro);
+        ro.flush();
+      }
+    });
+    for (Job& j : jobs)
+      if (!j.f->close()) wfail("write error on " + j.path);
   };
   int64_t n_assigned = 0;
+  int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
+  std::vector<int64_t> assigned(nt, 0);
+  std::vector<std::vector<int64_t>> rank(db->n_loci, std::vector<int64_t>(nt + 1, 0));
+  std::vector<int64_t> downS(db->n_loci, 0);
+  std::string header = "Read";
   try {
     // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
     for (int m = 0; m < (paired ? 2 : 1); m++)
       write_file(pre + "selected.trim." + (m == 0 ? tag : "R2") + ".fastq",
-                 [&](int t) {
+                 [&, m](int t) {
                    uint64_t b = 0;
                    for (size_t i = cut[t]; i < cut[t + 1]; i++)
                      b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].n1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].n2 + 5;
                    return b;
                  },
-                 [&](int t, RangeOut& w) {
+                 [&, m](int t, RangeOut& w) {
                    for (size_t i = cut[t]; i < cut[t + 1]; i++) {
                      const Kept& k = kept[i];
                      if (m == 0) {
@@ -1222,36 +1329,34 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                    }
                  });
     // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051, src/map_rna.cpp:945-1049)
+    auto row = [&](const Kept& k, std::string& line, bool& any) {
+      char num[32];
+      line.assign(k.idgen, k.idl);
+      for (int g = 0; g < T; g++) {
+        line += '\t';
+        if (!((k.visible >> g) & 1u)) {
+          line += '-';
+          continue;
+        }
+        int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
+        if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
+        int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
+        line.append(num, m);
+      }
+      line += '\t';
+      any = false;
+      for (int g = 0; g < T; g++)
+        if ((k.target >> g) & 1u) {
+          if (any) line += ',';
+          line += db->names[g];
+          any = true;
+        }
+      if (!any) line += '-';
+      line += '\n';
+    };
     if (!o.select_only) {
-      std::string header = "Read";
       for (int g = 0; g < T; g++) header += "\t" + db->names[g];
       header += "\tTarget\n";
-      std::vector<int64_t> assigned(nt, 0);
-      auto row = [&](const Kept& k, std::string& line, bool& any) {
-        char num[32];
-        line.assign(k.idgen, k.idl);
-        for (int g = 0; g < T; g++) {
-          line += '\t';
-          if (!((k.visible >> g) & 1u)) {
-            line += '-';
-            continue;
-          }
-          int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
-          if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
-          int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
-          line.append(num, m);
-        }
-        line += '\t';
-        any = false;
-        for (int g = 0; g < T; g++)
-          if ((k.target >> g) & 1u) {
-            if (any) line += ',';
-            line += db->names[g];
-            any = true;
-          }
-        if (!any) line += '-';
-        line += '\n';
-      };
       write_file(pre + "addressing_table.txt",
                  [&](int t) {
                    uint64_t b = t == 0 ? header.size() : 0;
@@ -1273,42 +1378,47 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                      w.add(line.data(), line.size());
                    }
                  });
-      for (int64_t a : assigned) n_assigned += a;
     }
     // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351, src/map_rna.cpp:1072-1344)
-    int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
+    auto member = [&](int g, const Kept& k) {
+      if (!((k.locus_mask >> g) & 1u)) return false;  // was in sorted_<gene>_R1.fastq
+      if (!((k.target >> g) & 1u)) return false;       // sequence_address[(gene, id)]
+      // the lookup key is the header token minus '@' (:1225): it only equals the id when the
+      // token carries no /1 /2 (always true for paired input, whose headers were normalised)
+      return k.tokl >= 1 && k.tokl - 1 == k.idl && memcmp(k.h1 + 1, k.idgen, k.idl) == 0;
+    };
+    if (!o.select_only) {
+      // rank of every range's first member, per gene: the first downS members also go to .trim
+      parallel_for(nt, [&](int t) {
+        for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+          const Kept& k = kept[i];
+          uint32_t m = k.locus_mask & k.target;
+          for (; m; m &= m - 1) {
+            int g = __builtin_ctz(m);
+            if (g < db->n_loci && member(g, k)) rank[g][t + 1]++;
+          }
+        }
+      });
+      for (int g = 0; g < db->n_loci; g++)
+        for (int t = 0; t < nt; t++) rank[g][t + 1] += rank[g][t];
+    }
     for (int g = 0; g < db->n_loci && !o.select_only; g++) {
       const std::string& gene = db->names[g];
       int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
-      int64_t downS = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
-      auto member = [&](const Kept& k) {
-        if (!((k.locus_mask >> g) & 1u)) return false;  // was in sorted_<gene>_R1.fastq
-        if (!((k.target >> g) & 1u)) return false;       // sequence_address[(gene, id)]
-        // the lookup key is the header token minus '@' (:1225): it only equals the id when the
-        // token carries no /1 /2 (always true for paired input, whose headers were normalised)
-        return k.tokl >= 1 && k.tokl - 1 == k.idl && memcmp(k.h1 + 1, k.idgen, k.idl) == 0;
-      };
-      // rank of every range's first member: the first downS members also go to the .trim files
-      std::vector<int64_t> rank(nt + 1, 0);
-      parallel_for(nt, [&](int t) {
-        int64_t c = 0;
-        for (size_t i = cut[t]; i < cut[t + 1]; i++) c += member(kept[i]) ? 1 : 0;
-        rank[t + 1] = c;
-      });
-      for (int t = 0; t < nt; t++) rank[t + 1] += rank[t];
+      downS[g] = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
       for (int m = 0; m < (paired ? 2 : 1); m++) {
         write_file(pre + gene + "_" + (m == 0 ? tag : "R2") + ".fastq",
-                   [&](int t) {
+                   [&, g, m](int t) {
                      uint64_t b = 0;
                      for (size_t i = cut[t]; i < cut[t + 1]; i++)
-                       if (member(kept[i]))
+                       if (member(g, kept[i]))
                          b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].l1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].l2 + 5;
                      return b;
                    },
-                   [&](int t, RangeOut& w) {
+                   [&, g, m](int t, RangeOut& w) {
                      for (size_t i = cut[t]; i < cut[t + 1]; i++) {
                        const Kept& k = kept[i];
-                       if (!member(k)) continue;
+                       if (!member(g, k)) continue;
                        if (m == 0) {
                          w.add(k.h1, k.h1l); w.add("\n", 1); w.add(k.s1, k.l1); w.add("\n+\n", 3); w.add(k.q1, k.l1);
                          w.add("\n", 1);
@@ -1319,21 +1429,21 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                      }
                    });
         write_file(pre + gene + ".trim." + (m == 0 ? tag : "R2") + ".fastq",
-                   [&](int t) {
+                   [&, g, m](int t) {
                      uint64_t b = 0;
-                     int64_t r = rank[t];
-                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS; i++)
-                       if (member(kept[i])) {
+                     int64_t r = rank[g][t];
+                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS[g]; i++)
+                       if (member(g, kept[i])) {
                          b += kept[i].tokl + 8 + 2 * (uint64_t)(m == 0 ? kept[i].n1 : kept[i].n2) + 4;
                          r++;
                        }
                      return b;
                    },
-                   [&](int t, RangeOut& w) {
-                     int64_t r = rank[t];
-                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS; i++) {
+                   [&, g, m](int t, RangeOut& w) {
+                     int64_t r = rank[g][t];
+                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS[g]; i++) {
                        const Kept& k = kept[i];
-                       if (!member(k)) continue;
+                       if (!member(g, k)) continue;
                        r++;
                        w.add(k.h1, k.tokl);
                        if (m == 0) {
@@ -1346,6 +1456,8 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                    });
       }
     }
+    run_jobs();
+    for (int64_t a : assigned) n_assigned += a;
     if (werr) {
       hlm_ctx_set_error(ctx, werr_msg);
       return werr;

@@ -926,7 +926,6 @@ k_expand(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
 // After round 1 no unevaluated candidate can tie or beat the best (cost >= lb).
 __global__ void __launch_bounds__(256)
 k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
-  __shared__ uint32_t s_hist[256];
   __shared__ int s_wcnt[8];
   __shared__ unsigned long long s_base;
   int64_t ncand = (int64_t)ck.counters[0];
@@ -935,8 +934,6 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int64_t nloop = (ncand + stride - 1) / stride;
   unsigned long long n_take = 0;
-  s_hist[threadIdx.x] = 0;  // blockDim.x == 256
-  __syncthreads();
   // the kernel is a chain of dependent loads per candidate (record -> locus -> task minimum ->
   // best): two candidates per thread are in flight at a time (more cost occupancy)
   constexpr int UN = 2;
@@ -992,9 +989,8 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
     // the DP list stays dense (no padding).  List slots are claimed once per BLOCK per iteration
     // (warp ballots -> shared-memory prefix -> one global atomic): a per-warp atomic on the one
     // list counter was what bounded this kernel.  The number of DP rows (= trimmed length) goes
-    // with every entry and into a histogram - per block in shared memory, flushed at the end:
-    // the list is counting-sorted by length before k_dp so that the 32 candidates of a DP warp
-    // are alike.
+    // with every entry: after k_dp_dedup the list is counting-sorted by length so that the 32
+    // candidates of a DP warp are alike.
     uint32_t bal[UN];
     int wcnt = 0;
 #pragma unroll
@@ -1027,15 +1023,106 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
         } else {
           ck.counters[2] = 1;
         }
-        atomicAdd(&s_hist[nrows], 1u);
       }
       pos += __popc(bal[u]);
     }
     n_take += wcnt;
   }
+  (void)n_take;  // the DP count (counters[6]) and the length histogram come from k_dp_dedup
+}
+
+// ------------------------------------------------------------------ DP list: footprint de-duplication
+// Two selected candidates of the same unit and strand whose tiles agree on the DP footprint
+// (columns off - BAND .. off + n + BAND) are the same alignment problem: the windows differ only
+// in columns the band cannot reach (typically two children of one rep that share the differing
+// column inside the footprint).  The DP depends on nothing else, so one of them is enough - the
+// result goes to the task minimum either way.  SURVEY.md section 8d counts algorithmic cells per
+// distinct footprint, as the oracle's fast port evaluates them; without this pass the DP did 1.35x
+// that.  Exact: a 32-bit tag of the footprint hash finds the earlier entry, the footprints are
+// then compared word for word before anything is dropped.  Table: open addressing, u64 slots
+// (tag << 32 | list index + 1), cleared per round; a full neighbourhood just keeps the entry.
+struct Footprint {
+  uint32_t w[21];  // 3 planes x 7 words: bits [0, n + 2 BAND) of the planes shifted to column off - BAND
+};
+__device__ __forceinline__ void footprint_of(const uint32_t* __restrict__ T, int off, int n, Footprint& f) {
+  int sh = off - HLM_BAND, width = n + 2 * HLM_BAND;  // sh in [0, 32), width <= 224
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      uint32_t lo = __ldg(T + 8 * p + k), hi = __ldg(T + 8 * p + k + 1);  // k + 1 <= 7
+      uint32_t x = __funnelshift_r(lo, hi, sh);
+      int bits = width - 32 * k;
+      if (bits <= 0) x = 0;
+      else if (bits < 32) x &= (1u << bits) - 1u;
+      f.w[7 * p + k] = x;
+    }
+  }
+}
+#define DP_TAB_PROBES 32
+__global__ void __launch_bounds__(256)
+k_dp_dedup(HlmDevDB db, HlmChunk ck, int dedup) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;  // blockDim.x == 256
+  __syncthreads();
+  int64_t nd = (int64_t)ck.counters[1];
+  if (nd > ck.dp_cap) nd = ck.dp_cap;
+  if (ck.counters[2]) nd = 0;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long n_keep = 0;
+  const uint64_t mask = ((uint64_t)1 << ck.dp_tab_bits) - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) {
+    int n = ck.dp_len[i];
+    bool keep = true;
+    if (dedup) {
+      uint64_t c = ck.cand[ck.dp_list[i]];
+      uint32_t unit = HLM_CAND_UNIT(c);
+      int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
+      Footprint f;
+      footprint_of(db.tiles + (size_t)HLM_CAND_TILE(c) * HLM_TILE_WORDS, off, n, f);
+      uint64_t h = ((uint64_t)unit * 2 + strand) * 0x9E3779B97F4A7C15ull + (uint64_t)n;
+#pragma unroll
+      for (int k = 0; k < 21; k++) h = (h ^ f.w[k]) * 0x100000001B3ull + (h >> 29);
+      h ^= h >> 32;
+      h *= 0xD6E8FEB86659FD93ull;
+      h ^= h >> 32;
+      uint64_t slot = h & mask;
+      unsigned long long mine = (h & 0xFFFFFFFF00000000ull) | (unsigned long long)(i + 1);
+      for (int probe = 0; probe < DP_TAB_PROBES; probe++) {
+        unsigned long long old = atomicCAS(&ck.dp_tab[slot], 0ull, mine);
+        if (old == 0ull) break;  // first of its footprint
+        if ((old >> 32) == (mine >> 32)) {
+          uint64_t c2 = ck.cand[ck.dp_list[(old & 0xFFFFFFFFull) - 1]];
+          if (HLM_CAND_UNIT(c2) == unit && (int)HLM_CAND_STRAND(c2) == strand) {
+            Footprint g;
+            footprint_of(db.tiles + (size_t)HLM_CAND_TILE(c2) * HLM_TILE_WORDS, (int)HLM_CAND_OFFM(c2) + HLM_OFF_MIN,
+                         n, g);
+            bool same = true;
+#pragma unroll
+            for (int k = 0; k < 21; k++) same = same && (f.w[k] == g.w[k]);
+            if (same) {
+              keep = false;
+              break;
+            }
+          }
+        }
+        slot = (slot + 1) & mask;
+      }
+    }
+    if (keep) {
+      atomicAdd(&s_hist[n], 1u);
+      n_keep++;
+    } else {
+      ck.dp_len[i] = 0;  // dropped: k_dp_scatter skips it
+    }
+  }
   __syncthreads();
   if (s_hist[threadIdx.x]) atomicAdd(&ck.dp_hist[threadIdx.x], s_hist[threadIdx.x]);
-  if (lane == 0 && n_take) atomicAdd(&ck.counters[6], n_take);
+  for (int o = 16; o; o >>= 1) n_keep += __shfl_xor_sync(FULL, n_keep, o);
+  if ((threadIdx.x & 31) == 0 && n_keep) {
+    atomicAdd(&ck.counters[6], n_keep);
+    atomicAdd(&ck.counters[13], n_keep);
+  }
 }
 
 // ------------------------------------------------------------------ DP list: counting sort by length
@@ -1067,7 +1154,7 @@ k_dp_scatter(HlmChunk ck) {
   int64_t nloop = (nd + stride - 1) / stride;
   for (int64_t it = 0; it < nloop; it++) {
     int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool act = i < nd;
+    bool act = i < nd && ck.dp_len[i] != 0;  // 0: dropped by k_dp_dedup
     int n = act ? (int)ck.dp_len[i] : -1 - lane;  // inactive lanes never match anyone
     uint32_t peers = __match_any_sync(FULL, n);
     if (act) {
@@ -1084,7 +1171,7 @@ k_dp_scatter(HlmChunk ck) {
 __global__ void __launch_bounds__(128)
 k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
   if (ck.counters[2]) return;  // a list overflowed: the host re-runs the chunk in halves
-  int64_t nd = (int64_t)ck.counters[1];
+  int64_t nd = (int64_t)ck.counters[13];  // entries of the sorted list (after de-duplication)
   if (nd > ck.dp_cap) nd = ck.dp_cap;
   int lane = threadIdx.x & 31;
   unsigned long long cells = 0;
@@ -1117,6 +1204,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
 __global__ void k_dp_round_end(HlmChunk ck) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ck.counters[1] = 0;
+    ck.counters[13] = 0;
     ck.counters[14] = 0;
   }
 }
@@ -1556,6 +1644,10 @@ void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk&
 }
 void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                    int sms, cudaStream_t st) {
+  // per-allele scoring keeps one result per candidate: no de-duplication there
+  int dedup = (ck.cand_res == nullptr && ck.dp_tab != nullptr) ? 1 : 0;
+  if (dedup) cudaMemsetAsync(ck.dp_tab, 0, (size_t)8 << ck.dp_tab_bits, st);
+  k_dp_dedup<<<grid_for(sms, 8), 256, 0, st>>>(db, ck, dedup);
   k_dp_scan<<<1, 256, 0, st>>>(ck);
   k_dp_scatter<<<grid_for(sms, 4), 256, 0, st>>>(ck);
   k_dp<<<grid_for(sms, 4), 128, 0, st>>>(db, kp, ck, n_targets);

@@ -39,12 +39,14 @@ struct HlmChunk {
   uint32_t* dp_hist;     // [256] rows histogram, then ...
   uint32_t* dp_cursor;   // [256] ... scatter cursors
   int64_t dp_cap;
+  unsigned long long* dp_tab;    // footprint de-duplication of the DP list: 2^dp_tab_bits u64 slots
+  int dp_tab_bits;
   unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
                                  // [3] n_kept, [4] dp cells, [5] myers rows, [6] n_dp total,
                                  // [7] read too long, [8] n_cand after the seed index,
                                  // [9] / [10] after expansion round 0 / 1 (slots incl. padding),
                                  // [11] real candidates, [12] real seed-index candidates,
-                                 // [14] / [15] work counters
+                                 // [13] DP list entries after de-duplication, [14] / [15] work counters
   uint32_t* task_emin;   // units * n_targets: minimum lower bound over evaluated candidates
   uint32_t* task_emin0;  // ... over the seed-index candidates only (expansion gate)
   uint32_t* task_pmin;   // capped scoring: minimum prefix bound (rows the trailing clip cannot reach)

@@ -100,6 +100,9 @@ typedef struct hlm_params {
                              its value.  target_mask, visible_mask, min_sum and every score of a
                              visible target - i.e. the addressing table and the per-gene files -
                              are identical to the exact mode            */
+  int32_t no_dp_dedup;    /* 1: switch off the footprint de-duplication of the DP list (A/B and
+                             test switch; results are identical either way)                   */
+  int32_t reserved1;
 } hlm_params;
 
 /* One record of the reference's sorted_spliced_<gene>.fastq (map_rna.cpp:740-790): a block of a

@@ -194,6 +194,19 @@ uint64_t hs_db_footprint(void* p, uint32_t cand, int n) {
   }
   return h;
 }
+// band minimum after every 8 rows (analysis of early termination): out[k] = bound after 8 (k + 1) rows
+int hs_db_lb_profile(void* p, const uint8_t* read, int n, uint32_t cand, int* out) {
+  hlm_db* db = (hlm_db*)p;
+  uint32_t rd[18];
+  pack_read(read, n, rd);
+  int k = 0;
+  for (int r = 8; r <= n; r += 8) {
+    int plb = 0;
+    hlm_myers_lb(rd, n, &db->tiles[(size_t)(cand >> 8) * HLM_TILE_WORDS], cand & 0xFF, r, &plb);
+    out[k++] = plb;
+  }
+  return k;
+}
 int hs_db_lb(void* p, const uint8_t* read, int n, uint32_t cand) {
   hlm_db* db = (hlm_db*)p;
   uint32_t rd[18];

@@ -296,3 +296,56 @@ def test_medium_db_fast_oracle_prefix_and_properties(orc, tmp_path_factory):
     home = ((got.target_mask >> np.maximum(tl, 0).astype(np.uint32)) & 1).astype(bool) & (tl >= 0)
     assert home.sum() > 0.8 * (kept & (tl >= 0)).sum()
     m.close(); gd.close()
+
+
+def test_dp_footprint_deduplication_is_exact_and_saves_work(orc, tmp_path_factory):
+    """the DP list is de-duplicated by exact DP footprint (k_dp_dedup): same results as without
+    it and as the oracle, on a database with many near-identical alleles; and fewer DP alignments -
+    the oracle's fast port counts algorithmic cells per distinct footprint"""
+    from hla_mapper_b200 import api
+
+    d = tmp_path_factory.mktemp("db_dedup")
+    db = synth.make_db(str(d / "db"), seed=5, n_loci=3, total_alleles=900, len_range=(500, 600), n_others=5,
+                       n_lineages=4)
+    rb = synth.make_reads(db, 1200, read_len=150, seed=3, on_target=1.0, frag_mu=300, frag_sd=20, lowq_tail=0.3,
+                          ragged=True)
+    p = _abi.default_params()
+    want, cells = orc.run(orc.OracleDB(db.path), p, rb, mode=1)
+    gdb = api.Database(db.path)
+    out = {}
+    for off in (0, 1):
+        m = api.Mapper(gdb, 0, p, no_dp_dedup=off)
+        got = m.run(rb)
+        out[off] = (m.profile()["n_dp"], m.profile()["n_dp_cells"])
+        m.close()
+        for k in want.FIELDS:
+            assert np.array_equal(getattr(want, k), getattr(got, k)), (off, k)
+    gdb.close()
+    assert out[0][0] < 0.97 * out[1][0], out
+    # within a few percent of the oracle's own count of cells (per distinct footprint)
+    print("dp cells: oracle", cells, "gpu dedup", out[0][1], "gpu no dedup", out[1][1])
+    assert out[0][1] < 1.15 * cells
+
+
+def test_file_pipeline_names_a_read_it_cannot_hold(small_db, tmp_path):
+    """a read longer than HLM_RAW_MAX ends hlm_map_fastq with the read named and no half-written
+    selected*.fastq left behind (the reference takes any length; this build says where it stops)"""
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 300, read_len=150, seed=5, on_target=0.9, frag_mu=300, frag_sd=30)
+    r1, r2 = str(tmp_path / "r1.fastq"), str(tmp_path / "r2.fastq")
+    synth.write_fastq(rb, r1, r2)
+    lines = open(r1).read().split("\n")
+    lines[4 * 200] = "@LONGREAD/1"
+    lines[4 * 200 + 1] = "ACGT" * 75
+    lines[4 * 200 + 3] = "?" * 300
+    open(r1, "w").write("\n".join(lines))
+    gdb = api.Database(small_db.path)
+    m = api.Mapper(gdb, 0, _abi.default_params())
+    out = tmp_path / "out"
+    out.mkdir()
+    with pytest.raises(api.HlmError, match="LONGREAD.* is 300 bases long"):
+        m.map_fastq(r1, r2, "S", out, batch_pairs=64)
+    assert not list(out.iterdir())
+    m.close()
+    gdb.close()
