@@ -45,6 +45,7 @@ struct Slot {
   Buf h_in, h_out, d_in, d_out, d_units, d_unit_meta, d_cand, d_dp, d_tasks, d_counters;
   Buf d_cres, d_albest, d_alout;  // hlm_score_alleles only
   Buf d_dptab;                    // footprint de-duplication table of the DP list
+  Buf d_prelist;                  // k_prescreen's list of pairs for k_screen
   HlmChunk ck;
   bool busy = false;
   int64_t first = 0, n = 0;
@@ -178,6 +179,7 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0, int n_al
   int tab_bits = 16;
   while (tab_bits < 26 && ((int64_t)1 << tab_bits) < std::min<int64_t>(dp_cap * 2, (int64_t)n * 256)) tab_bits++;
   if ((rc = ensure_dev(ctx, s.d_dptab, (size_t)8 << tab_bits))) return rc;
+  if ((rc = ensure_dev(ctx, s.d_prelist, (size_t)n * 4 + 256))) return rc;
   HlmChunk& ck = s.ck;
   ck.units_per_pair = U;
   ck.n_units = (int64_t)NU;
@@ -193,6 +195,7 @@ int ensure_work(hlm_ctx* ctx, Slot& s, int64_t n, int64_t n_blocks = 0, int n_al
   ck.dp_cursor = ck.dp_hist + 256;
   ck.dp_len = (uint8_t*)(ck.dp_cursor + 256);
   ck.dp_cap = dp_cap;
+  ck.pre_list = (uint32_t*)s.d_prelist.p;
   ck.dp_tab = ctx->p.no_dp_dedup ? nullptr : (unsigned long long*)s.d_dptab.p;
   ck.dp_tab_bits = tab_bits;
   ck.counters = (unsigned long long*)s.d_counters.p;
@@ -805,6 +808,10 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
     delete ctx;
     return fail("params.rna does not match the database kind");
   }
+  if (p.clip_mode < HLM_CLIP_LEAD_ONLY || p.clip_mode > HLM_CLIP_NONE) {
+    delete ctx;
+    return fail("params.clip_mode must be HLM_CLIP_LEAD_ONLY, HLM_CLIP_BOTH or HLM_CLIP_NONE");
+  }
   if (p.mm_max < 0 || p.mm_max > 100 || p.minhit < 0 || p.tolerance < 0) {
     delete ctx;
     return fail("params out of range (0 <= mm_max <= 100; the alignment band is fixed at +-20)");
@@ -849,6 +856,17 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
     double P = pow((double)10, (chr_phred / (double)(-10)));
     if (P <= p.mtrim_error) kp.good_q[c >> 5] |= 1u << (c & 31);
   }
+  // P falls with the byte value, so the good bytes are normally one run thr .. 127 (bytes >= 128
+  // are negative chars in the reference: never good): the kernel then tests eight bytes at once
+  kp.q_thr = -1;
+  {
+    int thr = 0;
+    while (thr < 128 && !((kp.good_q[thr >> 5] >> (thr & 31)) & 1u)) thr++;
+    bool run = thr < 128;
+    for (int c = 0; c < 256 && run; c++)
+      if ((((kp.good_q[c >> 5] >> (c & 31)) & 1u) != 0) != (c >= thr && c < 128)) run = false;
+    if (run) kp.q_thr = thr;
+  }
   if (upload_db(ctx, const_cast<hlm_db*>(db)) != 0) {
     std::string m = ctx->err;
     delete ctx;
@@ -872,7 +890,7 @@ void hlm_ctx_destroy(hlm_ctx* ctx) {
   for (int i = 0; i < HLM_MAX_SLOTS; i++) {
     Slot& s = ctx->slot[i];
     for (Buf* b : {&s.d_in, &s.d_out, &s.d_units, &s.d_unit_meta, &s.d_cand, &s.d_dp, &s.d_tasks, &s.d_counters,
-                   &s.d_cres, &s.d_albest, &s.d_alout, &s.d_dptab})
+                   &s.d_cres, &s.d_albest, &s.d_alout, &s.d_dptab, &s.d_prelist})
       if (b->p) cudaFree(b->p);
     for (Buf* b : {&s.h_in, &s.h_out})
       if (b->p) cudaFreeHost(b->p);

@@ -311,8 +311,10 @@ struct HlmAln {
   int S, cost, lead, trail;
 };
 
+// noclip (HLM_CLIP_NONE): no row may start a new alignment (no leading clip) and only the last
+// row may end one (no trailing clip); two row-level selects, nothing in the cell loop.
 HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_t* __restrict__ tile,
-                           int off, int one = 1) {
+                           int off, int one = 1, int noclip = 0) {
   const uint32_t* T0 = tile;
   const uint32_t* T1 = tile + 8;
   const uint32_t* TN = tile + 16;
@@ -346,6 +348,7 @@ HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_
     uint32_t eq_hi = ~(hlm_funnel(w0.b, w0.c, s) ^ m0) & ~(hlm_funnel(w1.b, w1.c, s) ^ m1) &
                      ~(hlm_funnel(wn.b, wn.c, s) | mn);
     start = (i == 1) ? -(HLM_V_CLIP + HLM_CU + 1) : start - (HLM_CU + 1);
+    if (noclip) start = HLM_V_NEG;
     trailpen -= HLM_CU;
     // Cell update, arranged so that the ALU pipe (min/max, DPX) sees 5.5 instructions per cell:
     //   e  = max(E[k+1] + GAPE, H[k+1] + GAPO)                  VIADDMNMX (+ add)
@@ -372,6 +375,7 @@ HLM_HD HlmAln hlm_dp_align(const uint32_t* __restrict__ rd, int n, const uint32_
     }
     rowmax = hlm_max(rowmax, hprev);  // NB is odd: the last cell
     int fin = rowmax - (i < n ? trailpen : 0);
+    if (noclip && i < n) fin = HLM_V_NEG - 1;
     if (fin >= best) {
       best = fin;
       best_i = i;

@@ -67,20 +67,37 @@ __device__ __forceinline__ uint64_t warp_load8(const uint8_t* p, int len, int la
 
 // 8 ASCII bases -> 2-bit stream (16 bits), plane bits (8 each).  Only upper-case ACGT are
 // bases (the reference compares raw strings); everything else, and padding, is N.
+// Byte-parallel on the two 32-bit halves: code = ((c >> 1) ^ (c >> 2)) & 3 maps A C G T to
+// 0 1 2 3; a byte is a base iff it equals the letter its code stands for
+// ('A' ^ (b0 << 1) ^ (b1 * 6) ^ (b0 & b1) * 0x11); the bits of the four bytes of a half are
+// gathered with one multiply each.
+__device__ __forceinline__ void encode4(uint32_t v, uint32_t& pk, uint32_t& b0, uint32_t& b1, uint32_t& bn) {
+  uint32_t code = ((v >> 1) ^ (v >> 2)) & 0x03030303u;
+  uint32_t c0 = code & 0x01010101u, c1 = (code >> 1) & 0x01010101u, c01 = c0 & c1;
+  uint32_t expect = 0x41414141u ^ (c0 << 1) ^ (c1 * 6u) ^ (c01 * 0x11u);
+  uint32_t t = v ^ expect;  // zero byte <=> a base
+  // 0x80 in every non-zero byte of t (exact, no carries across bytes)
+  uint32_t nz = (((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+  uint32_t keep = 0x01010101u ^ (nz >> 7);  // 1 in every base byte
+  c0 &= keep;
+  c1 &= keep;
+  // gather bit 0 of bytes 0..3 into bits 0..3: (x * 0x01020408) >> 24
+  b0 = (c0 * 0x01020408u) >> 24;
+  b1 = (c1 * 0x01020408u) >> 24;
+  bn = ((nz >> 7) * 0x01020408u) >> 24;
+  uint32_t two = c0 | (c1 << 1);  // 2-bit code per byte
+  // bytes 0..3 -> bit pairs 0..3: x | x >> 6 | x >> 12 | x >> 18, low byte
+  pk = (two | (two >> 6) | (two >> 12) | (two >> 18)) & 0xFFu;
+}
 __device__ __forceinline__ void encode8(uint64_t v, uint32_t& pk, uint32_t& b0, uint32_t& b1,
                                         uint32_t& bn) {
-  pk = 0; b0 = 0; b1 = 0; bn = 0;
-#pragma unroll
-  for (int x = 0; x < 8; x++) {
-    uint32_t c = (uint32_t)(v >> (8 * x)) & 0xFFu;
-    bool isb = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
-    uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
-    code = isb ? code : 0u;
-    pk |= code << (2 * x);
-    b0 |= (code & 1u) << x;
-    b1 |= (code >> 1) << x;
-    bn |= (isb ? 0u : 1u) << x;
-  }
+  uint32_t pl, p0l, p1l, pnl, ph, p0h, p1h, pnh;
+  encode4((uint32_t)v, pl, p0l, p1l, pnl);
+  encode4((uint32_t)(v >> 32), ph, p0h, p1h, pnh);
+  pk = pl | (ph << 8);
+  b0 = p0l | (p0h << 4);
+  b1 = p1l | (p1h << 4);
+  bn = pnl | (pnh << 4);
 }
 
 // Warp-level list appender: a warp reserves HLM_APPEND_BLOCK slots with ONE atomic and fills them
@@ -248,18 +265,120 @@ __device__ __forceinline__ void stage_quals(const uint8_t* p, int len, int lane,
                                             const HlmKParams& kp) {
   uint64_t v = warp_load8(p, len, lane);
   uint32_t g = 0;
+  if (kp.q_thr >= 0) {
+    // good <=> q_thr <= byte < 128, four bytes per 32-bit half, no carries across bytes
+    uint32_t thr4 = (uint32_t)kp.q_thr * 0x01010101u;
 #pragma unroll
-  for (int x = 0; x < 8; x++) {
-    uint32_t c = (uint32_t)(v >> (8 * x)) & 0xFFu;
-    uint32_t ok = (kp.good_q[c >> 5] >> (c & 31)) & 1u;
-    if (8 * lane + x >= len) ok = 0;
-    g |= ok << x;
+    for (int h = 0; h < 2; h++) {
+      uint32_t w = (uint32_t)(v >> (32 * h));
+      uint32_t ge = (((w | 0x80808080u) - thr4) & ~w) & 0x80808080u;
+      g |= (((ge >> 7) * 0x01020408u) >> 24) << (4 * h);
+    }
+    int rem = len - 8 * lane;  // padding bytes are zero: below any threshold unless q_thr == 0
+    if (rem < 8) g &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+  } else {
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      uint32_t c = (uint32_t)(v >> (8 * x)) & 0xFFu;
+      uint32_t ok = (kp.good_q[c >> 5] >> (c & 31)) & 1u;
+      if (8 * lane + x >= len) ok = 0;
+      g |= ok << x;
+    }
   }
   uint32_t x0 = g << (8 * (lane & 3));
   x0 |= __shfl_xor_sync(FULL, x0, 1); x0 |= __shfl_xor_sync(FULL, x0, 2);
   if ((lane & 3) == 0) ws.good[lane >> 2] = x0;
   if (lane == 0) ws.good[8] = 0;
   __syncwarp();
+}
+
+// ------------------------------------------------------------------ k_prescreen
+// The FASTQ loop (preselect.cpp:707-731: stride 2, one extra step after a hit) only leaves the
+// even positions of R1 through a hit, so a pair whose even positions hold no 20-mer of
+// motif_all.txt is rejected whatever else it contains - the common case on whole-genome / exome
+// input.  One THREAD per pair streams R1 as aligned 8-byte words, keeps the last 32 bases as a
+// 2-bit window and asks the Bloom front about the four new even positions of every word (four
+// independent L2 loads in flight); no shared memory, no shuffles.  A pair with a Bloom-positive
+// window (a real hit or a false positive), or anything the shortcut does not cover, goes on a list
+// for k_screen, which does the exact work.  Applies to: FASTQ stride rule, minhit >= 1, the screen
+// not skipped, no motif lines with non-ACGT bytes.
+__device__ __forceinline__ bool prescreen_applies(const HlmDevDB& db, const HlmKParams& kp) {
+  return kp.screen_variant == HLM_SCREEN_FASTQ && !kp.skip_screen && kp.minhit >= 1 && db.n_odd == 0;
+}
+__global__ void __launch_bounds__(128)
+k_prescreen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
+  int lane = threadIdx.x & 31;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nloop = (ck.n_pairs + stride - 1) / stride;
+  for (int64_t it = 0; it < nloop; it++) {
+    int64_t pair = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool maybe = false, have = pair < ck.n_pairs;
+    if (have) {
+      uint64_t o1 = ck.offs1[pair];
+      int l1 = (int)(ck.offs1[pair + 1] - o1);
+      bool ok = !(l1 < HLM_MOTIF || l1 < kp.v_size);
+      if (kp.paired) {
+        int l2 = (int)(ck.offs2[pair + 1] - ck.offs2[pair]);
+        if (l2 < HLM_MOTIF || l2 < kp.v_size) ok = false;
+      }
+      if (ok) {
+        uintptr_t a = (uintptr_t)(ck.bases1 + o1);
+        int shift = (int)(a & 7);
+        const uint64_t* q = (const uint64_t*)(a - shift);
+        int nwords = (l1 + 7) >> 3, npos = l1 - HLM_MOTIF;
+        uint64_t win = 0, w = ld_stream_u64(q);
+        uint32_t nwin = 0xFFFFFFFFu;
+        for (int k = 0; k < nwords && !maybe; k++) {
+          // bytes 8k .. 8k+7 of the read (the last aligned word may lie past the read: only loaded
+          // when the read's bytes reach into it)
+          uint64_t wn = (shift && shift + l1 > 8 * (k + 1)) ? ld_stream_u64(q + k + 1) : 0ull;
+          uint64_t v = shift ? (w >> (8 * shift)) | (wn << (64 - 8 * shift)) : w;
+          if (!shift && k + 1 < nwords) wn = ld_stream_u64(q + k + 1);
+          w = wn;
+          int rem = l1 - 8 * k;
+          if (rem < 8) v &= (1ull << (8 * rem)) - 1;
+          uint32_t pk, b0, b1, bn;
+          encode8(v, pk, b0, b1, bn);
+          // window = bases [8k - 24, 8k + 8): base j at bits 2 (j - 8k + 24)
+          win = (win >> 16) | ((uint64_t)pk << 48);
+          nwin = (nwin >> 8) | (bn << 24);
+          // the even positions that became complete with this word: 8k - 18, -16, -14, -12
+          uint64_t bm[4];
+          uint32_t bw[4];
+          bool act[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) {
+            int off = 6 + 2 * x, c = 8 * k - 24 + off;
+            act[x] = c >= 0 && c < npos && ((nwin >> off) & 0xFFFFFu) == 0;
+            uint64_t key = (win >> (2 * off)) & HLM_KT_KEYMASK;
+            bm[x] = hlm_kb_probe(key, db.kb_words, &bw[x]);
+          }
+          uint64_t word[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) word[x] = act[x] ? __ldg(db.kb + bw[x]) : 0ull;
+#pragma unroll
+          for (int x = 0; x < 4; x++) maybe = maybe || (act[x] && (word[x] & bm[x]) == bm[x]);
+        }
+        // (the last probed position, l1 - 21, is complete with the last word: 8 (nwords - 1) - 12 >= l1 - 21)
+      }
+      if (!maybe) {  // rejected: what k_screen writes for a pair that fails the screen
+        ck.flags[pair] = 0;
+        ck.trim_lo1[pair] = 0;
+        ck.trim_len1[pair] = 0;
+        ck.trim_lo2[pair] = 0;
+        ck.trim_len2[pair] = 0;
+        ck.locus_mask[pair] = 0;
+      }
+    }
+    // the others, in pair order inside the warp, one atomic per warp
+    uint32_t bal = __ballot_sync(FULL, maybe);
+    if (bal) {
+      unsigned long long base = 0;
+      if (lane == __ffs(bal) - 1) base = atomicAdd(&ck.counters[HLM_N_COUNTERS], (unsigned long long)__popc(bal));
+      base = __shfl_sync(FULL, base, __ffs(bal) - 1);
+      if (maybe) ck.pre_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)pair;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ k_screen
@@ -270,7 +389,11 @@ k_screen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   WarpScratch& ws = scratch[wib];
   int64_t nwarps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
   unsigned long long kept_local = 0;
-  for (int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; pair < ck.n_pairs; pair += nwarps) {
+  // with the prefilter (k_prescreen) only the pairs it could not reject arrive here, as a list
+  const bool listed = prescreen_applies(db, kp);
+  int64_t n_items = listed ? (int64_t)ck.counters[HLM_N_COUNTERS] : ck.n_pairs;
+  for (int64_t item = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib; item < n_items; item += nwarps) {
+    int64_t pair = listed ? (int64_t)ck.pre_list[item] : item;
     uint64_t o1 = ck.offs1[pair];
     int l1 = (int)(ck.offs1[pair + 1] - o1);
     uint64_t o2 = 0;
@@ -546,7 +669,7 @@ k_pack_units(HlmKParams kp, HlmChunk ck) {
 __global__ void k_clear_tasks(HlmChunk ck, int64_t n_tasks) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  if (i < HLM_N_COUNTERS) ck.counters[i] = 0;
+  if (i <= HLM_N_COUNTERS) ck.counters[i] = 0;  // [HLM_N_COUNTERS]: length of the k_prescreen list
   if (i < 256) ck.dp_hist[i] = 0;
   for (; i < n_tasks; i += stride) {
     ck.task_emin[i] = 0xFFFFFFFFu;
@@ -795,7 +918,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
       // capped scoring: the bound after the rows a trailing clip (<= mm_max bases of a reported
       // alignment) cannot reach; with both clips in the score the bound of the whole read
       int rstar = -1;
-      if (kp.score_cap && kp.clip_mode != HLM_CLIP_BOTH) rstar = n > kp.mm_max ? ((n - kp.mm_max) & ~7) : 0;
+      if (kp.score_cap && kp.clip_mode == HLM_CLIP_LEAD_ONLY) rstar = n > kp.mm_max ? ((n - kp.mm_max) & ~7) : 0;
       lb = hlm_myers_core_dev<256 * 4>(ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 2 * HLM_UNIT_WORDS +
                                            HLM_CODE_WORDS * strand,
                                        n, off, (uint32_t)__cvta_generic_to_shared(s_peq + threadIdx.x), (uint32_t)kp.one,
@@ -1032,7 +1155,7 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
 }
 
 // ------------------------------------------------------------------ DP list: footprint de-duplication
-// Two selected candidates of the same unit and strand whose tiles agree on the DP footprint
+// Two selected candidates of the same unit, strand and locus whose tiles agree on the DP footprint
 // (columns off - BAND .. off + n + BAND) are the same alignment problem: the windows differ only
 // in columns the band cannot reach (typically two children of one rep that share the differing
 // column inside the footprint).  The DP depends on nothing else, so one of them is enough - the
@@ -1080,7 +1203,10 @@ k_dp_dedup(HlmDevDB db, HlmChunk ck, int dedup) {
       int off = (int)HLM_CAND_OFFM(c) + HLM_OFF_MIN, strand = (int)HLM_CAND_STRAND(c);
       Footprint f;
       footprint_of(db.tiles + (size_t)HLM_CAND_TILE(c) * HLM_TILE_WORDS, off, n, f);
-      uint64_t h = ((uint64_t)unit * 2 + strand) * 0x9E3779B97F4A7C15ull + (uint64_t)n;
+      // (the same window content under two loci - close paralogs - is two tasks: the locus is part
+      // of the key)
+      int g = tile_locus(db, HLM_CAND_TILE(c));
+      uint64_t h = (((uint64_t)unit * 2 + strand) * 64 + (uint64_t)g) * 0x9E3779B97F4A7C15ull + (uint64_t)n;
 #pragma unroll
       for (int k = 0; k < 21; k++) h = (h ^ f.w[k]) * 0x100000001B3ull + (h >> 29);
       h ^= h >> 32;
@@ -1093,7 +1219,8 @@ k_dp_dedup(HlmDevDB db, HlmChunk ck, int dedup) {
         if (old == 0ull) break;  // first of its footprint
         if ((old >> 32) == (mine >> 32)) {
           uint64_t c2 = ck.cand[ck.dp_list[(old & 0xFFFFFFFFull) - 1]];
-          if (HLM_CAND_UNIT(c2) == unit && (int)HLM_CAND_STRAND(c2) == strand) {
+          if (HLM_CAND_UNIT(c2) == unit && (int)HLM_CAND_STRAND(c2) == strand &&
+              tile_locus(db, HLM_CAND_TILE(c2)) == g) {
             Footprint g;
             footprint_of(db.tiles + (size_t)HLM_CAND_TILE(c2) * HLM_TILE_WORDS, (int)HLM_CAND_OFFM(c2) + HLM_OFF_MIN,
                          n, g);
@@ -1190,7 +1317,7 @@ k_dp(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets) {
     int n = ck.unit_len[unit];
     const uint32_t* rd = ck.unit_planes + (size_t)unit * HLM_UNIT_STRIDE + 18 * strand;
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
-    HlmAln a = hlm_dp_align(rd, n, T, off, kp.one);
+    HlmAln a = hlm_dp_align(rd, n, T, off, kp.one, kp.clip_mode == HLM_CLIP_NONE);
     int g = tile_locus(db, tile);
     atomicMin(&ck.task_best[(int64_t)unit * n_targets + g],
               (unsigned long long)HLM_BEST_PACK(a.cost, a.S, a.lead, a.trail));
@@ -1607,6 +1734,8 @@ static inline int grid_for(int sms, int per_sm) { return sms * per_sm; }
 
 void hlm_launch_screen(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                        cudaStream_t st) {
+  if (kp.screen_variant == HLM_SCREEN_FASTQ && !kp.skip_screen && kp.minhit >= 1 && db.n_odd == 0)
+    k_prescreen<<<grid_for(sms, 8), 128, 0, st>>>(db, kp, ck);
   k_screen<<<grid_for(sms, 8), WARPS_PER_BLOCK * 32, 0, st>>>(db, kp, ck);
 }
 void hlm_launch_pack(const HlmKParams& kp, const HlmChunk& ck, int sms, cudaStream_t st) {

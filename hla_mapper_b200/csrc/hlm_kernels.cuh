@@ -39,6 +39,7 @@ struct HlmChunk {
   uint32_t* dp_hist;     // [256] rows histogram, then ...
   uint32_t* dp_cursor;   // [256] ... scatter cursors
   int64_t dp_cap;
+  uint32_t* pre_list;            // k_prescreen: pairs the Bloom-only prefilter could not reject
   unsigned long long* dp_tab;    // footprint de-duplication of the DP list: 2^dp_tab_bits u64 slots
   int dp_tab_bits;
   unsigned long long* counters;  // [0] n_cand, [1] n_dp (current round), [2] overflow flag,
@@ -70,6 +71,7 @@ struct HlmKParams {
   int allele_locus;  // >= 0: per-allele scoring of this target set (hlm_score_alleles); -1 otherwise
   double tolerance;
   uint32_t good_q[8];  // bit q: quality byte q passes mtrim's P <= error test
+  int q_thr;           // >= 0: the good bytes are exactly q_thr .. 127 (byte-parallel test); -1: use good_q
   int n_loci;
   int one;  // == 1; opaque multiplier that keeps the DP's adds on the FMA pipe (hlm_add_fma)
 };

@@ -67,6 +67,11 @@ extern "C" {
                                 splitcigar() is always "", so only the first CIGAR
                                 op is ever added (map_dna.cpp:60-78)            */
 #define HLM_CLIP_BOTH 1      /* what the code visibly intends: first + last op  */
+#define HLM_CLIP_NONE 2      /* the aligner itself never clips: the whole mate is aligned end to
+                                end, as `bwa aln` reports reads that lie inside a sequence (it
+                                has no soft clipping; trailing mismatches count in NM).  Read
+                                bases past an allele end align to padding and count as
+                                mismatches.  DESIGN.md section 3b                */
 
 /* hlm_screen_out.flags bits */
 #define HLM_F_SCREENED 1 /* passed the >=minhit k-mer screen                   */

@@ -416,6 +416,12 @@ static inline int refc(const uint8_t* t, int tlen, int x) { return (x < 0 || x >
  * is an infinite string of N outside [0,tlen); N never matches.
  * Among co-optimal paths: max S, then min (NM + clipped bases), then min leading clip,
  * then the end row with the shortest trailing clip. */
+/* HLM_CLIP_NONE (hlm_params.clip_mode = 2): the alignment never clips - no row starts a new
+ * alignment, only the last row ends one.  Set by the whole-stage entry points from the parameters
+ * (and by the stand-in bwa from HLM_ORACLE_NOCLIP); read-only while a stage runs. */
+static int g_noclip = 0;
+void orc_set_noclip(int on) { g_noclip = on ? 1 : 0; }
+
 void orc_align(const uint8_t* r, int n, const uint8_t* t, int tlen, int d, int* S_out,
                int* cost_out, int* lead_out, int* trail_out) {
   int Hp[NB], Ep[NB], Hc[NB], Ec[NB];
@@ -426,6 +432,7 @@ void orc_align(const uint8_t* r, int n, const uint8_t* t, int tlen, int d, int* 
   int best = V_NEG, best_i = 0;
   for (int i = 1; i <= n; i++) {
     int start = -(V_CLIP + i * CU + i); /* clip the first i bases and start here */
+    if (g_noclip) start = V_NEG;
     int rb = r[i - 1];
     int f = V_NEG, hleft = V_NEG;
     int rowmax = V_NEG;
@@ -443,6 +450,7 @@ void orc_align(const uint8_t* r, int n, const uint8_t* t, int tlen, int d, int* 
       rowmax = imax(rowmax, h);
     }
     int fin = rowmax - (i < n ? V_CLIP + (n - i) * CU : 0);
+    if (g_noclip && i < n) fin = V_NEG - 1;
     if (fin >= best) {
       best = fin;
       best_i = i;
@@ -758,6 +766,7 @@ static inline int hla_rna_score(const ares* a, int len, int clip_mode) {
 int orc_score(const orc_db* db, const hlm_params* p, const hlm_batch* in, const hlm_screen_out* scr,
               hlm_score_out* out, int mode, int nthreads, int64_t* n_dp_cells) {
   int64_t n = in->n_pairs;
+  g_noclip = p->clip_mode == HLM_CLIP_NONE;
   int T = db->n_loci + 1;
   int64_t total_cells = 0;
   int toolong = 0;
@@ -886,6 +895,7 @@ int orc_score_alleles(const orc_db* db, const hlm_params* p, const hlm_batch* in
                       const hlm_screen_out* scr, int locus, uint8_t* nm1, uint8_t* clip1, uint8_t* nm2,
                       uint8_t* clip2, int nthreads) {
   int64_t n = in->n_pairs;
+  g_noclip = p->clip_mode == HLM_CLIP_NONE;
   const olocus* L = &db->loc[locus];
   int64_t nA = L->n_al;
 #ifdef _OPENMP

@@ -42,6 +42,7 @@ uint32_t orc_locus_mask(const orc_db* db, const uint8_t* seq, int len);
 /* banded affine alignment of read codes (0..3, 4 = N) against ref codes on diagonal d */
 void orc_align(const uint8_t* r, int n, const uint8_t* t, int tlen, int d, int* S, int* cost,
                int* lead, int* trail);
+void orc_set_noclip(int on); /* unit-level calls: orc_align in HLM_CLIP_NONE mode (no clipping at all) */
 int orc_banded_ed(const uint8_t* r, int n, const uint8_t* t, int tlen, int d);
 /* SAM reducers on real SAM text (used to pin read_sam_dna / read_sam_rna) */
 int orc_sam_score_dna(const char* sam_line, int clip_mode, char* qname, size_t qlen);

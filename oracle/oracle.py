@@ -49,6 +49,7 @@ def lib():
         L.orc_locus_mask.argtypes = [C.c_void_p, _abi.u8p, C.c_int]
         L.orc_align.argtypes = [_abi.u8p, C.c_int, _abi.u8p, C.c_int, C.c_int] + \
             [C.POINTER(C.c_int)] * 4
+        L.orc_set_noclip.argtypes = [C.c_int]
         L.orc_banded_ed.argtypes = [_abi.u8p, C.c_int, _abi.u8p, C.c_int, C.c_int]
         L.orc_sam_score_dna.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.orc_sam_score_rna.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]

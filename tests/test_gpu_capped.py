@@ -47,7 +47,7 @@ def check_capped_against_exact(want, got, T, paired=True):
         assert np.array_equal(want.others_s2[ov], got.others_s2[ov])
 
 
-@pytest.mark.parametrize("clip", [0, 1])
+@pytest.mark.parametrize("clip", [0, 1, 2])
 @pytest.mark.parametrize("variant", [0, 1])
 def test_capped_equals_exact_where_it_matters(orc, small_db, small_reads, clip, variant):
     from hla_mapper_b200 import api

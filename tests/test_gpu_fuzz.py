@@ -190,7 +190,7 @@ def test_random_databases_reads_and_parameters(orc, tmp_path, seed):
                           frag_sd=int(rng.integers(1, 60)), lowq_tail=float(rng.choice([0.0, 0.1, 0.6])),
                           ragged=bool(rng.integers(0, 2)))
     kw = dict(rna=rna, paired=int(rng.integers(0, 2)) if not rna else 1,
-              screen_variant=int(rng.integers(0, 2)), clip_mode=int(rng.integers(0, 2)),
+              screen_variant=int(rng.integers(0, 2)), clip_mode=int(rng.integers(0, 3)),
               minhit=int(rng.integers(1, 5)), mm_max=int(rng.choice([3, 10, 20])),
               tolerance=float(rng.choice([0.0, 0.05, 0.08, 0.2])),
               mtrim_error=float(rng.choice([0.001, float(np.float32(0.08)), 0.5])),

@@ -32,7 +32,7 @@ def odb(orc, small_db):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("clip", [0, 1])
+@pytest.mark.parametrize("clip", [0, 1, 2])
 def test_fused_run_matches_exhaustive_oracle(orc, odb, gdb, small_reads, variant, clip):
     from hla_mapper_b200 import api
 

@@ -143,7 +143,7 @@ def test_screen_and_locus_mask_match_literal_loops(orc, small_db, small_reads):
 
 
 # ---------------------------------------------------------------- aligner definition
-def brute_align(r, t, d):
+def brute_align(r, t, d, noclip=False):
     """lexicographic (S, -cost, -lead) DP over the band, independent of the packed-integer
     formulation: match +1, mismatch -4, gap k -(6+k), end clip -5; cost = mismatches + gap
     bases + clipped bases; ties: max S, min cost, min lead clip, then shortest trailing clip"""
@@ -163,7 +163,7 @@ def brute_align(r, t, d):
         E[(0, k)] = NEG
     best, best_i = NEG, 0
     for i in range(1, n + 1):
-        start = (-5, -i, -i)
+        start = NEG if noclip else (-5, -i, -i)
         f = NEG
         rowmax = NEG
         for k in range(2 * BAND + 1):
@@ -183,6 +183,8 @@ def brute_align(r, t, d):
             E[(i, k)] = e
             rowmax = max(rowmax, h)
         fin = rowmax if i == n else add(rowmax, -5, n - i)
+        if noclip and i < n:
+            continue
         if fin >= best:
             best, best_i = fin, i
     return best[0], -best[1], -best[2], n - best_i
@@ -212,6 +214,14 @@ def test_align_matches_bruteforce_definition(orc, seed):
             r[-k:] = rng.integers(0, 4, size=k)
         d = p + int(rng.integers(-3, 4))
         assert orc.align(r, t, d) == brute_align(list(map(int, r)), list(map(int, t)), d)
+        # HLM_CLIP_NONE: the same recurrence without the two clipping moves
+        orc.lib().orc_set_noclip(1)
+        try:
+            got = orc.align(r, t, d)
+        finally:
+            orc.lib().orc_set_noclip(0)
+        assert got == brute_align(list(map(int, r)), list(map(int, t)), d, noclip=True)
+        assert got[2] == 0 and got[3] == 0
 
 
 def test_align_known_answers(orc):
