@@ -353,7 +353,9 @@ def kernel_rooflines(ks, n, read_len, int_peak, mix, mix_src, cells_ratio=None):
                     "ops_source": mix_src},
         "k_screen": {"bound": "hbm", "achieved": round(screen_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(screen_gbs / hbm_peak, 4),
-                     "traffic": tr.get("k_screen", {}).get("dram_bytes"), "traffic_source": tr.get("source"),
+                     "traffic": (tr.get("k_screen", {}).get("dram_bytes", 0) + tr.get("k_prescreen", {}).get("dram_bytes", 0))
+                     or None, "traffic_source": tr.get("source"),
+                     "kernels": "k_prescreen (thread per pair, Bloom only) + k_screen (warp per listed pair)",
                      "ms_per_step": round(sc_ms, 3), "bytes_per_step": int(screen_bytes),
                      "algorithmic_bytes_per_pair": 4 * read_len + 12, "peak_source": hbm_src},
         "k_seed": {"ms_per_step": round(per("ms_seed"), 3),
@@ -480,6 +482,32 @@ def run_shard_100m(args, api, D, gdb, db):
                     f"{args.shard_seconds:.0f}s of run time (generation excluded)"}
 
 
+def run_inprocess(args, api, gdb, db, world, w, n, db_path):
+    """SURVEY.md section 8e as written: ONE process, one host thread + context per GPU, the
+    caller's batch sharded by contiguous range, results gathered host-side into the caller's
+    arrays (hlm_multi_run); and hlm_multi_map_fastq, the file pipeline on all devices"""
+    T = gdb.n_loci + 1
+    n_total = world * n
+    rbm = synth.make_reads_fast(db, n_total, **w["reads"])
+    mm = api.MultiMapper(gdb, list(range(world)), _abi.default_params())
+    buf = _abi.Buffers(n_total, T, diag=False)
+    mm.run(rbm, buffers=buf)
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        mm.run(rbm, buffers=buf)
+    dt = time.perf_counter() - t0
+    e2e = {"value": round(n_total * reps / dt, 1), "unit": "pairs/s", "n_gpus": world,
+           "pairs_per_call": n_total, "seconds_per_call": round(dt / reps, 3),
+           "what": "hlm_multi_run: one process, one host batch, one host thread + context per GPU, results "
+                   "gathered into the caller's arrays (host staging, H2D, kernels, D2H inside the timed region)"}
+    files = file_pipeline(mm, rbm.slice(0, min(n_total, 4 * n)), db_path)
+    files["n_gpus"] = world
+    files["what"] = "hlm_multi_map_fastq: " + files["what"].split(": ", 1)[1] + ", batches dealt to all GPUs"
+    mm.close()
+    return {"e2e_inprocess": e2e, "file_pipeline_multi": files}
+
+
 # ------------------------------------------------------------------------------- our arm
 def run_b200(args):
     from hla_mapper_b200 import api, shard
@@ -541,6 +569,15 @@ def run_b200(args):
         else:
             extras["shard_100M"] = run_shard_100m(args, api, D, gdb, db)
     m.close()
+    # ---- one process driving every GPU of the box (N >= 2; rank 0 alone, the other ranks wait at
+    # the barrier with their contexts closed): hlm_multi_run on one host batch of N x 2M pairs, and
+    # the file pipeline fed to all N devices
+    inproc = None
+    if world > 1 and args.workload == "wgs_2x150" and not args.no_extras:
+        D.barrier()
+        if rank == 0:
+            inproc = run_inprocess(args, api, gdb, db, world, w, n, db_path)
+        D.barrier()
     gdb.close()
     if rank != 0:
         D.close()
@@ -592,6 +629,9 @@ def run_b200(args):
             "roofline": croof,
             "same_targets_and_visible_scores_as_exact": True,
         }
+    if inproc:
+        out["e2e_inprocess"] = inproc["e2e_inprocess"]
+        out["file_pipeline_multi"] = inproc["file_pipeline_multi"]
     if extras:
         out["configs"] = extras
     if cpu:

@@ -326,38 +326,43 @@ k_prescreen(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         int shift = (int)(a & 7);
         const uint64_t* q = (const uint64_t*)(a - shift);
         int nwords = (l1 + 7) >> 3, npos = l1 - HLM_MOTIF;
-        uint64_t win = 0, w = ld_stream_u64(q);
+        int last_aligned = (shift + l1 - 1) >> 3;  // aligned word that holds the read's last byte
+        uint64_t win = 0;
         uint32_t nwin = 0xFFFFFFFFu;
-        for (int k = 0; k < nwords && !maybe; k++) {
-          // bytes 8k .. 8k+7 of the read (the last aligned word may lie past the read: only loaded
-          // when the read's bytes reach into it)
-          uint64_t wn = (shift && shift + l1 > 8 * (k + 1)) ? ld_stream_u64(q + k + 1) : 0ull;
-          uint64_t v = shift ? (w >> (8 * shift)) | (wn << (64 - 8 * shift)) : w;
-          if (!shift && k + 1 < nwords) wn = ld_stream_u64(q + k + 1);
-          w = wn;
-          int rem = l1 - 8 * k;
-          if (rem < 8) v &= (1ull << (8 * rem)) - 1;
-          uint32_t pk, b0, b1, bn;
-          encode8(v, pk, b0, b1, bn);
-          // window = bases [8k - 24, 8k + 8): base j at bits 2 (j - 8k + 24)
-          win = (win >> 16) | ((uint64_t)pk << 48);
-          nwin = (nwin >> 8) | (bn << 24);
-          // the even positions that became complete with this word: 8k - 18, -16, -14, -12
-          uint64_t bm[4];
-          uint32_t bw[4];
-          bool act[4];
+        // four read words per round: their five aligned words are loaded together, the sixteen
+        // Bloom words they need are loaded together - two memory round trips per 32 bases
+        for (int k0 = 0; k0 < nwords && !maybe; k0 += 4) {
+          uint64_t aw[5];
+#pragma unroll
+          for (int x = 0; x < 5; x++) aw[x] = (k0 + x <= last_aligned) ? ld_stream_u64(q + k0 + x) : 0ull;
+          uint64_t bm[16];
+          uint32_t bw[16], act = 0;
 #pragma unroll
           for (int x = 0; x < 4; x++) {
-            int off = 6 + 2 * x, c = 8 * k - 24 + off;
-            act[x] = c >= 0 && c < npos && ((nwin >> off) & 0xFFFFFu) == 0;
-            uint64_t key = (win >> (2 * off)) & HLM_KT_KEYMASK;
-            bm[x] = hlm_kb_probe(key, db.kb_words, &bw[x]);
+            int k = k0 + x;
+            uint64_t v = shift ? (aw[x] >> (8 * shift)) | (aw[x + 1] << (64 - 8 * shift)) : aw[x];
+            int rem = l1 - 8 * k;
+            if (rem <= 0) v = 0;
+            else if (rem < 8) v &= (1ull << (8 * rem)) - 1;
+            uint32_t pk, b0, b1, bn;
+            encode8(v, pk, b0, b1, bn);
+            // window = bases [8k - 24, 8k + 8): base j at bits 2 (j - 8k + 24)
+            win = (win >> 16) | ((uint64_t)pk << 48);
+            nwin = (nwin >> 8) | (bn << 24);
+            // the even positions that became complete with this word: 8k - 18, -16, -14, -12
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+              int off = 6 + 2 * y, c = 8 * k - 24 + off;
+              if (c >= 0 && c < npos && ((nwin >> off) & 0xFFFFFu) == 0) act |= 1u << (4 * x + y);
+              uint64_t key = (win >> (2 * off)) & HLM_KT_KEYMASK;
+              bm[4 * x + y] = hlm_kb_probe(key, db.kb_words, &bw[4 * x + y]);
+            }
           }
-          uint64_t word[4];
+          uint64_t word[16];
 #pragma unroll
-          for (int x = 0; x < 4; x++) word[x] = act[x] ? __ldg(db.kb + bw[x]) : 0ull;
+          for (int z = 0; z < 16; z++) word[z] = ((act >> z) & 1u) ? __ldg(db.kb + bw[z]) : 0ull;
 #pragma unroll
-          for (int x = 0; x < 4; x++) maybe = maybe || (act[x] && (word[x] & bm[x]) == bm[x]);
+          for (int z = 0; z < 16; z++) maybe = maybe || (((act >> z) & 1u) && (word[z] & bm[z]) == bm[z]);
         }
         // (the last probed position, l1 - 21, is complete with the last word: 8 (nwords - 1) - 12 >= l1 - 21)
       }
@@ -696,8 +701,8 @@ __device__ __forceinline__ int tile_locus(const HlmDevDB& db, uint32_t tile) {
 // compare), so duplicates are dropped without touching the tile data; units with more index hits
 // than the set can hold fall back to testing the earlier seeds against the tile.
 #define SEED_WARPS 4
-#define SEED_HT 2048
-#define SEED_HT_MAX 1400
+#define SEED_HT 1024
+#define SEED_HT_MAX 700
 __global__ void __launch_bounds__(SEED_WARPS * 32)
 k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
   __shared__ uint32_t s_rd[SEED_WARPS][36];
@@ -789,7 +794,7 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         int g = tile_locus(db, tile);
         if ((umask >> g) & 1u) {
           uint32_t key = (tile << 6) | ((uint32_t)(off - HLM_OFF_MIN) << 1) | (uint32_t)strand;
-          uint32_t h = (key * 2654435761u) >> 21;
+          uint32_t h = (key * 2654435761u) >> 22;
           bool found = false;
           for (;;) {
             uint32_t old = insert ? atomicCAS(&ht[h], 0xFFFFFFFFu, key) : ht[h];
@@ -885,7 +890,7 @@ k_myers(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int phase) {
     const uint32_t* T = db.tiles + (size_t)tile * HLM_TILE_WORDS;
     int lb, plb = 0;
     bool dead = false;
-    if (phase != 0) {
+    if (phase == 1 || phase == 2) {
       // a child reached by expanding its rep: it is this path's candidate only when some seed
       // matches and none of its matching seeds covers a differing column (a covering seed is in
       // the seed index, which then emitted the candidate)
@@ -1747,7 +1752,7 @@ void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStre
 }
 void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                      cudaStream_t st) {
-  k_seed<<<grid_for(sms, 6), SEED_WARPS * 32, 0, st>>>(db, kp, ck);
+  k_seed<<<grid_for(sms, 10), SEED_WARPS * 32, 0, st>>>(db, kp, ck);
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {
@@ -1755,7 +1760,7 @@ void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& 
 }
 // per-device kernel attributes (call once per context, after cudaSetDevice)
 void hlm_kernels_init() {
-  // k_myers: 5 blocks x 42 KB of PEQ rows per SM; k_seed: 6 blocks x 34 KB of hash sets
+  // k_myers: 5 blocks x 42 KB of PEQ rows per SM; k_seed: 10 blocks x 18 KB of hash sets (register-bound)
   cudaFuncSetAttribute(k_myers, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_seed, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }

@@ -64,5 +64,28 @@ def kernel(path):
                 print(f"  {k:85s} {r[i]:>16s} {units[i]}")
 
 
+def traffic(path):
+    """profiles/r2_traffic.json: dram bytes (read + write) per launch of every captured kernel,
+    averaged over the captured launches - what bench.py reports as roofline.traffic"""
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv", "--print-units", "base"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h = rows[0]
+    ki, ri, wi, ti = (h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"),
+                      h.index("gpu__time_duration.sum"))
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r in rows[2:]:
+        n = r[ki].split("(")[0]
+        agg[n][0] += 1
+        agg[n][1] += float(r[ri].replace(",", "")) + float(r[wi].replace(",", ""))
+        agg[n][2] += float(r[ti].replace(",", ""))
+    res = {"source": f"ncu --set full --clock-control none, {path.split('/')[-1]} (summary: profiles/)"}
+    for n, (c, b, t) in agg.items():
+        res[n] = {"dram_bytes": int(b / c), "launches_captured": c, "avg_us_under_ncu": round(t / c / 1e3, 1)}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]](sys.argv[2])
