@@ -188,10 +188,18 @@ class Dist:
             torch.cuda.set_device(self.local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
+            # a CPU-side group for waits during which one rank uses EVERY GPU (the in-process arm):
+            # an NCCL barrier would leave a spinning kernel on the waiting ranks' GPUs, and two
+            # processes time-slice a GPU
+            self.cpu_group = dist.new_group(backend="gloo")
 
     def barrier(self):
         if self.dist is not None:
             self.dist.barrier()
+
+    def barrier_cpu(self):
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
 
     def _red(self, x, op):
         if self.dist is None:
@@ -308,10 +316,12 @@ def measure(api, D, gdb, rb, K, W, chunk=0, batch_kw=None, params_kw=None, kerne
     return out
 
 
-def kernel_rooflines(ks, n, read_len, int_peak, mix, mix_src, cells_ratio=None):
+def kernel_rooflines(ks, n, read_len, int_peak, mix, mix_src, cells_ratio=None, workload="wgs_2x150"):
     """every kernel of the step against its bound, from the serialised pass `ks`"""
     hbm_peak, hbm_src = peaks()
     tr = traffic()
+    if workload in tr:  # captures made on that workload (the screen kernels on the decoy-heavy config)
+        tr = dict(tr, **tr[workload])
     per = lambda k: ks.get(k, 0.0)  # noqa: E731
     dp, my = mix["k_dp"], mix["k_myers"]
     alu_peak = int_peak["viaddmnmx"]  # G lane-op/s on the ALU pipe (min/max, DPX)
@@ -574,10 +584,14 @@ def run_b200(args):
     # the file pipeline fed to all N devices
     inproc = None
     if world > 1 and args.workload == "wgs_2x150" and not args.no_extras:
+        import torch
+
         D.barrier()
+        torch.cuda.synchronize()  # nothing of this rank is left on its GPU while rank 0 uses it
+        D.barrier_cpu()
         if rank == 0:
             inproc = run_inprocess(args, api, gdb, db, world, w, n, db_path)
-        D.barrier()
+        D.barrier_cpu()
     gdb.close()
     if rank != 0:
         D.close()
@@ -656,7 +670,7 @@ def run_extra(args, api, D, name, gdb, db, int_peak, mix, mix_src):
     log(f"[bench] {name}: {n} pairs + database ready in {time.time() - t:.1f}s")
     r = measure(api, D, gdb, rb, 2, 1, batch_kw=batch_kw)
     r["mapper"].close()
-    rooflines, roof = kernel_rooflines(r["kstage"], n, w["reads"]["read_len"], int_peak, mix, mix_src)
+    rooflines, roof = kernel_rooflines(r["kstage"], n, w["reads"]["read_len"], int_peak, mix, mix_src, workload=name)
     ks = r["kstage"]
     out = {"baseline_config": w["config"], "workload": w["text"], "pairs_per_step": n, "reads": w["reads"],
            "steps": 2, "warmup": 1, "value": round(r["value"], 1), "unit": "pairs/s",
@@ -678,8 +692,8 @@ def run_extra(args, api, D, name, gdb, db, int_peak, mix, mix_src):
 def run_reference_arm(args):
     """the unmodified reference binary on the host cores (rank 0 only).  Its run time is a fixed
     part (about a hundred process launches and index loads per `hla-mapper dna` call) plus a part
-    that grows with the pairs; the timed steps use a sample large enough for the second to
-    dominate, and one extra untimed call on a tenth of it separates the two."""
+    that grows with the pairs: two untimed probe calls separate them (`cost_model`), and the
+    per-step sample is sized from them so that the W + K steps end within --ref-seconds."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -710,6 +724,17 @@ def run_reference_arm(args):
         return time.perf_counter() - t
 
     K, W = args.steps, args.warmup
+    # two probe calls separate the fixed cost of a call (about a hundred process launches and index
+    # loads) from the cost per pair; the per-step sample is then sized so that all W + K steps end
+    # within --ref-seconds (a few minutes), and never exceeds --ref-pairs
+    p1, p2 = 3000, 9000
+    t1, t2 = one(p1, "probe1"), one(p2, "probe2")
+    marginal = max(1e-6, (t2 - t1) / (p2 - p1))  # seconds per pair
+    fixed = max(0.0, t1 - marginal * p1)
+    per_step = args.ref_seconds / max(1, W + K)
+    n = int(max(2000, min(args.ref_pairs, (per_step - fixed) / marginal)))
+    log(f"[bench reference] probes: {p1} pairs {t1:.1f}s, {p2} pairs {t2:.1f}s -> fixed {fixed:.1f}s per call, "
+        f"{1 / marginal:.0f} pairs/s marginal; {n} pairs per step")
     times = []
     for it in range(W + K):
         dt = one(n, "full")
@@ -718,10 +743,7 @@ def run_reference_arm(args):
             times.append(dt)
     tot = sum(times)
     value = n * K / tot
-    small = max(1000, n // 10)
-    dt_small = one(small, "tenth")
-    marginal = (tot / K - dt_small) / max(1, n - small)  # seconds per pair
-    fixed = max(0.0, tot / K - marginal * n)
+    small, dt_small = p1, t1
     sample = (f"{n} pairs of the same workload per step through `hla-mapper dna` (screen, trim, "
               f"sort, bwa stand-in scoring, compare), threads={cores}")
     print(json.dumps({
@@ -734,7 +756,8 @@ def run_reference_arm(args):
                          "sample": sample},
         "cost_model": {"fixed_s_per_call": round(fixed, 2), "marginal_pairs_per_s": round(1.0 / marginal, 1)
                        if marginal > 0 else None,
-                       "from": f"one more call on {small} pairs ({dt_small:.1f}s) beside the {n}-pair steps"},
+                       "from": f"two probe calls ({p1} pairs {t1:.1f}s, {p2} pairs {t2:.1f}s) before the {n}-pair steps; "
+                               f"the per-step sample is sized for {args.ref_seconds:.0f}s over W + K steps"},
         "e2e": {"value": round(value, 2), "unit": "pairs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -751,7 +774,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--db", default=os.environ.get("HLM_BENCH_DB", "/tmp/hlm_bench/db_seed42_40k"))
     ap.add_argument("--cpu-pairs", type=int, default=20000)
-    ap.add_argument("--ref-pairs", type=int, default=60000)
+    ap.add_argument("--ref-pairs", type=int, default=60000, help="upper bound of the reference arm's per-step sample")
+    ap.add_argument("--ref-seconds", type=float, default=240.0, help="time budget of the reference arm's W + K steps")
     ap.add_argument("--extra-scale", type=float, default=1.0, help="scale of the extra configs' sizes")
     ap.add_argument("--shard-pairs", type=int, default=100_000_000)
     ap.add_argument("--shard-seconds", type=float, default=40.0)

@@ -47,6 +47,27 @@ const hlm_params* hlm_ctx_params(const hlm_ctx* ctx);
 
 namespace {
 
+// f(t) for t in [0, n) on n host threads; an exception in a worker becomes one in the caller
+template <class F>
+void parallel_for(int n, F f) {
+  if (n <= 1) {
+    f(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::atomic<int> failed(0);
+  for (int t = 0; t < n; t++)
+    th.emplace_back([&, t] {
+      try {
+        f(t);
+      } catch (const std::exception&) {
+        failed = 1;
+      }
+    });
+  for (auto& x : th) x.join();
+  if (failed) throw std::bad_alloc();
+}
+
 // reads 4-line records straight out of a large refill buffer (one memchr per line, one copy per
 // field into the SoA vectors)
 class FastqReader {
@@ -265,6 +286,193 @@ class FileSource : public PairSource {
  private:
   BatchStream in1_;
   std::unique_ptr<BatchStream> in2_;
+};
+
+// Plain (uncompressed) FASTQ files: mapped and parsed by several host threads.  A newline count
+// per region (parallel) places every batch boundary - record b * B starts after newline 4 b B - so
+// any thread can parse any batch of either file on its own; batches are delivered in order.
+// Same record rules as FastqReader: four lines per record, split at '\n' only; a last line
+// without newline completes its record; an incomplete record at the end is dropped.
+class MappedFastq {
+ public:
+  bool open(const char* path, int64_t batch, int nt) {
+    if (!map_.open(path)) return false;
+    if (map_.n >= 2 && map_.p[0] == 0x1f && map_.p[1] == 0x8b) return false;  // gzip / BGZF: not here
+    const char* p = (const char*)map_.p;
+    size_t n = map_.n;
+    nt = std::max(1, nt);
+    size_t R = (size_t)nt * 4;  // regions
+    std::vector<size_t> cut(R + 1), cnt(R + 1, 0);
+    for (size_t r = 0; r <= R; r++) cut[r] = n * r / R;
+    parallel_for(nt, [&](int t) {
+      for (size_t r = (size_t)t; r < R; r += (size_t)nt) {
+        size_t c = 0;
+        const char* q = p + cut[r];
+        const char* e = p + cut[r + 1];
+        while (q < e) {
+          const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));
+          if (!nl) break;
+          c++;
+          q = nl + 1;
+        }
+        cnt[r + 1] = c;
+      }
+    });
+    for (size_t r = 0; r < R; r++) cnt[r + 1] += cnt[r];
+    size_t lines = cnt[R] + ((n > 0 && p[n - 1] != '\n') ? 1 : 0);
+    n_records_ = (int64_t)(lines / 4);
+    batch_ = batch;
+    int64_t nb = (n_records_ + batch - 1) / batch;
+    start_.assign((size_t)nb + 1, n);
+    // byte offset of record k = one past newline number 4 k (1-based), 0 for k = 0
+    auto offset_of_record = [&](int64_t k) -> size_t {
+      if (k == 0) return 0;
+      size_t want = (size_t)k * 4;  // this many newlines precede the record
+      if (want > cnt[R]) return n;
+      size_t r = (size_t)(std::upper_bound(cnt.begin(), cnt.end(), want - 1) - cnt.begin()) - 1;  // cnt[r] <= want-1 < cnt[r+1]
+      size_t need = want - cnt[r];
+      const char* q = p + cut[r];
+      const char* e = p + cut[r + 1];
+      while (q < e) {
+        const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));
+        if (!nl) break;
+        q = nl + 1;
+        if (--need == 0) return (size_t)(q - p);
+      }
+      return n;
+    };
+    parallel_for(nt, [&](int t) {
+      for (int64_t b = t; b <= nb; b += nt) start_[(size_t)b] = offset_of_record(std::min<int64_t>(b * batch, n_records_));
+    });
+    return true;
+  }
+  int64_t n_records() const { return n_records_; }
+  int64_t n_batches() const { return (int64_t)start_.size() - 1; }
+  // parse batch b into out (cleared first)
+  void parse(int64_t b, MateBatch& out) const {
+    out.clear();
+    const char* base = (const char*)map_.p;
+    size_t p = start_[(size_t)b], end = map_.n;
+    int64_t want = std::min<int64_t>(batch_, n_records_ - b * batch_);
+    out.offs.reserve((size_t)want + 1);
+    out.hoff.reserve((size_t)want + 1);
+    size_t span = start_[(size_t)b + 1] - p;
+    out.bases.reserve(span / 2);
+    out.quals.reserve(span / 2);
+    for (int64_t k = 0; k < want; k++) {
+      size_t e[4], q = p;
+      for (int x = 0; x < 4; x++) {
+        const char* nl = (const char*)memchr(base + q, '\n', end - q);
+        e[x] = nl ? (size_t)(nl - base) : end;
+        q = nl ? e[x] + 1 : end;
+      }
+      size_t s0 = e[0] + 1, q0 = e[2] + 1;
+      size_t hl = e[0] - p, sl = e[1] - s0, ql = e[3] - q0;
+      out.hdr.insert(out.hdr.end(), base + p, base + p + hl);
+      out.hoff.push_back(out.hdr.size());
+      out.bases.insert(out.bases.end(), (const uint8_t*)base + s0, (const uint8_t*)base + s0 + sl);
+      size_t qq = std::min(sl, ql);
+      out.quals.insert(out.quals.end(), (const uint8_t*)base + q0, (const uint8_t*)base + q0 + qq);
+      if (qq < sl) out.quals.insert(out.quals.end(), sl - qq, (uint8_t)'!');
+      out.offs.push_back(out.bases.size());
+      p = q;
+    }
+    out.n = want;
+  }
+
+ private:
+  HlmMapped map_;
+  std::vector<size_t> start_;
+  int64_t n_records_ = 0, batch_ = 1;
+};
+
+// r1 (+ r2) plain FASTQ files parsed by a pool of host threads, batches delivered in order
+class MappedSource : public PairSource {
+ public:
+  MappedSource(int64_t batch, int nt) : batch_(batch), nt_(std::max(1, nt)) {}
+  ~MappedSource() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // false: not plain FASTQ (compressed, empty, unreadable) - the caller falls back to FileSource
+  bool open(const char* r1, const char* r2) {
+    if (!f1_.open(r1, batch_, nt_)) return false;
+    paired_ = r2 != nullptr;
+    if (paired_ && !f2_.open(r2, batch_, nt_)) return false;
+    return true;
+  }
+  bool counts_agree() const { return !paired_ || f1_.n_records() == f2_.n_records(); }
+  void start() {
+    nb_ = f1_.n_batches();
+    int workers = std::max(1, std::min(nt_, 8));
+    for (int w = 0; w < workers; w++) th_.emplace_back([this] { work(); });
+  }
+  bool next(MateBatch*& b1, MateBatch*& b2, int&, std::string&) override {
+    std::unique_lock<std::mutex> g(m_);
+    if (deliver_ >= nb_) return false;
+    cv_.wait(g, [this] { return ready_.count(deliver_) != 0; });
+    auto it = ready_.find(deliver_);
+    b1 = it->second.first;
+    b2 = it->second.second;
+    ready_.erase(it);
+    deliver_++;
+    cv_.notify_all();
+    return true;
+  }
+  void recycle(MateBatch* b1, MateBatch* b2) override {
+    std::lock_guard<std::mutex> g(m_);
+    if (b1) free_.push_back(b1);
+    if (b2) free_.push_back(b2);
+  }
+
+ private:
+  MateBatch* fresh() {  // m_ held
+    if (!free_.empty()) {
+      MateBatch* b = free_.back();
+      free_.pop_back();
+      return b;
+    }
+    pool_.emplace_back(new MateBatch());
+    return pool_.back().get();
+  }
+  void work() {
+    for (;;) {
+      int64_t b;
+      MateBatch *m1, *m2 = nullptr;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        // at most kAhead batches parsed ahead of the consumer
+        cv_.wait(g, [this] { return stop_ || claim_ >= nb_ || claim_ < deliver_ + kAhead; });
+        if (stop_ || claim_ >= nb_) return;
+        b = claim_++;
+        m1 = fresh();
+        if (paired_) m2 = fresh();
+      }
+      f1_.parse(b, *m1);
+      if (paired_) f2_.parse(b, *m2);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        ready_[b] = {m1, m2};
+      }
+      cv_.notify_all();
+    }
+  }
+  static constexpr int64_t kAhead = 6;
+  MappedFastq f1_, f2_;
+  bool paired_ = false;
+  int64_t batch_, nb_ = 0, claim_ = 0, deliver_ = 0;
+  int nt_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::map<int64_t, std::pair<MateBatch*, MateBatch*>> ready_;
+  std::vector<MateBatch*> free_;
+  std::vector<std::unique_ptr<MateBatch>> pool_;
+  bool stop_ = false;
 };
 
 void erase_all(std::string& s, const char* pat) {  // boost::replace_all(s, pat, "")
@@ -723,6 +931,17 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
   }
   int64_t batch = opts_in && opts_in->struct_size >= 12 && opts_in->batch_pairs > 0 ? opts_in->batch_pairs : 1 << 19;
   try {  // no exception crosses the C ABI
+    {  // plain FASTQ: mapped and parsed by several threads; anything else: one reader thread per file
+      MappedSource ms(batch, (int)std::max(1u, std::thread::hardware_concurrency()));
+      if (ms.open(r1_path, r2_path)) {
+        if (!ms.counts_agree()) {
+          hlm_ctx_set_error(ctx, "r1 and r2 hold different numbers of reads");
+          return HLM_E_IO;
+        }
+        ms.start();
+        return hlm_map_source(ctx, ms, paired, sample, out_dir, opts_in, stats);
+      }
+    }
     FileSource src(r1_path, r2_path, batch);
     if (!src.ok1() || !src.ok2()) {
       hlm_ctx_set_error(ctx, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
@@ -736,27 +955,6 @@ extern "C" int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_p
 }
 
 namespace {
-
-// f(t) for t in [0, n) on n host threads; an exception in a worker becomes one in the caller
-template <class F>
-void parallel_for(int n, F f) {
-  if (n <= 1) {
-    f(0);
-    return;
-  }
-  std::vector<std::thread> th;
-  std::atomic<int> failed(0);
-  for (int t = 0; t < n; t++)
-    th.emplace_back([&, t] {
-      try {
-        f(t);
-      } catch (const std::exception&) {
-        failed = 1;
-      }
-    });
-  for (auto& x : th) x.join();
-  if (failed) throw std::bad_alloc();
-}
 
 // A file whose records are produced by several threads at once: every thread formats a contiguous
 // range of the records into a local buffer and writes it with pwrite() at the offset the ranges
@@ -1499,12 +1697,22 @@ extern "C" int hlm_multi_map_fastq(hlm_multi* mm, const char* r1_path, const cha
   int64_t batch = opts_in && opts_in->struct_size >= 12 && opts_in->batch_pairs > 0 ? opts_in->batch_pairs : 1 << 19;
   int rc;
   try {  // no exception crosses the C ABI
-    FileSource src(r1_path, r2_path, batch);
-    if (!src.ok1() || !src.ok2()) {
-      hlm_multi_set_error(mm, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
-      return HLM_E_IO;
+    MappedSource ms(batch, (int)std::max(1u, std::thread::hardware_concurrency()));
+    if (ms.open(r1_path, r2_path)) {
+      if (!ms.counts_agree()) {
+        hlm_multi_set_error(mm, "r1 and r2 hold different numbers of reads");
+        return HLM_E_IO;
+      }
+      ms.start();
+      rc = hlm_map_source_multi(cs, n, ms, paired, sample, out_dir, opts_in, stats);
+    } else {
+      FileSource src(r1_path, r2_path, batch);
+      if (!src.ok1() || !src.ok2()) {
+        hlm_multi_set_error(mm, std::string("cannot open ") + (src.ok1() ? r2_path : r1_path));
+        return HLM_E_IO;
+      }
+      rc = hlm_map_source_multi(cs, n, src, paired, sample, out_dir, opts_in, stats);
     }
-    rc = hlm_map_source_multi(cs, n, src, paired, sample, out_dir, opts_in, stats);
   } catch (const std::exception& e) {
     hlm_multi_set_error(mm, std::string("hlm_multi_map_fastq: ") + e.what());
     return HLM_E_NOMEM;

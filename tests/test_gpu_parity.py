@@ -1,5 +1,7 @@
 """Parity tests proper: libhlamap (CUDA, through the C-ABI) vs the CPU oracle on the same seeded
 inputs - every output field bit-exact - plus size-independent properties at larger sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -347,5 +349,57 @@ def test_file_pipeline_names_a_read_it_cannot_hold(small_db, tmp_path):
     with pytest.raises(api.HlmError, match="LONGREAD.* is 300 bases long"):
         m.map_fastq(r1, r2, "S", out, batch_pairs=64)
     assert not list(out.iterdir())
+    m.close()
+    gdb.close()
+
+
+def test_plain_fastq_parallel_parser_edge_cases(small_db, tmp_path):
+    """plain FASTQ files are mapped and parsed by several threads (batch boundaries from a newline
+    count): a last line without newline completes its record, an incomplete record at the end is
+    dropped, r1 / r2 of different lengths are refused before anything is written - and the files
+    equal those of the single-reader path (the same input gzip-compressed)"""
+    import gzip
+    import hashlib
+
+    from hla_mapper_b200 import api
+
+    rb = synth.make_reads(small_db, 700, read_len=150, seed=8, on_target=0.8, frag_mu=300, frag_sd=30, ragged=True)
+    r1, r2 = str(tmp_path / "r1.fastq"), str(tmp_path / "r2.fastq")
+    synth.write_fastq(rb, r1, r2)
+    gdb = api.Database(small_db.path)
+    m = api.Mapper(gdb, 0, _abi.default_params())
+
+    def digest(d):
+        return {f: hashlib.sha256(open(d / f, "rb").read()).hexdigest() for f in sorted(os.listdir(d))}
+
+    def run(a, b, name, **kw):
+        out = tmp_path / name
+        out.mkdir()
+        st = m.map_fastq(a, b, "S", out, **kw)
+        return st, digest(out)
+
+    st0, ref = run(r1, r2, "plain", batch_pairs=64)
+    assert st0["n_pairs"] == 700 and st0["n_kept"] > 300
+    # the single-reader path on the same records
+    z1, z2 = r1 + ".gz", r2 + ".gz"
+    for src, dst in ((r1, z1), (r2, z2)):
+        open(dst, "wb").write(gzip.compress(open(src, "rb").read(), 1))
+    assert run(z1, z2, "gz", batch_pairs=64)[1] == ref
+    assert run(r1, r2, "one_batch", batch_pairs=100000)[1] == ref
+    # no newline at the end of the files; then two stray lines after the last record
+    for suffix, name in ((b"", "nonl"), (b"\n@partial\nACGT", "partial")):
+        a, b = str(tmp_path / (name + "1.fastq")), str(tmp_path / (name + "2.fastq"))
+        for src, dst in ((r1, a), (r2, b)):
+            open(dst, "wb").write(open(src, "rb").read().rstrip(b"\n") + suffix)
+        st, d = run(a, b, name, batch_pairs=97)
+        assert st["n_pairs"] == 700 and d == ref, name
+    # one record fewer in r2
+    short = str(tmp_path / "short2.fastq")
+    open(short, "w").write("\n".join(open(r2).read().split("\n")[:-5]) + "\n")
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    with pytest.raises(api.HlmError, match="different numbers"):
+        m.map_fastq(r1, short, "S", bad)
+    assert not list(bad.iterdir())
     m.close()
     gdb.close()
