@@ -101,7 +101,8 @@ __device__ __forceinline__ void encode8(uint64_t v, uint32_t& pk, uint32_t& b0, 
 }
 
 // Warp-level list appender: a warp reserves HLM_APPEND_BLOCK slots with ONE atomic and fills them
-// from its ballots; unused slots are padded with an invalid record that every consumer skips.
+// from its ballots; only the unused slots of a warp's LAST block are padded with an invalid record
+// that every consumer skips.
 // (One atomic per ballot on a single counter serialises in L2 at ~10^7 appends per chunk.)
 #define HLM_APPEND_BLOCK 128
 #define HLM_CAND_INVALID 0xFFFFFFFFFFFFFFFFull
@@ -127,16 +128,18 @@ struct WarpAppender {
     uint32_t bal = __ballot_sync(FULL, take);
     if (!bal) return;
     int cnt = __popc(bal);
+    unsigned long long rank = __popc(bal & ((1u << lane) - 1u)), at = pos + rank;
     if (pos + cnt > end) {
-      pad(lane);
-      unsigned long long np = 0;
+      // the block is finished with the first records of this push and the rest opens a new one:
+      // no padding inside the list (padding slots idle a k_myers lane each)
+      unsigned long long room = end - pos, np = 0;
       if (lane == 0) np = atomicAdd(counter, (unsigned long long)HLM_APPEND_BLOCK);
       np = __shfl_sync(FULL, np, 0);
-      pos = np;
+      if (rank >= room) at = np + (rank - room);
+      pos = np - room;  // so that pos + cnt below is the next free slot of the new block
       end = np + HLM_APPEND_BLOCK;
     }
     if (take) {
-      unsigned long long at = pos + __popc(bal & ((1u << lane) - 1u));
       if ((int64_t)at < cap) list[at] = v;
       else *overflow = 1;
     }
