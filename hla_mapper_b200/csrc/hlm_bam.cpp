@@ -114,7 +114,8 @@ struct Rec {
   bool sane() const {
     return size >= R_FIXED && (size_t)R_FIXED + l_name() + 4 * (size_t)n_cigar() + (l_seq() + 1) / 2 + l_seq() <= size;
   }
-  int32_t end() const {  // bam_endpos()
+  int32_t end() const {  // bam_endpos(): a record flagged unmapped covers one base whatever its CIGAR
+    if (flag() & 4u) return pos() + 1;
     int32_t len = 0;
     const uint8_t* c = cigar();
     for (uint32_t i = 0; i < n_cigar(); i++) {

@@ -743,6 +743,19 @@ k_seed(HlmDevDB db, HlmKParams kp, HlmChunk ck) {
         // both bounds at once: two independent chains of dependent loads instead of one after
         // the other (this part of the kernel is pure memory latency)
         uint32_t lo1 = a, hi1 = b, lo2 = a, hi2 = b;
+        if (b - a <= 16) {
+          // a small bucket (the common case: 5 entries on average) is counted through instead of
+          // searched: its loads do not depend on one another, a binary search's do
+          uint32_t below_lo = 0, below_hi = 0;
+#pragma unroll 4
+          for (uint32_t x = a; x < b; x++) {
+            uint32_t e = __ldg(db.seed_ent + x);
+            below_lo += e < klo ? 1u : 0u;
+            below_hi += e < khi ? 1u : 0u;
+          }
+          lo1 = hi1 = a + below_lo;
+          lo2 = hi2 = a + below_hi;
+        }
         while (lo1 < hi1 || lo2 < hi2) {
           uint32_t m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1;
           uint32_t e1 = lo1 < hi1 ? __ldg(db.seed_ent + m1) : 0u;
