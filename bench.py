@@ -511,8 +511,11 @@ def run_inprocess(args, api, gdb, db, world, w, n, db_path):
            "pairs_per_call": n_total, "seconds_per_call": round(dt / reps, 3),
            "what": "hlm_multi_run: one process, one host batch, one host thread + context per GPU, results "
                    "gathered into the caller's arrays (host staging, H2D, kernels, D2H inside the timed region)"}
+    mm.close()
+    mm = api.MultiMapper(gdb, list(range(world)), _abi.default_params(score_cap=1))  # as the command line runs
     files = file_pipeline(mm, rbm.slice(0, min(n_total, 2 * n)), db_path)
     files["n_gpus"] = world
+    files["scoring"] = "hlm_params.score_cap = 1"
     files["what"] = "hlm_multi_map_fastq: " + files["what"].split(": ", 1)[1] + ", batches dealt to all GPUs"
     mm.close()
     return {"e2e_inprocess": e2e, "file_pipeline_multi": files}
@@ -556,7 +559,12 @@ def run_b200(args):
         capped["mapper"].close()
     files = None
     if rank == 0 and not args.no_files and w["kind"] == "dna":
-        files = file_pipeline(m, rb, db_path)
+        # the file-level drop-in only produces files: it runs with tolerance-capped scoring, as the
+        # command line does (byte-identical files, tests/test_gpu_capped.py)
+        mf = api.Mapper(gdb, local, _abi.default_params(score_cap=1))
+        files = file_pipeline(mf, rb, db_path)
+        files["scoring"] = "hlm_params.score_cap = 1 (the command line's default; files identical to the exact mode)"
+        mf.close()
     D.barrier()
     int_peak = api.int32_peak(local) if rank == 0 else None
     dp_ab = api.dp_layout_ab(local, 1 << 18, 150) if rank == 0 else None

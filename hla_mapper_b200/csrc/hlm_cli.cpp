@@ -48,14 +48,15 @@ int main(int argc, char** argv) {
             "           hla-mapper-b200 dna bam=sample.bam sample=your_sample_name <options>\n"
             "           hla-mapper-b200 select r1=... r2=... sample=... <options>\n"
             "           hla-mapper-b200 rna r1=R1.gz r2=R2.gz sample=your_sample_name [star=STAR] <options>\n"
-            "Options:   db= output= size= tolerance= error= downsample= gpu= threads= --quiet --skip-unmapped\n");
+            "Options:   db= output= size= tolerance= error= downsample= gpu= threads= --quiet --skip-unmapped\n"
+            "           --exact-scores\n");
     return 1;
   }
   bool select_only = strcmp(argv[1], "select") == 0, quiet = false;
   const int rna = strcmp(argv[1], "rna") == 0 ? 1 : 0;
   std::string r0, r1, r2, bam, sample, db, output, star;
   double tolerance = -1, error = -1;
-  int size = 0, downsample = 30, gpu = 0, threads = 0, skip_unmapped = 0;
+  int size = 0, downsample = 30, gpu = 0, threads = 0, skip_unmapped = 0, exact_scores = 0;
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     if (starts(a, "r0=")) r0 = a.substr(3);
@@ -71,6 +72,7 @@ int main(int argc, char** argv) {
     else if (starts(a, "gpu=")) gpu = atoi(a.c_str() + 4);
     else if (a == "--quiet") quiet = true;
     else if (a == "--skip-unmapped") skip_unmapped = 1;  // src/main.cpp:626-630
+    else if (a == "--exact-scores") exact_scores = 1;
     else if (starts(a, "threads=")) threads = atoi(a.c_str() + 8);
     else if (starts(a, "bam=")) bam = a.substr(4);
     else if (starts(a, "star=")) star = a.substr(5);
@@ -125,6 +127,10 @@ int main(int argc, char** argv) {
   hlm_params_default(&p, rna);
   p.paired = paired ? 1 : 0;
   if (R) p.screen_variant = HLM_SCREEN_BAM;
+  // the command line only produces files: scores the compare step cannot use are not computed
+  // (tolerance-capped scoring: the files are byte-identical); --exact-scores
+  // switches it off
+  p.score_cap = exact_scores ? 0 : 1;
   if (size > 0) p.v_size = size;
   if (tolerance >= 0) p.tolerance = tolerance;
   if (error >= 0) p.mtrim_error = error;

@@ -1024,12 +1024,21 @@ struct RangeOut {
 // runs on nt host threads, then pairwise merges - and the records are gathered once at the end.
 struct IdKey {
   const char* s;
+  uint64_t k;  // the eight id bytes that follow the prefix ALL ids share, big-endian, zero-padded
   uint32_t l, part;
   uint32_t idx, pad;
 };
+// ids agree on their first `w0` bytes, so (k, then the whole id) orders like the whole id; most
+// comparisons are decided by k without touching the id bytes (Illumina ids share a long prefix)
 bool key_less(const IdKey& a, const IdKey& b) {
+  if (a.k != b.k) return a.k < b.k;
   int c = memcmp(a.s, b.s, std::min(a.l, b.l));
   return c < 0 || (c == 0 && a.l < b.l);
+}
+uint64_t id_window(const char* s, uint32_t l, uint32_t w0) {
+  uint64_t k = 0;
+  for (uint32_t x = 0; x < 8; x++) k = (k << 8) | (w0 + x < l ? (uint8_t)s[w0 + x] : 0u);
+  return k;
 }
 void sort_kept(std::vector<std::vector<Kept>>& parts, std::vector<Kept>& out, int nt) {
   size_t n = 0;
@@ -1038,10 +1047,30 @@ void sort_kept(std::vector<std::vector<Kept>>& parts, std::vector<Kept>& out, in
   n = first[parts.size()];
   std::vector<IdKey> keys(n);
   nt = std::max(1, nt);
+  // the prefix every id shares with the first one (exact: a minimum over all ids)
+  const Kept* k0 = nullptr;
+  for (auto& v : parts)
+    if (!v.empty()) {
+      k0 = &v[0];
+      break;
+    }
+  std::vector<uint32_t> lcp(nt, k0 ? k0->idl : 0);
+  parallel_for(nt, [&](int t) {
+    uint32_t m = lcp[t];
+    for (size_t p = (size_t)t; p < parts.size(); p += (size_t)nt)
+      for (const Kept& k : parts[p]) {
+        uint32_t x = 0, lim = std::min(m, k.idl);
+        while (x < lim && k.idgen[x] == k0->idgen[x]) x++;
+        m = x;
+      }
+    lcp[t] = m;
+  });
+  uint32_t w0 = k0 ? *std::min_element(lcp.begin(), lcp.end()) : 0;
   parallel_for(nt, [&](int t) {
     for (size_t p = (size_t)t; p < parts.size(); p += (size_t)nt)
       for (size_t i = 0; i < parts[p].size(); i++)
-        keys[first[p] + i] = IdKey{parts[p][i].idgen, parts[p][i].idl, (uint32_t)p, (uint32_t)i, 0};
+        keys[first[p] + i] = IdKey{parts[p][i].idgen, id_window(parts[p][i].idgen, parts[p][i].idl, w0),
+                                   parts[p][i].idl, (uint32_t)p, (uint32_t)i, 0};
   });
   int runs = 1;
   while (runs * 2 <= nt && runs < 64 && n >= (size_t)(1u << 14) * (size_t)(runs * 2)) runs *= 2;
