@@ -492,6 +492,31 @@ def run_shard_100m(args, api, D, gdb, db):
                     f"{args.shard_seconds:.0f}s of run time (generation excluded)"}
 
 
+def allele_matrix(api, gdb, rb, device):
+    """hlm_score_alleles: the reads that truly come from the first
+    locus against every allele of it - the NM matrix the reference's pseudo-typing step gets from
+    `bwa mem -a` runs (src/functions.cpp:347-520)"""
+    idx = np.flatnonzero(rb.truth_locus == 0)[:16384]
+    L = int(rb.offs1[1] - rb.offs1[0])
+    pick = (idx[:, None] * L + np.arange(L)[None, :]).reshape(-1)
+    offs = np.arange(len(idx) + 1, dtype=np.uint64) * np.uint64(L)
+    sub = synth.ReadBatch(len(idx), rb.bases1[pick], rb.quals1[pick], offs, rb.bases2[pick], rb.quals2[pick],
+                          offs.copy(), rb.truth_locus[idx], rb.seed, 0)
+    m = api.Mapper(gdb, device, _abi.default_params())
+    buf = m.screen_trim(sub)
+    m.score_alleles(sub, buf, 0)  # warm-up: allocations
+    t0 = time.perf_counter()
+    nm1, _, nm2, _ = m.score_alleles(sub, buf, 0)
+    dt = time.perf_counter() - t0
+    m.close()
+    na = nm1.shape[1]
+    return {"locus": gdb.loci[0], "pairs": len(idx), "alleles": na, "seconds": round(dt, 3),
+            "read_allele_scores_per_s": round(2 * len(idx) * na / dt, 1),
+            "aligned_fraction": round(float(((nm1 != 255).mean() + (nm2 != 255).mean()) / 2), 4),
+            "what": "hlm_score_alleles: NM + clips of every mate against every allele of the locus (what the "
+                    "reference's pseudo-typing step reads from `bwa mem -a` SAM), host buffers in, matrix out"}
+
+
 def run_inprocess(args, api, gdb, db, world, w, n, db_path):
     """SURVEY.md section 8e as written: ONE process, one host thread + context per GPU, the
     caller's batch sharded by contiguous range, results gathered host-side into the caller's
@@ -565,6 +590,9 @@ def run_b200(args):
         files = file_pipeline(mf, rb, db_path)
         files["scoring"] = "hlm_params.score_cap = 1 (the command line's default; files identical to the exact mode)"
         mf.close()
+    alleles = None
+    if rank == 0 and not args.no_extras and w["kind"] == "dna":
+        alleles = allele_matrix(api, gdb, rb, local)
     D.barrier()
     int_peak = api.int32_peak(local) if rank == 0 else None
     dp_ab = api.dp_layout_ab(local, 1 << 18, 150) if rank == 0 else None
@@ -651,6 +679,8 @@ def run_b200(args):
             "roofline": croof,
             "same_targets_and_visible_scores_as_exact": True,
         }
+    if alleles:
+        out["score_alleles"] = alleles
     if inproc:
         out["e2e_inprocess"] = inproc["e2e_inprocess"]
         out["file_pipeline_multi"] = inproc["file_pipeline_multi"]

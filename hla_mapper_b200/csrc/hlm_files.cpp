@@ -519,6 +519,24 @@ struct Kept {
   uint16_t os1, os2;
 };
 
+// the kept reads in id order: a plain array whose pages are first touched by the threads that fill
+// it (a std::vector would zero 100+ MB on one thread first)
+struct KeptVec {
+  std::unique_ptr<Kept[]> p;
+  size_t n = 0;
+  void allocate(size_t count) {
+    p.reset(new Kept[count]);
+    n = count;
+  }
+  size_t size() const { return n; }
+  Kept& operator[](size_t i) { return p[i]; }
+  const Kept& operator[](size_t i) const { return p[i]; }
+  Kept* begin() { return p.get(); }
+  Kept* end() { return p.get() + n; }
+  const Kept* begin() const { return p.get(); }
+  const Kept* end() const { return p.get() + n; }
+};
+
 struct Out {
   FILE* f = nullptr;
   std::string buf;
@@ -659,7 +677,7 @@ struct RnaBlocks {
 
 // <pre><gene>_splice_Aligned.out.sam -> blocks of the kept reads + sorted_spliced_<gene>.fastq
 int read_star_sam(const std::string& sam_path, const std::string& spliced_path, int gene,
-                  const std::vector<Kept>& kept, RnaBlocks& rb, std::mutex& mu, std::string& err) {
+                  const KeptVec& kept, RnaBlocks& rb, std::mutex& mu, std::string& err) {
   HlmMapped map;
   Out sp;
   if (!sp.open(spliced_path)) {
@@ -784,7 +802,7 @@ std::string shq(const std::string& s) {  // single-quoted for sh
 // the second half of `hla-mapper rna` for the kept reads (already sorted by id): per-gene sorted
 // FASTQs -> STAR (when a command is given) -> block lists -> hlm_score + hlm_assign
 int rna_score_kept(hlm_ctx* ctx, const hlm_db* db, const hlm_file_opts& o, const std::string& pre, bool paired,
-                   std::vector<Kept>& kept) {
+                   KeptVec& kept) {
   const char* tag = paired ? "R1" : "R0";
   int G = db->n_loci, T = G + 1;
   int nt = o.threads > 0 ? o.threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -1040,7 +1058,7 @@ uint64_t id_window(const char* s, uint32_t l, uint32_t w0) {
   for (uint32_t x = 0; x < 8; x++) k = (k << 8) | (w0 + x < l ? (uint8_t)s[w0 + x] : 0u);
   return k;
 }
-void sort_kept(std::vector<std::vector<Kept>>& parts, std::vector<Kept>& out, int nt) {
+void sort_kept(std::vector<std::vector<Kept>>& parts, KeptVec& out, int nt) {
   size_t n = 0;
   std::vector<size_t> first(parts.size() + 1, 0);
   for (size_t p = 0; p < parts.size(); p++) first[p + 1] = first[p] + parts[p].size();
@@ -1090,7 +1108,7 @@ void sort_kept(std::vector<std::vector<Kept>>& parts, std::vector<Kept>& out, in
     }
     if (src != &keys) keys.swap(tmp);
   }
-  out.resize(n);
+  out.allocate(n);
   parallel_for(nt, [&](int t) {
     for (size_t j = n * (size_t)t / nt; j < n * (size_t)(t + 1) / nt; j++) out[j] = parts[keys[j].part][keys[j].idx];
   });
@@ -1250,7 +1268,7 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
     std::lock_guard<std::mutex> g(err_mu);
     return rc_all != 0;
   };
-  std::vector<Kept> kept;
+  KeptVec kept;
   std::map<int64_t, std::unique_ptr<BatchOut>> pending;
   int64_t commit_seq = 0, n_pairs = 0, n_selected = 0, sel_bases = 0;
   double t_gpu = 0, t_post = 0, t_wait = 0;
