@@ -538,6 +538,8 @@ def run_inprocess(args, api, gdb, db, world, w, n, db_path):
                    "gathered into the caller's arrays (host staging, H2D, kernels, D2H inside the timed region)"}
     mm.close()
     mm = api.MultiMapper(gdb, list(range(world)), _abi.default_params(score_cap=1))  # as the command line runs
+    nw = min(n_total, 3 * 65536 * world)
+    mm.run(rbm.slice(0, nw), buffers=_abi.Buffers(nw, T, diag=False))  # every context's buffers allocated
     files = file_pipeline(mm, rbm.slice(0, min(n_total, 2 * n)), db_path)
     files["n_gpus"] = world
     files["scoring"] = "hlm_params.score_cap = 1"
@@ -587,6 +589,7 @@ def run_b200(args):
         # the file-level drop-in only produces files: it runs with tolerance-capped scoring, as the
         # command line does (byte-identical files, tests/test_gpu_capped.py)
         mf = api.Mapper(gdb, local, _abi.default_params(score_cap=1))
+        mf.run(rb.slice(0, min(n, 3 * 65536)), buffers=_abi.Buffers(min(n, 3 * 65536), gdb.n_loci + 1, diag=False))  # buffers allocated
         files = file_pipeline(mf, rb, db_path)
         files["scoring"] = "hlm_params.score_cap = 1 (the command line's default; files identical to the exact mode)"
         mf.close()
