@@ -193,7 +193,7 @@ def test_gpu_scores_reproduce_bwa_mem_records(tmp_path):
     got = m.run(rb)
     m.close()
     gdb.close()
-    same = cheaper = beyond = 0
+    same = cheaper = beyond = clipped_tail = 0
     for i, (r, t, lead, trail, score, nm, a_s) in enumerate(recs):
         if len(r) < 50:
             continue
@@ -203,9 +203,17 @@ def test_gpu_scores_reproduce_bwa_mem_records(tmp_path):
             beyond += 1
             continue
         want = nm + lead + 1  # read_sam_dna on bwa's record (map_dna.cpp:56-78; the trailing clip is never added)
+        if trail:
+            # the reported alignment is the one of minimum COST over all segments: an overlapping
+            # read's segment that reaches further can replace bwa's trailing clip by a few mismatches
+            # (fewer edits in all, but more NM): counted, not compared
+            clipped_tail += 1
+            assert s > 0, i
+            continue
         assert 0 < s <= want, (i, s, want)
         same += s == want
         cheaper += s < want
     print({"records": n, "score equals NM + lead + 1 of bwa's record": same,
-           "cheaper co-optimal path / other segment": cheaper, "beyond mm_max": beyond})
+           "cheaper co-optimal path / other segment": cheaper, "trailing clip in bwa's record": clipped_tail,
+           "beyond mm_max": beyond})
     assert same >= 0.97 * (same + cheaper) and same > 2000
