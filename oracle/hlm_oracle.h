@@ -12,10 +12,12 @@
  *
  * Parity status: screen / mtrim / pair filter / locus sort / SAM reducer / compare are
  * pinned against the unmodified reference sources compiled into oracle/_ref
- * (tests/test_oracle_vs_reference.py, tests/golden/).  The aligner itself is
- * "parity unpinned": the reference shells out to bwa 0.7.17 (hla-mapper.yml:12),
- * which is neither vendored nor installed, and the reference ships no expected
- * alignment output.
+ * (tests/test_oracle_vs_reference.py, tests/golden/).  The DP scoring (orc_align) is
+ * pinned to the real `bwa mem` records of the reference's test BAM
+ * (tests/test_bwa_mem_records.py: clips, CIGAR score, NM).  The aligner as a whole
+ * against `bwa aln` is "parity unpinned": the reference shells out to bwa 0.7.17
+ * (hla-mapper.yml:12), which is neither vendored nor installed, and the reference
+ * ships no `aln` output.
  */
 #ifndef HLM_ORACLE_H
 #define HLM_ORACLE_H
