@@ -334,6 +334,17 @@ class MultiMapper:
             raise HlmError(f"libhlamap rc={rc}: {lib().hlm_multi_last_error(self.h).decode()}")
         return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
 
+    def map_reads(self, reads, sample, out_dir, downsampling=30, batch_pairs=0, write_selected=1, select_only=0):
+        """hlm_multi_map_reads: reads extracted from a BAM, every GPU of the multi-context"""
+        o = _abi.HlmFileOpts(C.sizeof(_abi.HlmFileOpts), downsampling, batch_pairs, write_selected,
+                             select_only, 0, None)
+        st = _abi.HlmFileStats()
+        rc = lib().hlm_multi_map_reads(self.h, reads.h, sample.encode(), str(out_dir).encode(), C.byref(o),
+                                       C.byref(st))
+        if rc != 0:
+            raise HlmError(f"libhlamap rc={rc}: {lib().hlm_multi_last_error(self.h).decode()}")
+        return {k: getattr(st, k) for k, _ in _abi.HlmFileStats._fields_}
+
     def close(self):
         if self.h:
             lib().hlm_multi_destroy(self.h)

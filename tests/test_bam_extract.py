@@ -11,7 +11,9 @@ import bam_cases
 import bamlite
 from hla_mapper_b200 import api, synth
 
-REAL_BAM = "/root/reference/test_sequences/HG01890_HLA-A.bam"
+# the reference's own test BAM and the `samtools fastq` files shipped next to it, committed as fixtures
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REAL_BAM = os.path.join(GOLDEN, "HG01890_HLA-A.bam")
 DBK = dict(seed=7, n_loci=4, total_alleles=40, len_range=(500, 600), n_others=6)
 
 
@@ -104,7 +106,6 @@ def test_reference_error_messages(dbs, tmp_path):
         api.BamReads(db, sec)
 
 
-@pytest.mark.skipif(not os.path.exists(REAL_BAM), reason="reference test_sequences not mounted")
 def test_reference_test_bam(dbs, tmp_path):
     sdb, db = dbs
     text, refs, recs = bamlite.read_bam(REAL_BAM)
@@ -114,7 +115,12 @@ def test_reference_test_bam(dbs, tmp_path):
                               for r in recs)
     assert len(sets[0]) == 0
     for which, tag in ((1, "R1"), (2, "R2")):
-        rb, headers = synth.read_fastq_pair(REAL_BAM.replace(".bam", f"_{tag}.fastq"))
+        import gzip
+
+        plain = str(tmp_path / f"{tag}.fastq")
+        with gzip.open(REAL_BAM.replace(".bam", f"_{tag}.fastq.gz"), "rb") as f, open(plain, "wb") as o:
+            o.write(f.read())
+        rb, headers = synth.read_fastq_pair(plain)
         ship = {h.split(" ")[0]: (rb.bases1[int(rb.offs1[i]):int(rb.offs1[i + 1])].tobytes().decode(),
                                   rb.quals1[int(rb.offs1[i]):int(rb.offs1[i + 1])].tobytes().decode())
                 for i, h in enumerate(headers)}
