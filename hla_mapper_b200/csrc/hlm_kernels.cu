@@ -1079,7 +1079,7 @@ k_select(HlmDevDB db, HlmKParams kp, HlmChunk ck, int n_targets, int round) {
   int64_t nloop = (ncand + stride - 1) / stride;
   unsigned long long n_take = 0;
   // the kernel is a chain of dependent loads per candidate (record -> locus -> task minimum ->
-  // best): two candidates per thread are in flight at a time (more cost occupancy)
+  // best): two candidates per thread are in flight at a time (four measured: slower)
   constexpr int UN = 2;
   for (int64_t it = 0; it < nloop; it += UN) {
     int64_t idx[UN];
