@@ -364,8 +364,15 @@ void scatter_results(hlm_ctx* ctx, Slot& s, const HostIO& io) {
     copy_out(io.scr->locus_mask, b, o[O_MASK], f, n, 1);
   }
   if (io.sc) {
-    copy_out(io.sc->s1, b, o[O_S1], f, n, T);
-    copy_out(io.sc->s2, b, o[O_S2], f, n, T);
+    // the two score tables are most of the result bytes: copied side by side on large chunks
+    if (io.sc->s2 && (size_t)n * T >= ((size_t)1 << 19)) {
+      std::thread t2([&] { copy_out(io.sc->s2, b, o[O_S2], f, n, T); });
+      copy_out(io.sc->s1, b, o[O_S1], f, n, T);
+      t2.join();
+    } else {
+      copy_out(io.sc->s1, b, o[O_S1], f, n, T);
+      copy_out(io.sc->s2, b, o[O_S2], f, n, T);
+    }
     copy_out(io.sc->aln1, b, o[O_ALN1], f, n, T);
     copy_out(io.sc->aln2, b, o[O_ALN2], f, n, T);
     copy_out(io.sc->nm1, b, o[O_NM1], f, n, T);
@@ -503,14 +510,24 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
       if (nb) memcpy(h + io_off[10], in->rna_blocks + bf, (size_t)nb * sizeof(hlm_rna_block));
     }
     if (need_reads) {
-      memcpy(h + io_off[0] + 16, in->bases1 + f1, b1);
-      if (q) memcpy(h + io_off[1] + 16, in->quals1 + f1, b1);
-      memcpy(h + io_off[4], in->offs1 + first, (n + 1) * 8);
-      if (paired) {
-        memcpy(h + io_off[2] + 16, in->bases2 + f2, b2);
-        if (q) memcpy(h + io_off[3] + 16, in->quals2 + f2, b2);
-        memcpy(h + io_off[5], in->offs2 + first, (n + 1) * 8);
+      // the four read arrays of a large chunk are staged by four host threads: on screen-heavy
+      // input (config 3: the GPU needs 2.6 ms per 65 536-pair chunk) one thread's memcpy into the
+      // pinned buffer was the end-to-end limiter
+      auto c0 = [&] { memcpy(h + io_off[0] + 16, in->bases1 + f1, b1); };
+      auto c1 = [&] { if (q) memcpy(h + io_off[1] + 16, in->quals1 + f1, b1); };
+      auto c2 = [&] { if (paired) memcpy(h + io_off[2] + 16, in->bases2 + f2, b2); };
+      auto c3 = [&] { if (paired && q) memcpy(h + io_off[3] + 16, in->quals2 + f2, b2); };
+      if (b1 + b2 >= ((size_t)4 << 20)) {
+        std::thread t1(c1), t2(c2), t3(c3);
+        c0();
+        t1.join();
+        t2.join();
+        t3.join();
+      } else {
+        c0(); c1(); c2(); c3();
       }
+      memcpy(h + io_off[4], in->offs1 + first, (n + 1) * 8);
+      if (paired) memcpy(h + io_off[5], in->offs2 + first, (n + 1) * 8);
     }
     if (in->size_override1) memcpy(h + io_off[6], in->size_override1 + first, n * 4);
     if (in->rna_split1) memcpy(h + io_off[7], in->rna_split1 + first, n * 2);
