@@ -52,6 +52,12 @@ class HlmScreenOut(C.Structure):
                 ("trim_len2", u16p), ("locus_mask", u32p)]
 
 
+class HlmStarRec(C.Structure):
+    _fields_ = [("qname", C.c_void_p), ("qname_len", C.c_int32), ("flag", C.c_int32), ("seq_len", C.c_int32),
+                ("piece", C.c_int32), ("gene", C.c_uint8), ("mate", C.c_uint8), ("start", C.c_uint16),
+                ("len", C.c_uint16), ("reserved", C.c_uint16)]
+
+
 class HlmAlleleOut(C.Structure):
     _fields_ = [("n_alleles", C.c_int32), ("reserved0", C.c_int32),
                 ("nm1", C.POINTER(C.c_uint8)), ("clip1", C.POINTER(C.c_uint8)),

@@ -29,6 +29,7 @@ SYMBOLS = [
     "hlm_bam_extract", "hlm_reads_paired", "hlm_reads_count", "hlm_reads_free",
     "hlm_reads_write_fastq", "hlm_map_reads", "hlm_int32_peaks", "hlm_db_n_alleles",
     "hlm_db_allele_name", "hlm_score_alleles", "hlm_multi_map_fastq", "hlm_multi_map_reads",
+    "hlm_star_sam_read", "hlm_star_free",
 ]
 
 _lib = None
@@ -102,6 +103,9 @@ def lib():
                                       C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
     L.hlm_multi_map_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p,
                                       C.POINTER(_abi.HlmFileOpts), C.POINTER(_abi.HlmFileStats)]
+    L.hlm_star_sam_read.restype = C.c_int64
+    L.hlm_star_sam_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(_abi.HlmStarRec))]
+    L.hlm_star_free.argtypes = [C.POINTER(_abi.HlmStarRec)]
     L.hlm_bam_extract.restype = C.c_void_p
     L.hlm_bam_extract.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                   C.POINTER(_abi.HlmBamStats), C.c_char_p, C.c_size_t]
@@ -141,6 +145,19 @@ class Database:
         if self.h:
             lib().hlm_db_close(self.h)
             self.h = None
+
+
+def star_sam_blocks(sam_path, gene):
+    """hlm_star_sam_read: [(qname, flag, seq_len, piece, mate, start, len)] of a STAR SAM file"""
+    p = C.POINTER(_abi.HlmStarRec)()
+    n = lib().hlm_star_sam_read(str(sam_path).encode(), int(gene), C.byref(p))
+    if n < 0:
+        raise HlmError(f"hlm_star_sam_read rc={n}")
+    out = [(C.string_at(p[i].qname, p[i].qname_len).decode(), p[i].flag, p[i].seq_len, p[i].piece, p[i].mate,
+            p[i].start, p[i].len) for i in range(n)]
+    if n:
+        lib().hlm_star_free(p)
+    return out
 
 
 class BamReads:

@@ -1767,3 +1767,81 @@ extern "C" int hlm_multi_map_fastq(hlm_multi* mm, const char* r1_path, const cha
   if (rc) hlm_multi_set_error(mm, hlm_last_error(cs[0]));
   return rc;
 }
+
+// ---- public STAR SAM reader (include/hlamap.h): FLAG-based mate / orientation
+extern "C" int64_t hlm_star_sam_read(const char* sam_path, int gene, hlm_star_rec** out) {
+  if (!sam_path || !out || gene < 0 || gene > 255) return HLM_E_ARG;
+  *out = nullptr;
+  try {
+    HlmMapped map;
+    if (!map.open(sam_path)) return 0;
+    const char* base = (const char*)map.p;
+    size_t n = map.n, p = 0, pool = 0;
+    struct Tmp {
+      size_t q0;
+      int32_t ql, flag, L, piece;
+      hlm_rna_block b;
+    };
+    std::vector<Tmp> recs;
+    std::vector<std::pair<int, int>> pieces;
+    while (p < n) {
+      const char* nl = (const char*)memchr(base + p, '\n', n - p);
+      size_t e = nl ? (size_t)(nl - base) : n, ls = p;
+      p = e + 1;
+      if (e == ls || base[ls] == '@') continue;
+      const char* f[11];
+      size_t fl[11];
+      int nf = 0;
+      size_t a = ls;
+      while (nf < 11 && a <= e) {
+        const char* t = (const char*)memchr(base + a, '\t', e - a);
+        size_t b = t ? (size_t)(t - base) : e;
+        f[nf] = base + a;
+        fl[nf] = b - a;
+        nf++;
+        a = b + 1;
+      }
+      if (nf < 11) continue;
+      int flag = atoi(std::string(f[1], fl[1]).c_str());
+      size_t L = fl[9];
+      star_record_pieces(f[5], fl[5], L, pieces);
+      int k = 1;
+      for (auto& pc : pieces) {
+        size_t st = std::min<size_t>((size_t)pc.first, L), en = std::min<size_t>((size_t)pc.first + (size_t)pc.second, L);
+        Tmp t;
+        t.q0 = (size_t)(f[0] - base);
+        t.ql = (int32_t)fl[0];
+        t.flag = flag;
+        t.L = (int32_t)L;
+        t.piece = k++;
+        t.b.gene = (uint8_t)gene;
+        t.b.mate = (uint8_t)((flag & 0x80) ? 1 : 0);
+        t.b.start = (uint16_t)((flag & 0x10) ? L - en : st);
+        t.b.len = (uint16_t)(en - st);
+        t.b.reserved = 0;
+        recs.push_back(t);
+        pool += fl[0];
+      }
+    }
+    if (recs.empty()) return 0;
+    char* mem = (char*)malloc(recs.size() * sizeof(hlm_star_rec) + pool + 1);
+    if (!mem) return HLM_E_NOMEM;
+    hlm_star_rec* r = (hlm_star_rec*)mem;
+    char* sp = mem + recs.size() * sizeof(hlm_star_rec);
+    for (size_t i = 0; i < recs.size(); i++) {
+      memcpy(sp, base + recs[i].q0, (size_t)recs[i].ql);
+      r[i].qname = sp;
+      r[i].qname_len = recs[i].ql;
+      r[i].flag = recs[i].flag;
+      r[i].seq_len = recs[i].L;
+      r[i].piece = recs[i].piece;
+      r[i].block = recs[i].b;
+      sp += recs[i].ql;
+    }
+    *out = r;
+    return (int64_t)recs.size();
+  } catch (const std::exception&) {
+    return HLM_E_NOMEM;
+  }
+}
+extern "C" void hlm_star_free(hlm_star_rec* recs) { free(recs); }

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define HLM_ABI_VERSION 4
+#define HLM_ABI_VERSION 5
 
 /* limits of this build */
 #define HLM_MAX_LOCI 31   /* loci + "others" must fit a uint32 mask            */
@@ -311,6 +311,30 @@ int hlm_map_fastq(hlm_ctx* ctx, const char* r1_path, const char* r2_path, const 
  * devices */
 int hlm_multi_map_fastq(hlm_multi* m, const char* r1_path, const char* r2_path, const char* sample,
                         const char* out_dir, const hlm_file_opts* opts, hlm_file_stats* stats);
+
+/* ---- rna: STAR's SAM -> block records ----
+ * For callers that drive STAR themselves and score through hlm_batch.rna_blocks: every record of
+ * <sample>_<gene>_splice_Aligned.out.sam cut the way src/map_rna.cpp:740-790 cuts it into
+ * sorted_spliced_<gene>.fastq - the CIGAR split after every N, a piece's size = the sum of its
+ * operation lengths except N and D, piece k starting at the SIZE of piece k-1 (:784), a CIGAR
+ * without N = the whole SEQ; pieces clipped to SEQ.  One hlm_star_rec per piece, in file order.
+ * block.start / len are in the MATE's own orientation (FLAG 0x10: SEQ is printed reverse-
+ * complemented, the piece [s, e) of SEQ covers [L - e, L - s) of the mate), block.mate from FLAG
+ * 0x80, block.gene = `gene`.  The caller maps qname (the read id: first header token without
+ * /1 /2) to its pair index and concatenates the blocks per pair.  (hlm_map_fastq does all of this
+ * itself, and decides mate / orientation by comparing SEQ with the trimmed mates.)
+ * Returns the number of records (0 for a missing or empty file), < 0 on error; *out is one
+ * allocation released with hlm_star_free. */
+typedef struct hlm_star_rec {
+  const char* qname;   /* not NUL-terminated: qname_len bytes */
+  int32_t qname_len;
+  int32_t flag;        /* SAM FLAG of the record */
+  int32_t seq_len;     /* length of SEQ */
+  int32_t piece;       /* 1-based number of the piece inside its record ($block of the reference) */
+  hlm_rna_block block;
+} hlm_star_rec;
+int64_t hlm_star_sam_read(const char* sam_path, int gene, hlm_star_rec** out);
+void hlm_star_free(hlm_star_rec* recs);
 
 /* ---- BAM front end of the dna path ----
  * hlm_bam_extract replaces the four samtools processes of the reference's bam= input

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     L = api.lib()
     for n in names:
         assert getattr(L, n) is not None
-    assert L.hlm_abi_version() == 4  # 3: hlm_params.score_cap (was reserved0); 4: hlm_score_alleles
+    assert L.hlm_abi_version() == 5  # 3: hlm_params.score_cap; 4: hlm_score_alleles; 5: hlm_star_sam_read, multi file entry points
 
 
 def test_struct_layouts_match_the_header():
