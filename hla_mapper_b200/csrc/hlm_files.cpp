@@ -411,10 +411,15 @@ class MappedSource : public PairSource {
     int workers = std::max(1, std::min(nt_, 8));
     for (int w = 0; w < workers; w++) th_.emplace_back([this] { work(); });
   }
-  bool next(MateBatch*& b1, MateBatch*& b2, int&, std::string&) override {
+  bool next(MateBatch*& b1, MateBatch*& b2, int& rc, std::string& err) override {
     std::unique_lock<std::mutex> g(m_);
     if (deliver_ >= nb_) return false;
-    cv_.wait(g, [this] { return ready_.count(deliver_) != 0; });
+    cv_.wait(g, [this] { return failed_ || ready_.count(deliver_) != 0; });
+    if (failed_) {  // a parser thread ran out of memory
+      rc = HLM_E_NOMEM;
+      err = "out of memory while parsing the FASTQ files";
+      return false;
+    }
     auto it = ready_.find(deliver_);
     b1 = it->second.first;
     b2 = it->second.second;
@@ -452,11 +457,15 @@ class MappedSource : public PairSource {
         m1 = fresh();
         if (paired_) m2 = fresh();
       }
-      f1_.parse(b, *m1);
-      if (paired_) f2_.parse(b, *m2);
-      {
+      try {
+        f1_.parse(b, *m1);
+        if (paired_) f2_.parse(b, *m2);
         std::lock_guard<std::mutex> g(m_);
         ready_[b] = {m1, m2};
+      } catch (const std::exception&) {  // no exception leaves a library thread
+        std::lock_guard<std::mutex> g(m_);
+        failed_ = true;
+        stop_ = true;
       }
       cv_.notify_all();
     }
@@ -472,7 +481,7 @@ class MappedSource : public PairSource {
   std::map<int64_t, std::pair<MateBatch*, MateBatch*>> ready_;
   std::vector<MateBatch*> free_;
   std::vector<std::unique_ptr<MateBatch>> pool_;
-  bool stop_ = false;
+  bool stop_ = false, failed_ = false;
 };
 
 void erase_all(std::string& s, const char* pat) {  // boost::replace_all(s, pat, "")
