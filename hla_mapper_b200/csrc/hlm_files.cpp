@@ -215,6 +215,18 @@ class BatchStream {
 
  private:
   void run() {
+    try {
+      run_unguarded();
+    } catch (const std::exception&) {  // out of memory on the reader thread: the run ends with an
+      emergency_.clear();              // input error instead of std::terminate or a short input
+      emergency_.io_error = true;
+      std::lock_guard<std::mutex> g(m_);
+      q_.push(&emergency_);
+      done_ = true;
+      cv_.notify_all();
+    }
+  }
+  void run_unguarded() {
     for (;;) {
       MateBatch* b = nullptr;
       {
@@ -251,6 +263,7 @@ class BatchStream {
   std::queue<MateBatch*> q_;
   std::vector<MateBatch*> free_;
   std::vector<std::unique_ptr<MateBatch>> pool_;
+  MateBatch emergency_;
   bool stop_ = false, done_ = false;
 };
 
