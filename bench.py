@@ -822,7 +822,7 @@ def main():
     ap.add_argument("--db", default=os.environ.get("HLM_BENCH_DB", "/tmp/hlm_bench/db_seed42_40k"))
     ap.add_argument("--cpu-pairs", type=int, default=20000)
     ap.add_argument("--ref-pairs", type=int, default=60000, help="upper bound of the reference arm's per-step sample")
-    ap.add_argument("--ref-seconds", type=float, default=420.0, help="time budget of the reference arm's W + K steps")
+    ap.add_argument("--ref-seconds", type=float, default=300.0, help="time budget of the reference arm's W + K steps")
     ap.add_argument("--extra-scale", type=float, default=1.0, help="scale of the extra configs' sizes")
     ap.add_argument("--shard-pairs", type=int, default=100_000_000)
     ap.add_argument("--shard-seconds", type=float, default=40.0)
