@@ -26,7 +26,7 @@
 #define HLM_STAGE_SCORE 2
 #define HLM_STAGE_ASSIGN 4
 #define HLM_STAGE_ALLELES 8  /* hlm_score_alleles: needs provided screen results, excludes the others */
-#define HLM_MAX_SLOTS 3
+#define HLM_MAX_SLOTS 4
 #define HLM_E_OVERFLOW -100 /* internal: a chunk produced more candidates than cand_capacity */
 
 namespace {
@@ -641,8 +641,8 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
     if ((rc = complete(s))) break;  // drain the slot's previous chunk
     rc = submit(s, first, n);
   }
-  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
-    int r2 = complete(ctx->slot[(k + i) % HLM_MAX_SLOTS]);
+  for (int i = 0; i < ctx->n_slots; i++) {
+    int r2 = complete(ctx->slot[(k + i) % ctx->n_slots]);
     if (rc == 0) rc = r2;
   }
   ctx->prof.n_pairs = N;
@@ -843,7 +843,11 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   hlm_kernels_init();
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
-  ctx->n_slots = p.single_slot ? 1 : HLM_MAX_SLOTS;
+  ctx->n_slots = p.single_slot ? 1 : 3;
+  if (const char* e = getenv("HLM_SLOTS")) {  // measurement knob (tools/grid_sweep.py)
+    int v = atoi(e);
+    if (!p.single_slot && v >= 1 && v <= HLM_MAX_SLOTS) ctx->n_slots = v;
+  }
   ctx->chunk_pairs = p.chunk_pairs > 0 ? p.chunk_pairs : 65536;
   ctx->cand_cap = p.cand_capacity > 0 ? p.cand_capacity : ctx->chunk_pairs * 2048;
   if (ctx->cand_cap >= (1ll << 32)) ctx->cand_cap = (1ll << 32) - 1;
@@ -1140,8 +1144,8 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
     if ((rc = complete(s))) break;
     rc = submit(s, first, std::min(C, N - first));
   }
-  for (int i = 0; i < HLM_MAX_SLOTS; i++) {
-    int r2 = complete(ctx->slot[(k + i) % HLM_MAX_SLOTS]);
+  for (int i = 0; i < ctx->n_slots; i++) {
+    int r2 = complete(ctx->slot[(k + i) % ctx->n_slots]);
     if (rc == 0) rc = r2;
   }
   ctx->prof.n_pairs = N;

@@ -22,6 +22,8 @@
 //
 // All of it is integer / byte work: HBM-, L2- or INT32-bound, no tensor-core shape anywhere.
 #include "hlm_kernels.cuh"
+#include <cstdlib>
+#include <cstring>
 
 #include "hlm_core.cuh"
 
@@ -1753,6 +1755,26 @@ double hlm_int_peak_run(int which, int sms, cudaStream_t st) {
 // ------------------------------------------------------------------ launchers
 static inline int grid_for(int sms, int per_sm) { return sms * per_sm; }
 
+// blocks per SM of the persistent grids whose size decides what can run beside them on another
+// pipeline slot's stream (all of them take work from device counters, so any size is correct).
+// HLM_TUNE="myers=3,dp=3,seed=10,expand=8,select=8" overrides them when a context is created:
+// a measurement knob (tools/grid_sweep.py), not part of the interface.
+enum { TUNE_MYERS, TUNE_DP, TUNE_SEED, TUNE_EXPAND, TUNE_SELECT, TUNE_N };
+static int g_tune[TUNE_N] = {4, 4, 10, 8, 8};
+void hlm_tune_reload() {
+  static const char* names[TUNE_N] = {"myers", "dp", "seed", "expand", "select"};
+  static const int defaults[TUNE_N] = {4, 4, 10, 8, 8};
+  for (int i = 0; i < TUNE_N; i++) g_tune[i] = defaults[i];
+  const char* e = getenv("HLM_TUNE");
+  if (!e) return;
+  for (int i = 0; i < TUNE_N; i++) {
+    const char* q = strstr(e, names[i]);
+    if (!q || q[strlen(names[i])] != '=') continue;
+    int v = atoi(q + strlen(names[i]) + 1);
+    if (v >= 1 && v <= 32) g_tune[i] = v;
+  }
+}
+
 void hlm_launch_screen(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                        cudaStream_t st) {
   if (kp.screen_variant == HLM_SCREEN_FASTQ && !kp.skip_screen && kp.minhit >= 1 && db.n_odd == 0)
@@ -1768,14 +1790,15 @@ void hlm_launch_clear_tasks(const HlmChunk& ck, int n_targets, int sms, cudaStre
 }
 void hlm_launch_seed(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int sms,
                      cudaStream_t st) {
-  k_seed<<<grid_for(sms, 10), SEED_WARPS * 32, 0, st>>>(db, kp, ck);
+  k_seed<<<grid_for(sms, g_tune[TUNE_SEED]), SEED_WARPS * 32, 0, st>>>(db, kp, ck);
 }
 void hlm_launch_myers(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                       int phase, int sms, cudaStream_t st) {
-  k_myers<<<grid_for(sms, 4), 256, 0, st>>>(db, kp, ck, n_targets, phase);
+  k_myers<<<grid_for(sms, g_tune[TUNE_MYERS]), 256, 0, st>>>(db, kp, ck, n_targets, phase);
 }
 // per-device kernel attributes (call once per context, after cudaSetDevice)
 void hlm_kernels_init() {
+  hlm_tune_reload();
   // k_myers: 5 blocks x 42 KB of PEQ rows per SM; k_seed: 10 blocks x 18 KB of hash sets (register-bound)
   cudaFuncSetAttribute(k_myers, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(k_seed, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1785,12 +1808,12 @@ void hlm_launch_snapshot(const HlmChunk& ck, int which, cudaStream_t st) {
 }
 void hlm_launch_expand(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st) {
-  k_expand<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, round);
+  k_expand<<<grid_for(sms, g_tune[TUNE_EXPAND]), 256, 0, st>>>(db, kp, ck, n_targets, round);
   k_snapshot<<<1, 32, 0, st>>>(ck, round == 2 ? 1 : 1 + round);  // round 2 (per-allele): one expansion
 }
 void hlm_launch_select(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                        int round, int sms, cudaStream_t st) {
-  k_select<<<grid_for(sms, 8), 256, 0, st>>>(db, kp, ck, n_targets, round);
+  k_select<<<grid_for(sms, g_tune[TUNE_SELECT]), 256, 0, st>>>(db, kp, ck, n_targets, round);
 }
 void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, int n_targets,
                    int sms, cudaStream_t st) {
@@ -1800,7 +1823,7 @@ void hlm_launch_dp(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck,
   k_dp_dedup<<<grid_for(sms, 8), 256, 0, st>>>(db, ck, dedup);
   k_dp_scan<<<1, 256, 0, st>>>(ck);
   k_dp_scatter<<<grid_for(sms, 4), 256, 0, st>>>(ck);
-  k_dp<<<grid_for(sms, 4), 128, 0, st>>>(db, kp, ck, n_targets);
+  k_dp<<<grid_for(sms, g_tune[TUNE_DP]), 128, 0, st>>>(db, kp, ck, n_targets);
   k_dp_round_end<<<1, 32, 0, st>>>(ck);
 }
 void hlm_launch_allele_gather(const HlmDevDB& db, const HlmKParams& kp, const HlmChunk& ck, uint8_t* nm1,
