@@ -80,6 +80,16 @@ struct hlm_ctx {
   hlm_profile prof;
   cudaEvent_t run_start = nullptr;
   std::future<int> pending;  // hlm_run_async
+  // measurement aid (HLM_TRACE=<file>): the time of every stage event of every chunk relative
+  // to the start of the run, one line per chunk, appended when a run ends
+  std::vector<float> trace;
+  bool tracing = false;
+  // consecutive chunks run out of phase: a chunk's kernels start when the previous chunk (on
+  // another slot) has passed stage event `stagger_ev`, so that one chunk's list kernels run
+  // beside another chunk's ALU-bound kernels instead of beside the same kernels of the other
+  // slots (-1: the slots start together and stay in lockstep)
+  int stagger_ev = -1;
+  Slot* last_submitted = nullptr;
 };
 
 namespace {
@@ -315,6 +325,10 @@ int finish_slot(hlm_ctx* ctx, Slot& s, unsigned long long* counters_host) {
   pr.ms_d2h += ev_ms(s.ev[EV_ASSIGN], s.ev[EV_D2H]);
   float t = ev_ms(ctx->run_start, s.ev[EV_D2H]);
   if (t > pr.ms_total) pr.ms_total = t;
+  if (ctx->tracing) {
+    ctx->trace.push_back((float)(&s - ctx->slot));
+    for (int e = 0; e < EV_COUNT; e++) ctx->trace.push_back(ev_ms(ctx->run_start, s.ev[e]));
+  }
   if (counters_host) {
     pr.n_candidates += (int64_t)counters_host[11];
     pr.n_seed_candidates += (int64_t)counters_host[12];
@@ -581,6 +595,9 @@ int run_host_unguarded(hlm_ctx* ctx, const HostIO& io, int stages) {
       ctx->prof.h2d_bytes += (int64_t)(e - a);
     }
     CU(cudaEventRecord(s.ev[EV_H2D], st));
+    if (ctx->stagger_ev >= 0 && ctx->last_submitted && ctx->last_submitted != &s)
+      CU(cudaStreamWaitEvent(st, ctx->last_submitted->ev[ctx->stagger_ev], 0));
+    ctx->last_submitted = &s;
     launch_stages(ctx, s, stages, io.al_locus);
     CU(cudaMemcpyAsync((uint8_t*)s.d_out.p + s.out_off[O_COUNTERS], ck.counters, 8 * HLM_N_COUNTERS,
                        cudaMemcpyDeviceToDevice, st));
@@ -844,6 +861,11 @@ hlm_ctx* hlm_ctx_create(const hlm_db* db, int cuda_device, const hlm_params* par
   ctx->n_targets = db->n_loci + 1;
   ctx->units_per_pair = (p.paired ? 2 : 1) * (p.rna ? 3 : 1);
   ctx->n_slots = p.single_slot ? 1 : 3;
+  ctx->tracing = getenv("HLM_TRACE") != nullptr;
+  if (const char* e = getenv("HLM_STAGGER")) {  // measurement knob: stage event index, -1 = off
+    int v = atoi(e);
+    if (v >= -1 && v < EV_COUNT) ctx->stagger_ev = v;
+  }
   if (const char* e = getenv("HLM_SLOTS")) {  // measurement knob (tools/grid_sweep.py)
     int v = atoi(e);
     if (!p.single_slot && v >= 1 && v <= HLM_MAX_SLOTS) ctx->n_slots = v;
@@ -1118,6 +1140,9 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
     cudaStream_t st = s.st;
     CU(cudaEventRecord(s.ev[EV_START], st));
     CU(cudaEventRecord(s.ev[EV_H2D], st));
+    if (ctx->stagger_ev >= 0 && ctx->last_submitted && ctx->last_submitted != &s)
+      CU(cudaStreamWaitEvent(st, ctx->last_submitted->ev[ctx->stagger_ev], 0));
+    ctx->last_submitted = &s;
     launch_stages(ctx, s, HLM_STAGE_SCREEN | HLM_STAGE_SCORE | HLM_STAGE_ASSIGN);
     CU(cudaMemcpyAsync(s.h_out.p, ck.counters, 8 * HLM_N_COUNTERS, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(s.ev[EV_D2H], st));
@@ -1150,6 +1175,14 @@ int hlm_run_device(hlm_ctx* ctx, hlm_devbatch* b) {
   }
   ctx->prof.n_pairs = N;
   ctx->prof.bases_bytes = b->read_bytes;
+  if (ctx->tracing) {
+    if (FILE* f = fopen(getenv("HLM_TRACE"), "w")) {
+      for (size_t i = 0; i < ctx->trace.size(); i++)
+        fprintf(f, "%.3f%c", ctx->trace[i], (i + 1) % (EV_COUNT + 1) ? ' ' : '\n');
+      fclose(f);
+    }
+    ctx->trace.clear();
+  }
   cudaError_t e = cudaGetLastError();
   if (rc == 0 && e != cudaSuccess) {
     ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e);

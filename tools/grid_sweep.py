@@ -36,10 +36,13 @@ def main():
     for setting in ["default"] + list(args.settings):
         os.environ.pop("HLM_TUNE", None)
         os.environ.pop("HLM_SLOTS", None)
+        os.environ.pop("HLM_STAGGER", None)
         if setting != "default":
             for part in setting.split(";"):
                 if part.startswith("slots="):
                     os.environ["HLM_SLOTS"] = part[6:]
+                elif part.startswith("stagger="):
+                    os.environ["HLM_STAGGER"] = part[8:]
                 elif part:
                     os.environ["HLM_TUNE"] = part
         p = _abi.default_params(score_cap=args.capped)
