@@ -425,8 +425,11 @@ def cpu_baseline(args, api, D, gdb, rb, params_kw=None):
 
 
 def file_pipeline(m, rb, db_path):
-    """FASTQ text in, the reference's output files out (hlm_map_fastq), rank 0, one pass: reported
-    beside the metric, not part of it (text parsing is separate)"""
+    """FASTQ text in, the reference's output files out (hlm_map_fastq), rank 0: reported beside the
+    metric, not part of it (text parsing is separate).  Two passes over the
+    same input into fresh directories: the first call of a process pays for its first-touch page
+    faults, the cold output directory and the growth of the host buffers (`first_call`); `value`
+    is the second call, the rate of a process that maps sample after sample."""
     import shutil
     import tempfile
 
@@ -434,15 +437,20 @@ def file_pipeline(m, rb, db_path):
     try:
         r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
         synth.write_fastq_fast(rb, r1, r2)
-        os.makedirs(os.path.join(tmp, "out"))
-        t0 = time.perf_counter()
-        st = m.map_fastq(r1, r2, "B", os.path.join(tmp, "out"))
-        dt = time.perf_counter() - t0
-        return {"value": round(rb.n_pairs / dt, 1), "unit": "pairs/s",
-                "input_bytes": os.path.getsize(r1) + os.path.getsize(r2),
+        passes = []
+        for k in range(2):
+            out = os.path.join(tmp, f"out{k}")
+            os.makedirs(out)
+            t0 = time.perf_counter()
+            st = m.map_fastq(r1, r2, "B", out)
+            dt = time.perf_counter() - t0
+            shutil.rmtree(out, ignore_errors=True)
+            passes.append({"value": round(rb.n_pairs / dt, 1), "unit": "pairs/s",
+                           **{k_: (round(v, 3) if isinstance(v, float) else v) for k_, v in st.items()}})
+        return {**passes[1], "input_bytes": os.path.getsize(r1) + os.path.getsize(r2),
                 "what": "hlm_map_fastq: 2 plain FASTQ files -> selected / trim / addressing table / "
-                        "per-gene FASTQ files",
-                **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()}}
+                        "per-gene FASTQ files; second call of the process (first_call: the one before it)",
+                "first_call": passes[0]}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

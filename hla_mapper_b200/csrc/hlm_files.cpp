@@ -68,6 +68,32 @@ void parallel_for(int n, F f) {
   if (failed) throw std::bad_alloc();
 }
 
+// Batch sizes of a run.  The GPU cannot start before its first batch is parsed, and the last
+// batch is collected and written after the GPU has gone idle, so the run starts (and, where the
+// length of the input is known, ends) with small batches: B/8, B/8, B/4, B/2, then B pairs.
+// Runs with batches below 512 Ki pairs (the tests) are cut uniformly.
+constexpr int64_t kRampMin = (int64_t)8 << 16;
+int64_t batch_size(int64_t k, int64_t B) {
+  if (B < kRampMin) return B;
+  return k < 2 ? B / 8 : k == 2 ? B / 4 : k == 3 ? B / 2 : B;
+}
+// record index at which every batch of an input of N records starts (+ N at the end)
+std::vector<int64_t> batch_plan(int64_t N, int64_t B) {
+  std::vector<int64_t> rec(1, 0);
+  for (int64_t k = 0; rec.back() < N; k++) rec.push_back(std::min(N, rec.back() + batch_size(k, B)));
+  if (B >= kRampMin && rec.size() >= 2) {
+    // the last batch gives way to  rest | B/4 | B/8
+    int64_t a = rec[rec.size() - 2], R = N - a, t1 = B / 4, t2 = B / 8;
+    if (R > t1 + t2) {
+      rec.pop_back();
+      rec.push_back(N - t1 - t2);
+      rec.push_back(N - t2);
+      rec.push_back(N);
+    }
+  }
+  return rec;
+}
+
 // reads 4-line records straight out of a large refill buffer (one memchr per line, one copy per
 // field into the SoA vectors)
 class FastqReader {
@@ -243,11 +269,12 @@ class BatchStream {
         b = pool_.back().get();
       }
       b->clear();
-      int64_t got = rd_.read(*b, batch_);
+      int64_t want = batch_size(k_++, batch_);
+      int64_t got = rd_.read(*b, want);
       std::lock_guard<std::mutex> g(m_);
       if (got > 0 || b->io_error) q_.push(b);
       else free_.push_back(b);
-      if (got < batch_) {
+      if (got < want) {
         done_ = true;
         cv_.notify_all();
         break;
@@ -256,7 +283,7 @@ class BatchStream {
     }
   }
   FastqReader rd_;
-  int64_t batch_;
+  int64_t batch_, k_ = 0;
   std::thread th_;
   std::mutex m_;
   std::condition_variable cv_;
@@ -334,8 +361,8 @@ class MappedFastq {
     for (size_t r = 0; r < R; r++) cnt[r + 1] += cnt[r];
     size_t lines = cnt[R] + ((n > 0 && p[n - 1] != '\n') ? 1 : 0);
     n_records_ = (int64_t)(lines / 4);
-    batch_ = batch;
-    int64_t nb = (n_records_ + batch - 1) / batch;
+    rec_ = batch_plan(n_records_, batch);
+    int64_t nb = (int64_t)rec_.size() - 1;
     start_.assign((size_t)nb + 1, n);
     // byte offset of record k = one past newline number 4 k (1-based), 0 for k = 0
     auto offset_of_record = [&](int64_t k) -> size_t {
@@ -355,7 +382,7 @@ class MappedFastq {
       return n;
     };
     parallel_for(nt, [&](int t) {
-      for (int64_t b = t; b <= nb; b += nt) start_[(size_t)b] = offset_of_record(std::min<int64_t>(b * batch, n_records_));
+      for (int64_t b = t; b <= nb; b += nt) start_[(size_t)b] = offset_of_record(rec_[(size_t)b]);
     });
     return true;
   }
@@ -366,7 +393,7 @@ class MappedFastq {
     out.clear();
     const char* base = (const char*)map_.p;
     size_t p = start_[(size_t)b], end = map_.n;
-    int64_t want = std::min<int64_t>(batch_, n_records_ - b * batch_);
+    int64_t want = rec_[(size_t)b + 1] - rec_[(size_t)b];
     out.offs.reserve((size_t)want + 1);
     out.hoff.reserve((size_t)want + 1);
     size_t span = start_[(size_t)b + 1] - p;
@@ -396,7 +423,8 @@ class MappedFastq {
  private:
   HlmMapped map_;
   std::vector<size_t> start_;
-  int64_t n_records_ = 0, batch_ = 1;
+  std::vector<int64_t> rec_;  // first record of every batch (batch_plan)
+  int64_t n_records_ = 0;
 };
 
 // r1 (+ r2) plain FASTQ files parsed by a pool of host threads, batches delivered in order
@@ -427,15 +455,19 @@ class MappedSource : public PairSource {
   bool next(MateBatch*& b1, MateBatch*& b2, int& rc, std::string& err) override {
     std::unique_lock<std::mutex> g(m_);
     if (deliver_ >= nb_) return false;
-    cv_.wait(g, [this] { return failed_ || ready_.count(deliver_) != 0; });
+    const int M = paired_ ? 2 : 1;
+    cv_.wait(g, [&] {
+      auto it = ready_.find(deliver_);
+      return failed_ || (it != ready_.end() && it->second.done == M);
+    });
     if (failed_) {  // a parser thread ran out of memory
       rc = HLM_E_NOMEM;
       err = "out of memory while parsing the FASTQ files";
       return false;
     }
     auto it = ready_.find(deliver_);
-    b1 = it->second.first;
-    b2 = it->second.second;
+    b1 = it->second.m[0];
+    b2 = it->second.m[1];
     ready_.erase(it);
     deliver_++;
     cv_.notify_all();
@@ -457,24 +489,29 @@ class MappedSource : public PairSource {
     pool_.emplace_back(new MateBatch());
     return pool_.back().get();
   }
+  // a work item is one mate file of one batch, so that the two files of a batch are parsed at the
+  // same time (the consumer waits for the slower of the two, not for their sum)
   void work() {
+    const int M = paired_ ? 2 : 1;
     for (;;) {
       int64_t b;
-      MateBatch *m1, *m2 = nullptr;
+      int mate;
+      MateBatch* mb;
       {
         std::unique_lock<std::mutex> g(m_);
         // at most kAhead batches parsed ahead of the consumer
-        cv_.wait(g, [this] { return stop_ || claim_ >= nb_ || claim_ < deliver_ + kAhead; });
-        if (stop_ || claim_ >= nb_) return;
-        b = claim_++;
-        m1 = fresh();
-        if (paired_) m2 = fresh();
+        cv_.wait(g, [&] { return stop_ || claim_ >= nb_ * M || claim_ / M < deliver_ + kAhead; });
+        if (stop_ || claim_ >= nb_ * M) return;
+        b = claim_ / M;
+        mate = (int)(claim_ % M);
+        claim_++;
+        mb = fresh();
+        ready_[b].m[mate] = mb;
       }
       try {
-        f1_.parse(b, *m1);
-        if (paired_) f2_.parse(b, *m2);
+        (mate == 0 ? f1_ : f2_).parse(b, *mb);
         std::lock_guard<std::mutex> g(m_);
-        ready_[b] = {m1, m2};
+        ready_[b].done++;
       } catch (const std::exception&) {  // no exception leaves a library thread
         std::lock_guard<std::mutex> g(m_);
         failed_ = true;
@@ -483,6 +520,10 @@ class MappedSource : public PairSource {
       cv_.notify_all();
     }
   }
+  struct Parsed {
+    MateBatch* m[2] = {nullptr, nullptr};
+    int done = 0;
+  };
   static constexpr int64_t kAhead = 6;
   MappedFastq f1_, f2_;
   bool paired_ = false;
@@ -491,7 +532,7 @@ class MappedSource : public PairSource {
   std::vector<std::thread> th_;
   std::mutex m_;
   std::condition_variable cv_;
-  std::map<int64_t, std::pair<MateBatch*, MateBatch*>> ready_;
+  std::map<int64_t, Parsed> ready_;
   std::vector<MateBatch*> free_;
   std::vector<std::unique_ptr<MateBatch>> pool_;
   bool stop_ = false, failed_ = false;
@@ -1035,6 +1076,13 @@ class ParallelFile {
 
 // buffered writer of one thread's range of a ParallelFile
 struct RangeOut {
+  // bytes formatted between two pwrite() calls (HLM_OUT_BUF_KB: measurement knob)
+  size_t kBuf = buf_bytes();
+  static size_t buf_bytes() {
+    const char* e = getenv("HLM_OUT_BUF_KB");
+    long v = e ? atol(e) : 0;
+    return v > 0 ? (size_t)v << 10 : (size_t)1 << 22;
+  }
   ParallelFile* f = nullptr;
   uint64_t off = 0;
   std::string buf;
@@ -1042,15 +1090,20 @@ struct RangeOut {
     f = file;
     off = at;
     buf.clear();
-    buf.reserve(1 << 22);
+    buf.reserve(kBuf + 4096);
   }
   void add(const char* s, size_t n) {
     buf.append(s, n);
-    if (buf.size() > (1u << 22)) flush();
+    if (buf.size() > kBuf) flush();
   }
   void fill(char c, size_t n) {
     buf.append(n, c);
-    if (buf.size() > (1u << 22)) flush();
+    if (buf.size() > kBuf) flush();
+  }
+  void raw(const char* s, size_t n) {  // a block that is already text: no copy through the buffer
+    flush();
+    if (f && n) f->write_at(s, n, off);
+    off += n;
   }
   void flush() {
     if (f && !buf.empty()) f->write_at(buf.data(), buf.size(), off);
@@ -1080,12 +1133,78 @@ uint64_t id_window(const char* s, uint32_t l, uint32_t w0) {
   for (uint32_t x = 0; x < 8; x++) k = (k << 8) | (w0 + x < l ? (uint8_t)s[w0 + x] : 0u);
   return k;
 }
+// an array whose elements are not value-initialised (a std::vector would zero tens of MB on one
+// thread before the parallel code touches them)
+template <class Tp>
+struct RawArray {
+  std::unique_ptr<Tp[]> p;
+  size_t n = 0;
+  explicit RawArray(size_t count = 0) : p(count ? new Tp[count] : nullptr), n(count) {}
+  Tp* begin() { return p.get(); }
+  Tp* end() { return p.get() + n; }
+  Tp& operator[](size_t i) { return p[i]; }
+  size_t size() const { return n; }
+  void swap(RawArray& o) {
+    p.swap(o.p);
+    std::swap(n, o.n);
+  }
+};
+
+// keys into id order (stable) on nt host threads
+void sort_keys(RawArray<IdKey>& keys, int nt, size_t min_parallel = (size_t)1 << 15) {
+  // sample sort: splitters from a regular sample, every key classified once, a stable scatter
+  // into buckets (thread-major inside a bucket, so equal ids keep their input order), every
+  // bucket sorted on its own - no merge passes over the whole array
+  const size_t n = keys.size();
+  if (n < min_parallel || nt <= 1) {
+    std::stable_sort(keys.begin(), keys.end(), key_less);
+  } else {
+    const size_t NB = (size_t)std::min(256, 4 * nt), over = 32, S = NB * over;
+    std::vector<IdKey> sample(S);
+    for (size_t i = 0; i < S; i++) sample[i] = keys[(i * n + n / 2) / S];
+    std::sort(sample.begin(), sample.end(), key_less);
+    std::vector<IdKey> split(NB - 1);
+    for (size_t j = 1; j < NB; j++) split[j - 1] = sample[j * over];
+    RawArray<uint8_t> bucket(n);
+    std::vector<size_t> count((size_t)nt * NB, 0);
+    parallel_for(nt, [&](int t) {
+      size_t* c = count.data() + (size_t)t * NB;
+      for (size_t j = n * (size_t)t / nt; j < n * (size_t)(t + 1) / nt; j++) {
+        // number of splitters <= key: equal keys always land in the same bucket
+        size_t bk = (size_t)(std::upper_bound(split.begin(), split.end(), keys[j], key_less) - split.begin());
+        bucket[j] = (uint8_t)bk;
+        c[bk]++;
+      }
+    });
+    std::vector<size_t> bstart(NB + 1, 0), at((size_t)nt * NB);
+    for (size_t bk = 0; bk < NB; bk++) {
+      size_t o = bstart[bk];
+      for (int t = 0; t < nt; t++) {
+        at[(size_t)t * NB + bk] = o;
+        o += count[(size_t)t * NB + bk];
+      }
+      bstart[bk + 1] = o;
+    }
+    RawArray<IdKey> tmp(n);
+    parallel_for(nt, [&](int t) {
+      size_t* o = at.data() + (size_t)t * NB;
+      for (size_t j = n * (size_t)t / nt; j < n * (size_t)(t + 1) / nt; j++) tmp[o[bucket[j]]++] = keys[j];
+    });
+    std::atomic<size_t> next(0);
+    parallel_for(nt, [&](int) {
+      for (size_t bk; (bk = next.fetch_add(1)) < NB;)
+        std::stable_sort(tmp.begin() + bstart[bk], tmp.begin() + bstart[bk + 1], key_less);
+    });
+    keys.swap(tmp);
+  }
+}
+
 void sort_kept(std::vector<std::vector<Kept>>& parts, KeptVec& out, int nt) {
   size_t n = 0;
   std::vector<size_t> first(parts.size() + 1, 0);
   for (size_t p = 0; p < parts.size(); p++) first[p + 1] = first[p] + parts[p].size();
   n = first[parts.size()];
-  std::vector<IdKey> keys(n);
+  RawArray<IdKey> keys(n);
   nt = std::max(1, nt);
   // the prefix every id shares with the first one (exact: a minimum over all ids)
   const Kept* k0 = nullptr;
@@ -1112,32 +1231,58 @@ void sort_kept(std::vector<std::vector<Kept>>& parts, KeptVec& out, int nt) {
         keys[first[p] + i] = IdKey{parts[p][i].idgen, id_window(parts[p][i].idgen, parts[p][i].idl, w0),
                                    parts[p][i].idl, (uint32_t)p, (uint32_t)i, 0};
   });
-  int runs = 1;
-  while (runs * 2 <= nt && runs < 64 && n >= (size_t)(1u << 14) * (size_t)(runs * 2)) runs *= 2;
-  std::vector<size_t> cut(runs + 1);
-  for (int r = 0; r <= runs; r++) cut[r] = n * (size_t)r / runs;
-  parallel_for(runs, [&](int r) { std::stable_sort(keys.begin() + cut[r], keys.begin() + cut[r + 1], key_less); });
-  if (runs > 1) {
-    std::vector<IdKey> tmp(n);
-    std::vector<IdKey>*src = &keys, *dst = &tmp;
-    for (int w = 1; w < runs; w *= 2) {
-      int pairs = runs / (2 * w);
-      parallel_for(pairs, [&](int k) {
-        size_t a = cut[2 * w * k], m = cut[2 * w * k + w], b = cut[2 * w * k + 2 * w];
-        std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a, key_less);
-      });
-      std::swap(src, dst);
-    }
-    if (src != &keys) keys.swap(tmp);
-  }
+  sort_keys(keys, nt);
   out.allocate(n);
   parallel_for(nt, [&](int t) {
     for (size_t j = n * (size_t)t / nt; j < n * (size_t)(t + 1) / nt; j++) out[j] = parts[keys[j].part][keys[j].idx];
+  });
+  // the slices are released by the threads as well (one thread would spend milliseconds per GB)
+  parallel_for(nt, [&](int t) {
+    for (size_t p = (size_t)t; p < parts.size(); p += (size_t)nt) std::vector<Kept>().swap(parts[p]);
   });
   std::vector<std::vector<Kept>>().swap(parts);
 }
 
 }  // namespace
+
+// Self test of the parallel id sort (tests/test_host_sort.py; not part of the interface): n random
+// ids with a shared prefix, duplicates and different lengths, sorted by sort_keys() on `threads`
+// threads and by one std::stable_sort; 0 when both orders are the same.
+extern "C" int hlm_selftest_sort_keys(int64_t n, uint32_t seed, int threads) {
+  try {
+    std::vector<std::string> ids((size_t)n);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&] {
+      x ^= x << 13;
+      x ^= x >> 7;
+      x ^= x << 17;
+      return x;
+    };
+    for (auto& id : ids) {
+      id = "A00296:39:HFH3TDSXX:";
+      uint64_t r = rnd();
+      int extra = 1 + (int)(r % 14);
+      uint64_t v = (r >> 8) % (uint64_t)std::max<int64_t>(1, n / 2 + 1);  // about every second id twice
+      for (int k = 0; k < extra; k++) {
+        id += (char)('0' + v % 10);
+        v /= 10;
+      }
+    }
+    RawArray<IdKey> keys((size_t)n);
+    const uint32_t w0 = 20;  // the shared prefix
+    for (size_t i = 0; i < (size_t)n; i++)
+      keys[i] = IdKey{ids[i].data(), id_window(ids[i].data(), (uint32_t)ids[i].size(), w0), (uint32_t)ids[i].size(), 0,
+                      (uint32_t)i, 0};
+    std::vector<IdKey> want(keys.begin(), keys.end());
+    std::stable_sort(want.begin(), want.end(), key_less);
+    sort_keys(keys, threads, 64);
+    for (size_t i = 0; i < (size_t)n; i++)
+      if (keys[i].idx != want[i].idx) return 1;
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
 
 int hlm_map_source(hlm_ctx* ctx, PairSource& src, bool normalise_pair_headers, const char* sample,
                    const char* out_dir, const hlm_file_opts* opts_in, hlm_file_stats* stats) {
@@ -1177,6 +1322,16 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
 
   double t_start = now_s();
+  // HLM_FILE_TRACE: the moments of the run on stderr (seconds from its start), a measurement aid
+  const bool ftrace = getenv("HLM_FILE_TRACE") != nullptr;
+  std::mutex ftrace_mu;
+  auto mark = [&](const char* what, int64_t a = -1) {
+    if (!ftrace) return;
+    std::lock_guard<std::mutex> g(ftrace_mu);
+    fprintf(stderr, "[hlm_files] %8.3f s  %s", now_s() - t_start, what);
+    if (a >= 0) fprintf(stderr, " %lld", (long long)a);
+    fputc('\n', stderr);
+  };
   ParallelFile sel1, sel2;
   if (o.write_selected) {
     if (!sel1.open(pre + "selected." + tag + ".fastq") || (paired && !sel2.open(pre + "selected.R2.fastq"))) {
@@ -1404,6 +1559,7 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
         }
       }
       double dt_wait = now_s() - t0;
+      mark(end ? "input ended" : "batch read, seq", end ? -1 : seq);
       if (inflight) {  // finish the previous batch on the GPU
         int r2 = hlm_wait(c);
         hlm_profile pr;
@@ -1413,6 +1569,7 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
         }
         inflight = false;
         if (r2) fail(r2, hlm_last_error(c));
+        mark("gpu done, seq", seq_of[cur ^ 1]);
       }
       int prev = cur ^ 1;  // results of the batch that just finished
       bool have_prev = res[prev].b1 != nullptr;
@@ -1451,7 +1608,10 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
         if (rc) fail(rc, hlm_last_error(c));
       }
       double t1 = now_s();
-      if (have_prev && !failed()) collect(res[prev], seq_of[prev]);
+      if (have_prev && !failed()) {
+        collect(res[prev], seq_of[prev]);
+        mark("collected, seq", seq_of[prev]);
+      }
       {
         std::lock_guard<std::mutex> g(err_mu);
         t_wait += dt_wait;
@@ -1477,9 +1637,17 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
       });
     for (auto& t : drivers) t.join();
   }
-  sel_joiner.f();
-  bool sel_ok = sel1.close();
-  sel_ok = sel2.close() && sel_ok;
+  mark("drivers done");
+  // the two writers of selected.R*.fastq may still be behind: they finish while the kept reads are
+  // sorted and the other files prepared, and are waited for before the run returns
+  bool sel_ok = true;
+  auto finish_selected = [&] {
+    sel_joiner.f();
+    mark("selected files written");
+    sel_ok = sel1.close();
+    sel_ok = sel2.close() && sel_ok;
+  };
+  if (rc_all || rna) finish_selected();
   if (rc_all) {  // nothing half-written stays behind a failed run
     if (o.write_selected) {
       unlink((pre + "selected." + tag + ".fastq").c_str());
@@ -1488,10 +1656,6 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
     hlm_ctx_set_error(ctx, err_all);
     return rc_all;
   }
-  if (o.write_selected && !sel_ok) {
-    hlm_ctx_set_error(ctx, "cannot write " + pre + "selected.*.fastq");
-    return HLM_E_IO;
-  }
   if (n_ctx > 1) {  // per-driver times were summed over the drivers
     t_post /= n_ctx;
     t_wait /= n_ctx;
@@ -1499,8 +1663,55 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
 
   double t0 = now_s();
   const int nt = std::max(1, std::min(32, hw));
+  // The output files are created by a background thread while the kept reads are sorted and the
+  // files prepared: creating a hundred files in a cold directory takes tens of milliseconds.
+  // `paths` lists them in the order the jobs below are defined; a run that fails before the jobs
+  // start removes what was created.  (rna: STAR runs in between, the files are created afterwards.)
+  struct Opener {
+    std::vector<std::string> paths;
+    std::vector<std::unique_ptr<ParallelFile>> files;
+    std::thread th;
+    bool taken = false;
+    void start() {
+      files.resize(paths.size());
+      th = std::thread([this] {
+        try {
+          for (size_t i = 0; i < paths.size(); i++) {
+            std::unique_ptr<ParallelFile> f(new ParallelFile());
+            if (f->open(paths[i])) files[i] = std::move(f);
+          }
+        } catch (const std::exception&) {  // the files left out are reported by the jobs
+        }
+      });
+    }
+    void join() {
+      if (th.joinable()) th.join();
+    }
+    ~Opener() {
+      join();
+      if (taken) return;
+      for (size_t i = 0; i < files.size(); i++)
+        if (files[i]) {
+          files[i]->close();
+          unlink(paths[i].c_str());
+        }
+    }
+  } opener;
+  if (!rna) {
+    for (int m = 0; m < (paired ? 2 : 1); m++) opener.paths.push_back(pre + "selected.trim." + (m == 0 ? tag : "R2") + ".fastq");
+    if (!o.select_only) {
+      opener.paths.push_back(pre + "addressing_table.txt");
+      for (int g = 0; g < db->n_loci; g++)
+        for (int m = 0; m < (paired ? 2 : 1); m++) {
+          opener.paths.push_back(pre + db->names[g] + "_" + (m == 0 ? tag : "R2") + ".fastq");
+          opener.paths.push_back(pre + db->names[g] + ".trim." + (m == 0 ? tag : "R2") + ".fastq");
+        }
+    }
+    opener.start();
+  }
   sort_kept(kept_parts, kept, nt);
   double t_sort = now_s() - t0;
+  mark("kept reads sorted,", (int64_t)kept.size());
   if (rna && !o.select_only) {
     double tg = now_s();
     int rc = rna_score_kept(ctx, db, o, pre, paired, kept);
@@ -1540,10 +1751,18 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
   };
   auto run_jobs = [&] {
     const size_t J = jobs.size();
-    for (Job& j : jobs) {
+    opener.join();
+    opener.taken = true;  // from here on the files stay, as they did before they were pre-created
+    for (size_t k = 0; k < J; k++) {
+      Job& j = jobs[k];
       j.sz.assign(nt + 1, 0);
-      j.f.reset(new ParallelFile());
-      if (!j.f->open(j.path)) wfail("cannot write " + j.path);
+      if (k < opener.paths.size() && opener.paths[k] == j.path) {
+        j.f = std::move(opener.files[k]);  // created in the background (null: could not be)
+        if (!j.f) wfail("cannot write " + j.path);
+      } else {
+        j.f.reset(new ParallelFile());
+        if (!j.f->open(j.path)) wfail("cannot write " + j.path);
+      }
     }
     if (werr) return;
     std::atomic<size_t> next(0);
@@ -1552,6 +1771,7 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
     });
     for (Job& j : jobs)
       for (int t = 0; t < nt; t++) j.sz[t + 1] += j.sz[t];
+    mark("output sized, files:", (int64_t)J);
     next = 0;
     parallel_for(nt, [&](int) {
       RangeOut ro;
@@ -1570,19 +1790,140 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
   int64_t n_assigned = 0;
   int64_t read_mean_size = n_selected > 0 ? sel_bases / n_selected : 0;  // :1125-1133 (int division)
   std::vector<int64_t> assigned(nt, 0);
-  std::vector<std::vector<int64_t>> rank(db->n_loci, std::vector<int64_t>(nt + 1, 0));
   std::vector<int64_t> downS(db->n_loci, 0);
   std::string header = "Read";
+  // One pass over the kept reads per range (all ranges at once) prepares every file: the sizes of
+  // the two trim files, the rows of the addressing table as text (formatted once, written later),
+  // and per gene the list of its members with the bytes they take in the gene's files.  The
+  // (file, range) jobs below only copy.
+  struct RangePrep {
+    uint64_t trim_bytes[2] = {0, 0};
+    std::string table;
+    std::vector<std::vector<uint32_t>> members;     // per gene: indices into kept, ascending
+    std::vector<uint64_t> gene_bytes[2];            // per gene: bytes in <gene>_R1 / _R2.fastq
+    std::vector<uint64_t> gene_trim_bytes[2];       // per gene: bytes in <gene>.trim.R1 / R2 (after the ranks)
+    std::vector<int64_t> rank0;                     // per gene: members in the ranges before this one
+  };
+  std::vector<RangePrep> prep(nt);
   try {
+    const int G = db->n_loci;
+    for (int g = 0; g < T; g++) header += "\t" + db->names[g];
+    header += "\tTarget\n";
+    for (int g = 0; g < G; g++) {
+      int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
+      downS[g] = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
+    }
+    auto put_u = [](char* p, unsigned v) {  // decimal, returns one past the last digit
+      char tmp[12];
+      int n = 0;
+      do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+      } while (v);
+      while (n) *p++ = tmp[--n];
+      return p;
+    };
+    // row of <sample>_addressing_table.txt (src/map_dna.cpp:932-1051, src/map_rna.cpp:945-1049)
+    size_t names_len = 0;
+    for (int g = 0; g < T; g++) names_len += db->names[g].size() + 1;
+    auto row = [&](const Kept& k, std::string& out, std::string& scratch, bool& any) {
+      size_t need = k.idl + (size_t)T * 14 + names_len + 4;
+      if (scratch.size() < need) scratch.resize(need);
+      char* p0 = &scratch[0];
+      char* p = p0;
+      memcpy(p, k.idgen, k.idl);
+      p += k.idl;
+      for (int g = 0; g < T; g++) {
+        *p++ = '\t';
+        if (!((k.visible >> g) & 1u)) {
+          *p++ = '-';
+          continue;
+        }
+        unsigned a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
+        if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
+        p = put_u(p, a);
+        if (paired && !rna) {
+          *p++ = ',';
+          p = put_u(p, b);
+        }
+      }
+      *p++ = '\t';
+      any = false;
+      for (int g = 0; g < T; g++)
+        if ((k.target >> g) & 1u) {
+          if (any) *p++ = ',';
+          memcpy(p, db->names[g].data(), db->names[g].size());
+          p += db->names[g].size();
+          any = true;
+        }
+      if (!any) *p++ = '-';
+      *p++ = '\n';
+      out.append(p0, (size_t)(p - p0));
+    };
+    auto member = [&](int g, const Kept& k) {
+      if (!((k.locus_mask >> g) & 1u)) return false;  // was in sorted_<gene>_R1.fastq
+      if (!((k.target >> g) & 1u)) return false;       // sequence_address[(gene, id)]
+      // the lookup key is the header token minus '@' (:1225): it only equals the id when the
+      // token carries no /1 /2 (always true for paired input, whose headers were normalised)
+      return k.tokl >= 1 && k.tokl - 1 == k.idl && memcmp(k.h1 + 1, k.idgen, k.idl) == 0;
+    };
+    parallel_for(nt, [&](int t) {
+      RangePrep& R = prep[t];
+      R.members.assign(G, {});
+      for (int m = 0; m < 2; m++) {
+        R.gene_bytes[m].assign(G, 0);
+        R.gene_trim_bytes[m].assign(G, 0);
+      }
+      R.rank0.assign(G, 0);
+      std::string scratch;
+      if (!o.select_only) {
+        if (t == 0) R.table = header;
+        R.table.reserve(R.table.size() + (cut[t + 1] - cut[t]) * (size_t)(48 + 2 * T));
+      }
+      for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+        const Kept& k = kept[i];
+        R.trim_bytes[0] += k.h1l + 2 * (uint64_t)k.n1 + 5;
+        R.trim_bytes[1] += k.h2l + 2 * (uint64_t)k.n2 + 5;
+        if (o.select_only) continue;
+        bool any;
+        row(k, R.table, scratch, any);
+        assigned[t] += any ? 1 : 0;
+        for (uint32_t m = k.locus_mask & k.target; m; m &= m - 1) {
+          int g = __builtin_ctz(m);
+          if (g >= G || !member(g, k)) continue;
+          R.members[g].push_back((uint32_t)(i - cut[t]));
+          R.gene_bytes[0][g] += k.h1l + 2 * (uint64_t)k.l1 + 5;
+          R.gene_bytes[1][g] += k.h2l + 2 * (uint64_t)k.l2 + 5;
+        }
+      }
+    });
+    // the first downS members of a gene (in id order) also go to its .trim files
+    if (!o.select_only) {
+      for (int g = 0; g < G; g++) {
+        int64_t r = 0;
+        for (int t = 0; t < nt; t++) {
+          prep[t].rank0[g] = r;
+          r += (int64_t)prep[t].members[g].size();
+        }
+      }
+      parallel_for(nt, [&](int t) {
+        RangePrep& R = prep[t];
+        for (int g = 0; g < G; g++) {
+          int64_t r = R.rank0[g];
+          for (uint32_t x : R.members[g]) {
+            if (r++ >= downS[g]) break;
+            const Kept& k = kept[cut[t] + x];
+            R.gene_trim_bytes[0][g] += k.tokl + 8 + 2 * (uint64_t)k.n1 + 4;
+            R.gene_trim_bytes[1][g] += k.tokl + 8 + 2 * (uint64_t)k.n2 + 4;
+          }
+        }
+      });
+    }
+    mark("output prepared");
     // ---- selected.trim.R*.fastq (src/preselect.cpp:1121-1149, :1182-1203)
     for (int m = 0; m < (paired ? 2 : 1); m++)
       write_file(pre + "selected.trim." + (m == 0 ? tag : "R2") + ".fastq",
-                 [&, m](int t) {
-                   uint64_t b = 0;
-                   for (size_t i = cut[t]; i < cut[t + 1]; i++)
-                     b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].n1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].n2 + 5;
-                   return b;
-                 },
+                 [&, m](int t) { return prep[t].trim_bytes[m]; },
                  [&, m](int t, RangeOut& w) {
                    for (size_t i = cut[t]; i < cut[t + 1]; i++) {
                      const Kept& k = kept[i];
@@ -1595,97 +1936,22 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                      }
                    }
                  });
-    // ---- <sample>_addressing_table.txt (src/map_dna.cpp:932-1051, src/map_rna.cpp:945-1049)
-    auto row = [&](const Kept& k, std::string& line, bool& any) {
-      char num[32];
-      line.assign(k.idgen, k.idl);
-      for (int g = 0; g < T; g++) {
-        line += '\t';
-        if (!((k.visible >> g) & 1u)) {
-          line += '-';
-          continue;
-        }
-        int a = g == T - 1 ? k.os1 : k.sc1[g], b = g == T - 1 ? k.os2 : k.sc2[g];
-        if (rna) a = k.sc1[g];  // one summed score per target (src/map_rna.cpp:945-961)
-        int m = (paired && !rna) ? snprintf(num, sizeof num, "%d,%d", a, b) : snprintf(num, sizeof num, "%d", a);
-        line.append(num, m);
-      }
-      line += '\t';
-      any = false;
-      for (int g = 0; g < T; g++)
-        if ((k.target >> g) & 1u) {
-          if (any) line += ',';
-          line += db->names[g];
-          any = true;
-        }
-      if (!any) line += '-';
-      line += '\n';
-    };
-    if (!o.select_only) {
-      for (int g = 0; g < T; g++) header += "\t" + db->names[g];
-      header += "\tTarget\n";
-      write_file(pre + "addressing_table.txt",
-                 [&](int t) {
-                   uint64_t b = t == 0 ? header.size() : 0;
-                   std::string line;
-                   bool any;
-                   for (size_t i = cut[t]; i < cut[t + 1]; i++) {
-                     row(kept[i], line, any);
-                     b += line.size();
-                   }
-                   return b;
-                 },
+    // ---- <sample>_addressing_table.txt: the rows are already text
+    if (!o.select_only)
+      write_file(pre + "addressing_table.txt", [&](int t) { return (uint64_t)prep[t].table.size(); },
                  [&](int t, RangeOut& w) {
-                   if (t == 0) w.add(header.data(), header.size());
-                   std::string line;
-                   bool any;
-                   for (size_t i = cut[t]; i < cut[t + 1]; i++) {
-                     row(kept[i], line, any);
-                     assigned[t] += any ? 1 : 0;
-                     w.add(line.data(), line.size());
-                   }
+                   w.raw(prep[t].table.data(), prep[t].table.size());
+                   std::string().swap(prep[t].table);
                  });
-    }
     // ---- per-gene FASTQ files (src/map_dna.cpp:1056-1351, src/map_rna.cpp:1072-1344)
-    auto member = [&](int g, const Kept& k) {
-      if (!((k.locus_mask >> g) & 1u)) return false;  // was in sorted_<gene>_R1.fastq
-      if (!((k.target >> g) & 1u)) return false;       // sequence_address[(gene, id)]
-      // the lookup key is the header token minus '@' (:1225): it only equals the id when the
-      // token carries no /1 /2 (always true for paired input, whose headers were normalised)
-      return k.tokl >= 1 && k.tokl - 1 == k.idl && memcmp(k.h1 + 1, k.idgen, k.idl) == 0;
-    };
-    if (!o.select_only) {
-      // rank of every range's first member, per gene: the first downS members also go to .trim
-      parallel_for(nt, [&](int t) {
-        for (size_t i = cut[t]; i < cut[t + 1]; i++) {
-          const Kept& k = kept[i];
-          uint32_t m = k.locus_mask & k.target;
-          for (; m; m &= m - 1) {
-            int g = __builtin_ctz(m);
-            if (g < db->n_loci && member(g, k)) rank[g][t + 1]++;
-          }
-        }
-      });
-      for (int g = 0; g < db->n_loci; g++)
-        for (int t = 0; t < nt; t++) rank[g][t + 1] += rank[g][t];
-    }
-    for (int g = 0; g < db->n_loci && !o.select_only; g++) {
+    for (int g = 0; g < G && !o.select_only; g++) {
       const std::string& gene = db->names[g];
-      int64_t size = (int64_t)db->gene_opt_end[g] - db->gene_opt_start[g];
-      downS[g] = read_mean_size > 0 ? ((int64_t)o.downsampling * size) / read_mean_size : 0;  // :1198-1200
       for (int m = 0; m < (paired ? 2 : 1); m++) {
         write_file(pre + gene + "_" + (m == 0 ? tag : "R2") + ".fastq",
-                   [&, g, m](int t) {
-                     uint64_t b = 0;
-                     for (size_t i = cut[t]; i < cut[t + 1]; i++)
-                       if (member(g, kept[i]))
-                         b += m == 0 ? kept[i].h1l + 2 * (uint64_t)kept[i].l1 + 5 : kept[i].h2l + 2 * (uint64_t)kept[i].l2 + 5;
-                     return b;
-                   },
+                   [&, g, m](int t) { return prep[t].gene_bytes[m][g]; },
                    [&, g, m](int t, RangeOut& w) {
-                     for (size_t i = cut[t]; i < cut[t + 1]; i++) {
-                       const Kept& k = kept[i];
-                       if (!member(g, k)) continue;
+                     for (uint32_t x : prep[t].members[g]) {
+                       const Kept& k = kept[cut[t] + x];
                        if (m == 0) {
                          w.add(k.h1, k.h1l); w.add("\n", 1); w.add(k.s1, k.l1); w.add("\n+\n", 3); w.add(k.q1, k.l1);
                          w.add("\n", 1);
@@ -1696,22 +1962,12 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
                      }
                    });
         write_file(pre + gene + ".trim." + (m == 0 ? tag : "R2") + ".fastq",
-                   [&, g, m](int t) {
-                     uint64_t b = 0;
-                     int64_t r = rank[g][t];
-                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS[g]; i++)
-                       if (member(g, kept[i])) {
-                         b += kept[i].tokl + 8 + 2 * (uint64_t)(m == 0 ? kept[i].n1 : kept[i].n2) + 4;
-                         r++;
-                       }
-                     return b;
-                   },
+                   [&, g, m](int t) { return prep[t].gene_trim_bytes[m][g]; },
                    [&, g, m](int t, RangeOut& w) {
-                     int64_t r = rank[g][t];
-                     for (size_t i = cut[t]; i < cut[t + 1] && r < downS[g]; i++) {
-                       const Kept& k = kept[i];
-                       if (!member(g, k)) continue;
-                       r++;
+                     int64_t r = prep[t].rank0[g];
+                     for (uint32_t x : prep[t].members[g]) {
+                       if (r++ >= downS[g]) break;
+                       const Kept& k = kept[cut[t] + x];
                        w.add(k.h1, k.tokl);
                        if (m == 0) {
                          w.add(" 1:trim\n", 8); w.add(k.s1 + k.lo1, k.n1); w.add("\n+\n", 3); w.fill('A', k.n1);
@@ -1724,10 +1980,16 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
       }
     }
     run_jobs();
+    mark("output written");
+    if (!rna) finish_selected();
     for (int64_t a : assigned) n_assigned += a;
     if (werr) {
       hlm_ctx_set_error(ctx, werr_msg);
       return werr;
+    }
+    if (o.write_selected && !sel_ok) {
+      hlm_ctx_set_error(ctx, "cannot write " + pre + "selected.*.fastq");
+      return HLM_E_IO;
     }
     double t_write = now_s() - t0;
     if (stats) {

@@ -1,6 +1,8 @@
 """FASTQ ingest throughput of hlm_map_fastq on decoy-heavy input (the whole-genome case: almost
 nothing passes the screen, so the run is bound by the text path).  Usage (GPU box):
-    python tools/file_bench.py [n_pairs] [on_target] [plain|bgzf|gzip]
+    python tools/file_bench.py [n_pairs] [on_target] [plain|bgzf|gzip] [ENV=VALUE[,ENV=VALUE] ...]
+every further argument is a set of environment variables (the library's measurement knobs) to run
+the same input under, two passes each, after the default.
 bgzf = the FASTQ files bgzip-compressed (inflated block-parallel by the reader), gzip = plain gzip
 (zlib's single stream per file)."""
 import os
@@ -42,7 +44,7 @@ def main():
     kind = sys.argv[3] if len(sys.argv) > 3 else "plain"
     with tempfile.TemporaryDirectory(dir="/tmp") as tmp:
         db = synth.make_db(os.path.join(tmp, "db"), seed=42, n_loci=24, total_alleles=4000, n_others=200)
-        rb = synth.make_reads(db, n, read_len=150, seed=1003, on_target=on)
+        rb = synth.make_reads_fast(db, n, first_pair=0, read_len=150, seed=1003, on_target=on, indel_rate=1e-4)
         r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
         synth.write_fastq_fast(rb, r1, r2)
         size = os.path.getsize(r1) + os.path.getsize(r2)
@@ -52,15 +54,25 @@ def main():
                 os.remove(src)
             r1, r2 = r1 + ".gz", r2 + ".gz"
         gdb = api.Database(db.path)
-        m = api.Mapper(gdb, 0, _abi.default_params())
-        for rep in range(2):
-            out = os.path.join(tmp, f"out{rep}")
-            os.makedirs(out)
-            t = time.perf_counter()
-            st = m.map_fastq(r1, r2, "W", out)
-            dt = time.perf_counter() - t
-            print(f"rep {rep} [{kind}]: {n} pairs ({size / 1e9:.2f} GB of FASTQ) in {dt:.2f}s = {n / dt / 1e6:.2f} M pairs/s, "
-                  f"{size / dt / 1e9:.2f} GB/s text; stats {st}")
+        m = api.Mapper(gdb, 0, _abi.default_params(score_cap=1))  # as the command line runs
+        k = 0
+        for setting in [""] + sys.argv[4:]:
+            env = dict(kv.split("=", 1) for kv in setting.split(",") if kv)
+            os.environ.update(env)
+            for rep in range(2):
+                out = os.path.join(tmp, f"out{k}")
+                k += 1
+                os.makedirs(out)
+                t = time.perf_counter()
+                st = m.map_fastq(r1, r2, "W", out)
+                dt = time.perf_counter() - t
+                print(f"[{setting or 'default'}] rep {rep} [{kind}]: {n} pairs ({size / 1e9:.2f} GB of FASTQ) in {dt:.3f}s = "
+                      f"{n / dt / 1e6:.2f} M pairs/s, {size / dt / 1e9:.2f} GB/s text; stats "
+                      f"{ {a: (round(b, 3) if isinstance(b, float) else b) for a, b in st.items()} }", flush=True)
+                import shutil
+                shutil.rmtree(out)
+            for a in env:
+                del os.environ[a]
         m.close()
 
 
