@@ -596,9 +596,18 @@ def run_b200(args):
     if rank == 0 and not args.no_files and w["kind"] == "dna":
         # the file-level drop-in only produces files: it runs with tolerance-capped scoring, as the
         # command line does (byte-identical files, tests/test_gpu_capped.py)
+        # two contexts on the GPU, as the command line drives it (hlm_multi_create with the device
+        # listed twice: one context stages its next batch while the other one's kernels run); the
+        # single-context call (hlm_map_fastq) beside it
+        warm = min(n, 6 * 65536)
+        mm2 = api.MultiMapper(gdb, [local, local], _abi.default_params(score_cap=1))
+        mm2.run(rb.slice(0, warm), buffers=_abi.Buffers(warm, gdb.n_loci + 1, diag=False))  # buffers allocated
+        files = file_pipeline(mm2, rb, db_path)
+        files["what"] = files["what"].replace("hlm_map_fastq", "hlm_multi_map_fastq, two contexts on one GPU")
+        mm2.close()
         mf = api.Mapper(gdb, local, _abi.default_params(score_cap=1))
-        mf.run(rb.slice(0, min(n, 3 * 65536)), buffers=_abi.Buffers(min(n, 3 * 65536), gdb.n_loci + 1, diag=False))  # buffers allocated
-        files = file_pipeline(mf, rb, db_path)
+        mf.run(rb.slice(0, min(n, 3 * 65536)), buffers=_abi.Buffers(min(n, 3 * 65536), gdb.n_loci + 1, diag=False))
+        files["one_context"] = file_pipeline(mf, rb, db_path)
         files["scoring"] = "hlm_params.score_cap = 1 (the command line's default; files identical to the exact mode)"
         mf.close()
     alleles = None

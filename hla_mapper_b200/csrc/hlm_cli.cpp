@@ -13,8 +13,11 @@
 //                          `star=` line of ~/.hla-mapper; star=none: the *_splice_Aligned.out.sam
 //                          files are already in the output directory)
 //
-// Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= threads= --quiet
-// --skip-unmapped (threads= sizes the BAM reader only; buffer= is accepted and ignored).
+// Options honoured: db= output= sample= size= tolerance= error= downsample= gpu= gpus= threads=
+// --quiet --skip-unmapped (threads= sizes the BAM reader only; buffer= is accepted and ignored).
+// gpus=0,1,2,3 feeds several GPUs (batches dealt to the devices, files as from one); a device may
+// be listed twice.  Without gpus=, dna / select runs hold two contexts on the GPU gpu= names, so
+// that it stays busy across batch boundaries.
 // db defaults to the `db=` line of ~/.hla-mapper (home from getpwuid, src/main.cpp:266-273).
 #include <pwd.h>
 #include <sys/stat.h>
@@ -25,6 +28,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <vector>
 
 #include "../../include/hlamap.h"
 
@@ -48,13 +52,13 @@ int main(int argc, char** argv) {
             "           hla-mapper-b200 dna bam=sample.bam sample=your_sample_name <options>\n"
             "           hla-mapper-b200 select r1=... r2=... sample=... <options>\n"
             "           hla-mapper-b200 rna r1=R1.gz r2=R2.gz sample=your_sample_name [star=STAR] <options>\n"
-            "Options:   db= output= size= tolerance= error= downsample= gpu= threads= --quiet --skip-unmapped\n"
+            "Options:   db= output= size= tolerance= error= downsample= gpu= gpus= threads= --quiet --skip-unmapped\n"
             "           --exact-scores\n");
     return 1;
   }
   bool select_only = strcmp(argv[1], "select") == 0, quiet = false;
   const int rna = strcmp(argv[1], "rna") == 0 ? 1 : 0;
-  std::string r0, r1, r2, bam, sample, db, output, star;
+  std::string r0, r1, r2, bam, sample, db, output, star, gpus;
   double tolerance = -1, error = -1;
   int size = 0, downsample = 30, gpu = 0, threads = 0, skip_unmapped = 0, exact_scores = 0;
   for (int i = 2; i < argc; i++) {
@@ -69,6 +73,7 @@ int main(int argc, char** argv) {
     else if (starts(a, "tolerance=")) tolerance = atof(a.c_str() + 10);
     else if (starts(a, "error=")) error = std::stod(a.substr(6));  // stod, src/main.cpp:658-662
     else if (starts(a, "downsample=")) downsample = atoi(a.c_str() + 11);
+    else if (starts(a, "gpus=")) gpus = a.substr(5);
     else if (starts(a, "gpu=")) gpu = atoi(a.c_str() + 4);
     else if (a == "--quiet") quiet = true;
     else if (a == "--skip-unmapped") skip_unmapped = 1;  // src/main.cpp:626-630
@@ -134,8 +139,21 @@ int main(int argc, char** argv) {
   if (size > 0) p.v_size = size;
   if (tolerance >= 0) p.tolerance = tolerance;
   if (error >= 0) p.mtrim_error = error;
-  hlm_ctx* C = hlm_ctx_create(D, gpu, &p, err, sizeof err);
-  if (!C) {
+  // rna keeps one context (STAR and the block scoring run on it after the screen); dna / select
+  // go through hlm_multi: the listed devices, or two contexts on one GPU
+  std::vector<int> devs;
+  for (size_t at = 0; at < gpus.size();) {
+    size_t c = gpus.find(',', at);
+    if (c == std::string::npos) c = gpus.size();
+    if (c > at) devs.push_back(atoi(gpus.substr(at, c - at).c_str()));
+    at = c + 1;
+  }
+  if (devs.empty() && !rna) devs = {gpu, gpu};
+  hlm_ctx* C = nullptr;
+  hlm_multi* M = nullptr;
+  if (rna) C = hlm_ctx_create(D, devs.empty() ? gpu : devs[0], &p, err, sizeof err);
+  else M = hlm_multi_create(D, devs.data(), (int)devs.size(), &p, err, sizeof err);
+  if (!C && !M) {
     fprintf(stderr, "%s\n", err);
     hlm_reads_free(R);
     hlm_db_close(D);
@@ -150,17 +168,22 @@ int main(int argc, char** argv) {
   fo.threads = threads;
   fo.star_cmd = star.empty() ? nullptr : star.c_str();
   hlm_file_stats st;
-  int rc = R ? hlm_map_reads(C, R, sample.c_str(), output.c_str(), &fo, &st)
-             : hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
+  int rc;
+  if (M)
+    rc = R ? hlm_multi_map_reads(M, R, sample.c_str(), output.c_str(), &fo, &st)
+           : hlm_multi_map_fastq(M, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
+  else
+    rc = hlm_map_fastq(C, first.c_str(), paired ? r2.c_str() : nullptr, sample.c_str(), output.c_str(), &fo, &st);
   hlm_reads_free(R);
-  if (rc != HLM_OK) fprintf(stderr, "hla-mapper-b200: %s\n", hlm_last_error(C));
+  if (rc != HLM_OK) fprintf(stderr, "hla-mapper-b200: %s\n", M ? hlm_multi_last_error(M) : hlm_last_error(C));
   else if (!quiet)
     fprintf(stderr,
             "%lld pairs, %lld selected, %lld kept, %lld addressed; %.2fs (gpu wait %.2fs, input wait %.2fs, "
             "collect %.2fs, write %.2fs) -> %s\n",
             (long long)st.n_pairs, (long long)st.n_selected, (long long)st.n_kept, (long long)st.n_assigned,
             st.s_total, st.s_gpu, st.s_wait_input, st.s_collect, st.s_write, output.c_str());
-  hlm_ctx_destroy(C);
+  if (M) hlm_multi_destroy(M);
+  if (C) hlm_ctx_destroy(C);
   hlm_db_close(D);
   return rc == HLM_OK ? 0 : 4;
 }

@@ -638,10 +638,38 @@ double now_s() {
 }
 
 // result arrays of one batch
+// Zero-filled arrays that are never touched before the results land in them: calloc() of a large
+// block hands out untouched zero pages, so growing to the size of the largest batch costs nothing
+// up front (a std::vector would write 100 MB of zeros on the driver thread, between two batches).
+template <class Tp>
+struct ZeroArray {
+  Tp* p = nullptr;
+  size_t cap = 0;
+  ZeroArray() {}
+  ZeroArray(const ZeroArray&) = delete;
+  ZeroArray& operator=(const ZeroArray&) = delete;
+  ~ZeroArray() { free(p); }
+  void resize(size_t n) {  // contents are not kept: every batch rewrites them
+    if (n <= cap) return;
+    free(p);
+    cap = std::max(n, cap * 2);
+    p = (Tp*)calloc(cap, sizeof(Tp));
+    if (!p) {
+      cap = 0;
+      throw std::bad_alloc();
+    }
+  }
+  Tp* data() { return p; }
+  const Tp* data() const { return p; }
+  Tp* begin() { return p; }
+  Tp& operator[](size_t i) { return p[i]; }
+  const Tp& operator[](size_t i) const { return p[i]; }
+};
+
 struct Results {
-  std::vector<uint8_t> flags;
-  std::vector<uint16_t> lo1, len1, lo2, len2, s1, s2, minsum, os1, os2;
-  std::vector<uint32_t> lmask, target, visible;
+  ZeroArray<uint8_t> flags;
+  ZeroArray<uint16_t> lo1, len1, lo2, len2, s1, s2, minsum, os1, os2;
+  ZeroArray<uint32_t> lmask, target, visible;
   std::vector<int32_t> so;
   hlm_batch hb;
   hlm_screen_out scr;
@@ -1599,8 +1627,8 @@ int hlm_map_source_multi(hlm_ctx* const* ctxs, int n_ctx, PairSource& src, bool 
             std::lock_guard<std::mutex> g(err_mu);
             t_gpu += pr.ms_total * 1e-3;
           }
-          std::fill(res[cur].target.begin(), res[cur].target.end(), 0u);
-          std::fill(res[cur].visible.begin(), res[cur].visible.end(), 0u);
+          std::fill(res[cur].target.begin(), res[cur].target.begin() + b1->n, 0u);
+          std::fill(res[cur].visible.begin(), res[cur].visible.begin() + b1->n, 0u);
         } else {
           rc = hlm_run_async(c, &res[cur].hb, &res[cur].scr, &res[cur].sc, &res[cur].as);
           inflight = rc == 0;

@@ -265,7 +265,11 @@ int hlm_fetch(hlm_ctx* ctx, hlm_devbatch* b, hlm_screen_out* scr, hlm_score_out*
 
 /* all GPUs of one box: one context + host thread per device, the batch cut into one contiguous
  * range per device, results written straight into the caller's arrays (the pairs
- * are independent, src/map_dna.cpp:917-1029, so there is no collective).  devices == NULL: all. */
+ * are independent, src/map_dna.cpp:917-1029, so there is no collective).  devices == NULL: all.
+ * A device may be listed more than once: it then holds that many contexts.  For the file-level
+ * entry points (hlm_multi_map_fastq / hlm_multi_map_reads) two contexts on one GPU keep it busy
+ * across batch boundaries - one context stages and copies its next batch while the other one's
+ * kernels run - which is how the command line drives a single GPU. */
 typedef struct hlm_multi hlm_multi;
 hlm_multi* hlm_multi_create(const hlm_db* db, const int* devices, int n_devices,
                             const hlm_params* params, char* err, size_t errlen);

@@ -43,7 +43,9 @@ def main():
     on = float(sys.argv[2]) if len(sys.argv) > 2 else 0.01
     kind = sys.argv[3] if len(sys.argv) > 3 else "plain"
     with tempfile.TemporaryDirectory(dir="/tmp") as tmp:
-        db = synth.make_db(os.path.join(tmp, "db"), seed=42, n_loci=24, total_alleles=4000, n_others=200)
+        big = os.environ.get("HLM_FILE_BENCH_DB") == "40k"  # the benchmark's database instead of the small one
+        db = synth.make_db(os.path.join(tmp, "db"), seed=42, n_loci=24, total_alleles=40000 if big else 4000,
+                           n_others=2000 if big else 200)
         rb = synth.make_reads_fast(db, n, first_pair=0, read_len=150, seed=1003, on_target=on, indel_rate=1e-4)
         r1, r2 = os.path.join(tmp, "r1.fastq"), os.path.join(tmp, "r2.fastq")
         synth.write_fastq_fast(rb, r1, r2)
@@ -54,10 +56,13 @@ def main():
                 os.remove(src)
             r1, r2 = r1 + ".gz", r2 + ".gz"
         gdb = api.Database(db.path)
-        m = api.Mapper(gdb, 0, _abi.default_params(score_cap=1))  # as the command line runs
+        m1 = api.Mapper(gdb, 0, _abi.default_params(score_cap=1))  # as the command line runs
         k = 0
         for setting in [""] + sys.argv[4:]:
             env = dict(kv.split("=", 1) for kv in setting.split(",") if kv)
+            # CTX=k: k contexts on GPU 0 behind hlm_multi_map_fastq (batches of different contexts overlap)
+            nctx = int(env.pop("CTX", "1"))
+            m = m1 if nctx == 1 else api.MultiMapper(gdb, [0] * nctx, _abi.default_params(score_cap=1))
             os.environ.update(env)
             for rep in range(2):
                 out = os.path.join(tmp, f"out{k}")
@@ -73,7 +78,9 @@ def main():
                 shutil.rmtree(out)
             for a in env:
                 del os.environ[a]
-        m.close()
+            if m is not m1:
+                m.close()
+        m1.close()
 
 
 if __name__ == "__main__":
