@@ -71,17 +71,21 @@ void parallel_for(int n, F f) {
 // Batch sizes of a run.  The GPU cannot start before its first batch is parsed, and the last
 // batch is collected and written after the GPU has gone idle, so the run starts (and, where the
 // length of the input is known, ends) with small batches: B/8, B/8, B/4, B/2, then B pairs.
-// Runs with batches below 512 Ki pairs (the tests) are cut uniformly.
-constexpr int64_t kRampMin = (int64_t)8 << 16;
+// Runs with batches below 512 Ki pairs are cut uniformly.
+int64_t ramp_min() {  // HLM_RAMP_MIN_PAIRS: lets the tests run the ramp on their small inputs
+  const char* e = getenv("HLM_RAMP_MIN_PAIRS");
+  long long v = e ? atoll(e) : 0;
+  return v >= 8 ? (int64_t)v : (int64_t)8 << 16;
+}
 int64_t batch_size(int64_t k, int64_t B) {
-  if (B < kRampMin) return B;
+  if (B < ramp_min()) return B;
   return k < 2 ? B / 8 : k == 2 ? B / 4 : k == 3 ? B / 2 : B;
 }
 // record index at which every batch of an input of N records starts (+ N at the end)
 std::vector<int64_t> batch_plan(int64_t N, int64_t B) {
   std::vector<int64_t> rec(1, 0);
   for (int64_t k = 0; rec.back() < N; k++) rec.push_back(std::min(N, rec.back() + batch_size(k, B)));
-  if (B >= kRampMin && rec.size() >= 2) {
+  if (B >= ramp_min() && rec.size() >= 2) {
     // the last batch gives way to  rest | B/4 | B/8
     int64_t a = rec[rec.size() - 2], R = N - a, t1 = B / 4, t2 = B / 8;
     if (R > t1 + t2) {
@@ -1272,6 +1276,72 @@ void sort_kept(std::vector<std::vector<Kept>>& parts, KeptVec& out, int nt) {
 }
 
 }  // namespace
+
+// Self test of the FASTQ sources (tests/test_host_sources.py; not part of the interface): the
+// mapped, multi-threaded source (batch boundaries from the newline count, batch sizes ramped up at
+// the start and down at the end) and the sequential reader must deliver the same records in the
+// same order - headers, bases, qualities - for the same files, the two mates of a batch always
+// side by side.  0 when they do, else the number of the check that failed.
+extern "C" int hlm_selftest_fastq_sources(const char* r1, const char* r2, int64_t batch, int threads,
+                                          int64_t* n_batches, int64_t* n_records) {
+  try {
+    struct All {
+      std::vector<char> hdr[2];
+      std::vector<uint8_t> bases[2], quals[2];
+      std::vector<uint64_t> hl[2], sl[2];
+      int64_t batches = 0, records = 0;
+      bool ok = true;
+      void add(const MateBatch* m, int k) {
+        if (!m) return;
+        hdr[k].insert(hdr[k].end(), m->hdr.begin(), m->hdr.end());
+        bases[k].insert(bases[k].end(), m->bases.begin(), m->bases.end());
+        quals[k].insert(quals[k].end(), m->quals.begin(), m->quals.end());
+        if ((int64_t)m->offs.size() != m->n + 1 || (int64_t)m->hoff.size() != m->n + 1) ok = false;
+        for (int64_t i = 0; i < m->n && ok; i++) {
+          hl[k].push_back(m->hoff[i + 1] - m->hoff[i]);
+          sl[k].push_back(m->offs[i + 1] - m->offs[i]);
+        }
+      }
+    } A, B;
+    auto drain = [&](PairSource& src, All& out) -> int {
+      for (;;) {
+        MateBatch *m1 = nullptr, *m2 = nullptr;
+        int rc = 0;
+        std::string err;
+        if (!src.next(m1, m2, rc, err)) return rc ? 4 : 0;
+        if (m2 && m1->n != m2->n) return 5;
+        out.add(m1, 0);
+        out.add(m2, 1);
+        out.batches++;
+        out.records += m1->n;
+        src.recycle(m1, m2);
+      }
+    };
+    {
+      MappedSource ms(batch, threads);
+      if (!ms.open(r1, r2)) return 1;
+      if (!ms.counts_agree()) return 2;
+      ms.start();
+      if (int rc = drain(ms, A)) return rc;
+    }
+    {
+      FileSource fs(r1, r2, batch);
+      if (!fs.ok1() || !fs.ok2()) return 3;
+      if (int rc = drain(fs, B)) return 10 + rc;
+    }
+    if (!A.ok || !B.ok) return 6;
+    if (A.records != B.records) return 7;
+    for (int k = 0; k < 2; k++)
+      if (A.hdr[k] != B.hdr[k] || A.bases[k] != B.bases[k] || A.quals[k] != B.quals[k] || A.hl[k] != B.hl[k] ||
+          A.sl[k] != B.sl[k])
+        return 8 + k;
+    if (n_batches) *n_batches = A.batches;
+    if (n_records) *n_records = A.records;
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
 
 // Self test of the parallel id sort (tests/test_host_sort.py; not part of the interface): n random
 // ids with a shared prefix, duplicates and different lengths, sorted by sort_keys() on `threads`
