@@ -352,13 +352,13 @@ void set_err(char* err, size_t errlen, const std::string& m) {
 // reads held in memory, served in slices
 class MemSource : public PairSource {
  public:
-  MemSource(const hlm_reads* r, int64_t batch) : r_(r), batch_(batch) {}
+  MemSource(const hlm_reads* r, int64_t batch) : r_(r), plan_(hlm_batch_plan(r->m1.n, batch)) {}
   bool next(MateBatch*& b1, MateBatch*& b2, int&, std::string&) override {
-    if (at_ >= r_->m1.n) return false;
-    int64_t hi = std::min(r_->m1.n, at_ + batch_);
-    b1 = slice(r_->m1, at_, hi);
-    b2 = r_->paired ? slice(r_->m2, at_, hi) : nullptr;
-    at_ = hi;
+    if (k_ + 1 >= plan_.size()) return false;
+    int64_t lo = plan_[k_], hi = plan_[k_ + 1];
+    k_++;
+    b1 = slice(r_->m1, lo, hi);
+    b2 = r_->paired ? slice(r_->m2, lo, hi) : nullptr;
     return true;
   }
   void recycle(MateBatch* b1, MateBatch* b2) override {
@@ -388,7 +388,8 @@ class MemSource : public PairSource {
     return b;
   }
   const hlm_reads* r_;
-  int64_t batch_, at_ = 0;
+  std::vector<int64_t> plan_;  // first record of every batch
+  size_t k_ = 0;
   std::vector<MateBatch*> free_;
   std::vector<std::unique_ptr<MateBatch>> pool_;
 };

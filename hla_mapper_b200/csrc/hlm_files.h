@@ -34,6 +34,10 @@ struct MateBatch {
   }
 };
 
+// record index at which every batch of an input of N records starts (+ N at the end): batches of
+// B pairs, small ones at the start and at the end of a large run (hlm_files.cpp)
+std::vector<int64_t> hlm_batch_plan(int64_t N, int64_t B);
+
 // where the batches of the mapping loop come from
 class PairSource {
  public:
