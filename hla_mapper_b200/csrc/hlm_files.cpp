@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "hlm_bgzf.h"
+#include "hlm_pgzip.h"
 #include "hlm_db.h"
 #include "hlm_files.h"
 
@@ -114,10 +115,13 @@ class FastqReader {
       if (r >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         close(fd_);
         fd_ = -1;
+        int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
         if (hlm_is_bgzf(magic, (size_t)r) && map_.open(path)) {
-          int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
           bg_.reset(new HlmBgzf(map_.p, map_.n, nt));
-        } else {
+        } else if (!getenv("HLM_GZIP_ZLIB") && map_.open(path)) {
+          // plain gzip: one deflate stream, inflated by several threads (hlm_pgzip.h)
+          pg_.reset(new HlmPgzip(map_.p, map_.n, nt));
+        } else {  // HLM_GZIP_ZLIB=1 (or a file that cannot be mapped): zlib's single-threaded reader
           f_ = gzopen(path, "rb");
           if (f_) gzbuffer(f_, 1 << 22);
         }
@@ -131,7 +135,7 @@ class FastqReader {
     if (f_) gzclose(f_);
     if (fd_ >= 0) close(fd_);
   }
-  bool ok() const { return f_ != nullptr || fd_ >= 0 || bg_ != nullptr; }
+  bool ok() const { return f_ != nullptr || fd_ >= 0 || bg_ != nullptr || pg_ != nullptr; }
   // appends up to max_pairs records to b; returns number appended
   int64_t read(MateBatch& b, int64_t max_pairs) {
     int64_t got = 0;
@@ -191,6 +195,9 @@ class FastqReader {
     if (bg_) {
       r = bg_->fill((uint8_t*)buf_.data() + have_, want, 512);
       if (r < 0) corrupt_ = true;
+    } else if (pg_) {
+      r = pg_->fill((uint8_t*)buf_.data() + have_, want);
+      if (r < 0) corrupt_ = true;
     } else if (f_) {
       r = (long)gzread(f_, buf_.data() + have_, (unsigned)want);
       int en = Z_OK;
@@ -206,6 +213,7 @@ class FastqReader {
   int fd_ = -1;
   HlmMapped map_;
   std::unique_ptr<HlmBgzf> bg_;
+  std::unique_ptr<HlmPgzip> pg_;
   bool corrupt_ = false;
   std::vector<char> buf_;
   size_t pos_ = 0, have_ = 0;
@@ -1276,9 +1284,11 @@ void sort_kept(std::vector<std::vector<Kept>>& parts, KeptVec& out, int nt) {
 // mapped, multi-threaded source (batch boundaries from the newline count, batch sizes ramped up at
 // the start and down at the end) and the sequential reader must deliver the same records in the
 // same order - headers, bases, qualities - for the same files, the two mates of a batch always
-// side by side.  0 when they do, else the number of the check that failed.
+// side by side; the sequential reader may be given the same reads compressed (gzip: inflated by
+// several threads, hlm_pgzip.h; bgzip: hlm_bgzf.h).  0 when they do, else the failed check.
 extern "C" int hlm_selftest_fastq_sources(const char* r1, const char* r2, int64_t batch, int threads,
-                                          int64_t* n_batches, int64_t* n_records) {
+                                          int64_t* n_batches, int64_t* n_records, const char* seq1,
+                                          const char* seq2) {
   try {
     struct All {
       std::vector<char> hdr[2];
@@ -1320,7 +1330,8 @@ extern "C" int hlm_selftest_fastq_sources(const char* r1, const char* r2, int64_
       if (int rc = drain(ms, A)) return rc;
     }
     {
-      FileSource fs(r1, r2, batch);
+      // seq1 / seq2: the same reads in other files (gzip, bgzip) for the sequential reader
+      FileSource fs(seq1 ? seq1 : r1, seq1 ? seq2 : r2, batch);
       if (!fs.ok1() || !fs.ok2()) return 3;
       if (int rc = drain(fs, B)) return 10 + rc;
     }
@@ -1333,6 +1344,59 @@ extern "C" int hlm_selftest_fastq_sources(const char* r1, const char* r2, int64_
     if (n_batches) *n_batches = A.batches;
     if (n_records) *n_records = A.records;
     return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+
+// Self test of the parallel gzip reader (tests/test_pgzip.py; not part of the interface): the
+// file inflated by HlmPgzip on `threads` threads with chunks of `chunk_kb` KiB of compressed data,
+// and by zlib's gzread.  0: same text (its length and CRC-32 are returned, with the number of
+// chunks and of chunks that had to be decoded a second time); 1: the texts differ; 2: HlmPgzip
+// reports an error (`zlib_ok` tells whether zlib read the file without one); -1: out of memory.
+extern "C" int hlm_selftest_pgzip(const char* path, int threads, int chunk_kb, int64_t* length, uint32_t* crc,
+                                  int64_t* n_chunks, int64_t* n_slow, int* zlib_ok, double* seconds) {
+  try {
+    std::vector<uint8_t> want;
+    bool zok = true;
+    {
+      gzFile f = gzopen(path, "rb");
+      if (!f) return 3;
+      gzbuffer(f, 1 << 20);
+      std::vector<uint8_t> buf((size_t)1 << 22);
+      for (;;) {
+        int r = gzread(f, buf.data(), (unsigned)buf.size());
+        if (r < 0) zok = false;
+        if (r <= 0) break;
+        want.insert(want.end(), buf.begin(), buf.begin() + r);
+      }
+      int en = Z_OK;
+      gzerror(f, &en);
+      if (en != Z_OK && en != Z_STREAM_END) zok = false;
+      gzclose(f);
+    }
+    if (zlib_ok) *zlib_ok = zok ? 1 : 0;
+    HlmMapped m;
+    if (!m.open(path)) return 3;
+    char kb[32];
+    snprintf(kb, sizeof kb, "%d", chunk_kb);
+    if (chunk_kb > 0) setenv("HLM_PGZIP_CHUNK_KB", kb, 1);
+    double t0 = now_s();
+    HlmPgzip pg(m.p, m.n, threads);
+    if (chunk_kb > 0) unsetenv("HLM_PGZIP_CHUNK_KB");
+    std::vector<uint8_t> got, buf((size_t)3 << 20);
+    for (;;) {
+      long r = pg.fill(buf.data(), buf.size());
+      if (r < 0) return 2;
+      if (r == 0) break;
+      got.insert(got.end(), buf.begin(), buf.begin() + r);
+    }
+    if (seconds) *seconds = now_s() - t0;
+    if (n_chunks) *n_chunks = pg.n_chunks;
+    if (n_slow) *n_slow = pg.n_slow;
+    if (length) *length = (int64_t)got.size();
+    if (crc) *crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), got.data(), (uInt)got.size());
+    return got == want ? 0 : 1;
   } catch (const std::exception&) {
     return -1;
   }

@@ -24,12 +24,14 @@ def write_fastq(path, n, seed, mate, last_newline=True, ragged=True):
             f.write(f"@read{i:07d}/{mate} extra field\n{seq}\n+\n{qual}{end}")
 
 
-def sources(r1, r2, batch, threads):
+def sources(r1, r2, batch, threads, seq1=None, seq2=None):
     f = api.lib().hlm_selftest_fastq_sources
-    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                  C.c_char_p, C.c_char_p]
     f.restype = C.c_int
     nb, nr = C.c_int64(0), C.c_int64(0)
-    rc = f(r1.encode(), r2.encode() if r2 else None, batch, threads, C.byref(nb), C.byref(nr))
+    rc = f(r1.encode(), r2.encode() if r2 else None, batch, threads, C.byref(nb), C.byref(nr),
+           seq1.encode() if seq1 else None, seq2.encode() if seq2 else None)
     return rc, nb.value, nr.value
 
 
@@ -58,3 +60,27 @@ def test_incomplete_last_record_is_dropped(tmp_path):
         f.write("@partial\nACGT\n+\n")  # no quality line
     rc, nb, nr = sources(r1, None, 4, 2)
     assert rc == 0 and nr == 10
+
+
+@pytest.mark.parametrize("reader", ["threads", "zlib"])
+def test_gzip_input_gives_the_same_records(tmp_path, monkeypatch, reader):
+    """plain gzip files go through the multi-threaded inflater (csrc/hlm_pgzip.h; HLM_GZIP_ZLIB=1:
+    zlib's gzread): same records as the plain files, here with chunks of 4 KiB of compressed data"""
+    import gzip
+
+    r1, r2 = str(tmp_path / "r1.fastq"), str(tmp_path / "r2.fastq")
+    write_fastq(r1, 30000, 5, 1)
+    write_fastq(r2, 30000, 6, 2)
+    for p in (r1, r2):
+        with open(p, "rb") as f, open(p + ".gz", "wb") as o:
+            o.write(gzip.compress(f.read(), 6))
+    monkeypatch.setenv("HLM_PGZIP_CHUNK_KB", "4")
+    if reader == "zlib":
+        monkeypatch.setenv("HLM_GZIP_ZLIB", "1")
+    rc, nb, nr = sources(r1, r2, 7000, 4, r1 + ".gz", r2 + ".gz")
+    assert rc == 0 and nr == 30000
+    # a truncated file is an error of the reader
+    data = open(r2 + ".gz", "rb").read()
+    open(r2 + ".gz", "wb").write(data[:len(data) // 2])
+    rc, _, _ = sources(r1, r2, 7000, 4, r1 + ".gz", r2 + ".gz")
+    assert rc != 0
