@@ -555,7 +555,11 @@ class HlmPgzip {
     double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     const uint64_t total_bits = (uint64_t)n_ * 8;
     const size_t K = chunks_.size();
-    const uint64_t cb = (uint64_t)chunk_bytes_ * 8;
+    // the first rounds use smaller chunks (1/8, 1/4, 1/2 of the size): the consumer gets its first
+    // text after a fraction of a full round
+    const int shrink = round_no_ < 3 ? 3 - round_no_ : 0;
+    round_no_++;
+    const uint64_t cb = (uint64_t)std::max<size_t>(chunk_bytes_ >> shrink, 1024) * 8;
     // nominal cuts: chunk i covers compressed bits [cut[i], cut[i + 1])
     std::vector<uint64_t> cut(K + 1);
     for (size_t i = 0; i <= K; i++) cut[i] = std::min(total_bits, next_bit_ + cb * i);
@@ -718,6 +722,7 @@ class HlmPgzip {
   size_t n_;
   int threads_;
   size_t chunk_bytes_ = (size_t)2 << 20;
+  int round_no_ = 0;
   std::vector<std::unique_ptr<hlm_pgz::Chunk>> chunks_;
   uint64_t next_bit_ = 0;
   bool next_member_start_ = true;

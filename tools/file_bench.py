@@ -33,8 +33,13 @@ def bgzf_write(src, dst, block=0xff00):
 def gzip_write(src, dst):
     import gzip
     import shutil
+    import subprocess
 
-    with open(src, "rb") as f, gzip.open(dst, "wb", compresslevel=1) as o:
+    if shutil.which("gzip"):  # the usual writer of .fastq.gz files, at its default level
+        with open(dst, "wb") as o:
+            subprocess.check_call(["gzip", "-6", "-c", src], stdout=o)
+        return
+    with open(src, "rb") as f, gzip.open(dst, "wb", compresslevel=6) as o:
         shutil.copyfileobj(f, o, 1 << 24)
 
 
@@ -51,10 +56,18 @@ def main():
         synth.write_fastq_fast(rb, r1, r2)
         size = os.path.getsize(r1) + os.path.getsize(r2)
         if kind != "plain":
+            import threading
+
+            ths = [threading.Thread(target=bgzf_write if kind == "bgzf" else gzip_write, args=(src, src + ".gz"))
+                   for src in (r1, r2)]
+            for t_ in ths:
+                t_.start()
+            for t_ in ths:
+                t_.join()
             for src in (r1, r2):
-                (bgzf_write if kind == "bgzf" else gzip_write)(src, src + ".gz")
                 os.remove(src)
             r1, r2 = r1 + ".gz", r2 + ".gz"
+            print(f"compressed: {(os.path.getsize(r1) + os.path.getsize(r2)) / 1e9:.2f} GB", flush=True)
         gdb = api.Database(db.path)
         m1 = api.Mapper(gdb, 0, _abi.default_params(score_cap=1))  # as the command line runs
         k = 0
