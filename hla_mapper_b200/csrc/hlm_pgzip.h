@@ -701,6 +701,14 @@ class HlmPgzip {
       parts.emplace_back();
       parts.back().swap(c.out);  // the text leaves with the round: no copy
     }
+    // text that expands far more than FASTQ does (long runs of one byte: up to 1032 : 1) would make
+    // a round of full-size chunks hold gigabytes: the chunks shrink when a round expanded > 12 : 1
+    {
+      size_t text = 0;
+      for (auto& part : parts) text += part.size();
+      uint64_t used = (expect - next_bit_) / 8 + 1;
+      if (text / used > 12 && chunk_bytes_ > ((size_t)64 << 10)) chunk_bytes_ /= 2;
+    }
     if (trace)
       fprintf(stderr, "[pgzip] round: find %.1f ms, decode %.1f, stitch %.1f, resolve %.1f, hand over %.1f (%zu chunks)\n",
               (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, (now() - t4) * 1e3, order.size());
