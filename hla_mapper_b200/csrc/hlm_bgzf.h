@@ -13,6 +13,9 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -147,6 +150,87 @@ class HlmBgzf {
   const uint8_t* d_;
   size_t n_, pos_ = 0;
   int threads_;
+};
+
+// BGZF text inflated AHEAD of its consumer: one producer thread keeps two blocks of text (24 MB
+// each, every one inflated on all of the reader's threads) ready while the caller parses the
+// block before them.  fill(): up to `cap` bytes; 0 at the end of the file, -1 with the reader's
+// `err` set.
+class HlmBgzfAhead {
+ public:
+  explicit HlmBgzfAhead(HlmBgzf* bg) : bg_(bg) {
+    th_ = std::thread([this] { run(); });
+  }
+  ~HlmBgzfAhead() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (th_.joinable()) th_.join();
+  }
+  HlmBgzfAhead(const HlmBgzfAhead&) = delete;
+  HlmBgzfAhead& operator=(const HlmBgzfAhead&) = delete;
+  long fill(uint8_t* dst, size_t cap) {
+    size_t got = 0;
+    while (got < cap) {
+      if (at_ >= cur_.size()) {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return !q_.empty() || finished_; });
+        if (q_.empty()) {
+          if (failed_ && !got) return -1;
+          break;
+        }
+        cur_.swap(q_.front());
+        q_.pop_front();
+        at_ = 0;
+        cv_.notify_all();
+        continue;
+      }
+      size_t k = std::min(cap - got, cur_.size() - at_);
+      memcpy(dst + got, cur_.data() + at_, k);
+      got += k;
+      at_ += k;
+    }
+    return (long)got;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || q_.size() < 2; });
+        if (stop_) return;
+      }
+      std::vector<uint8_t> blk;
+      long r = -1;
+      try {
+        blk.resize((size_t)24 << 20);
+        r = bg_->fill(blk.data(), blk.size(), 384);
+        if (r > 0) blk.resize((size_t)r);
+      } catch (const std::exception&) {
+        bg_->err = "out of memory while inflating";
+        r = -1;
+      }
+      std::lock_guard<std::mutex> g(mu_);
+      if (r > 0) q_.push_back(std::move(blk));
+      if (r <= 0) {
+        failed_ = r < 0;
+        finished_ = true;
+      }
+      cv_.notify_all();
+      if (r <= 0) return;
+    }
+  }
+  HlmBgzf* bg_;
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::vector<uint8_t>> q_;
+  std::vector<uint8_t> cur_;
+  size_t at_ = 0;
+  bool stop_ = false, finished_ = false, failed_ = false;
 };
 
 #endif

@@ -118,6 +118,7 @@ class FastqReader {
         int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
         if (hlm_is_bgzf(magic, (size_t)r) && map_.open(path)) {
           bg_.reset(new HlmBgzf(map_.p, map_.n, nt));
+          bga_.reset(new HlmBgzfAhead(bg_.get()));  // inflated ahead of the parser
         } else if (!getenv("HLM_GZIP_ZLIB") && map_.open(path)) {
           // plain gzip: one deflate stream, inflated by several threads (hlm_pgzip.h)
           pg_.reset(new HlmPgzip(map_.p, map_.n, nt));
@@ -192,8 +193,8 @@ class FastqReader {
     if (buf_.size() - have_ < (1u << 16)) buf_.resize(buf_.size() * 2);  // room for one BGZF block
     size_t want = std::min<size_t>(buf_.size() - have_, 1u << 30);
     long r;
-    if (bg_) {
-      r = bg_->fill((uint8_t*)buf_.data() + have_, want, 512);
+    if (bga_) {
+      r = bga_->fill((uint8_t*)buf_.data() + have_, want);
       if (r < 0) corrupt_ = true;
     } else if (pg_) {
       r = pg_->fill((uint8_t*)buf_.data() + have_, want);
@@ -213,6 +214,7 @@ class FastqReader {
   int fd_ = -1;
   HlmMapped map_;
   std::unique_ptr<HlmBgzf> bg_;
+  std::unique_ptr<HlmBgzfAhead> bga_;  // declared after bg_: destroyed (its thread joined) first
   std::unique_ptr<HlmPgzip> pg_;
   bool corrupt_ = false;
   std::vector<char> buf_;
@@ -1397,6 +1399,36 @@ extern "C" int hlm_selftest_pgzip(const char* path, int threads, int chunk_kb, i
     if (length) *length = (int64_t)got.size();
     if (crc) *crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), got.data(), (uInt)got.size());
     return got == want ? 0 : 1;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+
+// Reader throughput (tools/reader_bench.py; not part of the interface): the sequential-reader
+// source drained over r1 (+ r2), whatever their compression; seconds and records out.
+extern "C" int hlm_selftest_reader_speed(const char* r1, const char* r2, int64_t batch, double* seconds,
+                                         int64_t* n_records, int64_t* n_bases) {
+  try {
+    double t0 = now_s();
+    FileSource fs(r1, r2, batch);
+    if (!fs.ok1() || !fs.ok2()) return 3;
+    int64_t nr = 0, nbs = 0;
+    for (;;) {
+      MateBatch *m1 = nullptr, *m2 = nullptr;
+      int rc = 0;
+      std::string err;
+      if (!fs.next(m1, m2, rc, err)) {
+        if (rc) return 4;
+        break;
+      }
+      nr += m1->n;
+      nbs += (int64_t)m1->bases.size() + (m2 ? (int64_t)m2->bases.size() : 0);
+      fs.recycle(m1, m2);
+    }
+    if (seconds) *seconds = now_s() - t0;
+    if (n_records) *n_records = nr;
+    if (n_bases) *n_bases = nbs;
+    return 0;
   } catch (const std::exception&) {
     return -1;
   }

@@ -157,7 +157,7 @@ struct Huff {
   }
 };
 
-typedef Huff<10, 288> LitHuff;
+typedef Huff<11, 288> LitHuff;
 typedef Huff<8, 32> DistHuff;
 typedef Huff<7, 19> PreHuff;
 
@@ -375,8 +375,13 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
         } else {
           const uint16_t* src = o + pos - dd;
           uint16_t* dst = o + pos;
-          if (dd >= (size_t)len) memcpy(dst, src, (size_t)len * 2);
-          else for (int k = 0; k < len; k++) dst[k] = src[k];
+          if (dd >= 8) {
+            // eight symbols per step; up to seven are written past the match, inside the slack
+            // every buffer keeps behind `limit`
+            for (int k = 0; k < len; k += 8) memcpy(dst + k, src + k, 16);
+          } else {
+            for (int k = 0; k < len; k++) dst[k] = src[k];
+          }
           pos += (size_t)len;
         }
       }

@@ -84,3 +84,25 @@ def test_gzip_input_gives_the_same_records(tmp_path, monkeypatch, reader):
     open(r2 + ".gz", "wb").write(data[:len(data) // 2])
     rc, _, _ = sources(r1, r2, 7000, 4, r1 + ".gz", r2 + ".gz")
     assert rc != 0
+
+
+def test_bgzip_input_gives_the_same_records(tmp_path):
+    """bgzip-compressed files (BGZF blocks inflated on several threads, ahead of the parser:
+    csrc/hlm_bgzf.h): same records as the plain files; a truncated file is an error"""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import bamlite
+
+    r1, r2 = str(tmp_path / "r1.fastq"), str(tmp_path / "r2.fastq")
+    write_fastq(r1, 30000, 8, 1)
+    write_fastq(r2, 30000, 9, 2)
+    for p in (r1, r2):
+        with open(p, "rb") as f, open(p + ".gz", "wb") as o:
+            o.write(bamlite.bgzf_deflate(f.read(), block=20000))
+    rc, nb, nr = sources(r1, r2, 7000, 4, r1 + ".gz", r2 + ".gz")
+    assert rc == 0 and nr == 30000
+    data = open(r1 + ".gz", "rb").read()
+    open(r1 + ".gz", "wb").write(data[:len(data) // 3])
+    rc, _, _ = sources(r1, r2, 7000, 4, r1 + ".gz", r2 + ".gz")
+    assert rc != 0
