@@ -105,8 +105,8 @@ class FastqReader {
  public:
   explicit FastqReader(const char* path) {
     // plain text goes through read(2) directly; bgzip-compressed files (BGZF: independent
-    // deflate blocks) are inflated on several host threads; only plain gzip streams are left to
-    // zlib's single-threaded gzread
+    // deflate blocks) and plain gzip files (one deflate stream: hlm_pgzip.h) are inflated on
+    // several host threads, ahead of this reader's parsing
     fd_ = open(path, O_RDONLY);
     if (fd_ >= 0) {
       unsigned char magic[64];
