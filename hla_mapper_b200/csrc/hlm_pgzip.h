@@ -55,6 +55,11 @@ struct BitIn {
     take((int)(bit & 7));
   }
   inline void refill() {
+    if (cnt < 0) {  // the fast decode loop takes bits without looking: past the end of the data
+      overrun = true;
+      cnt = 0;
+      buf = 0;
+    }
     if (end - p >= 8) {
       uint64_t v;
       memcpy(&v, p, 8);
@@ -157,8 +162,10 @@ struct Huff {
   }
 };
 
-typedef Huff<11, 288> LitHuff;
-typedef Huff<8, 32> DistHuff;
+constexpr int kLitBits = 11, kDistBits = 8;
+constexpr uint32_t kFLit = 1u << 4, kFEob = 1u << 5;
+typedef Huff<kLitBits, 288> LitHuff;
+typedef Huff<kDistBits, 32> DistHuff;
 typedef Huff<7, 19> PreHuff;
 
 static const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -300,6 +307,7 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
   BitIn in(d, n, c.start_bit);
   LitHuff lit;
   DistHuff dist;
+  uint32_t flit[1 << kLitBits], fdist[1 << kDistBits];
   SymBuf& sb = c.sym;
   sb.clear();
   size_t pos = 0;           // symbols produced
@@ -340,31 +348,91 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
     } else {
       if (btype == 1) fixed_codes(lit, dist);
       else if (!read_dynamic(in, lit, dist, false)) return false;
+      // direct tables for the loop below: what a code means, ready to use (literal byte / length
+      // base and number of extra bits / end of block), so that a literal costs one look-up and up
+      // to three literals are taken per refill of the bit buffer
+      for (uint32_t i = 0; i < (1u << kLitBits); i++) {
+        uint16_t e = lit.tab[i];
+        uint32_t l = e & 15u, sy = e >> 4, f = 0;
+        if (l) {
+          if (sy < 256) f = kFLit | (sy << 16) | l;
+          else if (sy == 256) f = kFEob | l;
+          else if (sy - 257 < 29) f = ((uint32_t)kLenBase[sy - 257] << 16) | ((uint32_t)kLenExtra[sy - 257] << 8) | l;
+        }
+        flit[i] = f;  // 0: a longer (or invalid) code - the generic decoder takes over
+      }
+      for (uint32_t i = 0; i < (1u << kDistBits); i++) {
+        uint16_t e = dist.tab[i];
+        uint32_t l = e & 15u, sy = e >> 4;
+        fdist[i] = (l && sy < 30) ? (((uint32_t)kDistBase[sy] << 16) | ((uint32_t)kDistExtra[sy] << 8) | l) : 0;
+      }
       size_t limit = sb.cap - 1024;
       for (;;) {
         if (pos >= limit) {
           // also the place where a decode that ran off the data, or a candidate start that is
           // not one and expands without bound, is stopped
-          if (in.overrun || pos > max_sym) return false;
+          if (in.cnt < 0 || in.overrun || pos > max_sym) return false;
           if (!sb.grow(sb.cap * 2)) return false;
           o = sb.p;
           limit = sb.cap - 1024;
         }
         in.refill();
-        int s = lit.decode(in);
-        if (s < 256) {
-          if (s < 0) return false;
-          o[pos++] = (uint16_t)s;
-          continue;
+        uint32_t f = flit[in.buf & ((1u << kLitBits) - 1)];
+        if (f & kFLit) {
+          o[pos++] = (uint16_t)(f >> 16);
+          in.buf >>= (f & 15);
+          in.cnt -= (int)(f & 15);
+          f = flit[in.buf & ((1u << kLitBits) - 1)];
+          if (f & kFLit) {
+            o[pos++] = (uint16_t)(f >> 16);
+            in.buf >>= (f & 15);
+            in.cnt -= (int)(f & 15);
+            f = flit[in.buf & ((1u << kLitBits) - 1)];
+            if (f & kFLit) {
+              o[pos++] = (uint16_t)(f >> 16);
+              in.buf >>= (f & 15);
+              in.cnt -= (int)(f & 15);
+              continue;
+            }
+          }
+          in.refill();  // a match needs up to 48 bits
         }
-        if (s == 256) break;
-        s -= 257;
-        if (s >= 29) return false;
-        int len = kLenBase[s] + (int)in.get(kLenExtra[s]);
-        int ds = dist.decode(in);
-        if (ds < 0 || ds >= 30) return false;
-        size_t dd = kDistBase[ds] + (size_t)in.get(kDistExtra[ds]);
-        if (in.overrun) return false;
+        int len;
+        if (f == 0) {  // a code longer than the table's index, or an invalid one
+          int sl = lit.decode(in);
+          if (sl < 256) {
+            if (sl < 0) return false;
+            o[pos++] = (uint16_t)sl;
+            continue;
+          }
+          if (sl == 256) break;
+          sl -= 257;
+          if (sl >= 29) return false;
+          len = kLenBase[sl] + (int)in.get(kLenExtra[sl]);
+        } else {
+          in.buf >>= (f & 15);
+          in.cnt -= (int)(f & 15);
+          if (f & kFEob) break;
+          uint32_t xb = (f >> 8) & 31u;
+          len = (int)(f >> 16) + (int)(in.buf & ((1u << xb) - 1));
+          in.buf >>= xb;
+          in.cnt -= (int)xb;
+        }
+        size_t dd;
+        uint32_t fd = fdist[in.buf & ((1u << kDistBits) - 1)];
+        if (fd) {
+          in.buf >>= (fd & 15);
+          in.cnt -= (int)(fd & 15);
+          uint32_t xb = (fd >> 8) & 31u;
+          dd = (size_t)(fd >> 16) + (size_t)(in.buf & ((1u << xb) - 1));
+          in.buf >>= xb;
+          in.cnt -= (int)xb;
+        } else {
+          int ds = dist.decode(in);
+          if (ds < 0 || ds >= 30) return false;
+          dd = kDistBase[ds] + (size_t)in.get(kDistExtra[ds]);
+        }
+        if (in.cnt < 0 || in.overrun) return false;
         size_t avail = pos - member_base;
         if (dd > avail) {
           // reaches before the text this chunk has produced in the current member
@@ -385,7 +453,7 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
           pos += (size_t)len;
         }
       }
-      if (in.overrun) return false;
+      if (in.cnt < 0 || in.overrun) return false;
     }
     if (pos > max_sym) return false;
     if (bfinal) {
