@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhlamap.so")
 CLI = os.path.join(HERE, "hla-mapper-b200")
 SOURCES = ["hlm_api.cu", "hlm_kernels.cu", "hlm_db.cpp", "hlm_files.cpp", "hlm_bam.cpp"]
-HEADERS = ["hlm_cli.cpp", "hlm_common.h", "hlm_files.h", "hlm_bgzf.h", "hlm_pgzip.h", "hlm_core.cuh", "hlm_db.h", "hlm_kernels.cuh", "../../include/hlamap.h"]
+HEADERS = ["hlm_cli.cpp", "hlm_common.h", "hlm_files.h", "hlm_bgzf.h", "hlm_pgzip.h", "hlm_crc32.h", "hlm_core.cuh", "hlm_db.h", "hlm_kernels.cuh", "../../include/hlamap.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

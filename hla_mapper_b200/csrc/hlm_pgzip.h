@@ -24,6 +24,8 @@
 
 #include <zlib.h>
 
+#include "hlm_crc32.h"
+
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -265,13 +267,11 @@ struct Chunk {
   bool ok = false;                      // decoded without an error up to end_bit
   bool hit_end = false;                 // the data ended here (after a final block and its trailer)
   SymBuf sym;                           // literals and markers
-  std::vector<uint8_t> out;             // resolved text
   std::vector<MemberEnd> ends;
   std::vector<uint32_t> seg_crc;        // CRC-32 of the output segments between member ends
   void reset() {
     has_start = known_start = member_start = ok = hit_end = false;
     sym.clear();
-    out.clear();
     ends.clear();
     seg_crc.clear();
   }
@@ -535,17 +535,30 @@ class HlmPgzip {
     }
     cv_.notify_all();
     if (producer_.joinable()) producer_.join();
+    for (Text& t : free_texts_) free(t.p);
+    for (auto& r : queue_)
+      for (Text& t : r) free(t.p);
+    for (Text& t : cur_) free(t.p);
   }
   HlmPgzip(const HlmPgzip&) = delete;
   HlmPgzip& operator=(const HlmPgzip&) = delete;
   std::string err;
   int64_t n_slow = 0, n_chunks = 0;  // chunks decoded again from a corrected start / all chunks
+  // a block of text; its memory is recycled between the producer and fill() and never zeroed
+  struct Text {
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+  };
   // Up to `cap` bytes of text to dst; 0 at the end of the file, -1 with `err` set.
   long fill(uint8_t* dst, size_t cap) {
     size_t got = 0;
     while (got < cap) {
       if (cur_part_ >= cur_.size()) {  // next round
         std::unique_lock<std::mutex> g(mu_);
+        for (Text& t : cur_) free_texts_.push_back(t);
+        cur_.clear();
+        cur_part_ = 0;
+        cur_at_ = 0;
         cv_.wait(g, [this] { return !queue_.empty() || finished_; });
         if (queue_.empty()) {  // finished: the end of the file, or an error after the last good round
           if (failed_ && !got) return -1;
@@ -553,18 +566,15 @@ class HlmPgzip {
         }
         cur_.swap(queue_.front());
         queue_.pop_front();
-        cur_part_ = 0;
-        cur_at_ = 0;
         cv_.notify_all();
         continue;
       }
-      std::vector<uint8_t>& part = cur_[cur_part_];
-      size_t k = std::min(cap - got, part.size() - cur_at_);
-      memcpy(dst + got, part.data() + cur_at_, k);
+      Text& part = cur_[cur_part_];
+      size_t k = std::min(cap - got, part.n - cur_at_);
+      memcpy(dst + got, part.p + cur_at_, k);
       got += k;
       cur_at_ += k;
-      if (cur_at_ >= part.size()) {
-        std::vector<uint8_t>().swap(part);
+      if (cur_at_ >= part.n) {
         cur_part_++;
         cur_at_ = 0;
       }
@@ -580,7 +590,7 @@ class HlmPgzip {
         cv_.wait(g, [this] { return stop_ || queue_.size() < 2; });
         if (stop_) break;
       }
-      std::vector<std::vector<uint8_t>> parts;
+      std::vector<Text> parts;
       bool ok = false, last = false;
       try {
         ok = !failed_ && round(parts);
@@ -589,8 +599,12 @@ class HlmPgzip {
         err = "out of memory while inflating";
       }
       std::lock_guard<std::mutex> g(mu_);
-      if (ok) queue_.push_back(std::move(parts));
-      else failed_ = true;
+      if (ok) {
+        queue_.push_back(std::move(parts));
+      } else {
+        for (Text& t : parts) free_texts_.push_back(t);
+        failed_ = true;
+      }
       if (!ok || last) {
         finished_ = true;
         cv_.notify_all();
@@ -622,7 +636,30 @@ class HlmPgzip {
   static double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   }
-  bool round(std::vector<std::vector<uint8_t>>& parts) {
+  // a recycled block of at least n bytes (the smallest that fits, else a new one)
+  Text text_buffer(size_t n) {
+    Text t;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      size_t best = (size_t)-1;
+      for (size_t i = 0; i < free_texts_.size(); i++)
+        if (free_texts_[i].cap >= n && (best == (size_t)-1 || free_texts_[i].cap < free_texts_[best].cap)) best = i;
+      if (best == (size_t)-1 && !free_texts_.empty()) best = 0;  // too small: replaced below
+      if (best != (size_t)-1) {
+        t = free_texts_[best];
+        free_texts_.erase(free_texts_.begin() + (long)best);
+      }
+    }
+    if (t.cap < n) {
+      free(t.p);
+      t.cap = n + (n >> 3) + 4096;
+      t.p = (uint8_t*)malloc(t.cap);
+      if (!t.p) throw std::bad_alloc();
+    }
+    t.n = n;
+    return t;
+  }
+  bool round(std::vector<Text>& parts) {
     using namespace hlm_pgz;
     const bool trace = getenv("HLM_PGZIP_TRACE") != nullptr;
     double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
@@ -723,12 +760,13 @@ class HlmPgzip {
       if (take < (size_t)kWin) memcpy(nw.data(), w.data() + take, kWin - take);
       w.swap(nw);
     }
+    parts.resize(order.size());
+    for (size_t q = 0; q < order.size(); q++) parts[q] = text_buffer(chunks_[order[q]]->sym.size());
     parallel(order.size(), [&](size_t q) {
       Chunk& c = *chunks_[order[q]];
       const std::vector<uint8_t>& pw = win[q];
-      c.out.resize(c.sym.size());
       const uint16_t* s = c.sym.data();
-      uint8_t* o = c.out.data();
+      uint8_t* o = parts[q].p;
       size_t ns = c.sym.size();
       size_t k = 0;
       for (; k + 64 <= ns; k += 64) {  // markers are rare: 64 symbols at a time when there is none
@@ -750,7 +788,7 @@ class HlmPgzip {
       size_t a = 0;
       for (size_t e = 0; e <= c.ends.size(); e++) {
         size_t b = e < c.ends.size() ? c.ends[e].off : ns;
-        c.seg_crc.push_back((uint32_t)crc32(crc32(0L, Z_NULL, 0), o + a, (uInt)(b - a)));
+        c.seg_crc.push_back(hlm_crc32(0, o + a, b - a));
         a = b;
       }
     });
@@ -760,7 +798,7 @@ class HlmPgzip {
       Chunk& c = *chunks_[i];
       size_t a = 0;
       for (size_t e = 0; e <= c.ends.size(); e++) {
-        size_t b = e < c.ends.size() ? c.ends[e].off : c.out.size();
+        size_t b = e < c.ends.size() ? c.ends[e].off : c.sym.size();
         run_crc_ = (uint32_t)crc32_combine(run_crc_, c.seg_crc[e], (z_off_t)(b - a));
         run_len_ += b - a;
         if (e < c.ends.size()) {
@@ -771,14 +809,12 @@ class HlmPgzip {
         }
         a = b;
       }
-      parts.emplace_back();
-      parts.back().swap(c.out);  // the text leaves with the round: no copy
     }
     // text that expands far more than FASTQ does (long runs of one byte: up to 1032 : 1) would make
     // a round of full-size chunks hold gigabytes: the chunks shrink when a round expanded > 12 : 1
     {
       size_t text = 0;
-      for (auto& part : parts) text += part.size();
+      for (Text& part : parts) text += part.n;
       uint64_t used = (expect - next_bit_) / 8 + 1;
       if (text / used > 12 && chunk_bytes_ > ((size_t)64 << 10)) chunk_bytes_ /= 2;
     }
@@ -812,9 +848,10 @@ class HlmPgzip {
   std::thread producer_;
   std::mutex mu_;
   std::condition_variable cv_;
-  std::deque<std::vector<std::vector<uint8_t>>> queue_;
+  std::deque<std::vector<Text>> queue_;
+  std::vector<Text> free_texts_;  // consumed blocks on their way back to the producer
   bool stop_ = false, finished_ = false;
-  std::vector<std::vector<uint8_t>> cur_;
+  std::vector<Text> cur_;
   size_t cur_part_ = 0, cur_at_ = 0;
   uint32_t run_crc_ = 0;
   uint64_t run_len_ = 0;
