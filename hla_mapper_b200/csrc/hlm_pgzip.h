@@ -230,6 +230,161 @@ inline void fixed_codes(LitHuff& lit, DistHuff& dist) {
   dist.build(d, 30);  // 30 of 32 codes: incomplete by definition, codes 30 / 31 never decode
 }
 
+// The symbols of one Huffman-coded block (its code descriptions already read into lit / dist) up to
+// its end-of-block code.  T = uint16_t with MARK: matches that reach before the output become
+// window markers (a chunk entered in the middle of a stream); T = uint8_t without: such a match
+// is an error.  `room(pos)` is called when pos passes `limit`: it makes space (and may move the
+// buffer, returned through `o`) or fails; after it, 1024 more symbols must fit.
+// Returns false on invalid data or when the input ran out.
+template <class T, bool MARK, class Room>
+inline bool decode_block(BitIn& in, const LitHuff& lit, const DistHuff& dist, T*& o, size_t& pos, size_t& limit,
+                         size_t member_base, bool member_known, Room room) {
+  uint32_t flit[1 << kLitBits], fdist[1 << kDistBits];
+  // direct tables: what a code means, ready to use (literal byte / length base and number of extra
+  // bits / end of block), so that a literal costs one look-up and up to three literals are taken
+  // per refill of the bit buffer
+  for (uint32_t i = 0; i < (1u << kLitBits); i++) {
+    uint16_t e = lit.tab[i];
+    uint32_t l = e & 15u, sy = e >> 4, f = 0;
+    if (l) {
+      if (sy < 256) f = kFLit | (sy << 16) | l;
+      else if (sy == 256) f = kFEob | l;
+      else if (sy - 257 < 29) f = ((uint32_t)kLenBase[sy - 257] << 16) | ((uint32_t)kLenExtra[sy - 257] << 8) | l;
+    }
+    flit[i] = f;  // 0: a longer (or invalid) code - the generic decoder takes over
+  }
+  for (uint32_t i = 0; i < (1u << kDistBits); i++) {
+    uint16_t e = dist.tab[i];
+    uint32_t l = e & 15u, sy = e >> 4;
+    fdist[i] = (l && sy < 30) ? (((uint32_t)kDistBase[sy] << 16) | ((uint32_t)kDistExtra[sy] << 8) | l) : 0;
+  }
+  for (;;) {
+    if (pos >= limit) {
+      // also the place where a decode that ran off the data, or a candidate start that is not one
+      // and expands without bound, is stopped
+      if (in.cnt < 0 || in.overrun) return false;
+      if (!room(pos)) return false;
+    }
+    in.refill();
+    uint32_t f = flit[in.buf & ((1u << kLitBits) - 1)];
+    if (f & kFLit) {
+      o[pos++] = (T)(f >> 16);
+      in.buf >>= (f & 15);
+      in.cnt -= (int)(f & 15);
+      f = flit[in.buf & ((1u << kLitBits) - 1)];
+      if (f & kFLit) {
+        o[pos++] = (T)(f >> 16);
+        in.buf >>= (f & 15);
+        in.cnt -= (int)(f & 15);
+        f = flit[in.buf & ((1u << kLitBits) - 1)];
+        if (f & kFLit) {
+          o[pos++] = (T)(f >> 16);
+          in.buf >>= (f & 15);
+          in.cnt -= (int)(f & 15);
+          continue;
+        }
+      }
+      in.refill();  // a match needs up to 48 bits
+    }
+    int len;
+    if (f == 0) {  // a code longer than the table's index, or an invalid one
+      int sl = lit.decode(in);
+      if (sl < 256) {
+        if (sl < 0) return false;
+        o[pos++] = (T)sl;
+        continue;
+      }
+      if (sl == 256) break;
+      sl -= 257;
+      if (sl >= 29) return false;
+      len = kLenBase[sl] + (int)in.get(kLenExtra[sl]);
+    } else {
+      in.buf >>= (f & 15);
+      in.cnt -= (int)(f & 15);
+      if (f & kFEob) break;
+      uint32_t xb = (f >> 8) & 31u;
+      len = (int)(f >> 16) + (int)(in.buf & ((1u << xb) - 1));
+      in.buf >>= xb;
+      in.cnt -= (int)xb;
+    }
+    size_t dd;
+    uint32_t fd = fdist[in.buf & ((1u << kDistBits) - 1)];
+    if (fd) {
+      in.buf >>= (fd & 15);
+      in.cnt -= (int)(fd & 15);
+      uint32_t xb = (fd >> 8) & 31u;
+      dd = (size_t)(fd >> 16) + (size_t)(in.buf & ((1u << xb) - 1));
+      in.buf >>= xb;
+      in.cnt -= (int)xb;
+    } else {
+      int ds = dist.decode(in);
+      if (ds < 0 || ds >= 30) return false;
+      dd = kDistBase[ds] + (size_t)in.get(kDistExtra[ds]);
+    }
+    if (in.cnt < 0 || in.overrun) return false;
+    size_t avail = pos - member_base;
+    if (dd > avail) {
+      // reaches before the text produced in the current member
+      // (member_base == 0 here: an unknown member start can only be the chunk's own start)
+      if (!MARK || member_known || dd > avail + kWin) return false;
+      for (int k = 0; k < len; k++, pos++)
+        o[pos] = pos >= dd ? o[pos - dd] : (T)(kMarker + (kWin - (dd - pos)));
+    } else {
+      const T* src = o + pos - dd;
+      T* dst = o + pos;
+      if (dd * sizeof(T) >= 16) {
+        // sixteen bytes per step; the last step may write past the match, inside the slack every
+        // buffer keeps behind `limit`
+        for (size_t k = 0; k < (size_t)len * sizeof(T); k += 16) memcpy((char*)dst + k, (const char*)src + k, 16);
+      } else {
+        for (int k = 0; k < len; k++) dst[k] = src[k];
+      }
+      pos += (size_t)len;
+    }
+  }
+  return in.cnt >= 0 && !in.overrun;
+}
+
+// One raw deflate stream (a BGZF block) of known size into bytes: the stream must end with its
+// final block exactly at out_len bytes.  `scratch` holds at least out_len + 2048 bytes.
+inline bool inflate_raw(const uint8_t* d, size_t n, uint8_t* scratch, size_t out_len) {
+  BitIn in(d, n, 0);
+  LitHuff lit;
+  DistHuff dist;
+  uint8_t* o = scratch;
+  size_t pos = 0, limit = out_len + 1;  // room() is only ever asked when the stream is too long
+  for (;;) {
+    in.refill();
+    uint32_t bfinal = in.get(1), btype = in.get(2);
+    if (in.overrun || btype == 3) return false;
+    if (btype == 0) {
+      in.align();
+      in.refill();
+      uint32_t len = in.get(16), nlen = in.get(16);
+      if (in.overrun || (len ^ 0xFFFFu) != nlen || pos + len > out_len) return false;
+      while (len && in.cnt >= 8) {
+        o[pos++] = (uint8_t)in.get(8);
+        len--;
+      }
+      if (len) {
+        if ((size_t)(in.end - in.p) < len) return false;
+        in.buf = 0;
+        in.cnt = 0;
+        memcpy(o + pos, in.p, len);
+        pos += len;
+        in.p += len;
+      }
+    } else {
+      if (btype == 1) fixed_codes(lit, dist);
+      else if (!read_dynamic(in, lit, dist, false)) return false;
+      if (!decode_block<uint8_t, false>(in, lit, dist, o, pos, limit, 0, true, [](size_t) { return false; }))
+        return false;
+    }
+    if (pos > out_len) return false;
+    if (bfinal) return pos == out_len;
+  }
+}
+
 // growable array of 16-bit symbols that is never zero-filled
 struct SymBuf {
   uint16_t* p = nullptr;
@@ -307,7 +462,6 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
   BitIn in(d, n, c.start_bit);
   LitHuff lit;
   DistHuff dist;
-  uint32_t flit[1 << kLitBits], fdist[1 << kDistBits];
   SymBuf& sb = c.sym;
   sb.clear();
   size_t pos = 0;           // symbols produced
@@ -348,112 +502,15 @@ inline bool decode_chunk(const uint8_t* d, size_t n, Chunk& c, uint64_t stop_bit
     } else {
       if (btype == 1) fixed_codes(lit, dist);
       else if (!read_dynamic(in, lit, dist, false)) return false;
-      // direct tables for the loop below: what a code means, ready to use (literal byte / length
-      // base and number of extra bits / end of block), so that a literal costs one look-up and up
-      // to three literals are taken per refill of the bit buffer
-      for (uint32_t i = 0; i < (1u << kLitBits); i++) {
-        uint16_t e = lit.tab[i];
-        uint32_t l = e & 15u, sy = e >> 4, f = 0;
-        if (l) {
-          if (sy < 256) f = kFLit | (sy << 16) | l;
-          else if (sy == 256) f = kFEob | l;
-          else if (sy - 257 < 29) f = ((uint32_t)kLenBase[sy - 257] << 16) | ((uint32_t)kLenExtra[sy - 257] << 8) | l;
-        }
-        flit[i] = f;  // 0: a longer (or invalid) code - the generic decoder takes over
-      }
-      for (uint32_t i = 0; i < (1u << kDistBits); i++) {
-        uint16_t e = dist.tab[i];
-        uint32_t l = e & 15u, sy = e >> 4;
-        fdist[i] = (l && sy < 30) ? (((uint32_t)kDistBase[sy] << 16) | ((uint32_t)kDistExtra[sy] << 8) | l) : 0;
-      }
       size_t limit = sb.cap - 1024;
-      for (;;) {
-        if (pos >= limit) {
-          // also the place where a decode that ran off the data, or a candidate start that is
-          // not one and expands without bound, is stopped
-          if (in.cnt < 0 || in.overrun || pos > max_sym) return false;
-          if (!sb.grow(sb.cap * 2)) return false;
-          o = sb.p;
-          limit = sb.cap - 1024;
-        }
-        in.refill();
-        uint32_t f = flit[in.buf & ((1u << kLitBits) - 1)];
-        if (f & kFLit) {
-          o[pos++] = (uint16_t)(f >> 16);
-          in.buf >>= (f & 15);
-          in.cnt -= (int)(f & 15);
-          f = flit[in.buf & ((1u << kLitBits) - 1)];
-          if (f & kFLit) {
-            o[pos++] = (uint16_t)(f >> 16);
-            in.buf >>= (f & 15);
-            in.cnt -= (int)(f & 15);
-            f = flit[in.buf & ((1u << kLitBits) - 1)];
-            if (f & kFLit) {
-              o[pos++] = (uint16_t)(f >> 16);
-              in.buf >>= (f & 15);
-              in.cnt -= (int)(f & 15);
-              continue;
-            }
-          }
-          in.refill();  // a match needs up to 48 bits
-        }
-        int len;
-        if (f == 0) {  // a code longer than the table's index, or an invalid one
-          int sl = lit.decode(in);
-          if (sl < 256) {
-            if (sl < 0) return false;
-            o[pos++] = (uint16_t)sl;
-            continue;
-          }
-          if (sl == 256) break;
-          sl -= 257;
-          if (sl >= 29) return false;
-          len = kLenBase[sl] + (int)in.get(kLenExtra[sl]);
-        } else {
-          in.buf >>= (f & 15);
-          in.cnt -= (int)(f & 15);
-          if (f & kFEob) break;
-          uint32_t xb = (f >> 8) & 31u;
-          len = (int)(f >> 16) + (int)(in.buf & ((1u << xb) - 1));
-          in.buf >>= xb;
-          in.cnt -= (int)xb;
-        }
-        size_t dd;
-        uint32_t fd = fdist[in.buf & ((1u << kDistBits) - 1)];
-        if (fd) {
-          in.buf >>= (fd & 15);
-          in.cnt -= (int)(fd & 15);
-          uint32_t xb = (fd >> 8) & 31u;
-          dd = (size_t)(fd >> 16) + (size_t)(in.buf & ((1u << xb) - 1));
-          in.buf >>= xb;
-          in.cnt -= (int)xb;
-        } else {
-          int ds = dist.decode(in);
-          if (ds < 0 || ds >= 30) return false;
-          dd = kDistBase[ds] + (size_t)in.get(kDistExtra[ds]);
-        }
-        if (in.cnt < 0 || in.overrun) return false;
-        size_t avail = pos - member_base;
-        if (dd > avail) {
-          // reaches before the text this chunk has produced in the current member
-          // (member_base == 0 here: an unknown member start can only be the chunk's own start)
-          if (member_known || dd > avail + kWin) return false;
-          for (int k = 0; k < len; k++, pos++)
-            o[pos] = pos >= dd ? o[pos - dd] : (uint16_t)(kMarker + (kWin - (dd - pos)));
-        } else {
-          const uint16_t* src = o + pos - dd;
-          uint16_t* dst = o + pos;
-          if (dd >= 8) {
-            // eight symbols per step; up to seven are written past the match, inside the slack
-            // every buffer keeps behind `limit`
-            for (int k = 0; k < len; k += 8) memcpy(dst + k, src + k, 16);
-          } else {
-            for (int k = 0; k < len; k++) dst[k] = src[k];
-          }
-          pos += (size_t)len;
-        }
-      }
-      if (in.cnt < 0 || in.overrun) return false;
+      auto room = [&](size_t at) {
+        if (at > max_sym) return false;
+        if (!sb.grow(sb.cap * 2)) return false;
+        o = sb.p;
+        limit = sb.cap - 1024;
+        return true;
+      };
+      if (!decode_block<uint16_t, true>(in, lit, dist, o, pos, limit, member_base, member_known, room)) return false;
     }
     if (pos > max_sym) return false;
     if (bfinal) {

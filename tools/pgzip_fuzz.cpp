@@ -37,6 +37,33 @@ int main(int argc, char** argv) {
     else if (!pok && !zok) n_err++;
     else { printf("DISAGREE it %d kind %d pok %d zok %d got %zu want %zu\n", it, kind, pok, zok, got.size(), want.size()); n_mismatch++; }
   }
+  // the byte-mode decoder of single raw deflate streams (BGZF blocks): slices of the text deflated
+  // at random levels, intact or damaged, against zlib
+  {
+    std::vector<uint8_t> text;
+    { z_stream zs; memset(&zs,0,sizeof zs); inflateInit2(&zs, 31); zs.next_in = z.data(); zs.avail_in = z.size(); std::vector<uint8_t> buf(1<<20);
+      for(;;){ zs.next_out = buf.data(); zs.avail_out = buf.size(); int r = inflate(&zs, Z_NO_FLUSH); text.insert(text.end(), buf.data(), buf.data()+(buf.size()-zs.avail_out)); if (r != Z_OK) break; }
+      inflateEnd(&zs); }
+    int raw_ok = 0, raw_err = 0;
+    for (int it = 0; it < iters * 4 && text.size() > 70000; it++) {
+      size_t len = 1 + rng() % 65536, at = rng() % (text.size() - len);
+      if (it % 7 == 0) len = rng() % 40;
+      std::vector<uint8_t> comp(len + len / 8 + 256);
+      z_stream zs; memset(&zs,0,sizeof zs); deflateInit2(&zs, (int)(rng() % 10), Z_DEFLATED, -15, 8, it % 5 == 0 ? Z_FIXED : Z_DEFAULT_STRATEGY);
+      zs.next_in = text.data() + at; zs.avail_in = len; zs.next_out = comp.data(); zs.avail_out = comp.size(); deflate(&zs, Z_FINISH); comp.resize(zs.total_out); deflateEnd(&zs);
+      int kind = rng() % 3;
+      if (kind == 1 && comp.size() > 2) comp[rng() % comp.size()] ^= 1 << (rng() % 8);
+      if (kind == 2 && comp.size() > 2) comp.resize(1 + rng() % (comp.size() - 1));
+      std::vector<uint8_t> want(len + 1); bool zok;
+      { z_stream is; memset(&is,0,sizeof is); inflateInit2(&is, -15); is.next_in = comp.data(); is.avail_in = comp.size(); is.next_out = want.data(); is.avail_out = want.size();
+        int r = inflate(&is, Z_FINISH); zok = r == Z_STREAM_END && is.total_out == len; inflateEnd(&is); }
+      std::vector<uint8_t> scratch(len + 2048);
+      bool pok = hlm_pgz::inflate_raw(comp.data(), comp.size(), scratch.data(), len);
+      if (pok != zok || (pok && memcmp(scratch.data(), want.data(), len) != 0)) { n_mismatch++; printf("RAW MISMATCH it %d kind %d len %zu pok %d zok %d\n", it, kind, len, pok, zok); }
+      else if (pok) raw_ok++; else raw_err++;
+    }
+    printf("raw streams: ok %d err %d\n", raw_ok, raw_err);
+  }
   printf("ok %d err %d mismatch %d\n", n_ok, n_err, n_mismatch);
   return n_mismatch != 0;
 }
