@@ -167,6 +167,17 @@ class FastqReader {
       }
       size_t h0 = pos_, s0 = e[0] + 1, q0 = e[2] + 1;
       size_t hl = e[0] - h0, sl = e[1] - s0, ql = e[3] - q0;
+      if (got == 0 && b.n == 0) {
+        // room for the whole batch, sized from its first record: vectors that grow by doubling
+        // were copied (and their fresh pages faulted in) about twice over - most of the parsing
+        // time.  Untouched reserve costs nothing; longer reads later on still grow the vectors.
+        size_t m = (size_t)max_pairs;
+        b.hdr.reserve(m * (hl + 4));
+        b.bases.reserve(m * (sl + 1));
+        b.quals.reserve(m * (sl + 1));
+        b.offs.reserve(m + 1);
+        b.hoff.reserve(m + 1);
+      }
       b.hdr.insert(b.hdr.end(), base + h0, base + h0 + hl);
       b.hoff.push_back(b.hdr.size());
       b.bases.insert(b.bases.end(), (const uint8_t*)base + s0, (const uint8_t*)base + s0 + sl);
@@ -422,6 +433,7 @@ class MappedFastq {
       }
       size_t s0 = e[0] + 1, q0 = e[2] + 1;
       size_t hl = e[0] - p, sl = e[1] - s0, ql = e[3] - q0;
+      if (k == 0) out.hdr.reserve((size_t)want * (hl + 4));  // sized from the first header line
       out.hdr.insert(out.hdr.end(), base + p, base + p + hl);
       out.hoff.push_back(out.hdr.size());
       out.bases.insert(out.bases.end(), (const uint8_t*)base + s0, (const uint8_t*)base + s0 + sl);
