@@ -1446,6 +1446,33 @@ extern "C" int hlm_selftest_reader_speed(const char* r1, const char* r2, int64_t
   }
 }
 
+// Self test of hlm_crc32 (csrc/hlm_crc32.h; tests/test_pgzip.py): random buffers, offsets, lengths
+// and start values against zlib's crc32().  Returns the number of disagreements; *fast tells
+// whether the carry-less-multiplication path is in use on this CPU.
+extern "C" int hlm_selftest_crc32(int iterations, uint32_t seed, int* fast) {
+  std::vector<uint8_t> d((size_t)1 << 20);
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&] {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return x;
+  };
+  for (auto& b : d) b = (uint8_t)rnd();
+  int bad = 0;
+  for (int it = 0; it < iterations; it++) {
+    size_t off = rnd() % 100, n = rnd() % (it % 8 ? 3000 : d.size() - 100);
+    uint32_t start = it % 3 ? (uint32_t)rnd() : 0;
+    if ((uint32_t)crc32(start, d.data() + off, (uInt)n) != hlm_crc32(start, d.data() + off, n)) bad++;
+  }
+#ifdef HLM_CRC32_CLMUL
+  if (fast) *fast = hlm_crc32_clmul_ok();
+#else
+  if (fast) *fast = 0;
+#endif
+  return bad;
+}
+
 // Self test of the parallel id sort (tests/test_host_sort.py; not part of the interface): n random
 // ids with a shared prefix, duplicates and different lengths, sorted by sort_keys() on `threads`
 // threads and by one std::stable_sort; 0 when both orders are the same.

@@ -98,3 +98,14 @@ def test_truncated_and_damaged_files_are_errors(tmp_path):
     p = tmp_path / "crc.gz"
     p.write_bytes(bytes(b))
     assert pgzip(p, 4, 16)["rc"] == 2
+
+
+def test_crc32_equals_zlib():
+    """csrc/hlm_crc32.h: the carry-less-multiplication CRC-32 (used only after it reproduced zlib on
+    a test vector in this process) against zlib's crc32() on random buffers"""
+    f = api.lib().hlm_selftest_crc32
+    f.argtypes = [C.c_int, C.c_uint32, C.POINTER(C.c_int)]
+    f.restype = C.c_int
+    fast = C.c_int(-1)
+    assert f(4000, 7, C.byref(fast)) == 0
+    assert fast.value in (0, 1)
